@@ -1,0 +1,89 @@
+"""State-record layout and capacities, read from include/dynenv_b200.h (single source of truth).
+
+The header's `#define NAME value` lines and the `enum { NAME = expr, ... }` block are
+evaluated in order, so Python sees exactly the word offsets the CUDA kernels and the C-ABI
+use.  `RC_FIELDS` maps a field name to (offset, count, kind) with kind 'f' (float32) or
+'i' (int32) for viewing a state record as named arrays.
+"""
+import os
+import re
+
+_HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include",
+                       "dynenv_b200.h")
+
+
+def _parse(path):
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    env = {}
+    for m in re.finditer(r"^\s*#define\s+(\w+)\s+(.+?)\s*$", txt, flags=re.M):
+        name, expr = m.group(1), m.group(2)
+        expr = re.sub(r"(\d+)u\b", r"\1", expr)
+        try:
+            env[name] = eval(expr, {"__builtins__": {}}, env)
+        except Exception:
+            pass
+    for block in re.finditer(r"enum\s*\{(.*?)\}\s*;", txt, flags=re.S):
+        nxt = 0
+        for item in block.group(1).split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, expr = [s.strip() for s in item.split("=", 1)]
+                val = eval(expr.replace("/", "//"), {"__builtins__": {}}, env)
+            else:
+                name, val = item, nxt
+            env[name] = int(val)
+            nxt = int(val) + 1
+    return env
+
+
+C = _parse(_HEADER)
+globals().update({k: v for k, v in C.items() if isinstance(v, int)})
+
+_NB, _NP, _NA = C["RC_NBODY"], C["RC_MAXP"], C["RC_MAXARB"]
+RC_FIELDS = {
+    # bodies
+    "px": (C["RC_S_PX"], _NB, "f"), "py": (C["RC_S_PY"], _NB, "f"), "angle": (C["RC_S_ANG"], _NB, "f"),
+    "vx": (C["RC_S_VX"], _NB, "f"), "vy": (C["RC_S_VY"], _NB, "f"), "w": (C["RC_S_W"], _NB, "f"),
+    "fx": (C["RC_S_FX"], _NB, "f"), "fy": (C["RC_S_FY"], _NB, "f"), "torque": (C["RC_S_TQ"], _NB, "f"),
+    "vbx": (C["RC_S_VBX"], _NB, "f"), "vby": (C["RC_S_VBY"], _NB, "f"), "wb": (C["RC_S_WB"], _NB, "f"),
+    "cax": (C["RC_S_CAX"], _NB, "f"), "cay": (C["RC_S_CAY"], _NB, "f"),
+    "cbx": (C["RC_S_CBX"], _NB, "f"), "cby": (C["RC_S_CBY"], _NB, "f"),
+    # robots
+    "headAngle": (C["RC_S_HEAD"], _NP, "f"), "headMoving": (C["RC_S_HEADMOV"], _NP, "f"),
+    "moveTime": (C["RC_S_MOVET"], _NP, "f"), "initX": (C["RC_S_INITX"], _NP, "f"),
+    "initY": (C["RC_S_INITY"], _NP, "f"), "fallTime": (C["RC_S_FALLT"], _NP, "f"),
+    "penalTime": (C["RC_S_PENT"], _NP, "f"), "prevX": (C["RC_S_PREVX"], _NP, "f"),
+    "prevY": (C["RC_S_PREVY"], _NP, "f"), "pivJx": (C["RC_S_PIVJX"], _NP, "f"),
+    "pivJy": (C["RC_S_PIVJY"], _NP, "f"), "rotJ": (C["RC_S_ROTJ"], _NP, "f"),
+    "rflags": (C["RC_S_RFLAGS"], _NP, "i"), "fallCntr": (C["RC_S_FALLCNT"], _NP, "i"),
+    "touchCntr": (C["RC_S_TOUCHCNT"], _NP, "i"),
+    "episodeRewards": (C["RC_S_EPR"], _NP, "f"), "episodePosRewards": (C["RC_S_EPPR"], _NP, "f"),
+    "episodeObsRewards": (C["RC_S_EPOR"], _NP, "f"),
+    # ball + env
+    "ballPrevX": (C["RC_S_BPREVX"], 1, "f"), "ballPrevY": (C["RC_S_BPREVY"], 1, "f"),
+    "lastKicked": (C["RC_S_LASTK"], 4, "i"), "nLastKicked": (C["RC_S_NLASTK"], 1, "i"),
+    "elapsed": (C["RC_S_ELAPSED"], 1, "i"), "episode": (C["RC_S_EPISODE"], 1, "i"),
+    "ballOwned": (C["RC_S_BALLOWNED"], 1, "i"), "ballFreeCntr": (C["RC_S_BALLFREE"], 1, "f"),
+    "gracePeriod": (C["RC_S_GRACE"], 1, "f"), "goals": (C["RC_S_GOALS"], 2, "i"),
+    "closestID": (C["RC_S_CLOSEST"], 2, "i"), "defenders": (C["RC_S_DEFENDERS"], 4, "i"),
+    "nDefenders": (C["RC_S_NDEF"], 2, "i"), "penalTimes": (C["RC_S_PENALTIMES"], 2, "i"),
+    "stepped": (C["RC_S_STEPPED"], 1, "i"),
+    # cached contact pairs
+    "nArb": (C["RC_S_NARB"], 1, "i"), "arbKey": (C["RC_S_ARBKEY"], _NA, "i"),
+    "arbCon": (C["RC_S_ARBCON"], _NA, "i"), "arbJn0": (C["RC_S_ARBJN0"], _NA, "f"),
+    "arbJt0": (C["RC_S_ARBJT0"], _NA, "f"), "arbJn1": (C["RC_S_ARBJN1"], _NA, "f"),
+    "arbJt1": (C["RC_S_ARBJT1"], _NA, "f"),
+}
+
+
+def rc_int_mask():
+    """Boolean list over RC_STATE_WORDS: True where the word is an int32."""
+    mask = [False] * C["RC_STATE_WORDS"]
+    for off, cnt, kind in RC_FIELDS.values():
+        if kind == "i":
+            for k in range(off, off + cnt):
+                mask[k] = True
+    return mask

@@ -1,0 +1,258 @@
+/*
+ * dynenv_b200 — C ABI of the B200-native batched simulator for DynEnv's rollout hot path.
+ *
+ * Plain C, no torch types: device pointers + sizes only.  Every entry point returns 0 on
+ * success or a negative DYNENV_E_* code; dynenv_last_error() gives the message.  Calls are
+ * asynchronous on the given CUDA stream (no hidden device synchronisation) unless stated.
+ * One handle owns the persistent simulation state of nEnvs environments on one GPU.
+ *
+ * What each entry point replaces in the reference (szemenyeim/DynEnv, paths under DynEnv/):
+ *   dynenv_create       RoboCupEnvironment.__init__  RoboCupEnvironment.py:23-64
+ *                       DrivingEnvironment.__init__  DrivingEnvironment.py:20-56
+ *                       make_dyn_env                 __init__.py:6-25 (num_envs -> nEnvs)
+ *   dynenv_reset        EnvironmentBase.reset        environment_base.py:205-224
+ *                       + auto-reset of SubprocVecEnv._worker  utils/subproc_vec_env.py:17-23
+ *   dynenv_step         RoboCupEnvironment.step      RoboCupEnvironment.py:446-524
+ *                       DrivingEnvironment.step      DrivingEnvironment.py:248-322
+ *                       (the pymunk Space.step inside it: environment_base.py:126-128,
+ *                        RoboCupEnvironment.py:482, DrivingEnvironment.py:278)
+ *   dynenv_set_seed     EnvironmentBase.set_random_seed  environment_base.py:190-193
+ *   dynenv_get_state /  no reference equivalent (the reference pokes pymunk bodies directly);
+ *   dynenv_set_state    needed for state injection in parity tests
+ */
+#ifndef DYNENV_B200_H
+#define DYNENV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYNENV_ABI_VERSION 1
+
+/* ---- error codes */
+#define DYNENV_OK 0
+#define DYNENV_E_INVALID (-1)   /* bad argument / configuration */
+#define DYNENV_E_CUDA (-2)      /* CUDA runtime error */
+#define DYNENV_E_NODEVICE (-3)  /* no CUDA device: there is no CPU fallback */
+#define DYNENV_E_UNSUPPORTED (-4)
+
+/* ---- enums (values follow DynEnv/cutils.py:10-64,152-165) */
+#define DYNENV_KIND_ROBOCUP 0
+#define DYNENV_KIND_DRIVING 1
+#define DYNENV_OBS_FULL 0
+#define DYNENV_OBS_PARTIAL 1
+#define DYNENV_OBS_IMAGE 2
+#define DYNENV_NOISE_RANDOM 0
+#define DYNENV_NOISE_REALISTIC 1
+
+/* class-level toggles of RoboCupEnvironment (RoboCupEnvironment.py:18-21) */
+#define DYNENV_FLAG_RANDOM_INIT 1u
+#define DYNENV_FLAG_DETERMINISTIC_TURN 2u
+#define DYNENV_FLAG_CAN_FALL 4u
+#define DYNENV_FLAG_USE_OBS_REWARDS 8u
+#define DYNENV_FLAG_AUTO_RESET 16u /* vec-env semantics: done envs are re-initialised in step */
+
+typedef struct DynEnvConfig {
+  int32_t abi_version;      /* DYNENV_ABI_VERSION */
+  int32_t kind;             /* DYNENV_KIND_* */
+  int32_t n_envs;           /* environments owned by this handle */
+  int32_t n_players;        /* per team (RoboCup, clamped to 5) / cars (Driving, clamped to 10) */
+  int32_t obs_type;         /* DYNENV_OBS_* */
+  int32_t noise_type;       /* DYNENV_NOISE_* */
+  float noise_magnitude;    /* 0..5 */
+  int32_t continuous;       /* RoboCup: allowHeadTurn, Driving: continuousActions */
+  uint32_t flags;           /* DYNENV_FLAG_* */
+  uint64_t seed;            /* Philox key */
+  int64_t env_id_offset;    /* global id of env 0 (multi-GPU sharding: results do not depend on
+                               how many GPUs the env range is split over) */
+  int32_t device;           /* CUDA device ordinal */
+} DynEnvConfig;
+
+typedef struct DynEnvHandle_s* DynEnvHandle;
+
+/* ---- RoboCup fixed capacities (rows per observer and tick, after false positives) */
+#define RC_MAXP 10        /* robots per env (2 teams x 5) */
+#define RC_NBODY 21       /* 20 feet + ball; body 2r = left foot of robot r, 2r+1 = right, 20 = ball */
+#define RC_NTICK 5        /* observation ticks per step (substeps 9,19,29,39,49) */
+#define RC_SUBSTEPS 50
+#define RC_CAP_BALL 8
+#define RC_CAP_ROBOT 12
+#define RC_CAP_POST 6
+#define RC_CAP_CROSS 6
+#define RC_CAP_FCROSS 18
+#define RC_CAP_LINE 11
+#define RC_F_BALL 5
+#define RC_F_ROBOT 7
+#define RC_F_POST 6
+#define RC_F_CROSS 6
+#define RC_F_FCROSS 8
+#define RC_F_LINE 5
+#define RC_NTYPES 6       /* ball, robot, post, cross, fcross, line */
+#define RC_MAXARB 32      /* cached contact pairs per env */
+
+/*
+ * RoboCup persistent state: one record of RC_STATE_WORDS 32-bit words per environment,
+ * records contiguous ([nEnvs][RC_STATE_WORDS]) so that the warp that owns an environment
+ * loads/stores it with fully coalesced 128-byte transactions.  F = float32, I = int32.
+ * (Appendix D of SURVEY.md lists where each field lives in the reference.)
+ */
+enum {
+  /* bodies, arrays of RC_NBODY */
+  RC_S_PX = 0,                       /* F position x          */
+  RC_S_PY = RC_S_PX + RC_NBODY,      /* F position y          */
+  RC_S_ANG = RC_S_PY + RC_NBODY,     /* F angle               */
+  RC_S_VX = RC_S_ANG + RC_NBODY,     /* F velocity            */
+  RC_S_VY = RC_S_VX + RC_NBODY,
+  RC_S_W = RC_S_VY + RC_NBODY,       /* F angular velocity    */
+  RC_S_FX = RC_S_W + RC_NBODY,       /* F pending force       */
+  RC_S_FY = RC_S_FX + RC_NBODY,
+  RC_S_TQ = RC_S_FY + RC_NBODY,      /* F pending torque      */
+  RC_S_VBX = RC_S_TQ + RC_NBODY,     /* F bias velocity (position correction, consumed next substep) */
+  RC_S_VBY = RC_S_VBX + RC_NBODY,
+  RC_S_WB = RC_S_VBY + RC_NBODY,
+  /* world geometry of the shapes as of the last substep's collision phase (feet: segment end
+     points a, b; ball: centre in a) — what point queries made before the next substep see */
+  RC_S_CAX = RC_S_WB + RC_NBODY,
+  RC_S_CAY = RC_S_CAX + RC_NBODY,
+  RC_S_CBX = RC_S_CAY + RC_NBODY,
+  RC_S_CBY = RC_S_CBX + RC_NBODY,
+  /* robots, arrays of RC_MAXP (Robot.py:58-88) */
+  RC_S_HEAD = RC_S_CBY + RC_NBODY,   /* F headAngle   */
+  RC_S_HEADMOV = RC_S_HEAD + RC_MAXP,/* F headMoving  */
+  RC_S_MOVET = RC_S_HEADMOV + RC_MAXP,/* F moveTime   */
+  RC_S_INITX = RC_S_MOVET + RC_MAXP, /* F initPos (kick) */
+  RC_S_INITY = RC_S_INITX + RC_MAXP,
+  RC_S_FALLT = RC_S_INITY + RC_MAXP, /* F fallTime    */
+  RC_S_PENT = RC_S_FALLT + RC_MAXP,  /* F penalTime   */
+  RC_S_PREVX = RC_S_PENT + RC_MAXP,  /* F prevPos     */
+  RC_S_PREVY = RC_S_PREVX + RC_MAXP,
+  RC_S_PIVJX = RC_S_PREVY + RC_MAXP, /* F pivot joint accumulated impulse */
+  RC_S_PIVJY = RC_S_PIVJX + RC_MAXP,
+  RC_S_ROTJ = RC_S_PIVJY + RC_MAXP,  /* F rotary-limit joint accumulated impulse */
+  RC_S_RFLAGS = RC_S_ROTJ + RC_MAXP, /* I RC_RF_* bits */
+  RC_S_FALLCNT = RC_S_RFLAGS + RC_MAXP, /* I fallCntr */
+  RC_S_TOUCHCNT = RC_S_FALLCNT + RC_MAXP, /* I touchCntr */
+  RC_S_EPR = RC_S_TOUCHCNT + RC_MAXP,  /* F episodeRewards    */
+  RC_S_EPPR = RC_S_EPR + RC_MAXP,      /* F episodePosRewards */
+  RC_S_EPOR = RC_S_EPPR + RC_MAXP,     /* F episodeObsRewards */
+  /* ball (Ball.py:20-24) */
+  RC_S_BPREVX = RC_S_EPOR + RC_MAXP, /* F */
+  RC_S_BPREVY = RC_S_BPREVX + 1,     /* F */
+  RC_S_LASTK = RC_S_BPREVY + 1,      /* I lastKicked[4] */
+  RC_S_NLASTK = RC_S_LASTK + 4,      /* I */
+  /* env scalars (RoboCupEnvironment.py:42-59) */
+  RC_S_ELAPSED = RC_S_NLASTK + 1,    /* I */
+  RC_S_EPISODE = RC_S_ELAPSED + 1,   /* I episode counter (RNG stream id) */
+  RC_S_BALLOWNED = RC_S_EPISODE + 1, /* I -1/0/1 */
+  RC_S_BALLFREE = RC_S_BALLOWNED + 1,/* F ballFreeCntr */
+  RC_S_GRACE = RC_S_BALLFREE + 1,    /* F gracePeriod  */
+  RC_S_GOALS = RC_S_GRACE + 1,       /* I [2] */
+  RC_S_CLOSEST = RC_S_GOALS + 2,     /* I closestID[2] */
+  RC_S_DEFENDERS = RC_S_CLOSEST + 2, /* I defenders[2][2] */
+  RC_S_NDEF = RC_S_DEFENDERS + 4,    /* I [2] */
+  RC_S_PENALTIMES = RC_S_NDEF + 2,   /* I penalTimes[2] */
+  RC_S_STEPPED = RC_S_PENALTIMES + 2,/* I 0 until the first substep after (re)initialisation (warm-start gate) */
+  /* cached contact pairs (Chipmunk arbiters): RC_MAXARB entries */
+  RC_S_NARB = RC_S_STEPPED + 1,      /* I */
+  RC_S_ARBKEY = RC_S_NARB + 1,       /* I a | b<<8 | state<<16 | age<<24   (shape ids: body id, posts 21..24) */
+  RC_S_ARBCON = RC_S_ARBKEY + RC_MAXARB, /* I ncontacts | hash0<<8 | hash1<<16 */
+  RC_S_ARBJN0 = RC_S_ARBCON + RC_MAXARB, /* F */
+  RC_S_ARBJT0 = RC_S_ARBJN0 + RC_MAXARB,
+  RC_S_ARBJN1 = RC_S_ARBJT0 + RC_MAXARB,
+  RC_S_ARBJT1 = RC_S_ARBJN1 + RC_MAXARB,
+  RC_STATE_WORDS_RAW = RC_S_ARBJT1 + RC_MAXARB,
+  RC_STATE_WORDS = (RC_STATE_WORDS_RAW + 31) / 32 * 32 /* records start 128-byte aligned */
+};
+
+/* robot flag bits (RC_S_RFLAGS) */
+#define RC_RF_KICKING 1
+#define RC_RF_FOOT 2          /* 1 = right foot kicks */
+#define RC_RF_FALLEN 4
+#define RC_RF_PENALIZED 8
+#define RC_RF_TOUCHING 16
+#define RC_RF_MIGHTPUSH 32
+#define RC_RF_JOINT_REMOVED 64 /* robot.jointRemoved (logical flag) */
+#define RC_RF_JOINT_ABSENT 128 /* pivot joint currently not in the space (differs from the flag
+                                  while a re-add issued inside a collision callback is deferred) */
+#define RC_RF_JOINT_ADD_PENDING 256
+
+/* cached-pair states (Chipmunk cpArbiterState) */
+#define RC_ARB_FIRST 0
+#define RC_ARB_NORMAL 1
+#define RC_ARB_IGNORE 2
+#define RC_ARB_CACHED 3
+
+/*
+ * Step/reset outputs: caller-owned device buffers (NULL = not wanted).  Shapes use
+ * E = nEnvs, T = RC_NTICK, P = 2*n_players.  Observation rows beyond the count are zero.
+ * Row orders follow the reference's list orders (RoboCupEnvironment.py:1192-1561).
+ */
+typedef struct DynEnvRoboCupOut {
+  /* PARTIAL observations, float32 [E][T][P][cap][feat] */
+  float* ball;    /* RC_CAP_BALL  x RC_F_BALL   */
+  float* robot;   /* RC_CAP_ROBOT x RC_F_ROBOT  */
+  float* post;    /* RC_CAP_POST  x RC_F_POST   */
+  float* cross;   /* RC_CAP_CROSS x RC_F_CROSS  */
+  float* fcross;  /* RC_CAP_FCROSS x RC_F_FCROSS */
+  float* line;    /* RC_CAP_LINE  x RC_F_LINE   */
+  int32_t* counts;      /* [E][T][P][RC_NTYPES] */
+  int32_t* num_landmarks; /* [E][T][P] */
+  uint8_t* robots_seen; /* [E][T][P][RC_MAXP-1] (first P-1 used) */
+  uint8_t* balls_seen;  /* [E][T][P] */
+  /* FULL observations (get_full_obs, written when obs_type == FULL), float32 */
+  float* full_ball;   /* [E][T][P][4]       */
+  float* full_self;   /* [E][T][P][8]       */
+  float* full_others; /* [E][T][P][RC_MAXP-1][6] (first P-1 rows used) */
+  /* info['Recon States'] = getFullState(robot) at the end of the step (always written) */
+  float* recon_ball;   /* [E][P][4]       */
+  float* recon_self;   /* [E][P][8]       */
+  float* recon_others; /* [E][P][RC_MAXP-1][6] */
+  /* info['Full State'] (getFullState()) at the end of the step */
+  float* state_robots; /* [E][P][6] */
+  float* state_ball;   /* [E][3]    */
+  /* rewards, done, episode statistics */
+  float* rewards;   /* [E][P] */
+  uint8_t* done;    /* [E]    */
+  float* episode_r;   /* [E][P] valid where done */
+  float* episode_p_r; /* [E][P] */
+  float* episode_o_r; /* [E][P] */
+  int32_t* episode_g; /* [E][2] */
+} DynEnvRoboCupOut;
+
+/* ---- entry points */
+int dynenv_abi_version(void);
+const char* dynenv_last_error(void);
+
+int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out);
+int dynenv_destroy(DynEnvHandle h);
+
+/* words per environment record of this handle's state (RC_STATE_WORDS / DRV_STATE_WORDS) */
+int dynenv_state_words(DynEnvHandle h);
+
+/* Re-initialise environments (all if env_mask_dev == NULL, else those with mask != 0) and
+   write the initial observations (nTimeSteps ticks of the initial scene) into `out`.
+   `out` points to a DynEnvRoboCupOut / DynEnvDrivingOut according to the handle's kind. */
+int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* stream);
+
+/* One env step for every environment.  actions_dev: RoboCup float32 [E][P][4]
+   (move, turn, kick, head), Driving float32 [E][N][2].  With DYNENV_FLAG_AUTO_RESET,
+   `terminal_out` (same struct type, may be NULL) receives the observations of environments
+   that finished this step while `out` receives their post-reset observations. */
+int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* terminal_out,
+                void* stream);
+
+int dynenv_set_seed(DynEnvHandle h, uint64_t seed);
+
+/* copy the whole state ([nEnvs][state_words] 32-bit words) to / from a device buffer */
+int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream);
+int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);
+
+/* number of kernels launched by the last dynenv_step / dynenv_reset call on this handle */
+int dynenv_last_launch_count(DynEnvHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNENV_B200_H */

@@ -1,0 +1,43 @@
+/*
+ * RNG stream layout shared by the CUDA kernels and the CPU oracle.
+ *
+ * The reference draws from Python's global `random` / `np.random` sequentially
+ * (environment_base.py:190-193).  The batched simulator uses the counter-based
+ * Philox4x32-10 generator (Salmon et al., SC'11) instead, so that every draw is addressed
+ * by WHERE it is consumed and results do not depend on execution order or GPU count:
+ *
+ *   key     = (seed low 32, seed high 32)
+ *   counter = (global env id, episode, tick, site<<24 | a<<16 | b<<8 | block)
+ *   uniform k of a site = word (k & 3) of block (k >> 2), u = (word >> 8) * 2^-24  in [0,1)
+ *
+ * tick: substep index `elapsed` (before the increment) for draws made inside the substep
+ * loop; `elapsed` at snapshot time for observation ticks; DYNENV_TICK_RESETOBS | t for the
+ * nTimeSteps initial observations; DYNENV_TICK_RESET for scene generation.
+ */
+#ifndef DYNENV_RNG_H
+#define DYNENV_RNG_H
+
+#define DYNENV_TICK_RESET 0xFFFFFFFFu
+#define DYNENV_TICK_RESETOBS 0x80000000u
+
+/* RoboCup sites (a, b = the two 8-bit indices) */
+#define RC_SITE_ACTION 1   /* a = robot; k: 0 move fall, 1 turn fall, 2 kick fall  (RoboCupEnvironment.py:557,565,577) */
+#define RC_SITE_REFALL 2   /* a = robot; k: 0                                      (:932) */
+#define RC_SITE_ROBCOL 3   /* a, b = shape ids of the pair; k: 0 robot1, 1 robot2  (:1064,1068) */
+#define RC_SITE_POSTCOL 4  /* a, b = shape ids of the pair; k: 0                   (:1121) */
+#define RC_SITE_RESET 5    /* a = 0; k: draws of _create_robot_spots/_create_agents/_create_ball in call order (:239-336) */
+/* observation sites: a = observer, b = object index
+   k for addNoise (cutils.py:417-468): 0,1 position, 2 false negative, 3 misclassification, 4 size, 5 angle
+   k for addNoiseLine (cutils.py:352-378): 0..3 end-point noise, 4 false negative */
+#define RC_SITE_OBS_BALL 16
+#define RC_SITE_OBS_ROBOT 17
+#define RC_SITE_OBS_POST 18
+#define RC_SITE_OBS_CROSS 19
+#define RC_SITE_OBS_FCROSS 20
+#define RC_SITE_OBS_CIRCLE 21
+#define RC_SITE_OBS_LINE 22
+#define RC_SITE_OBS_MISCROSS 23 /* k: 0,1 the two randint(-1,1) tags of a ball misclassified as cross (:1260) */
+#define RC_SITE_OBS_FP 24       /* b = loop index 0..9; k: 0 test, 1 class, 2 distance, 3 angle, 4.. class draws (:1279-1305) */
+#define RC_SITE_OBS_FPBALL 25   /* b = row in the robot list; k: 0 test, 1 drop test, 2,3 offset, 4 size (:1308-1316) */
+
+#endif

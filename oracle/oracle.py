@@ -1,0 +1,172 @@
+"""ctypes binding of the CPU oracle (oracle/rc_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module; the product package dynenv_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from dynenv_b200 import layout as L
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_DIR, "_build", "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _DIR] + (["-B"] if force else []),
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.rc_create.restype = C.c_void_p
+        _LIB.rc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint,
+                                   C.c_uint64, C.c_uint32]
+        for name in ("rc_destroy", "rc_reset"):
+            getattr(_LIB, name).argtypes = [C.c_void_p]
+            getattr(_LIB, name).restype = None
+        _LIB.rc_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _LIB.rc_set_tape.restype = None
+        for name in ("rc_tape_pos", "rc_tape_underflow", "rc_arb_overflow"):
+            getattr(_LIB, name).argtypes = [C.c_void_p]
+            getattr(_LIB, name).restype = C.c_int
+        _LIB.rc_store_state.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB.rc_load_state.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB.rc_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB.rc_reset_obs.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB.rc_stepout_size.restype = C.c_int
+        assert _LIB.rc_stepout_size() == C.sizeof(RcStepOut), (
+            _LIB.rc_stepout_size(), C.sizeof(RcStepOut))
+    return _LIB
+
+
+_T, _P = L.RC_NTICK, L.RC_MAXP
+
+
+def _arr(ctype, *shape):
+    t = ctype
+    for s in reversed(shape):
+        t = t * s
+    return t
+
+
+class RcStepOut(C.Structure):
+    _fields_ = [
+        ("ball", _arr(C.c_double, _T, _P, L.RC_CAP_BALL, L.RC_F_BALL)),
+        ("robot", _arr(C.c_double, _T, _P, L.RC_CAP_ROBOT, L.RC_F_ROBOT)),
+        ("post", _arr(C.c_double, _T, _P, L.RC_CAP_POST, L.RC_F_POST)),
+        ("cross", _arr(C.c_double, _T, _P, L.RC_CAP_CROSS, L.RC_F_CROSS)),
+        ("fcross", _arr(C.c_double, _T, _P, L.RC_CAP_FCROSS, L.RC_F_FCROSS)),
+        ("line", _arr(C.c_double, _T, _P, L.RC_CAP_LINE, L.RC_F_LINE)),
+        ("counts", _arr(C.c_int32, _T, _P, L.RC_NTYPES)),
+        ("num_landmarks", _arr(C.c_int32, _T, _P)),
+        ("robots_seen", _arr(C.c_int32, _T, _P, _P - 1)),
+        ("balls_seen", _arr(C.c_int32, _T, _P)),
+        ("full_ball", _arr(C.c_double, _T, _P, 4)),
+        ("full_self", _arr(C.c_double, _T, _P, 8)),
+        ("full_others", _arr(C.c_double, _T, _P, _P - 1, 6)),
+        ("recon_ball", _arr(C.c_double, _P, 4)),
+        ("recon_self", _arr(C.c_double, _P, 8)),
+        ("recon_others", _arr(C.c_double, _P, _P - 1, 6)),
+        ("state_robots", _arr(C.c_double, _P, 6)),
+        ("state_ball", _arr(C.c_double, 3)),
+        ("rewards", _arr(C.c_double, _P)),
+        ("done", C.c_int32),
+        ("episode_r", _arr(C.c_double, _P)),
+        ("episode_p_r", _arr(C.c_double, _P)),
+        ("episode_o_r", _arr(C.c_double, _P)),
+        ("episode_g", _arr(C.c_int32, 2)),
+    ]
+
+    def to_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = int(v) if isinstance(v, int) else np.ctypeslib.as_array(v).copy()
+        return out
+
+
+class RcOracle(object):
+    """One RoboCup environment of the CPU oracle."""
+
+    def __init__(self, nPlayers, obsType=1, noiseType=1, noiseMagnitude=2.0, allowHeadTurn=False,
+                 flags=L.DYNENV_FLAG_CAN_FALL | L.DYNENV_FLAG_USE_OBS_REWARDS, seed=0, env_id=0):
+        self._lib = lib()
+        self._h = self._lib.rc_create(int(nPlayers), int(obsType), int(noiseType), float(noiseMagnitude),
+                                      int(bool(allowHeadTurn)), int(flags), int(seed), int(env_id))
+        self.nPlayers = min(int(nPlayers), 5)
+        self.P = 2 * self.nPlayers
+        self._tape = None
+        self._out = RcStepOut()
+
+    def __del__(self):
+        try:
+            self._lib.rc_destroy(self._h)
+        except Exception:
+            pass
+
+    def set_tape(self, tape):
+        if tape is None:
+            self._tape = None
+            self._lib.rc_set_tape(self._h, None, 0)
+        else:
+            self._tape = np.ascontiguousarray(tape, dtype=np.float64)
+            self._lib.rc_set_tape(self._h, self._tape.ctypes.data, len(self._tape))
+
+    def tape_pos(self):
+        return self._lib.rc_tape_pos(self._h)
+
+    def tape_underflow(self):
+        return bool(self._lib.rc_tape_underflow(self._h))
+
+    def arb_overflow(self):
+        return bool(self._lib.rc_arb_overflow(self._h))
+
+    def reset(self):
+        self._lib.rc_reset(self._h)
+
+    def reset_obs(self):
+        self._lib.rc_reset_obs(self._h, C.byref(self._out))
+        return self._out.to_dict()
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.P, 4)
+        self._lib.rc_step(self._h, a.ctypes.data, C.byref(self._out))
+        return self._out.to_dict()
+
+    def get_state(self):
+        w = np.zeros(L.RC_STATE_WORDS, dtype=np.float64)
+        self._lib.rc_store_state(self._h, w.ctypes.data)
+        return w
+
+    def set_state(self, words):
+        w = np.ascontiguousarray(words, dtype=np.float64)
+        assert w.shape == (L.RC_STATE_WORDS,)
+        self._lib.rc_load_state(self._h, w.ctypes.data)
+
+
+def words_to_f32_record(words):
+    """float64 word list -> the uint32 record the C-ABI uses (floats rounded to float32)."""
+    w = np.asarray(words, dtype=np.float64)
+    mask = np.array(L.rc_int_mask())
+    rec = np.zeros(w.shape, dtype=np.uint32)
+    rec[..., mask] = w[..., mask].astype(np.int64).astype(np.int32).view(np.uint32)
+    rec[..., ~mask] = w[..., ~mask].astype(np.float32).view(np.uint32)
+    return rec
+
+
+def f32_record_to_words(rec):
+    r = np.asarray(rec, dtype=np.uint32)
+    mask = np.array(L.rc_int_mask())
+    w = np.zeros(r.shape, dtype=np.float64)
+    w[..., mask] = r[..., mask].view(np.int32).astype(np.float64)
+    w[..., ~mask] = r[..., ~mask].view(np.float32).astype(np.float64)
+    return w
