@@ -1674,9 +1674,10 @@ void rc_store_state(const RcEnv* e, double* w) {
   for (int k = 0; k < e->nArb; k++) {
     const Arbiter* a = &e->arb[k];
     w[RC_S_ARBKEY + k] = a->a | (a->b << 8) | (a->state << 16) | (a->age << 24);
-    w[RC_S_ARBCON + k] = a->ncon | (a->con[0].hash << 8) | (a->con[1].hash << 16);
-    w[RC_S_ARBJN0 + k] = a->con[0].jnAcc; w[RC_S_ARBJT0 + k] = a->con[0].jtAcc;
-    w[RC_S_ARBJN1 + k] = a->con[1].jnAcc; w[RC_S_ARBJT1 + k] = a->con[1].jtAcc;
+    int h0 = a->ncon > 0 ? a->con[0].hash : 0, h1 = a->ncon > 1 ? a->con[1].hash : 0;
+    w[RC_S_ARBCON + k] = a->ncon | (h0 << 8) | (h1 << 16);
+    w[RC_S_ARBJN0 + k] = a->ncon > 0 ? a->con[0].jnAcc : 0; w[RC_S_ARBJT0 + k] = a->ncon > 0 ? a->con[0].jtAcc : 0;
+    w[RC_S_ARBJN1 + k] = a->ncon > 1 ? a->con[1].jnAcc : 0; w[RC_S_ARBJT1 + k] = a->ncon > 1 ? a->con[1].jtAcc : 0;
   }
 }
 

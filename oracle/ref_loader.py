@@ -75,6 +75,7 @@ class UniformTape(object):
         self._gen = np.random.Generator(np.random.PCG64(seed))
         self._source = None if source is None else list(source)
         self._pos = 0
+        self.count = 0  # uniforms handed out so far
         self.log = []
 
     def u(self):
@@ -84,6 +85,7 @@ class UniformTape(object):
         else:
             v = float(self._gen.random())
         self.log.append(v)
+        self.count += 1
         return v
 
     def take_log(self):
@@ -119,6 +121,12 @@ class UniformTape(object):
             j = int(self.u() * (i + 1))
             arr[i], arr[j] = arr[j], arr[i]
         return arr
+
+    @staticmethod
+    def regenerate(seed, start, stop):
+        """The uniforms [start, stop) of the stream UniformTape(seed) hands out."""
+        g = np.random.Generator(np.random.PCG64(int(seed)))
+        return np.array([float(g.random()) for _ in range(int(stop))][int(start):], dtype=np.float64)
 
     @contextlib.contextmanager
     def installed(self):

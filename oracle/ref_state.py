@@ -125,6 +125,7 @@ def robocup_get_state(env, episode=1):
 
 def robocup_set_state(env, w, ns):
     """Injects a word list into a freshly reset reference env (same nPlayers)."""
+    w = [float(v) for v in w]  # plain Python floats, as the reference itself would hold
     pm = ns.pymunk
     shapes = []
     for rob in env.agents:

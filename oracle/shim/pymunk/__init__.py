@@ -105,7 +105,7 @@ class Vec2d(object):
         return self
 
     def __mul__(self, o):
-        if hasattr(o, "__getitem__"):
+        if isinstance(o, (Vec2d, tuple, list)):
             return Vec2d(self.x * o[0], self.y * o[1])
         return Vec2d(self.x * o, self.y * o)
 
