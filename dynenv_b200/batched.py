@@ -1,0 +1,154 @@
+"""Batched simulator handles: nEnvs environments stepped by one kernel launch.
+
+Host side only: PyTorch owns the device buffers and the stream, the simulation runs in
+dynenv_b200/libdynenv_b200.so through the C ABI (include/dynenv_b200.h).  Outputs are
+padded-with-counts device tensors (views into packed per-observer records); the ragged
+nested-list format of the reference is produced lazily by `dynenv_b200.reference_format`.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from . import layout as L
+from .enums import NoiseType, ObservationType
+
+_TYPES = [("ball", L.RC_O_BALL, L.RC_CAP_BALL, L.RC_F_BALL), ("robot", L.RC_O_ROBOT, L.RC_CAP_ROBOT, L.RC_F_ROBOT),
+          ("post", L.RC_O_POST, L.RC_CAP_POST, L.RC_F_POST), ("cross", L.RC_O_CROSS, L.RC_CAP_CROSS, L.RC_F_CROSS),
+          ("fcross", L.RC_O_FCROSS, L.RC_CAP_FCROSS, L.RC_F_FCROSS), ("line", L.RC_O_LINE, L.RC_CAP_LINE, L.RC_F_LINE)]
+
+
+def _flags(randomInit, deterministicTurn, canFall, useObsRewards, auto_reset):
+    return ((L.DYNENV_FLAG_RANDOM_INIT if randomInit else 0) | (L.DYNENV_FLAG_DETERMINISTIC_TURN if deterministicTurn else 0)
+            | (L.DYNENV_FLAG_CAN_FALL if canFall else 0) | (L.DYNENV_FLAG_USE_OBS_REWARDS if useObsRewards else 0)
+            | (L.DYNENV_FLAG_AUTO_RESET if auto_reset else 0))
+
+
+class RoboCupOutputs(object):
+    """Named views of one set of output buffers (no copies)."""
+
+    def __init__(self, nEnvs, P, obs_type, device):
+        T = L.RC_NTICK
+        self.P = P
+        self.obs = self.full = None
+        if obs_type == int(ObservationType.PARTIAL):
+            self.obs = torch.zeros((nEnvs, T, P, L.RC_OBS_WORDS), dtype=torch.float32, device=device)
+        else:
+            self.full = torch.zeros((nEnvs, T, P, L.RC_FULL_WORDS), dtype=torch.float32, device=device)
+        self.info = torch.zeros((nEnvs, L.RC_INFO_WORDS), dtype=torch.float32, device=device)
+        self.c_struct = _lib.DynEnvRoboCupOut(self.obs.data_ptr() if self.obs is not None else None,
+                                              self.full.data_ptr() if self.full is not None else None,
+                                              self.info.data_ptr())
+        self._build_views()
+
+    def _build_views(self):
+        P = self.P
+        info_i = self.info.view(torch.int32)
+        self.rewards = self.info[:, L.RC_I_REWARDS:L.RC_I_REWARDS + P]
+        self.done = info_i[:, L.RC_I_DONE]
+        self.diag = info_i[:, L.RC_I_FLAGS]
+        self.episode_r = self.info[:, L.RC_I_EPR:L.RC_I_EPR + P]
+        self.episode_p_r = self.info[:, L.RC_I_EPPR:L.RC_I_EPPR + P]
+        self.episode_o_r = self.info[:, L.RC_I_EPOR:L.RC_I_EPOR + P]
+        self.episode_g = info_i[:, L.RC_I_EPG:L.RC_I_EPG + 2]
+        E = self.info.shape[0]
+        self.state_robots = self.info[:, L.RC_I_STATE_ROBOTS:L.RC_I_STATE_ROBOTS + L.RC_MAXP * 6].view(E, L.RC_MAXP, 6)[:, :P]
+        self.state_ball = self.info[:, L.RC_I_STATE_BALL:L.RC_I_STATE_BALL + 3]
+        recon = self.info[:, L.RC_I_RECON:L.RC_I_RECON + L.RC_MAXP * L.RC_FULL_WORDS].view(E, L.RC_MAXP, L.RC_FULL_WORDS)[:, :P]
+        self.recon_ball = recon[..., L.RC_U_BALL:L.RC_U_BALL + 4]
+        self.recon_self = recon[..., L.RC_U_SELF:L.RC_U_SELF + 8]
+        self.recon_others = recon[..., L.RC_U_OTHERS:L.RC_U_OTHERS + (L.RC_MAXP - 1) * 6].unflatten(-1, (L.RC_MAXP - 1, 6))
+        if self.obs is not None:
+            obs_i = self.obs.view(torch.int32)
+            for name, off, cap, feat in _TYPES:
+                setattr(self, name, self.obs[..., off:off + cap * feat].unflatten(-1, (cap, feat)))
+            self.counts = obs_i[..., L.RC_O_COUNTS:L.RC_O_COUNTS + L.RC_NTYPES]
+            self.num_landmarks = obs_i[..., L.RC_O_NLANDMARKS]
+            self.balls_seen = obs_i[..., L.RC_O_BALLSEEN]
+            self.robots_seen = obs_i[..., L.RC_O_ROBSEEN:L.RC_O_ROBSEEN + L.RC_MAXP - 1]
+        if self.full is not None:
+            self.full_ball = self.full[..., L.RC_U_BALL:L.RC_U_BALL + 4]
+            self.full_self = self.full[..., L.RC_U_SELF:L.RC_U_SELF + 8]
+            self.full_others = self.full[..., L.RC_U_OTHERS:L.RC_U_OTHERS + (L.RC_MAXP - 1) * 6].unflatten(-1, (L.RC_MAXP - 1, 6))
+
+
+class BatchedRoboCup(object):
+    """nEnvs RoboCup environments on one GPU (reference: DynEnv/RoboCupEnvironment.py:23-64 per env,
+    DynEnv/__init__.py:6-25 for the batch)."""
+
+    nTimeSteps = L.RC_NTICK
+    stepIterCnt = L.RC_SUBSTEPS
+
+    def __init__(self, nEnvs, nPlayers, observationType=ObservationType.PARTIAL, noiseType=NoiseType.REALISTIC,
+                 noiseMagnitude=2.0, allowHeadTurn=False, randomInit=False, deterministicTurn=False, canFall=True,
+                 useObsRewards=True, auto_reset=False, seed=0, device=0, env_id_offset=0, terminal_outputs=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dynenv_b200 needs a CUDA device (no CPU fallback)")
+        self._lib = _lib.lib()
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.nEnvs = int(nEnvs)
+        self.nPlayers = min(int(nPlayers), 5)
+        self.P = 2 * self.nPlayers
+        self.obs_type = int(observationType)
+        cfg = _lib.DynEnvConfig(L.DYNENV_ABI_VERSION, L.DYNENV_KIND_ROBOCUP, self.nEnvs, int(nPlayers), self.obs_type,
+                                int(noiseType), float(noiseMagnitude), int(bool(allowHeadTurn)),
+                                _flags(randomInit, deterministicTurn, canFall, useObsRewards, auto_reset),
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset), self.device.index or 0)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.dynenv_create(C.byref(cfg), C.byref(self._h)))
+        self.state_words = self._lib.dynenv_state_words(self._h)
+        with torch.cuda.device(self.device):
+            self.out = RoboCupOutputs(self.nEnvs, self.P, self.obs_type, self.device)
+            self.terminal = RoboCupOutputs(self.nEnvs, self.P, self.obs_type, self.device) if terminal_outputs else None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dynenv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_random_seed(self, seed):
+        _lib.check(self._lib.dynenv_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def reset(self, env_mask=None):
+        """Re-initialises all (or the masked) environments; returns the output views."""
+        mask_ptr = None
+        if env_mask is not None:
+            env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert env_mask.numel() == self.nEnvs
+            mask_ptr = env_mask.data_ptr()
+        _lib.check(self._lib.dynenv_reset(self._h, mask_ptr, C.byref(self.out.c_struct), self._stream()))
+        return self.out
+
+    def step(self, actions):
+        """actions: float32 CUDA tensor [nEnvs, 2*nPlayers, 4] (move, turn, kick, head)."""
+        if actions.shape != (self.nEnvs, self.P, 4):
+            raise Exception("Error: There must be %d actions of length 4" % self.P)  # RoboCupEnvironment.py:462-463
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
+        _lib.check(self._lib.dynenv_step(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
+        return self.out
+
+    def last_launch_count(self):
+        return self._lib.dynenv_last_launch_count(self._h)
+
+    def get_state(self):
+        """[nEnvs, state_words] int32 tensor holding the raw 32-bit words of every state record."""
+        st = torch.empty((self.nEnvs, self.state_words), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.dynenv_get_state(self._h, st.data_ptr(), self._stream()))
+        return st
+
+    def set_state(self, st):
+        st = st.to(device=self.device).contiguous()
+        assert st.shape == (self.nEnvs, self.state_words) and st.element_size() == 4
+        _lib.check(self._lib.dynenv_set_state(self._h, st.data_ptr(), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # `st` may be a temporary

@@ -1,0 +1,37 @@
+"""Builds the C-ABI shared library (dynenv_b200/libdynenv_b200.so) with nvcc for sm_100a.
+
+In-tree build: the .so is git-ignored but travels to the GPU box with the repo snapshot.
+nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libdynenv_b200.so")
+SOURCES = ["csrc/dynenv_api.cu"]
+HEADERS = ["csrc/dynenv_common.cuh", "csrc/rc_sim.cuh", "../include/dynenv_b200.h", "../include/dynenv_rng.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(os.path.join(_DIR, p)) > t for p in SOURCES + HEADERS
+               if os.path.exists(os.path.join(_DIR, p)))
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
+          [os.path.join(_DIR, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

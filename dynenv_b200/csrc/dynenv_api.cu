@@ -1,0 +1,242 @@
+/*
+ * dynenv_b200 — kernels' entry points and the C ABI of include/dynenv_b200.h.
+ * No torch types here: device pointers and sizes only.  Every call is asynchronous on the
+ * caller's stream; nothing in this file synchronises the device.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "rc_sim.cuh"
+
+using namespace dynenv;
+
+namespace {
+
+constexpr int RC_WPC = 4; /* environments (warps) per CTA */
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return DYNENV_E_CUDA;
+}
+
+/* coalesced copy of one environment's state record between HBM and the warp's shared memory */
+__device__ __forceinline__ void load_record(uint32_t* S, const uint32_t* g, int lane) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(S);
+  for (int w = lane; w < RC_STATE_WORDS / 4; w += 32) dst[w] = src[w];
+  __syncwarp();
+}
+__device__ __forceinline__ void store_record(uint32_t* g, const uint32_t* S, int lane) {
+  __syncwarp();
+  const uint4* src = reinterpret_cast<const uint4*>(S);
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  for (int w = lane; w < RC_STATE_WORDS / 4; w += 32) dst[w] = src[w];
+}
+
+__device__ __forceinline__ rc::Env make_env(uint32_t* S, const SimCfg& cfg, int e, int lane) {
+  rc::Env E;
+  E.f = reinterpret_cast<float*>(S);
+  E.i = reinterpret_cast<int*>(S);
+  E.c = &cfg;
+  E.lane = lane;
+  E.rng.k0 = cfg.seed_lo;
+  E.rng.k1 = cfg.seed_hi;
+  E.rng.env_id = cfg.env_id_offset + (uint32_t)e;
+  E.rng.episode = (uint32_t)E.i[RC_S_EPISODE];
+  return E;
+}
+
+/*
+ * One env step of every environment: all 50 substeps and 5 observation ticks in one launch.
+ * grid = ceil(nEnvs / RC_WPC) CTAs of RC_WPC warps; warp w of CTA b owns environment b*RC_WPC + w.
+ */
+__global__ void __launch_bounds__(RC_WPC * 32)
+rc_step_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
+               float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info,
+               float* __restrict__ term_obs, float* __restrict__ term_full) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * RC_WPC + warp;
+  if (e >= cfg.n_envs) return;
+  uint32_t* S = smem + warp * rc::ENV_SMEM_WORDS;
+  load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
+  rc::Env E = make_env(S, cfg, e, lane);
+  const int P = cfg.P;
+  const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
+  const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + RC_SUBSTEPS >= rc::MAXTIME;
+  float* o = obs ? obs + e * obs_stride : nullptr;
+  float* f = full ? full + e * full_stride : nullptr;
+  float* inf = info ? info + (size_t)e * RC_INFO_WORDS : nullptr;
+  if (finishing) { /* the finished episode's last observations go to the terminal buffers */
+    rc::step_env(E, actions + (size_t)e * P * 4, term_obs ? term_obs + e * obs_stride : nullptr,
+                 term_full ? term_full + e * full_stride : nullptr, inf);
+    rc::reset_env(E, o, f, inf, false);
+  } else {
+    rc::step_env(E, actions + (size_t)e * P * 4, o, f, inf);
+  }
+  store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
+}
+
+__global__ void __launch_bounds__(RC_WPC * 32)
+rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const uint8_t* __restrict__ mask,
+                float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * RC_WPC + warp;
+  if (e >= cfg.n_envs) return;
+  if (mask && !mask[e]) return;
+  uint32_t* S = smem + warp * rc::ENV_SMEM_WORDS;
+  load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
+  rc::Env E = make_env(S, cfg, e, lane);
+  const int P = cfg.P;
+  const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
+  rc::reset_env(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr,
+                info ? info + (size_t)e * RC_INFO_WORDS : nullptr, true);
+  store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
+}
+
+}  // namespace
+
+struct DynEnvHandle_s {
+  DynEnvConfig cfg;
+  SimCfg sim;
+  uint32_t* state;
+  int state_words;
+  int last_launches;
+};
+
+extern "C" {
+
+int dynenv_abi_version(void) { return DYNENV_ABI_VERSION; }
+const char* dynenv_last_error(void) { return g_err.c_str(); }
+
+int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
+  if (!cfg || !out) return fail(DYNENV_E_INVALID, "null argument");
+  if (cfg->abi_version != DYNENV_ABI_VERSION) return fail(DYNENV_E_INVALID, "ABI version mismatch");
+  if (cfg->n_envs <= 0) return fail(DYNENV_E_INVALID, "n_envs must be positive");
+  if (cfg->n_players <= 0) return fail(DYNENV_E_INVALID, "n_players must be positive");
+  if (cfg->noise_magnitude < 0 || cfg->noise_magnitude > 5)
+    return fail(DYNENV_E_INVALID, "Error: The noise magnitude must be between 0 and 5!"); /* environment_base.py:162-164 */
+  if (cfg->kind != DYNENV_KIND_ROBOCUP) return fail(DYNENV_E_UNSUPPORTED, "only DYNENV_KIND_ROBOCUP is built so far");
+  if (cfg->obs_type != DYNENV_OBS_FULL && cfg->obs_type != DYNENV_OBS_PARTIAL)
+    return fail(DYNENV_E_UNSUPPORTED, "observation type not built (FULL and PARTIAL are)");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return fail(DYNENV_E_NODEVICE, "no CUDA device: dynenv_b200 has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(DYNENV_E_INVALID, "bad device ordinal");
+  if ((ce = cudaSetDevice(cfg->device)) != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+  DynEnvHandle_s* h = new DynEnvHandle_s();
+  h->cfg = *cfg;
+  SimCfg& s = h->sim;
+  s.n_envs = cfg->n_envs;
+  s.n_players = cfg->n_players > 5 ? 5 : cfg->n_players; /* environment_base.py:56-57 */
+  s.P = 2 * s.n_players;
+  s.obs_type = cfg->obs_type;
+  s.noise_type = cfg->noise_type;
+  s.continuous = cfg->continuous;
+  s.noise_mag = cfg->noise_magnitude;
+  s.rand_base = 0.01f * cfg->noise_magnitude; /* environment_base.py:170 */
+  s.random_init = !!(cfg->flags & DYNENV_FLAG_RANDOM_INIT);
+  s.deterministic_turn = !!(cfg->flags & DYNENV_FLAG_DETERMINISTIC_TURN);
+  s.can_fall = !!(cfg->flags & DYNENV_FLAG_CAN_FALL);
+  s.use_obs_rewards = !!(cfg->flags & DYNENV_FLAG_USE_OBS_REWARDS);
+  s.auto_reset = !!(cfg->flags & DYNENV_FLAG_AUTO_RESET);
+  s.seed_lo = (uint32_t)cfg->seed;
+  s.seed_hi = (uint32_t)(cfg->seed >> 32);
+  s.env_id_offset = (uint32_t)cfg->env_id_offset;
+  h->state_words = RC_STATE_WORDS;
+  h->last_launches = 0;
+  size_t bytes = (size_t)cfg->n_envs * h->state_words * sizeof(uint32_t);
+  if ((ce = cudaMalloc(&h->state, bytes)) != cudaSuccess) {
+    delete h;
+    return cuda_fail(ce, "cudaMalloc(state)");
+  }
+  if ((ce = cudaMemset(h->state, 0, bytes)) != cudaSuccess) {
+    cudaFree(h->state);
+    delete h;
+    return cuda_fail(ce, "cudaMemset(state)");
+  }
+  *out = h;
+  return DYNENV_OK;
+}
+
+int dynenv_destroy(DynEnvHandle h) {
+  if (!h) return DYNENV_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->state);
+  delete h;
+  return DYNENV_OK;
+}
+
+int dynenv_state_words(DynEnvHandle h) { return h ? h->state_words : DYNENV_E_INVALID; }
+
+int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* stream) {
+  if (!h || !out) return fail(DYNENV_E_INVALID, "null argument");
+  const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
+  cudaSetDevice(h->cfg.device);
+  int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
+  size_t smem = (size_t)RC_WPC * rc::ENV_SMEM_WORDS * sizeof(uint32_t);
+  rc_reset_kernel<<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(h->sim, h->state, env_mask_dev, o->obs,
+                                                                                   o->full, o->info);
+  h->last_launches = 1;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "rc_reset_kernel launch");
+  return DYNENV_OK;
+}
+
+int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* terminal_out, void* stream) {
+  if (!h || !out || !actions_dev) return fail(DYNENV_E_INVALID, "null argument");
+  const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
+  const DynEnvRoboCupOut* t = static_cast<const DynEnvRoboCupOut*>(terminal_out);
+  cudaSetDevice(h->cfg.device);
+  int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
+  size_t smem = (size_t)RC_WPC * rc::ENV_SMEM_WORDS * sizeof(uint32_t);
+  rc_step_kernel<<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      h->sim, h->state, actions_dev, o->obs, o->full, o->info, t ? t->obs : nullptr, t ? t->full : nullptr);
+  h->last_launches = 1;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "rc_step_kernel launch");
+  return DYNENV_OK;
+}
+
+int dynenv_set_seed(DynEnvHandle h, uint64_t seed) {
+  if (!h) return fail(DYNENV_E_INVALID, "null handle");
+  h->cfg.seed = seed;
+  h->sim.seed_lo = (uint32_t)seed;
+  h->sim.seed_hi = (uint32_t)(seed >> 32);
+  return DYNENV_OK;
+}
+
+int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream) {
+  if (!h || !state_dev) return fail(DYNENV_E_INVALID, "null argument");
+  cudaSetDevice(h->cfg.device);
+  cudaError_t ce = cudaMemcpyAsync(state_dev, h->state, (size_t)h->sim.n_envs * h->state_words * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(get_state)");
+  return DYNENV_OK;
+}
+
+int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream) {
+  if (!h || !state_dev) return fail(DYNENV_E_INVALID, "null argument");
+  cudaSetDevice(h->cfg.device);
+  cudaError_t ce = cudaMemcpyAsync(h->state, state_dev, (size_t)h->sim.n_envs * h->state_words * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(set_state)");
+  return DYNENV_OK;
+}
+
+int dynenv_last_launch_count(DynEnvHandle h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+/*
+ * dynenv_b200 — shared device helpers: warp-per-environment conventions, Philox4x32-10
+ * counter RNG with the stream layout of include/dynenv_rng.h, small 2-D vector math.
+ *
+ * Execution model of every simulation kernel in this directory: ONE WARP owns ONE
+ * environment.  The environment's state record lives in that warp's slice of shared
+ * memory for the whole step (all substeps + all observation ticks); HBM is touched only
+ * at the step boundary (coalesced record load/store, action load, observation store).
+ * Lane-parallel phases map lanes to bodies / robots / sighted objects; phases that the
+ * reference executes as ordered side effects (collision callbacks, falls, penalties,
+ * Gauss-Seidel contact impulses) run on lane 0 in the reference's order.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dynenv_b200.h"
+#include "../../include/dynenv_rng.h"
+
+#define FULLMASK 0xffffffffu
+
+namespace dynenv {
+
+struct SimCfg {
+  int n_envs, n_players, P;
+  int obs_type, noise_type, continuous;
+  float noise_mag, rand_base;
+  int random_init, deterministic_turn, can_fall, use_obs_rewards, auto_reset;
+  uint32_t seed_lo, seed_hi;
+  uint32_t env_id_offset;
+};
+
+struct V2 {
+  float x, y;
+};
+__device__ __forceinline__ V2 v2(float x, float y) {
+  V2 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+__device__ __forceinline__ V2 operator+(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ V2 operator*(V2 a, float s) { return v2(a.x * s, a.y * s); }
+__device__ __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ float lensq(V2 a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ float len(V2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ V2 rot_cs(V2 a, float c, float s) { return v2(a.x * c - a.y * s, a.x * s + a.y * c); }
+__device__ __forceinline__ V2 rot(V2 a, float ang) {
+  float s, c;
+  sincosf(ang, &s, &c);
+  return rot_cs(a, c, s);
+}
+
+/* Philox4x32-10 (Salmon et al., SC'11) */
+__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                              uint32_t c3, uint32_t w[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  w[0] = c0;
+  w[1] = c1;
+  w[2] = c2;
+  w[3] = c3;
+}
+
+/* six 21-bit uniforms of one block (include/dynenv_rng.h) */
+struct Rand6 {
+  uint32_t w[4];
+  __device__ __forceinline__ float u(int s) const {
+    uint32_t v;
+    switch (s) {
+      case 0: v = w[0]; break;
+      case 1: v = __funnelshift_r(w[0], w[1], 21); break;
+      case 2: v = w[1] >> 10; break;
+      case 3: v = __funnelshift_r(w[1], w[2], 31); break;
+      case 4: v = __funnelshift_r(w[2], w[3], 20); break;
+      default: v = w[3] >> 9; break;
+    }
+    return (float)(v & 0x1FFFFFu) * (1.0f / 2097152.0f);
+  }
+};
+
+struct RngCtx {
+  uint32_t k0, k1, env_id, episode;
+  __device__ __forceinline__ Rand6 block(uint32_t tick, int site, int a, int b, int blk) const {
+    Rand6 r;
+    philox4x32_10(k0, k1, env_id, episode, tick,
+                  ((uint32_t)site << 24) | ((uint32_t)(a & 255) << 16) | ((uint32_t)(b & 255) << 8) | (uint32_t)blk,
+                  r.w);
+    return r;
+  }
+};
+
+/* random.randint(lo, hi) from a uniform, as the oracle derives it (oracle/ref_loader.py) */
+__device__ __forceinline__ int randint_from(float u, int lo, int hi) { return lo + (int)(u * (float)(hi - lo + 1)); }
+
+}  // namespace dynenv

@@ -1,0 +1,7 @@
+#!/bin/bash
+# dev helper run on the GPU box: tests + quick bench
+set -x
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log

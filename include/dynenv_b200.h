@@ -185,40 +185,63 @@ enum {
 #define RC_ARB_CACHED 3
 
 /*
- * Step/reset outputs: caller-owned device buffers (NULL = not wanted).  Shapes use
- * E = nEnvs, T = RC_NTICK, P = 2*n_players.  Observation rows beyond the count are zero.
- * Row orders follow the reference's list orders (RoboCupEnvironment.py:1192-1561).
+ * Step/reset outputs: caller-owned device buffers (NULL = not wanted), written as packed
+ * 32-bit-word records so that the warp owning an environment stores them with fully
+ * coalesced 128-byte transactions.  E = nEnvs, T = RC_NTICK, P = 2*n_players.
+ * Observation rows beyond the count are zero.  Row orders follow the reference's list
+ * orders (RoboCupEnvironment.py:1192-1561).  F = float32, I = int32.
+ *
+ * PARTIAL observation record, one per (env, tick, observer): obs[E][T][P][RC_OBS_WORDS]
+ * (what getAgentVision returns, RoboCupEnvironment.py:1537-1561)
  */
+enum {
+  RC_O_BALL = 0,                                       /* F [RC_CAP_BALL][RC_F_BALL]     */
+  RC_O_ROBOT = RC_O_BALL + RC_CAP_BALL * RC_F_BALL,    /* F [RC_CAP_ROBOT][RC_F_ROBOT]   */
+  RC_O_POST = RC_O_ROBOT + RC_CAP_ROBOT * RC_F_ROBOT,  /* F [RC_CAP_POST][RC_F_POST]     */
+  RC_O_CROSS = RC_O_POST + RC_CAP_POST * RC_F_POST,    /* F [RC_CAP_CROSS][RC_F_CROSS]   */
+  RC_O_FCROSS = RC_O_CROSS + RC_CAP_CROSS * RC_F_CROSS,/* F [RC_CAP_FCROSS][RC_F_FCROSS] */
+  RC_O_LINE = RC_O_FCROSS + RC_CAP_FCROSS * RC_F_FCROSS,/* F [RC_CAP_LINE][RC_F_LINE]    */
+  RC_O_COUNTS = RC_O_LINE + RC_CAP_LINE * RC_F_LINE,   /* I [RC_NTYPES] rows per type    */
+  RC_O_NLANDMARKS = RC_O_COUNTS + RC_NTYPES,           /* I numLandMarks (before false positives) */
+  RC_O_BALLSEEN = RC_O_NLANDMARKS + 1,                 /* I ballsSeen                    */
+  RC_O_ROBSEEN = RC_O_BALLSEEN + 1,                    /* I robotsSeen[RC_MAXP-1] (first P-1 used) */
+  RC_OBS_WORDS_RAW = RC_O_ROBSEEN + RC_MAXP - 1,
+  RC_OBS_WORDS = (RC_OBS_WORDS_RAW + 31) / 32 * 32
+};
+
+/* FULL observation record (getFullState(robot), RoboCupEnvironment.py:1162-1188), one per
+ * (env, tick, observer) in full[E][T][P][RC_FULL_WORDS] when obs_type == FULL, and one per
+ * (env, observer) inside the info record (info['Recon States']) */
+enum {
+  RC_U_BALL = 0,                 /* F [4]            */
+  RC_U_SELF = 4,                 /* F [8]            */
+  RC_U_OTHERS = 12,              /* F [RC_MAXP-1][6] (first P-1 rows used) */
+  RC_FULL_WORDS = 12 + (RC_MAXP - 1) * 6 + 2 /* 68 */
+};
+
+/* per-environment result record: info[E][RC_INFO_WORDS] */
+enum {
+  RC_I_REWARDS = 0,                         /* F [RC_MAXP] robotRewards                       */
+  RC_I_DONE = RC_I_REWARDS + RC_MAXP,       /* I finished                                     */
+  RC_I_EPR = RC_I_DONE + 1,                 /* F [RC_MAXP] episode_r   (valid where done)     */
+  RC_I_EPPR = RC_I_EPR + RC_MAXP,           /* F [RC_MAXP] episode_p_r                        */
+  RC_I_EPOR = RC_I_EPPR + RC_MAXP,          /* F [RC_MAXP] episode_o_r                        */
+  RC_I_EPG = RC_I_EPOR + RC_MAXP,           /* I [2] episode_g                                */
+  RC_I_FLAGS = RC_I_EPG + 2,                /* I RC_IF_* diagnostics of this step             */
+  RC_I_STATE_ROBOTS = RC_I_FLAGS + 1,       /* F [RC_MAXP][6] info['Full State'][0]           */
+  RC_I_STATE_BALL = RC_I_STATE_ROBOTS + RC_MAXP * 6, /* F [3] info['Full State'][1]           */
+  RC_I_RECON = RC_I_STATE_BALL + 3,         /* F [RC_MAXP][RC_FULL_WORDS] info['Recon States'] */
+  RC_INFO_WORDS_RAW = RC_I_RECON + RC_MAXP * RC_FULL_WORDS,
+  RC_INFO_WORDS = (RC_INFO_WORDS_RAW + 31) / 32 * 32
+};
+#define RC_IF_ARB_OVERFLOW 1    /* more than RC_MAXARB cached contact pairs: a pair was dropped   */
+#define RC_IF_ACTIVE_OVERFLOW 2 /* more than RC_MAXACTIVE touching pairs in one substep           */
+#define RC_MAXACTIVE 16
+
 typedef struct DynEnvRoboCupOut {
-  /* PARTIAL observations, float32 [E][T][P][cap][feat] */
-  float* ball;    /* RC_CAP_BALL  x RC_F_BALL   */
-  float* robot;   /* RC_CAP_ROBOT x RC_F_ROBOT  */
-  float* post;    /* RC_CAP_POST  x RC_F_POST   */
-  float* cross;   /* RC_CAP_CROSS x RC_F_CROSS  */
-  float* fcross;  /* RC_CAP_FCROSS x RC_F_FCROSS */
-  float* line;    /* RC_CAP_LINE  x RC_F_LINE   */
-  int32_t* counts;      /* [E][T][P][RC_NTYPES] */
-  int32_t* num_landmarks; /* [E][T][P] */
-  uint8_t* robots_seen; /* [E][T][P][RC_MAXP-1] (first P-1 used) */
-  uint8_t* balls_seen;  /* [E][T][P] */
-  /* FULL observations (get_full_obs, written when obs_type == FULL), float32 */
-  float* full_ball;   /* [E][T][P][4]       */
-  float* full_self;   /* [E][T][P][8]       */
-  float* full_others; /* [E][T][P][RC_MAXP-1][6] (first P-1 rows used) */
-  /* info['Recon States'] = getFullState(robot) at the end of the step (always written) */
-  float* recon_ball;   /* [E][P][4]       */
-  float* recon_self;   /* [E][P][8]       */
-  float* recon_others; /* [E][P][RC_MAXP-1][6] */
-  /* info['Full State'] (getFullState()) at the end of the step */
-  float* state_robots; /* [E][P][6] */
-  float* state_ball;   /* [E][3]    */
-  /* rewards, done, episode statistics */
-  float* rewards;   /* [E][P] */
-  uint8_t* done;    /* [E]    */
-  float* episode_r;   /* [E][P] valid where done */
-  float* episode_p_r; /* [E][P] */
-  float* episode_o_r; /* [E][P] */
-  int32_t* episode_g; /* [E][2] */
+  float* obs;   /* [E][T][P][RC_OBS_WORDS]  PARTIAL observations (obs_type PARTIAL), else NULL */
+  float* full;  /* [E][T][P][RC_FULL_WORDS] FULL observations (obs_type FULL), else NULL       */
+  float* info;  /* [E][RC_INFO_WORDS]       rewards, done, episode stats, full/recon state     */
 } DynEnvRoboCupOut;
 
 /* ---- entry points */

@@ -8,7 +8,12 @@
  *
  *   key     = (seed low 32, seed high 32)
  *   counter = (global env id, episode, tick, site<<24 | a<<16 | b<<8 | block)
- *   uniform k of a site = word (k & 3) of block (k >> 2), u = (word >> 8) * 2^-24  in [0,1)
+ *   uniform k of a site = 21-bit slot (k % 6) of block (k / 6): the block's four words
+ *   w0..w3 are read as one 128-bit little-endian integer, slot s = bits [21 s, 21 s + 21),
+ *   u = slot * 2^-21 in [0,1).  Six uniforms per Philox evaluation is what every noise
+ *   routine of the observation path needs (cutils.py:352-468), so each sighting costs ONE
+ *   Philox block; 21 bits are exact in float32, so the float32 kernels and the float64
+ *   oracle see identical uniforms.
  *
  * tick: substep index `elapsed` (before the increment) for draws made inside the substep
  * loop; `elapsed` at snapshot time for observation ticks; DYNENV_TICK_RESETOBS | t for the

@@ -49,10 +49,15 @@ static inline double oracle_uniform(OracleRng* g, uint32_t episode, uint32_t tic
   }
   uint32_t ctr[4] = {g->env_id, episode, tick,
                      ((uint32_t)site << 24) | ((uint32_t)(a & 255) << 16) | ((uint32_t)(b & 255) << 8) |
-                         (uint32_t)(k >> 2)};
+                         (uint32_t)(k / 6)};
   uint32_t o[4];
   oracle_philox((uint32_t)g->seed, (uint32_t)(g->seed >> 32), ctr, o);
-  return (double)(o[k & 3] >> 8) * (1.0 / 16777216.0);
+  /* 21-bit slot (k % 6) of the 128-bit little-endian block (include/dynenv_rng.h) */
+  int bit = 21 * (k % 6);
+  int wi = bit >> 5, sh = bit & 31;
+  uint64_t two = (uint64_t)o[wi] | ((uint64_t)(wi < 3 ? o[wi + 1] : 0) << 32);
+  uint32_t slot = (uint32_t)(two >> sh) & 0x1FFFFFu;
+  return (double)slot * (1.0 / 2097152.0);
 }
 
 #endif

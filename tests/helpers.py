@@ -49,3 +49,77 @@ def field_errors(wa, wb, tol):
         if e > tol:
             out.append((name, e))
     return out
+
+
+# ---------------------------------------------------------------- GPU <-> oracle comparison
+def oracle_step_batch(cfg, recs, actions, seed, env_id0=0):
+    """Runs the CPU oracle (Philox mode) one step from each state record.  recs: uint32 [N, W]
+    (the C-ABI record, float32 words), actions [N, P, 4].  Returns (list of output dicts, records after)."""
+    from oracle.oracle import RcOracle, f32_record_to_words, words_to_f32_record
+    outs, after = [], []
+    for i in range(len(recs)):
+        orc = RcOracle(cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"], cfg["allowHeadTurn"],
+                       cfg["flags"], seed=seed, env_id=env_id0 + i)
+        orc.set_state(f32_record_to_words(recs[i]))
+        outs.append(orc.step(actions[i]))
+        after.append(orc.get_state())
+        assert not orc.arb_overflow()
+    return outs, np.array(after)
+
+
+def compare_step(cfg, sim_out, gpu_state_words, outs, oracle_words, tol=1e-4):
+    """Compares one batched GPU step with per-env oracle results.  Returns a list of
+    (env, what, detail) mismatches: integer / flag / count fields must be equal, floats within
+    tol * (1 + |ref|)."""
+    P = 2 * cfg["nPlayers"]
+    bad = []
+    int_mask = np.array(L.rc_int_mask())
+    full = cfg["obsType"] == 0
+    g = {}
+    for k in (FULL_KEYS if full else OBS_KEYS + SEEN_KEYS) + ["rewards", "done", "state_robots", "state_ball",
+                                                              "recon_ball", "recon_self", "recon_others", "diag"]:
+        g[k] = getattr(sim_out, k).detach().cpu().numpy()
+    for e, o in enumerate(outs):
+        if g["diag"][e] != 0:
+            bad.append((e, "diag", int(g["diag"][e])))
+        # state record
+        ws, wo = gpu_state_words[e], oracle_words[e]
+        for name, (off, cnt, kind) in L.RC_FIELDS.items():
+            a, b = ws[off:off + cnt], wo[off:off + cnt]
+            if kind == "i":
+                if not np.array_equal(a, b):
+                    bad.append((e, "state." + name, (a.tolist(), b.tolist())))
+            elif rel_err(a, b) > tol:
+                bad.append((e, "state." + name, rel_err(a, b)))
+        if rel_err(g["rewards"][e], o["rewards"][:P]) > tol:
+            bad.append((e, "rewards", rel_err(g["rewards"][e], o["rewards"][:P])))
+        if bool(g["done"][e]) != bool(o["done"]):
+            bad.append((e, "done", None))
+        for k, sl in (("state_robots", np.s_[:P]), ("state_ball", np.s_[:]), ("recon_ball", np.s_[:P]),
+                      ("recon_self", np.s_[:P]), ("recon_others", np.s_[:P, :P - 1])):
+            ref = o[k][sl]
+            got = g[k][e][sl] if k == "recon_others" else g[k][e]
+            if rel_err(got, ref) > tol:
+                bad.append((e, k, rel_err(got, ref)))
+        if full:
+            for k in FULL_KEYS:
+                ref = o[k][:, :P]
+                got = g[k][e]
+                if k == "full_others":
+                    ref, got = ref[:, :, :P - 1], got[:, :, :P - 1]
+                if rel_err(got, ref) > tol:
+                    bad.append((e, k, rel_err(got, ref)))
+        else:
+            for k in SEEN_KEYS:
+                ref = o[k][:, :P]
+                got = g[k][e]
+                if k == "robots_seen":
+                    ref, got = ref[..., :P - 1], got[..., :P - 1]
+                if not np.array_equal(ref, got):
+                    bad.append((e, k, np.argwhere(ref != got)[:4].tolist()))
+            for k in OBS_KEYS:
+                ref = o[k][:, :P]
+                got = g[k][e]
+                if rel_err(got, ref) > tol:
+                    bad.append((e, k, rel_err(got, ref)))
+    return bad
