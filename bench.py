@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout hot path: env-steps/s of RoboCup 5v5 (50 substeps + 5 observation ticks x 10
+observers per env-step), PARTIAL observation, REALISTIC noise magnitude 2 (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
+
+One process per GPU (torchrun for N > 1); environments are sharded by contiguous env-id range with no
+data-path collective (weak scaling: E environments per GPU).  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the CPU implementation of the same path on the host cores: the reference is
+pure Python over pymunk, neither of which exists on the GPU box, so this is the repo's C restatement of
+it (oracle/rc_oracle.c, pinned against the reference's own Python by tests/golden), one environment per
+host thread.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (RoboCup 5v5, 50 substeps)"
+UNIT = "env-steps/s"
+WORKLOAD = "RoboCup 5v5 PARTIAL REALISTIC noise 2, canFall, auto-reset"
+N_PLAYERS = 5
+P = 2 * N_PLAYERS
+FLOP_PER_ENV_STEP = 1.0e6  # SURVEY.md 8d contract figure
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def algorithmic_bytes_per_env_step():
+    """step-boundary HBM traffic of one env-step: state record in + out, actions in,
+    5 x 10 observation records, result record."""
+    from dynenv_b200 import layout as L
+    return 4 * (2 * L.RC_STATE_WORDS + P * 4 + L.RC_NTICK * P * L.RC_OBS_WORDS + L.RC_INFO_WORDS)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)"""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(0.05)
+
+    def stop(self):
+        self._halt.set()
+        if self.ok:
+            self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_env_steps_per_s(n_steps, threads=None):
+    """the C oracle, one environment per host thread (ctypes releases the GIL), all threads stepping
+    n_steps env-steps; returns (env-steps/s over all threads, threads)"""
+    import ctypes as C
+    from oracle import oracle as O
+    O.lib()
+    threads = threads or os.cpu_count() or 1
+    out = [0.0] * threads
+    barrier = threading.Barrier(threads)
+
+    def work(i):
+        env = O.RcOracle(N_PLAYERS, 1, 1, 2.0, False, seed=42, env_id=i)
+        env.reset()
+        rng = np.random.default_rng(1234 + i)
+        acts = np.stack([rng.integers(0, 5, (n_steps, P)), rng.integers(0, 3, (n_steps, P)),
+                         rng.integers(0, 3, (n_steps, P)), rng.integers(0, 7, (n_steps, P))], -1).astype(np.float64)
+        acts = np.ascontiguousarray(acts)
+        ref = C.byref(env._out)
+        barrier.wait()
+        t0 = time.perf_counter()
+        for s in range(n_steps):
+            env._lib.rc_step(env._h, acts[s].ctypes.data, ref)
+        out[i] = time.perf_counter() - t0
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return threads * n_steps / max(out), threads, max(out)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each "step" = every host thread advancing a bounded sample of env-steps of the same workload
+    per_step = 200
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_env_steps_per_s(50)
+    t_total, n_total, threads = 0.0, 0, 0
+    for _ in range(args.steps):
+        rate, threads, dt = cpu_env_steps_per_s(per_step)
+        t_total += dt
+        n_total += threads * per_step
+    value = n_total / t_total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "envs": threads, "env_steps_per_step": threads * per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d host threads x %d env-steps per bench step, C restatement of the reference "
+                                       "(pymunk and the reference's Python are not installable on this box)" % (threads, per_step)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E = args.envs
+    sim = dynenv_b200.BatchedRoboCup(E, N_PLAYERS, dynenv_b200.ObservationType.PARTIAL, dynenv_b200.NoiseType.REALISTIC,
+                                     2.0, canFall=True, useObsRewards=True, auto_reset=True, seed=42, device=local,
+                                     env_id_offset=rank * E)
+    sim.reset()
+    # synthetic actions: int uniform move [0,5) turn [0,3) kick [0,3) head [0,7), generator seed 1234
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    n_pool = 4
+    hi = torch.tensor([5, 3, 3, 7], device=dev)
+    pool = [(torch.rand((E, P, 4), generator=g, device=dev) * hi).floor().contiguous() for _ in range(n_pool)]
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        sim.step(pool[w % n_pool])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    t_start.record(stream)
+    for s in range(args.steps):
+        evs[s][0].record(stream)
+        sim.step(pool[s % n_pool])
+        evs[s][1].record(stream)
+        launches += sim.last_launch_count()
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    diag = int(sim.out.diag.max().item())
+
+    # end to end through the host-facing call: pinned host actions in, rewards + done out, every step
+    h_act = [p.cpu().pin_memory() for p in pool]
+    d_act = torch.empty((E, P, 4), device=dev)
+    h_rew = torch.empty((E, P), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((E,), dtype=torch.int32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(args.steps):
+        d_act.copy_(h_act[s % n_pool], non_blocking=True)
+        out = sim.step(d_act)
+        h_rew.copy_(out.rewards, non_blocking=True)
+        h_done.copy_(out.done, non_blocking=True)
+        stream.synchronize()
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e, kernel_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e, kernel_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        peaks, which = measured_peaks()
+        total_envs = E * world
+        value = total_envs * args.steps / (ms_total * 1e-3)
+        e2e = total_envs * args.steps / (ms_e2e * 1e-3)
+        bytes_launch = algorithmic_bytes_per_env_step() * E
+        achieved = bytes_launch / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "envs_per_gpu": E, "envs_total": total_envs, "substeps": L.RC_SUBSTEPS,
+                           "obs_ticks": L.RC_NTICK, "observers": P,
+                           "l2": "state + outputs per step (%.1f GB) exceed the 126 MB L2" % (bytes_launch / 1e9)},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * P * 4 * 4,
+                        "d2h_bytes_per_step": E * P * 4 + E * 4,
+                        "note": "observations stay device-resident for the learner; rewards + done return to the host"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+                             "kernel": "rc_step_kernel", "kernel_ms": kernel_ms,
+                             "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(),
+                             "fp32": {"flop_per_env_step": FLOP_PER_ENV_STEP,
+                                      "achieved_tflops": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12,
+                                      "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
+                                      "frac": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12 / FP32_NOMINAL_TFLOPS}},
+                "diag_flags": diag}
+        if not args.no_cpu and world == 1:
+            rate, threads, dt = cpu_env_steps_per_s(args.cpu_steps)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d host threads x %d env-steps of the same workload (%.1f s), C restatement "
+                                              "of the reference" % (threads, args.cpu_steps, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=1500, help="env-steps per host thread of the cpu_baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,7 @@ _LIB = None
 
 EXPORTS = ["dynenv_abi_version", "dynenv_last_error", "dynenv_create", "dynenv_destroy", "dynenv_state_words",
            "dynenv_reset", "dynenv_step", "dynenv_set_seed", "dynenv_get_state", "dynenv_set_state",
-           "dynenv_last_launch_count"]
+           "dynenv_last_launch_count", "dynenv_debug_substep_range"]
 
 
 class DynEnvConfig(C.Structure):
@@ -49,6 +49,7 @@ def lib():
         lb.dynenv_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lb.dynenv_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lb.dynenv_last_launch_count.argtypes = [C.c_void_p]
+        lb.dynenv_debug_substep_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
         if lb.dynenv_abi_version() != L.DYNENV_ABI_VERSION:
             raise RuntimeError("dynenv_b200: library ABI %d != header ABI %d" % (lb.dynenv_abi_version(),
                                                                                  L.DYNENV_ABI_VERSION))

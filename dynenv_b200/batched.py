@@ -138,6 +138,9 @@ class BatchedRoboCup(object):
         _lib.check(self._lib.dynenv_step(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
         return self.out
 
+    def debug_substep_range(self, begin, end):
+        _lib.check(self._lib.dynenv_debug_substep_range(self._h, int(begin), int(end)))
+
     def last_launch_count(self):
         return self._lib.dynenv_last_launch_count(self._h)
 

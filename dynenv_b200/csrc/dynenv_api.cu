@@ -72,7 +72,7 @@ rc_step_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
   rc::Env E = make_env(S, cfg, e, lane);
   const int P = cfg.P;
   const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
-  const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + RC_SUBSTEPS >= rc::MAXTIME;
+  const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + (cfg.sub_end - cfg.sub_begin) >= rc::MAXTIME;
   float* o = obs ? obs + e * obs_stride : nullptr;
   float* f = full ? full + e * full_stride : nullptr;
   float* inf = info ? info + (size_t)e * RC_INFO_WORDS : nullptr;
@@ -156,6 +156,8 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   s.seed_lo = (uint32_t)cfg->seed;
   s.seed_hi = (uint32_t)(cfg->seed >> 32);
   s.env_id_offset = (uint32_t)cfg->env_id_offset;
+  s.sub_begin = 0;
+  s.sub_end = RC_SUBSTEPS;
   h->state_words = RC_STATE_WORDS;
   h->last_launches = 0;
   size_t bytes = (size_t)cfg->n_envs * h->state_words * sizeof(uint32_t);
@@ -238,5 +240,12 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream) {
 }
 
 int dynenv_last_launch_count(DynEnvHandle h) { return h ? h->last_launches : 0; }
+
+int dynenv_debug_substep_range(DynEnvHandle h, int begin, int end) {
+  if (!h || begin < 0 || end > RC_SUBSTEPS || begin > end) return fail(DYNENV_E_INVALID, "bad substep range");
+  h->sim.sub_begin = begin;
+  h->sim.sub_end = end;
+  return DYNENV_OK;
+}
 
 }  // extern "C"

@@ -28,6 +28,7 @@ struct SimCfg {
   int random_init, deterministic_turn, can_fall, use_obs_rewards, auto_reset;
   uint32_t seed_lo, seed_hi;
   uint32_t env_id_offset;
+  int sub_begin, sub_end; /* substeps run by one step call: 0..RC_SUBSTEPS (a debugging aid narrows it) */
 };
 
 struct V2 {
@@ -44,8 +45,9 @@ __device__ __forceinline__ V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y -
 __device__ __forceinline__ V2 operator*(V2 a, float s) { return v2(a.x * s, a.y * s); }
 __device__ __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
 __device__ __forceinline__ float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
-__device__ __forceinline__ float lensq(V2 a) { return a.x * a.x + a.y * a.y; }
-__device__ __forceinline__ float len(V2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+/* one fixed evaluation order, so that equal vectors always have equal lengths */
+__device__ __forceinline__ float lensq(V2 a) { return __fmaf_rn(a.x, a.x, __fmul_rn(a.y, a.y)); }
+__device__ __forceinline__ float len(V2 a) { return sqrtf(lensq(a)); }
 __device__ __forceinline__ V2 rot_cs(V2 a, float c, float s) { return v2(a.x * c - a.y * s, a.x * s + a.y * c); }
 __device__ __forceinline__ V2 rot(V2 a, float ang) {
   float s, c;

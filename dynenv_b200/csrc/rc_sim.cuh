@@ -125,9 +125,33 @@ __device__ __forceinline__ V2 post_pos(int k) { return v2(k < 2 ? SIDE : W_ - SI
 __device__ __forceinline__ int team_of(const Env& E, int r) { return r < E.c->n_players ? 1 : -1; }
 __device__ __forceinline__ bool shape_active(const Env& E, int s) { return s >= 20 || s < 2 * E.c->P; }
 
-__device__ __forceinline__ V2 body_pos(const Env& E, int s) {
+__device__ __forceinline__ V2 body_pos(const Env& E, int s) { /* hi words: float32 view */
   if (s < RC_NBODY) return v2(E.f[RC_S_PX + s], E.f[RC_S_PY + s]);
   return post_pos(s - POST0);
+}
+/* Two-float coordinates (hi + lo, include/dynenv_b200.h): accumulate d into (hi, lo) without losing
+   the bits that do not fit hi (Knuth two-sum + renormalisation) */
+__device__ __forceinline__ void two_add(float& hi, float& lo, float d) {
+  float s = __fadd_rn(hi, d);
+  float bb = __fsub_rn(s, hi);
+  float err = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(d, bb));
+  lo = __fadd_rn(lo, err);
+  float h2 = __fadd_rn(s, lo);
+  lo = __fsub_rn(lo, __fsub_rn(h2, s));
+  hi = h2;
+}
+/* position of body b relative to body a, from both words: exact where it matters (close bodies) */
+__device__ __forceinline__ V2 pos_diff(const Env& E, int b, int a) {
+  float bx, by, bxl = 0.f, byl = 0.f, ax, ay, axl = 0.f, ayl = 0.f;
+  if (b < RC_NBODY) { bx = E.f[RC_S_PX + b]; by = E.f[RC_S_PY + b]; bxl = E.f[RC_S_PXL + b]; byl = E.f[RC_S_PYL + b]; }
+  else { V2 p = post_pos(b - POST0); bx = p.x; by = p.y; }
+  if (a < RC_NBODY) { ax = E.f[RC_S_PX + a]; ay = E.f[RC_S_PY + a]; axl = E.f[RC_S_PXL + a]; ayl = E.f[RC_S_PYL + a]; }
+  else { V2 p = post_pos(a - POST0); ax = p.x; ay = p.y; }
+  return v2(__fadd_rn(__fsub_rn(bx, ax), __fsub_rn(bxl, axl)), __fadd_rn(__fsub_rn(by, ay), __fsub_rn(byl, ayl)));
+}
+__device__ __forceinline__ void set_pose(Env& E, int s, float x, float y, float ang) {
+  E.f[RC_S_PX + s] = x; E.f[RC_S_PY + s] = y; E.f[RC_S_ANG + s] = ang;
+  E.f[RC_S_PXL + s] = 0.f; E.f[RC_S_PYL + s] = 0.f; E.f[RC_S_ANGL + s] = 0.f;
 }
 __device__ __forceinline__ V2 robot_pos(const Env& E, int r) { /* Robot.getPos (Robot.py:90-91) */
   return v2((E.f[RC_S_PX + 2 * r] + E.f[RC_S_PX + 2 * r + 1]) * 0.5f,
@@ -275,7 +299,7 @@ __device__ __noinline__ void penalize(Env& E, int r) {
   free_penalty_spot(E, r, &pos, &ang);
   for (int k = 0; k < 2; k++) {
     int b = 2 * r + k;
-    E.f[RC_S_PX + b] = pos.x; E.f[RC_S_PY + b] = pos.y; E.f[RC_S_ANG + b] = ang;
+    set_pose(E, b, pos.x, pos.y, ang);
     E.f[RC_S_VX + b] = 0.f; E.f[RC_S_VY + b] = 0.f; E.f[RC_S_W + b] = 0.f;
   }
   if ((fl & RC_RF_KICKING) && (fl & RC_RF_JOINT_REMOVED)) {
@@ -324,8 +348,8 @@ __device__ void process_action(Env& E, int r, float4 act, const Rand6& ru) {
     if (u > 0.99f) { fall(E, r, 0); return; }
     int foot = (int)kick - 1;
     int fb = 2 * r + (foot ? 1 : 0);
-    E.f[RC_S_INITX + r] = E.f[RC_S_PX + fb];
-    E.f[RC_S_INITY + r] = E.f[RC_S_PY + fb];
+    E.f[RC_S_INITX + r] = E.f[RC_S_PX + fb]; E.f[RC_S_INITXL + r] = E.f[RC_S_PXL + fb];
+    E.f[RC_S_INITY + r] = E.f[RC_S_PY + fb]; E.f[RC_S_INITYL + r] = E.f[RC_S_PYL + fb];
     E.i[RC_S_RFLAGS + r] = (E.i[RC_S_RFLAGS + r] & ~RC_RF_FOOT) | RC_RF_KICKING | (foot ? RC_RF_FOOT : 0);
     E.f[RC_S_MOVET + r] = 1000.f;
   }
@@ -357,8 +381,8 @@ __device__ void tick_robot(Env& E, int r) {
         E.f[RC_S_VX + foot] = 0.f;
         E.f[RC_S_VY + foot] = 0.f;
         fl &= ~RC_RF_KICKING;
-        E.f[RC_S_PX + foot] = E.f[RC_S_INITX + r];
-        E.f[RC_S_PY + foot] = E.f[RC_S_INITY + r];
+        E.f[RC_S_PX + foot] = E.f[RC_S_INITX + r]; E.f[RC_S_PXL + foot] = E.f[RC_S_INITXL + r];
+        E.f[RC_S_PY + foot] = E.f[RC_S_INITY + r]; E.f[RC_S_PYL + foot] = E.f[RC_S_INITYL + r];
         if (fl & RC_RF_JOINT_REMOVED) fl &= ~(RC_RF_JOINT_REMOVED | RC_RF_JOINT_ABSENT);
       }
     }
@@ -392,8 +416,8 @@ __device__ void tick_robot(Env& E, int r) {
       V2 pos;
       float ang;
       free_penalty_spot(E, r, &pos, &ang);
-      E.f[RC_S_PX + L] = pos.x; E.f[RC_S_PY + L] = pos.y; E.f[RC_S_ANG + L] = ang;
-      E.f[RC_S_PX + R] = pos.x; E.f[RC_S_PY + R] = pos.y; E.f[RC_S_ANG + R] = ang;
+      set_pose(E, L, pos.x, pos.y, ang);
+      set_pose(E, R, pos.x, pos.y, ang);
     }
     E.f[RC_S_PENT + r] = pt;
   } else {
@@ -550,6 +574,7 @@ __device__ void ball_out_of_field(Env& E) {
         }
       }
       E.f[RC_S_PX + BALL] = x; E.f[RC_S_PY + BALL] = y;
+      E.f[RC_S_PXL + BALL] = 0.f; E.f[RC_S_PYL + BALL] = 0.f;
       E.f[RC_S_VX + BALL] = 0; E.f[RC_S_VY + BALL] = 0; E.f[RC_S_W + BALL] = 0;
     }
     ball_free_kick(E, -team);
@@ -745,10 +770,29 @@ __device__ void seg_seg_closest(V2 a0, V2 a1, V2 b0, V2 b1, V2* nOut, float* dOu
 __device__ __forceinline__ float clamp01(float t) { return fminf(fmaxf(t, 0.f), 1.f); }
 __device__ __forceinline__ V2 vlerp(V2 a, V2 b, float t) { return a * (1.f - t) + b * t; }
 
-__device__ __noinline__ void narrowphase(const Env& E, int a, int b, Manifold* m) {
+/* Shape geometry relative to its own body: feet are the segments (-10, +-10)-(10, +-10) (Robot.py:24-27) */
+__device__ __forceinline__ void shape_local(const Env& E, int s, V2* oa, V2* ob) {
+  if (is_foot(s)) {
+    float ly = (s & 1) ? -ROB_LEN : ROB_LEN;
+    float sn, cs;
+    sincosf(E.f[RC_S_ANG + s], &sn, &cs);
+    *oa = v2(-ROB_LEN * cs - ly * sn, -ROB_LEN * sn + ly * cs);
+    *ob = v2(ROB_LEN * cs - ly * sn, ROB_LEN * sn + ly * cs);
+  } else {
+    *oa = v2(0, 0);
+    *ob = v2(0, 0);
+  }
+}
+
+/* Narrow phase in the frame of body a (origin = a's position, dab = position of b relative to a from
+   the two-float coordinates), so that penetration depths of ~0.1 px are not lost in float32
+   coordinates of ~500 px.  Contact points come out relative to a's position. */
+__device__ __noinline__ void narrowphase(const Env& E, int a, int b, V2 dab, Manifold* m) {
   V2 ata, atb, bta, btb;
-  shape_geom(E, a, &ata, &atb);
-  shape_geom(E, b, &bta, &btb);
+  shape_local(E, a, &ata, &atb);
+  shape_local(E, b, &bta, &btb);
+  bta = bta + dab;
+  btb = btb + dab;
   m->cnt = 0;
   if (!is_foot(a) && !is_foot(b)) { /* CircleToCircleQuery */
     float mind = 20.f;
@@ -812,8 +856,15 @@ __device__ __noinline__ void narrowphase(const Env& E, int a, int b, Manifold* m
 __device__ __noinline__ void collide_pair(Env& E, int i, int j) {
   int a = i, b = j;
   if (is_foot(a) && !is_foot(b)) { a = j; b = i; } /* cpCollide orders by primitive type */
+  if (b == a + 1 && !(a & 1) && b < 20) {
+    /* the two feet of one robot: their core segments are 20 apart (> 2 x 7.5) while the joints hold */
+    V2 d = pos_diff(E, b, a);
+    float da = __fadd_rn(__fsub_rn(E.f[RC_S_ANG + b], E.f[RC_S_ANG + a]), __fsub_rn(E.f[RC_S_ANGL + b], E.f[RC_S_ANGL + a]));
+    if (fabsf(d.x) + fabsf(d.y) < 2.f && fabsf(da) < 0.1f) return;
+  }
   Manifold m;
-  narrowphase(E, a, b, &m);
+  V2 dab = pos_diff(E, b, a);
+  narrowphase(E, a, b, dab, &m);
   if (m.cnt == 0) return;
   int nArb = E.i[RC_S_NARB];
   int key16 = a | (b << 8);
@@ -832,15 +883,14 @@ __device__ __noinline__ void collide_pair(Env& E, int i, int j) {
   int con = E.i[RC_S_ARBCON + k];
   int oldN = con & 255, oh0 = (con >> 8) & 255, oh1 = (con >> 16) & 255;
   float ojn0 = E.f[RC_S_ARBJN0 + k], ojt0 = E.f[RC_S_ARBJT0 + k], ojn1 = E.f[RC_S_ARBJN1 + k], ojt1 = E.f[RC_S_ARBJT1 + k];
-  V2 pa = body_pos(E, a), pb = body_pos(E, b);
   for (int c = 0; c < 2; c++) {
     int ci = 2 * nact + c;
     float jn = 0, jt = 0;
     if (c < m.cnt) {
       if (oldN > 0 && m.hash[c] == oh0) { jn = ojn0; jt = ojt0; }
       if (oldN > 1 && m.hash[c] == oh1) { jn = ojn1; jt = ojt1; }
-      E.f[X_CR1X + ci] = m.p1[c].x - pa.x; E.f[X_CR1Y + ci] = m.p1[c].y - pa.y;
-      E.f[X_CR2X + ci] = m.p2[c].x - pb.x; E.f[X_CR2Y + ci] = m.p2[c].y - pb.y;
+      E.f[X_CR1X + ci] = m.p1[c].x; E.f[X_CR1Y + ci] = m.p1[c].y;
+      E.f[X_CR2X + ci] = m.p2[c].x - dab.x; E.f[X_CR2Y + ci] = m.p2[c].y - dab.y;
     }
     E.f[X_CJN + ci] = jn;
     E.f[X_CJT + ci] = jt;
@@ -950,32 +1000,37 @@ __device__ void space_step(Env& E) {
     if (((key >> 16) & 255) == RC_ARB_FIRST) E.i[RC_S_ARBKEY + lane] = (key & ~0xff0000) | (RC_ARB_NORMAL << 16);
   }
   /* integrate positions (cpBodyUpdatePosition), refresh shape geometry, bounding boxes in registers */
-  float bl = 0, br = 0, bb = 0, bt = 0;
+  float bcx = 0, bcy = 0, bcr = 0; /* bounding circle of this lane's shape */
   bool active = lane < NSHAPE && shape_active(E, lane);
   if (lane <= BALL && active) {
-    float px = E.f[RC_S_PX + lane] + (E.f[RC_S_VX + lane] + E.f[RC_S_VBX + lane]) * dt;
-    float py = E.f[RC_S_PY + lane] + (E.f[RC_S_VY + lane] + E.f[RC_S_VBY + lane]) * dt;
-    float an = E.f[RC_S_ANG + lane] + (E.f[RC_S_W + lane] + E.f[RC_S_WB + lane]) * dt;
+    float px = E.f[RC_S_PX + lane], pxl = E.f[RC_S_PXL + lane];
+    float py = E.f[RC_S_PY + lane], pyl = E.f[RC_S_PYL + lane];
+    float an = E.f[RC_S_ANG + lane], anl = E.f[RC_S_ANGL + lane];
+    two_add(px, pxl, __fmul_rn(E.f[RC_S_VX + lane] + E.f[RC_S_VBX + lane], dt));
+    two_add(py, pyl, __fmul_rn(E.f[RC_S_VY + lane] + E.f[RC_S_VBY + lane], dt));
+    two_add(an, anl, __fmul_rn(E.f[RC_S_W + lane] + E.f[RC_S_WB + lane], dt));
     E.f[RC_S_PX + lane] = px; E.f[RC_S_PY + lane] = py; E.f[RC_S_ANG + lane] = an;
+    E.f[RC_S_PXL + lane] = pxl; E.f[RC_S_PYL + lane] = pyl; E.f[RC_S_ANGL + lane] = anl;
     E.f[RC_S_VBX + lane] = 0.f; E.f[RC_S_VBY + lane] = 0.f; E.f[RC_S_WB + lane] = 0.f;
     V2 ta, tb;
     shape_world(lane, px, py, an, &ta, &tb);
     E.f[RC_S_CAX + lane] = ta.x; E.f[RC_S_CAY + lane] = ta.y;
     E.f[RC_S_CBX + lane] = tb.x; E.f[RC_S_CBY + lane] = tb.y;
-    float r = shape_radius(lane);
-    bl = fminf(ta.x, tb.x) - r; br = fmaxf(ta.x, tb.x) + r;
-    bb = fminf(ta.y, tb.y) - r; bt = fmaxf(ta.y, tb.y) + r;
+    bcx = (ta.x + tb.x) * 0.5f; bcy = (ta.y + tb.y) * 0.5f;
+    bcr = lane < 20 ? ROB_LEN + ROB_RAD : 10.f;
   } else if (lane >= POST0 && lane < NSHAPE) {
     V2 p = post_pos(lane - POST0);
-    bl = p.x - 10.f; br = p.x + 10.f; bb = p.y - 10.f; bt = p.y + 10.f;
+    bcx = p.x; bcy = p.y; bcr = 10.f;
   }
   __syncwarp();
-  /* collide: pairs in ascending (i, j) insertion order; lane j tests its box against shape i */
+  /* collide: pairs in ascending (i, j) insertion order; lane j tests its bounding circle against shape i.
+     (Chipmunk's bounding-box test is implied: shapes that touch have overlapping boxes; the margin
+     covers the float32 rounding of the absolute centres.) */
   for (int i = 0; i <= BALL; i++) {
     if (!shape_active(E, i)) continue;
-    float il = __shfl_sync(FULLMASK, bl, i), ir = __shfl_sync(FULLMASK, br, i);
-    float ib = __shfl_sync(FULLMASK, bb, i), it = __shfl_sync(FULLMASK, bt, i);
-    bool hit = active && lane > i && il <= br && bl <= ir && ib <= bt && bb <= it;
+    float dx = __shfl_sync(FULLMASK, bcx, i) - bcx, dy = __shfl_sync(FULLMASK, bcy, i) - bcy;
+    float rr = __shfl_sync(FULLMASK, bcr, i) + bcr + 0.05f;
+    bool hit = active && lane > i && dx * dx + dy * dy < rr * rr;
     unsigned hits = __ballot_sync(FULLMASK, hit);
     if (hits) {
       if (lane == 0) {
@@ -1039,6 +1094,11 @@ __device__ void space_step(Env& E) {
     __syncwarp();
     if (lane < nact) E.i[X_ACTIVE + lane] = remapped;
     if (lane == 0) E.i[RC_S_NARB] = __popc(keepmask);
+    if (have && lane >= __popc(keepmask)) { /* records stay canonical: unused slots are zero */
+      E.i[RC_S_ARBKEY + lane] = 0; E.i[RC_S_ARBCON + lane] = 0;
+      E.f[RC_S_ARBJN0 + lane] = 0.f; E.f[RC_S_ARBJT0 + lane] = 0.f;
+      E.f[RC_S_ARBJN1 + lane] = 0.f; E.f[RC_S_ARBJT1 + lane] = 0.f;
+    }
     __syncwarp();
   }
   const int nact = E.i[X_NACTIVE];
@@ -1061,7 +1121,7 @@ __device__ void space_step(Env& E) {
         float r1ct = cross(r1, t), r2ct = cross(r2, t);
         E.f[X_CNMASS + lane] = 1.f / (ami + aii * r1cn * r1cn + bmi + bii * r2cn * r2cn);
         E.f[X_CTMASS + lane] = 1.f / (ami + aii * r1ct * r1ct + bmi + bii * r2ct * r2ct);
-        V2 bd = body_pos(E, b) - body_pos(E, a);
+        V2 bd = pos_diff(E, b, a);
         float dist = dot(r2 - r1 + bd, n);
         E.f[X_CBIAS + lane] = -biasCoef * fminf(0.f, dist + slop) / dt;
         E.f[X_CJBIAS + lane] = 0.f;
@@ -1074,6 +1134,22 @@ __device__ void space_step(Env& E) {
     }
     __syncwarp();
   }
+#ifdef RC_DEBUG_PRINT
+  if (lane == 0 && nact && E.rng.env_id == RC_DEBUG_PRINT) {
+    for (int q = 0; q < nact; q++) {
+      int k = E.i[X_ACTIVE + q];
+      int key = E.i[RC_S_ARBKEY + k];
+      for (int c = 0; c < (E.i[RC_S_ARBCON + k] & 255); c++) {
+        int ci = 2 * q + c;
+        printf("GPU q%d (%d,%d) st%d c%d n=(%.7f,%.7f) r1=(%.6f,%.6f) r2=(%.6f,%.6f) nMass=%.4f tMass=%.4f bias=%.6f bounce=%.6f jn=%.3f jt=%.3f\n",
+               q, key & 255, (key >> 8) & 255, (key >> 16) & 255, c, E.f[X_ANX + q], E.f[X_ANY + q], E.f[X_CR1X + ci], E.f[X_CR1Y + ci],
+               E.f[X_CR2X + ci], E.f[X_CR2Y + ci], E.f[X_CNMASS + ci], E.f[X_CTMASS + ci], E.f[X_CBIAS + ci], E.f[X_CBOUNCE + ci],
+               E.f[X_CJN + ci], E.f[X_CJT + ci]);
+      }
+    }
+  }
+  __syncwarp();
+#endif
   /* joints pre-step (lane = robot): pivot with both anchors at the centres of gravity, rotary limit 0..0 */
   const int L = 2 * lane, R = 2 * lane + 1;
   const bool isRobot = lane < P;
@@ -1085,10 +1161,11 @@ __device__ void space_step(Env& E) {
     pivJx = E.f[RC_S_PIVJX + lane]; pivJy = E.f[RC_S_PIVJY + lane]; rotJ = E.f[RC_S_ROTJ + lane];
     if (pivOn) {
       const float c = -2.2762779044e+00f; /* -(1 - errorBias^dt) / dt, joint.error_bias = 0.1 (Robot.py:59) */
-      pivBx = (E.f[RC_S_PX + R] - E.f[RC_S_PX + L]) * c;
-      pivBy = (E.f[RC_S_PY + R] - E.f[RC_S_PY + L]) * c;
+      V2 d = pos_diff(E, R, L);
+      pivBx = d.x * c;
+      pivBy = d.y * c;
     }
-    float dist = E.f[RC_S_ANG + R] - E.f[RC_S_ANG + L];
+    float dist = __fadd_rn(__fsub_rn(E.f[RC_S_ANG + R], E.f[RC_S_ANG + L]), __fsub_rn(E.f[RC_S_ANGL + R], E.f[RC_S_ANGL + L]));
     float pdist = -dist; /* min = max = 0 */
     rotBias = -biasCoef * pdist / dt;
     if (rotBias == 0) rotJ = 0;
@@ -1164,8 +1241,17 @@ __device__ void space_step(Env& E) {
         E.f[RC_S_VX + R] = rvx; E.f[RC_S_VY + R] = rvy; E.f[RC_S_W + R] = rw;
       }
       __syncwarp();
+#ifdef RC_DEBUG_PRINT
+      if (lane == 0 && E.rng.env_id == RC_DEBUG_PRINT && (it < 2))
+        for (int b = 4; b < 10; b++) printf("GPU it%d pre-contacts body %d v=(%.6f,%.6f) w=%.6f\n", it, b, E.f[RC_S_VX + b], E.f[RC_S_VY + b], E.f[RC_S_W + b]);
+#endif
       if (lane == 0) contacts_iteration(E);
       __syncwarp();
+#ifdef RC_DEBUG_PRINT
+      if (lane == 0 && E.rng.env_id == RC_DEBUG_PRINT && (it < 2))
+        for (int b = 4; b < 10; b++) printf("GPU it%d post-contacts body %d v=(%.6f,%.6f) w=%.6f\n", it, b, E.f[RC_S_VX + b], E.f[RC_S_VY + b], E.f[RC_S_W + b]);
+      if (isRobot && lane >= 2 && lane < 5 && E.rng.env_id == RC_DEBUG_PRINT && it < 2) printf("GPU it%d robot %d pivOn %d pivB=(%.6f,%.6f) rotBias=%.6f pivJ=(%.3f,%.3f) rotJ=%.3f\n", it, lane, (int)pivOn, pivBx, pivBy, rotBias, pivJx, pivJy, rotJ);
+#endif
       if (isRobot) {
         lvx = E.f[RC_S_VX + L]; lvy = E.f[RC_S_VY + L]; lw = E.f[RC_S_W + L];
         rvx = E.f[RC_S_VX + R]; rvy = E.f[RC_S_VY + R]; rw = E.f[RC_S_W + R];
@@ -1455,7 +1541,10 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
           if (seen == S_DISTANT) mult = range * 3;
           else if (seen == S_PARTIAL) mult = range * 4;
           V2 newPos = p + v2(noiseVec.x * mult / 4, noiseVec.y * mult / 4);
-          float diff = len(newPos) - len(p);
+          /* |newPos| - |p| without cancellation: (2 p.d + d.d) / (|newPos| + |p|) */
+          V2 dsp = v2(noiseVec.x * mult / 4, noiseVec.y * mult / 4);
+          float lsum = len(newPos) + len(p);
+          float diff = lsum > 0 ? (2.f * dot(p, dsp) + dot(dsp, dsp)) / lsum : 0.f;
           if (ru.u(2) < randB * mult) seen = S_NO;
           if ((kind == 0 || kind == 3) && ru.u(3) < randB * mult / 2) seen = S_MISCLASS;
           p = newPos;
@@ -1812,7 +1901,7 @@ __device__ void step_env(Env& E, const float* actions_env, float* obs_env, float
   const int lane = E.lane;
   const int P = E.c->P;
   clear_step_scratch(E);
-  for (int sub = 0; sub < RC_SUBSTEPS; sub++) {
+  for (int sub = E.c->sub_begin; sub < E.c->sub_end; sub++) {
     robots_phase(E, sub, actions_env);
     ball_out_of_field(E);
     space_step(E);

@@ -76,7 +76,12 @@ RC_FIELDS = {
     "arbCon": (C["RC_S_ARBCON"], _NA, "i"), "arbJn0": (C["RC_S_ARBJN0"], _NA, "f"),
     "arbJt0": (C["RC_S_ARBJT0"], _NA, "f"), "arbJn1": (C["RC_S_ARBJN1"], _NA, "f"),
     "arbJt1": (C["RC_S_ARBJT1"], _NA, "f"),
+    # low-order words of the two-float coordinates
+    "pxLo": (C["RC_S_PXL"], _NB, "f"), "pyLo": (C["RC_S_PYL"], _NB, "f"), "angleLo": (C["RC_S_ANGL"], _NB, "f"),
+    "initXLo": (C["RC_S_INITXL"], _NP, "f"), "initYLo": (C["RC_S_INITYL"], _NP, "f"),
 }
+# coordinate fields stored as hi + lo float32 pairs: hi field -> lo field
+RC_SPLIT = {"px": "pxLo", "py": "pyLo", "angle": "angleLo", "initX": "initXLo", "initY": "initYLo"}
 
 
 def rc_int_mask():

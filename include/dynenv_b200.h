@@ -162,7 +162,16 @@ enum {
   RC_S_ARBJT0 = RC_S_ARBJN0 + RC_MAXARB,
   RC_S_ARBJN1 = RC_S_ARBJT0 + RC_MAXARB,
   RC_S_ARBJT1 = RC_S_ARBJN1 + RC_MAXARB,
-  RC_STATE_WORDS_RAW = RC_S_ARBJT1 + RC_MAXARB,
+  /* low-order parts of positions and angles: a coordinate is the unevaluated sum hi + lo of two
+     float32 words (RC_S_PX + RC_S_PXL, ...), which keeps the small differences the joint and
+     contact solvers work on (foot-to-foot offsets, penetration depths) exact to ~1e-13 although
+     all arithmetic is float32.  Consumers that do not need that read the hi word alone. */
+  RC_S_PXL = RC_S_ARBJT1 + RC_MAXARB,   /* F [RC_NBODY] */
+  RC_S_PYL = RC_S_PXL + RC_NBODY,
+  RC_S_ANGL = RC_S_PYL + RC_NBODY,
+  RC_S_INITXL = RC_S_ANGL + RC_NBODY,   /* F [RC_MAXP] */
+  RC_S_INITYL = RC_S_INITXL + RC_MAXP,
+  RC_STATE_WORDS_RAW = RC_S_INITYL + RC_MAXP,
   RC_STATE_WORDS = (RC_STATE_WORDS_RAW + 31) / 32 * 32 /* records start 128-byte aligned */
 };
 
@@ -274,6 +283,11 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);
 
 /* number of kernels launched by the last dynenv_step / dynenv_reset call on this handle */
 int dynenv_last_launch_count(DynEnvHandle h);
+
+/* Debugging aid for parity work: the following dynenv_step calls run only substeps [begin, end) of
+   the step (actions are applied at substep 0, observations are emitted at substeps 9, 19, ...;
+   rewards of a partial step cover only the substeps run).  Default 0, RC_SUBSTEPS. */
+int dynenv_debug_substep_range(DynEnvHandle h, int begin, int end);
 
 #ifdef __cplusplus
 }

@@ -127,6 +127,9 @@ class RcOracle(object):
     def tape_underflow(self):
         return bool(self._lib.rc_tape_underflow(self._h))
 
+    def debug_substep_range(self, begin, end):
+        self._lib.rc_debug_substep_range(C.c_void_p(self._h), int(begin), int(end))
+
     def arb_overflow(self):
         return bool(self._lib.rc_arb_overflow(self._h))
 
@@ -148,14 +151,31 @@ class RcOracle(object):
         return w
 
     def set_state(self, words):
-        w = np.ascontiguousarray(words, dtype=np.float64)
+        w = np.ascontiguousarray(pad_words(words), dtype=np.float64)
         assert w.shape == (L.RC_STATE_WORDS,)
         self._lib.rc_load_state(self._h, w.ctypes.data)
 
 
-def words_to_f32_record(words):
-    """float64 word list -> the uint32 record the C-ABI uses (floats rounded to float32)."""
+def pad_words(words):
+    """float64 word lists of an older (shorter) record layout -> current width (new fields are zero)."""
     w = np.asarray(words, dtype=np.float64)
+    if w.shape[-1] == L.RC_STATE_WORDS:
+        return w
+    out = np.zeros(w.shape[:-1] + (L.RC_STATE_WORDS,), dtype=np.float64)
+    out[..., :w.shape[-1]] = w
+    return out
+
+
+def words_to_f32_record(words):
+    """float64 word list -> the uint32 record the C-ABI uses: floats rounded to float32, two-float
+    coordinates (layout.RC_SPLIT) split into hi = f32(v), lo = f32(v - hi)."""
+    w = pad_words(words).copy()
+    for hi, lo in L.RC_SPLIT.items():
+        (oh, cnt, _), (ol, _, _) = L.RC_FIELDS[hi], L.RC_FIELDS[lo]
+        v = w[..., oh:oh + cnt] + w[..., ol:ol + cnt]
+        h = v.astype(np.float32).astype(np.float64)
+        w[..., oh:oh + cnt] = h
+        w[..., ol:ol + cnt] = v - h
     mask = np.array(L.rc_int_mask())
     rec = np.zeros(w.shape, dtype=np.uint32)
     rec[..., mask] = w[..., mask].astype(np.int64).astype(np.int32).view(np.uint32)
@@ -164,9 +184,14 @@ def words_to_f32_record(words):
 
 
 def f32_record_to_words(rec):
+    """inverse of words_to_f32_record; two-float coordinates are merged into the hi word (lo = 0)"""
     r = np.asarray(rec, dtype=np.uint32)
     mask = np.array(L.rc_int_mask())
     w = np.zeros(r.shape, dtype=np.float64)
     w[..., mask] = r[..., mask].view(np.int32).astype(np.float64)
     w[..., ~mask] = r[..., ~mask].view(np.float32).astype(np.float64)
+    for hi, lo in L.RC_SPLIT.items():
+        (oh, cnt, _), (ol, _, _) = L.RC_FIELDS[hi], L.RC_FIELDS[lo]
+        w[..., oh:oh + cnt] += w[..., ol:ol + cnt]
+        w[..., ol:ol + cnt] = 0
     return w

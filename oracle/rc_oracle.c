@@ -15,6 +15,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -138,6 +139,7 @@ struct RcEnv {
   double teamRewards[2], obsRewards[RC_MAXP], robotRewards[RC_MAXP], robotPosRewards[RC_MAXP];
   int active[RC_MAXARB], nActive;
   int arbOverflow;
+  int subBegin, subEnd; /* debugging aid: substeps run by rc_step (0 = unset -> 0..RC_SUBSTEPS) */
 };
 typedef struct RcEnv RcEnv;
 
@@ -936,6 +938,16 @@ static void space_step(RcEnv* e, double dt) {
       con->bounce = vdot(vr, n) * arb->e;
     }
   }
+  if (getenv("RC_ORACLE_DEBUG"))
+    for (int q = 0; q < e->nActive; q++) {
+      Arbiter* arb = &e->arb[e->active[q]];
+      for (int c = 0; c < arb->ncon; c++) {
+        Contact* con = &arb->con[c];
+        printf("ORC q%d (%d,%d) st%d c%d n=(%.7f,%.7f) r1=(%.6f,%.6f) r2=(%.6f,%.6f) nMass=%.4f tMass=%.4f bias=%.6f bounce=%.6f jn=%.3f jt=%.3f\n",
+               q, arb->a, arb->b, arb->state, c, arb->n.x, arb->n.y, con->r1.x, con->r1.y, con->r2.x, con->r2.y, con->nMass, con->tMass,
+               con->bias, con->bounce, con->jnAcc, con->jtAcc);
+      }
+    }
   for (int r = 0; r < e->P; r++) {
     Robot* rb = &e->rob[r];
     Body* a = &e->body[2 * r];
@@ -981,6 +993,10 @@ static void space_step(RcEnv* e, double dt) {
   }
   /* solver: 10 iterations of {all arbiters, then all constraints} */
   for (int it = 0; it < 10; it++) {
+    if (getenv("RC_ORACLE_DEBUG") && it < 2) {
+      for (int b = 4; b < 10; b++) printf("ORC it%d pre-contacts body %d v=(%.6f,%.6f) w=%.6f\n", it, b, e->body[b].vx, e->body[b].vy, e->body[b].w);
+      for (int r = 2; r < 5; r++) printf("ORC it%d robot %d pivOn %d pivB=(%.6f,%.6f) rotBias=%.6f pivJ=(%.3f,%.3f) rotJ=%.3f\n", it, r, !e->rob[r].jointAbsent, e->rob[r].pivBias.x, e->rob[r].pivBias.y, e->rob[r].rotBias, e->rob[r].pivJ.x, e->rob[r].pivJ.y, e->rob[r].rotJ);
+    }
     for (int q = 0; q < e->nActive; q++) {
       Arbiter* arb = &e->arb[e->active[q]];
       Body* a = &e->body[arb->a];
@@ -1529,6 +1545,7 @@ void rc_set_tape(RcEnv* e, const double* tape, int n) { e->rng.mode = tape ? 1 :
 int rc_tape_pos(RcEnv* e) { return e->rng.tape_pos; }
 int rc_tape_underflow(RcEnv* e) { return e->rng.tape_underflow; }
 int rc_arb_overflow(RcEnv* e) { return e->arbOverflow; }
+void rc_debug_substep_range(RcEnv* e, int begin, int end) { e->subBegin = begin; e->subEnd = end; }
 
 static void init_body_consts(RcEnv* e) {
   for (int s = 0; s < NSHAPE; s++) {
@@ -1685,7 +1702,9 @@ void rc_load_state(RcEnv* e, const double* w) {
   init_body_consts(e);
   for (int s = 0; s < RC_NBODY; s++) {
     Body* b = &e->body[s];
-    b->px = w[RC_S_PX + s]; b->py = w[RC_S_PY + s]; b->a = w[RC_S_ANG + s];
+    /* two-float coordinates of the float32 record: hi + lo (the oracle itself stores lo = 0) */
+    b->px = w[RC_S_PX + s] + w[RC_S_PXL + s]; b->py = w[RC_S_PY + s] + w[RC_S_PYL + s];
+    b->a = w[RC_S_ANG + s] + w[RC_S_ANGL + s];
     b->vx = w[RC_S_VX + s]; b->vy = w[RC_S_VY + s]; b->w = w[RC_S_W + s];
     b->fx = w[RC_S_FX + s]; b->fy = w[RC_S_FY + s]; b->t = w[RC_S_TQ + s];
     b->vbx = w[RC_S_VBX + s]; b->vby = w[RC_S_VBY + s]; b->wb = w[RC_S_WB + s];
@@ -1695,7 +1714,7 @@ void rc_load_state(RcEnv* e, const double* w) {
   for (int r = 0; r < RC_MAXP; r++) {
     Robot* rb = &e->rob[r];
     rb->headAngle = w[RC_S_HEAD + r]; rb->headMoving = w[RC_S_HEADMOV + r]; rb->moveTime = w[RC_S_MOVET + r];
-    rb->initPos = v2(w[RC_S_INITX + r], w[RC_S_INITY + r]);
+    rb->initPos = v2(w[RC_S_INITX + r] + w[RC_S_INITXL + r], w[RC_S_INITY + r] + w[RC_S_INITYL + r]);
     rb->fallTime = w[RC_S_FALLT + r]; rb->penalTime = w[RC_S_PENT + r];
     rb->prevPos = v2(w[RC_S_PREVX + r], w[RC_S_PREVY + r]);
     rb->pivJ = v2(w[RC_S_PIVJX + r], w[RC_S_PIVJY + r]); rb->rotJ = w[RC_S_ROTJ + r];
@@ -1782,7 +1801,7 @@ void rc_step(RcEnv* e, const double* actions /*[P][4]*/, RcStepOut* out) {
   memset(out, 0, sizeof(*out));
   e->teamRewards[0] = e->teamRewards[1] = 0;
   for (int r = 0; r < RC_MAXP; r++) { e->obsRewards[r] = 0; e->robotRewards[r] = 0; e->robotPosRewards[r] = 0; }
-  for (int i = 0; i < RC_SUBSTEPS; i++) {
+  for (int i = e->subBegin; i < (e->subEnd ? e->subEnd : RC_SUBSTEPS); i++) {
     for (int r = 0; r < e->P; r++) {
       if (i == 0) { process_action(e, r, actions + 4 * r); joint_add_now(e); }
       tick_robot(e, r);
