@@ -1434,7 +1434,7 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
     bool has = false;
     V2 p = v2(0, 0);
     float radius = 0, ex0 = 0, ex1 = 0, ex2 = 0, maxDist = maxVis0;
-    V2 lp1 = v2(0, 0), lp2 = v2(0, 0); /* lines */
+    V2 lp1 = v2(0, 0), lp2 = v2(0, 0), ldir = v2(0, 0); /* lines: end points and lp2 - lp1 */
     if (kind >= 0 && kind <= 4) {
       V2 pt;
       if (kind == 0) { pt = ball_pos(E); radius = BALL_RADIUS * 2; ex0 = (float)(E.i[RC_S_BALLOWNED] * team_of(E, ag)); }
@@ -1472,12 +1472,14 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
         if (!(dist21 < 0 && dist22 < 0)) {
           seen = S_NORMAL;
           V2 pt1, pt2;
+          float t1 = 0.f, t2 = 1.f; /* line parameters of the clipped end points */
           if (dist11 <= 0 && dist21 >= 0) pt1 = p1;
           else {
             float inter1 = cross(p1, vec1) / (cross(vec1, p2 - p1) + 1e-7f);
             float inter2 = cross(p1, vec2) / (cross(vec2, p2 - p1) + 1e-7f);
             float inter = (inter1 < 1 && inter2 < 1) ? fmaxf(inter1, inter2) : fminf(inter1, inter2);
             pt1 = p1 + (p2 - p1) * inter;
+            t1 = inter;
             seen = S_PARTIAL;
           }
           if (dist12 <= 0 && dist22 >= 0) pt2 = p2;
@@ -1486,11 +1488,15 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
             float inter2 = cross(p2, vec2) / cross(vec2, p1 - p2);
             float inter = (inter1 < 1 && inter2 < 1) ? fmaxf(inter1, inter2) : fminf(inter1, inter2);
             pt2 = p2 + (p1 - p2) * inter;
+            t2 = 1.f - inter;
             seen = S_PARTIAL;
           }
           if (lensq(pt1) > maxDist || lensq(pt2) > maxDist) seen = S_DISTANT;
           lp1 = rot_cs(pt1, hc, -hs);
           lp2 = rot_cs(pt2, hc, -hs);
+          /* lp2 - lp1 from the line's own direction: a clipped piece can be a fraction of a pixel
+             long, which the difference of two float32 end points (~300 px) cannot resolve */
+          ldir = rot_cs(p2 - p1, hc, -hs) * (t2 - t1);
           if (lp1.x < 0 || lp2.x < 0) seen = S_NO;
           has = true;
         }
@@ -1560,13 +1566,20 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
         if (ru.u(4) < randB) seen = S_NO;
         lp1 = lp1 + n1;
         lp2 = lp2 + n2;
+        ldir = ldir + (n2 - n1);
       } else {
         float m1 = 0.25f + 3.75f * lensq(lp1) / maxDist;
         float m2 = 0.25f + 3.75f * lensq(lp2) / maxDist;
         float m = (m1 + m2) * 0.5f;
+#ifdef RC_DEBUG_PRINT
+        if (E.rng.env_id == RC_DEBUG_PRINT && ag == 8 && E.i[RC_S_ELAPSED] % 50 == 0)
+          printf("GPU line %d lp1=(%.5f,%.5f) lp2=(%.5f,%.5f) m1=%.6f m2=%.6f n1=(%.6f,%.6f) n2=(%.6f,%.6f) u4=%.6f\n", idx, lp1.x, lp1.y, lp2.x, lp2.y, m1, m2, n1.x, n1.y, n2.x, n2.y, ru.u(4));
+#endif
         if (ru.u(4) < randB * m) seen = S_NO;
-        lp1 = lp1 + v2(n1.x * m1 / 2, n1.y * m1 / 2);
-        lp2 = lp2 + v2(n2.x * m2 / 2, n2.y * m2 / 2);
+        V2 a1 = v2(n1.x * m1 / 2, n1.y * m1 / 2), a2 = v2(n2.x * m2 / 2, n2.y * m2 / 2);
+        lp1 = lp1 + a1;
+        lp2 = lp2 + a2;
+        ldir = ldir + (a2 - a1);
       }
     }
     /* list membership (RoboCupEnvironment.py:1254-1276) */
@@ -1621,9 +1634,9 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
     } else if (kind == 5 && seen != S_NO) {
       rtype = 5; rrow = __popc(mLine & lt);
       /* normalizeLine: cutils.py:333-347 */
-      V2 d = lp2 - lp1;
+      V2 d = ldir; /* = lp2 - lp1; |lp2 x lp1| = |d x lp1| */
       float ld = len(d);
-      float dist = fabsf(lp2.x * lp1.y - lp2.y * lp1.x) / (ld + 1e-7f);
+      float dist = fabsf(cross(d, lp1)) / (ld + 1e-7f);
       row[0] = (dist * STDNORM - 0.5f) / 0.5f;
       row[1] = ld > 0 ? d.x / ld : 1.f;
       row[2] = ld > 0 ? d.y / ld : 0.f;

@@ -1201,6 +1201,8 @@ static void add_noise_line(NoiseCtx* nc, int idx, LineSight* obj, double maxDist
       double m1 = 0.25 + 3.75 * vlensq(obj->p1) / maxDist;
       double m2 = 0.25 + 3.75 * vlensq(obj->p2) / maxDist;
       double m = (m1 + m2) * 0.5;
+      if (getenv("RC_ORACLE_DEBUG") && nc->obs == 8 && e->elapsed % 50 == 0)
+        printf("ORC line %d lp1=(%.5f,%.5f) lp2=(%.5f,%.5f) m1=%.6f m2=%.6f n1=(%.6f,%.6f) n2=(%.6f,%.6f) u4=%.6f\n", idx, obj->p1.x, obj->p1.y, obj->p2.x, obj->p2.y, m1, m2, n1.x, n1.y, n2.x, n2.y, rnd(e, nc->tick, RC_SITE_OBS_LINE, nc->obs, idx, 4));
       if (rnd(e, nc->tick, RC_SITE_OBS_LINE, nc->obs, idx, 4) < rand_ * m) obj->seen = S_NO;
       obj->p1 = vadd(obj->p1, v2(n1.x * m1 / 2, n1.y * m1 / 2));
       obj->p2 = vadd(obj->p2, v2(n2.x * m2 / 2, n2.y * m2 / 2));
