@@ -42,16 +42,19 @@ __device__ __forceinline__ void store_record(uint32_t* g, const uint32_t* S, int
   for (int w = lane; w < RC_STATE_WORDS / 4; w += 32) dst[w] = src[w];
 }
 
-__device__ __forceinline__ rc::Env make_env(uint32_t* S, const SimCfg& cfg, int e, int lane) {
+/* the kernel parameter block -> shared memory, where every function of the simulation reads it */
+__device__ __forceinline__ void stage_cfg(const SimCfg& cfg) {
+  if (threadIdx.x < sizeof(SimCfg) / 4) rc::g_smem[threadIdx.x] = reinterpret_cast<const uint32_t*>(&cfg)[threadIdx.x];
+  __syncthreads();
+}
+
+__device__ __forceinline__ rc::Env make_env(int base, const SimCfg& cfg, int e, int lane) {
   rc::Env E;
-  E.f = reinterpret_cast<float*>(S);
-  E.i = reinterpret_cast<int*>(S);
-  E.c = &cfg;
+  E.f.base = base;
+  E.i.base = base;
   E.lane = lane;
-  E.rng.k0 = cfg.seed_lo;
-  E.rng.k1 = cfg.seed_hi;
-  E.rng.env_id = cfg.env_id_offset + (uint32_t)e;
-  E.rng.episode = (uint32_t)E.i[RC_S_EPISODE];
+  if (lane == 0) E.i[rc::X_ENVID] = (int)(cfg.env_id_offset + (uint32_t)e);
+  __syncwarp();
   return E;
 }
 
@@ -63,40 +66,40 @@ __global__ void __launch_bounds__(RC_WPC * 32)
 rc_step_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
                float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info,
                float* __restrict__ term_obs, float* __restrict__ term_full) {
-  extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
+  stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
-  uint32_t* S = smem + warp * rc::ENV_SMEM_WORDS;
+  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = rc::g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
-  rc::Env E = make_env(S, cfg, e, lane);
+  rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
   const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
   const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + (cfg.sub_end - cfg.sub_begin) >= rc::MAXTIME;
   float* o = obs ? obs + e * obs_stride : nullptr;
   float* f = full ? full + e * full_stride : nullptr;
   float* inf = info ? info + (size_t)e * RC_INFO_WORDS : nullptr;
-  if (finishing) { /* the finished episode's last observations go to the terminal buffers */
-    rc::step_env(E, actions + (size_t)e * P * 4, term_obs ? term_obs + e * obs_stride : nullptr,
-                 term_full ? term_full + e * full_stride : nullptr, inf);
-    rc::reset_env(E, o, f, inf, false);
-  } else {
-    rc::step_env(E, actions + (size_t)e * P * 4, o, f, inf);
-  }
+  /* a finishing episode's last observations go to the terminal buffers, its first ones to `out` */
+  float* so = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : o;
+  float* sf = finishing ? (term_full ? term_full + e * full_stride : nullptr) : f;
+  rc::step_env(E, actions + (size_t)e * P * 4, so, sf, inf);
+  if (finishing) rc::reset_env(E, o, f, inf, false);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
 }
 
 __global__ void __launch_bounds__(RC_WPC * 32)
 rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const uint8_t* __restrict__ mask,
                 float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info) {
-  extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
+  stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
   if (mask && !mask[e]) return;
-  uint32_t* S = smem + warp * rc::ENV_SMEM_WORDS;
+  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = rc::g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
-  rc::Env E = make_env(S, cfg, e, lane);
+  rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
   const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
   rc::reset_env(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr,
@@ -189,7 +192,7 @@ int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* s
   const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
   cudaSetDevice(h->cfg.device);
   int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
-  size_t smem = (size_t)RC_WPC * rc::ENV_SMEM_WORDS * sizeof(uint32_t);
+  size_t smem = ((size_t)rc::CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
   rc_reset_kernel<<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(h->sim, h->state, env_mask_dev, o->obs,
                                                                                    o->full, o->info);
   h->last_launches = 1;
@@ -204,7 +207,7 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
   const DynEnvRoboCupOut* t = static_cast<const DynEnvRoboCupOut*>(terminal_out);
   cudaSetDevice(h->cfg.device);
   int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
-  size_t smem = (size_t)RC_WPC * rc::ENV_SMEM_WORDS * sizeof(uint32_t);
+  size_t smem = ((size_t)rc::CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
   rc_step_kernel<<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       h->sim, h->state, actions_dev, o->obs, o->full, o->info, t ? t->obs : nullptr, t ? t->full : nullptr);
   h->last_launches = 1;

@@ -49,15 +49,31 @@ __device__ __forceinline__ float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.
 __device__ __forceinline__ float lensq(V2 a) { return __fmaf_rn(a.x, a.x, __fmul_rn(a.y, a.y)); }
 __device__ __forceinline__ float len(V2 a) { return sqrtf(lensq(a)); }
 __device__ __forceinline__ V2 rot_cs(V2 a, float c, float s) { return v2(a.x * c - a.y * s, a.x * s + a.y * c); }
+/* sin and cos for the bounded angles of the simulation (|x| < ~1e4 rad): three-term Cody-Waite
+   reduction by pi/2 and degree-7 / degree-8 minimax polynomials on [-pi/4, pi/4] (~1 ulp).  Unlike
+   sincosf there is no huge-argument path, which would be inlined -- local-memory table included --
+   at every call site of a kernel that is already instruction-cache bound. */
+__device__ __forceinline__ void sincos_b(float x, float* sn, float* cs) {
+  float k = rintf(x * 0.636619772367581343f);
+  float r = fmaf(k, -1.57079601287841797e+00f, x);
+  r = fmaf(k, -3.13916473e-07f, r);
+  r = fmaf(k, -5.39030253e-15f, r);
+  int q = (int)k;
+  float r2 = r * r;
+  float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+  float pc = fmaf(fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2, -0.5f), r2, 1.0f);
+  float s0 = (q & 1) ? pc : ps, c0 = (q & 1) ? ps : pc;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
 __device__ __forceinline__ V2 rot(V2 a, float ang) {
   float s, c;
-  sincosf(ang, &s, &c);
+  sincos_b(ang, &s, &c);
   return rot_cs(a, c, s);
 }
 
 /* Philox4x32-10 (Salmon et al., SC'11) */
-__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
-                                              uint32_t c3, uint32_t w[4]) {
+__device__ __noinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -71,10 +87,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
-  w[0] = c0;
-  w[1] = c1;
-  w[2] = c2;
-  w[3] = c3;
+  return make_uint4(c0, c1, c2, c3);
 }
 
 /* six 21-bit uniforms of one block (include/dynenv_rng.h) */
@@ -91,17 +104,6 @@ struct Rand6 {
       default: v = w[3] >> 9; break;
     }
     return (float)(v & 0x1FFFFFu) * (1.0f / 2097152.0f);
-  }
-};
-
-struct RngCtx {
-  uint32_t k0, k1, env_id, episode;
-  __device__ __forceinline__ Rand6 block(uint32_t tick, int site, int a, int b, int blk) const {
-    Rand6 r;
-    philox4x32_10(k0, k1, env_id, episode, tick,
-                  ((uint32_t)site << 24) | ((uint32_t)(a & 255) << 16) | ((uint32_t)(b & 255) << 8) | (uint32_t)blk,
-                  r.w);
-    return r;
   }
 };
 

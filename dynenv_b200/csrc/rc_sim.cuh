@@ -61,7 +61,8 @@ enum {
   X_RSEEN = X_BSUM + 10,       /* I[10][9] sum of robotsSeen           */
   X_NACTIVE = X_RSEEN + 90,    /* I */
   X_ACTIVE = X_NACTIVE + 1,    /* I[RC_MAXACTIVE] index of the cached pair */
-  X_UNION = (X_ACTIVE + RC_MAXACTIVE + 3) / 4 * 4,
+  X_ENVID = X_ACTIVE + RC_MAXACTIVE, /* I global environment id (RNG counter word 0) */
+  X_UNION = (X_ENVID + 1 + 3) / 4 * 4,
   /* physics view of the union: active pairs and their contacts */
   X_ANX = X_UNION,             /* F[16] normal */
   X_ANY = X_ANX + RC_MAXACTIVE,
@@ -92,7 +93,7 @@ enum {
 
 /* ---- static scene tables (RoboCupEnvironment.py:153-227,296-302) */
 /* point landmarks seen by getAgentVision: 4 posts, 3 penalty crosses, 16 line crosses: x, y, tag1, tag2 */
-__device__ const float g_marks[23][4] = {
+__device__ __align__(16) const float g_marks[23][4] = {
     {70, 450, 1, -0.27f},   {70, 290, 1, 0.27f},    {970, 450, -1, -0.27f}, {970, 290, -1, 0.27f},
     {520, 370, 0, 0},       {200, 370, 1, 0},       {840, 370, -1, 0},
     {70, 70, 1, 1},         {70, 670, 1, -1},       {970, 70, -1, 1},       {970, 670, -1, -1},
@@ -106,13 +107,35 @@ __device__ const float g_lines[11][6] = {
     {70, 480, 130, 480, 1, -0.37f}, {130, 260, 130, 480, 0.87f, 0},  {910, 260, 970, 260, -1, 0.37f},
     {910, 480, 970, 480, -1, -0.37f}, {910, 260, 910, 480, -0.87f, 0}};
 
+/* The CTA's dynamic shared memory: [0, CFG_WORDS) a copy of the SimCfg, then one ENV_SMEM_WORDS slice
+   per warp.  Everything is addressed through this symbol so that the compiler emits LDS/STS (a pointer
+   handed to a non-inlined function would degrade to generic loads). */
+extern __shared__ __align__(16) uint32_t g_smem[];
+constexpr int CFG_WORDS = 32;
+static_assert(sizeof(SimCfg) <= CFG_WORDS * 4, "SimCfg must fit its shared-memory slot");
+
+struct SharedF { /* this warp's slice viewed as float */
+  int base;
+  __device__ __forceinline__ float& operator[](int k) const { return reinterpret_cast<float*>(g_smem)[base + k]; }
+  __device__ __forceinline__ float* operator+(int k) const { return reinterpret_cast<float*>(g_smem) + base + k; }
+};
+struct SharedI { /* ... and as int */
+  int base;
+  __device__ __forceinline__ int& operator[](int k) const { return reinterpret_cast<int*>(g_smem)[base + k]; }
+};
+struct SharedCfg {
+  __device__ __forceinline__ const SimCfg* operator->() const { return reinterpret_cast<const SimCfg*>(g_smem); }
+  __device__ __forceinline__ const SimCfg& operator*() const { return *reinterpret_cast<const SimCfg*>(g_smem); }
+};
 struct Env {
-  float* f;
-  int* i;
-  const SimCfg* c;
-  RngCtx rng;
+  SharedF f;
+  SharedI i;
+  SharedCfg c;
   int lane;
 };
+
+/* one Philox block of this environment's stream (include/dynenv_rng.h) */
+__device__ __forceinline__ Rand6 rng_block(const Env E, uint32_t tick, int site, int a, int b, int blk);
 
 __device__ __forceinline__ bool is_foot(int s) { return s < 20; }
 __device__ __forceinline__ float shape_radius(int s) { return s < 20 ? ROB_RAD : 10.f; } /* Ball.py:13, Goalpost.py:11 */
@@ -122,10 +145,10 @@ __device__ __forceinline__ float body_minv(int s) { return s < 20 ? FOOT_MINV : 
 __device__ __forceinline__ float body_iinv(int s) { return s < 20 ? FOOT_IINV : (s == BALL ? BALL_IINV : 0.f); }
 __device__ __forceinline__ float body_m(int s) { return s < 20 ? ROB_MASS : 10.f; }
 __device__ __forceinline__ V2 post_pos(int k) { return v2(k < 2 ? SIDE : W_ - SIDE, (k & 1) ? H_ / 2 - GOAL_W : H_ / 2 + GOAL_W); }
-__device__ __forceinline__ int team_of(const Env& E, int r) { return r < E.c->n_players ? 1 : -1; }
-__device__ __forceinline__ bool shape_active(const Env& E, int s) { return s >= 20 || s < 2 * E.c->P; }
+__device__ __forceinline__ int team_of(const Env E, int r) { return r < E.c->n_players ? 1 : -1; }
+__device__ __forceinline__ bool shape_active(const Env E, int s) { return s >= 20 || s < 2 * E.c->P; }
 
-__device__ __forceinline__ V2 body_pos(const Env& E, int s) { /* hi words: float32 view */
+__device__ __forceinline__ V2 body_pos(const Env E, int s) { /* hi words: float32 view */
   if (s < RC_NBODY) return v2(E.f[RC_S_PX + s], E.f[RC_S_PY + s]);
   return post_pos(s - POST0);
 }
@@ -141,7 +164,7 @@ __device__ __forceinline__ void two_add(float& hi, float& lo, float d) {
   hi = h2;
 }
 /* position of body b relative to body a, from both words: exact where it matters (close bodies) */
-__device__ __forceinline__ V2 pos_diff(const Env& E, int b, int a) {
+__device__ __forceinline__ V2 pos_diff(const Env E, int b, int a) {
   float bx, by, bxl = 0.f, byl = 0.f, ax, ay, axl = 0.f, ayl = 0.f;
   if (b < RC_NBODY) { bx = E.f[RC_S_PX + b]; by = E.f[RC_S_PY + b]; bxl = E.f[RC_S_PXL + b]; byl = E.f[RC_S_PYL + b]; }
   else { V2 p = post_pos(b - POST0); bx = p.x; by = p.y; }
@@ -149,21 +172,28 @@ __device__ __forceinline__ V2 pos_diff(const Env& E, int b, int a) {
   else { V2 p = post_pos(a - POST0); ax = p.x; ay = p.y; }
   return v2(__fadd_rn(__fsub_rn(bx, ax), __fsub_rn(bxl, axl)), __fadd_rn(__fsub_rn(by, ay), __fsub_rn(byl, ayl)));
 }
-__device__ __forceinline__ void set_pose(Env& E, int s, float x, float y, float ang) {
+__device__ __forceinline__ void set_pose(const Env E, int s, float x, float y, float ang) {
   E.f[RC_S_PX + s] = x; E.f[RC_S_PY + s] = y; E.f[RC_S_ANG + s] = ang;
   E.f[RC_S_PXL + s] = 0.f; E.f[RC_S_PYL + s] = 0.f; E.f[RC_S_ANGL + s] = 0.f;
 }
-__device__ __forceinline__ V2 robot_pos(const Env& E, int r) { /* Robot.getPos (Robot.py:90-91) */
+__device__ __forceinline__ V2 robot_pos(const Env E, int r) { /* Robot.getPos (Robot.py:90-91) */
   return v2((E.f[RC_S_PX + 2 * r] + E.f[RC_S_PX + 2 * r + 1]) * 0.5f,
             (E.f[RC_S_PY + 2 * r] + E.f[RC_S_PY + 2 * r + 1]) * 0.5f);
 }
-__device__ __forceinline__ float robot_angle(const Env& E, int r) { /* Robot.getAngle (Robot.py:94-100) */
+__device__ __forceinline__ float robot_angle(const Env E, int r) { /* Robot.getAngle (Robot.py:94-100) */
   return (E.f[RC_S_ANG + 2 * r] + E.f[RC_S_ANG + 2 * r + 1]) * 0.5f;
 }
-__device__ __forceinline__ V2 ball_pos(const Env& E) { return v2(E.f[RC_S_PX + BALL], E.f[RC_S_PY + BALL]); }
+__device__ __forceinline__ V2 ball_pos(const Env E) { return v2(E.f[RC_S_PX + BALL], E.f[RC_S_PY + BALL]); }
 
-__device__ __forceinline__ float rnd(const Env& E, uint32_t tick, int site, int a, int b, int k) {
-  return E.rng.block(tick, site, a, b, k / 6).u(k % 6);
+__device__ __forceinline__ Rand6 rng_block(const Env E, uint32_t tick, int site, int a, int b, int blk) {
+  Rand6 r;
+  uint4 w = philox4x32_10(E.c->seed_lo, E.c->seed_hi, (uint32_t)E.i[X_ENVID], (uint32_t)E.i[RC_S_EPISODE], tick,
+                          ((uint32_t)site << 24) | ((uint32_t)(a & 255) << 16) | ((uint32_t)(b & 255) << 8) | (uint32_t)blk);
+  r.w[0] = w.x; r.w[1] = w.y; r.w[2] = w.z; r.w[3] = w.w;
+  return r;
+}
+__device__ __forceinline__ float rnd(const Env E, uint32_t tick, int site, int a, int b, int k) {
+  return rng_block(E, tick, site, a, b, k / 6).u(k % 6);
 }
 
 /* world geometry of a shape from its body (cpShapeCacheBB): feet are segments (-10,+-10)-(10,+-10) */
@@ -171,7 +201,7 @@ __device__ __forceinline__ void shape_world(int s, float px, float py, float ang
   if (is_foot(s)) {
     float ly = (s & 1) ? -ROB_LEN : ROB_LEN; /* Robot.py:24-27 */
     float sn, cs;
-    sincosf(ang, &sn, &cs);
+    sincos_b(ang, &sn, &cs);
     *ta = v2(px - ROB_LEN * cs - ly * sn, py - ROB_LEN * sn + ly * cs);
     *tb = v2(px + ROB_LEN * cs - ly * sn, py + ROB_LEN * sn + ly * cs);
   } else {
@@ -179,7 +209,7 @@ __device__ __forceinline__ void shape_world(int s, float px, float py, float ang
     *tb = *ta;
   }
 }
-__device__ __forceinline__ void shape_cache_store(Env& E, int s) {
+__device__ __forceinline__ void shape_cache_store(const Env E, int s) {
   V2 ta, tb;
   shape_world(s, E.f[RC_S_PX + s], E.f[RC_S_PY + s], E.f[RC_S_ANG + s], &ta, &tb);
   E.f[RC_S_CAX + s] = ta.x;
@@ -187,7 +217,7 @@ __device__ __forceinline__ void shape_cache_store(Env& E, int s) {
   E.f[RC_S_CBX + s] = tb.x;
   E.f[RC_S_CBY + s] = tb.y;
 }
-__device__ __forceinline__ void shape_geom(const Env& E, int s, V2* ta, V2* tb) { /* cached geometry */
+__device__ __forceinline__ void shape_geom(const Env E, int s, V2* ta, V2* tb) { /* cached geometry */
   if (s < RC_NBODY) {
     *ta = v2(E.f[RC_S_CAX + s], E.f[RC_S_CAY + s]);
     *tb = v2(E.f[RC_S_CBX + s], E.f[RC_S_CBY + s]);
@@ -211,28 +241,28 @@ __device__ __forceinline__ V2 closest_on_seg(V2 p, V2 a, V2 b) {
 }
 
 /* ================================================================= game rules (serial code) */
-__device__ void penalize(Env& E, int r);
+__device__ void penalize(const Env E, int r);
 
-__device__ float point_query_dist(const Env& E, int s, V2 p) { /* cpShapePointQuery distance */
+__device__ float point_query_dist(const Env E, int s, V2 p) { /* cpShapePointQuery distance */
   V2 ta, tb;
   shape_geom(E, s, &ta, &tb);
   if (is_foot(s)) return len(p - closest_on_seg(p, ta, tb)) - ROB_RAD;
   return len(p - ta) - 10.f;
 }
 
-__device__ __forceinline__ void last_kicked_push(Env& E, int r) {
+__device__ __forceinline__ void last_kicked_push(const Env E, int r) {
   int n = E.i[RC_S_NLASTK] < 4 ? E.i[RC_S_NLASTK] : 3;
   for (int k = n; k > 0; k--) E.i[RC_S_LASTK + k] = E.i[RC_S_LASTK + k - 1];
   E.i[RC_S_LASTK] = r;
   E.i[RC_S_NLASTK] = n + 1;
 }
-__device__ __forceinline__ bool in_last_kicked(const Env& E, int r) {
+__device__ __forceinline__ bool in_last_kicked(const Env E, int r) {
   bool f = false;
   for (int k = 0; k < E.i[RC_S_NLASTK]; k++) f |= (E.i[RC_S_LASTK + k] == r);
   return f;
 }
 
-__device__ __noinline__ void fall(Env& E, int r, int punish) {
+__device__ __noinline__ void fall(const Env E, int r, int punish) {
   /* RoboCupEnvironment.py:735-791 */
   V2 pos = robot_pos(E, r);
   if (punish) E.f[X_REW + r] -= 2.f;
@@ -265,7 +295,7 @@ __device__ __noinline__ void fall(Env& E, int r, int punish) {
   if (E.i[RC_S_FALLCNT + r] > 2) penalize(E, r);
 }
 
-__device__ void free_penalty_spot(const Env& E, int r, V2* spot, float* angle) {
+__device__ __noinline__ void free_penalty_spot(const Env E, int r, V2* spot, float* angle) {
   /* RoboCupEnvironment.py:793-821; spots :139-151 */
   int team = team_of(E, r);
   float y = E.f[RC_S_PY + BALL];
@@ -287,7 +317,7 @@ __device__ void free_penalty_spot(const Env& E, int r, V2* spot, float* angle) {
   *spot = sel;
 }
 
-__device__ __noinline__ void penalize(Env& E, int r) {
+__device__ __noinline__ void penalize(const Env E, int r) {
   /* RoboCupEnvironment.py:824-859 */
   int teamIdx = team_of(E, r) > 0 ? 0 : 1;
   int fl = E.i[RC_S_RFLAGS + r] | RC_RF_PENALIZED;
@@ -309,12 +339,12 @@ __device__ __noinline__ void penalize(Env& E, int r) {
   E.i[RC_S_RFLAGS + r] = fl;
 }
 
-__device__ __forceinline__ void joint_add_now(Env& E, int r) {
+__device__ __forceinline__ void joint_add_now(const Env E, int r) {
   int fl = E.i[RC_S_RFLAGS + r];
   if (fl & RC_RF_JOINT_ADD_PENDING) E.i[RC_S_RFLAGS + r] = fl & ~(RC_RF_JOINT_ADD_PENDING | RC_RF_JOINT_ABSENT);
 }
 
-__device__ void process_action(Env& E, int r, float4 act, const Rand6& ru) {
+__device__ __noinline__ void process_action(const Env E, int r, float4 act, const Rand6& ru) {
   /* RoboCupEnvironment.py:527-581, Robot.py:103-138 */
   float move = act.x, turn = act.y, kick = act.z, head = act.w;
   int team = team_of(E, r);
@@ -355,7 +385,7 @@ __device__ void process_action(Env& E, int r, float4 act, const Rand6& ru) {
   }
 }
 
-__device__ void tick_robot(Env& E, int r) {
+__device__ __noinline__ void tick_robot(const Env E, int r) {
   /* RoboCupEnvironment.py:862-1007 */
   const float time = 10.f;
   int L = 2 * r, R = 2 * r + 1;
@@ -462,7 +492,7 @@ __device__ void tick_robot(Env& E, int r) {
    falls (random draws of processAction, re-fall after getting up), penalties (3rd fall, third
    defender, leaving the field), the penalty re-entry (reads the other robots) and changes of the
    defenders lists.  When no lane says yes, the ten robots tick in parallel, else in robot order. */
-__device__ bool robot_phase_needs_order(const Env& E, int r, int sub, float4 act, const Rand6& ru) {
+__device__ __noinline__ bool robot_phase_needs_order(const Env E, int r, int sub, float4 act, const Rand6& ru) {
   int fl = E.i[RC_S_RFLAGS + r];
   bool need = false;
   if (sub == 0 && E.c->can_fall && !(fl & (RC_RF_PENALIZED | RC_RF_KICKING | RC_RF_FALLEN)))
@@ -492,7 +522,7 @@ __device__ bool robot_phase_needs_order(const Env& E, int r, int sub, float4 act
   return need;
 }
 
-__device__ void robots_phase(Env& E, int sub, const float* actions) {
+__device__ __noinline__ void robots_phase(const Env E, int sub, const float* actions) {
   int lane = E.lane;
   int P = E.c->P;
   float4 act = make_float4(0, 0, 0, 0);
@@ -501,7 +531,7 @@ __device__ void robots_phase(Env& E, int sub, const float* actions) {
   bool mine = lane < P;
   if (sub == 0 && mine) {
     act = *reinterpret_cast<const float4*>(actions + 4 * lane);
-    if (E.c->can_fall) ru = E.rng.block((uint32_t)E.i[RC_S_ELAPSED], RC_SITE_ACTION, lane, 0, 0);
+    if (E.c->can_fall) ru = rng_block(E, (uint32_t)E.i[RC_S_ELAPSED], RC_SITE_ACTION, lane, 0, 0);
   }
   bool need = mine && robot_phase_needs_order(E, lane, sub, act, ru);
   unsigned ordered = __ballot_sync(FULLMASK, need);
@@ -521,7 +551,7 @@ __device__ void robots_phase(Env& E, int sub, const float* actions) {
 }
 
 /* ---- ball rules */
-__device__ void ball_free_kick(Env& E, int team) {
+__device__ void ball_free_kick(const Env E, int team) {
   /* RoboCupEnvironment.py:600-619 */
   if (team == 0) {
     const float time = 10.f;
@@ -542,7 +572,7 @@ __device__ void ball_free_kick(Env& E, int team) {
   }
 }
 
-__device__ void ball_out_of_field(Env& E) {
+__device__ __noinline__ void ball_out_of_field(const Env E) {
   /* RoboCupEnvironment.py:622-732 */
   int lane = E.lane;
   int P = E.c->P, nPl = E.c->n_players;
@@ -631,7 +661,7 @@ __device__ void ball_out_of_field(Env& E) {
 }
 
 /* ================================================================= collision callbacks (serial) */
-__device__ void cb_robot_pushing_det(Env& E, int sa, int sb) {
+__device__ void cb_robot_pushing_det(const Env E, int sa, int sb) {
   /* begin, (Robot, Robot): RoboCupEnvironment.py:1010-1035 */
   int r1 = sa / 2, r2 = sb / 2;
   V2 v1 = v2(E.f[RC_S_VX + sa], E.f[RC_S_VY + sa]);
@@ -652,7 +682,7 @@ __device__ void cb_robot_pushing_det(Env& E, int sa, int sb) {
   E.i[RC_S_TOUCHCNT + r2] = 0;
 }
 
-__device__ void cb_robot_collision(Env& E, int sa, int sb) {
+__device__ void cb_robot_collision(const Env E, int sa, int sb) {
   /* post_solve, (Robot, Robot): RoboCupEnvironment.py:1038-1081 */
   if (!E.c->can_fall) return;
   int i1 = sa / 2, i2 = sb / 2;
@@ -661,14 +691,15 @@ __device__ void cb_robot_collision(Env& E, int sa, int sb) {
   int* f2 = &E.i[RC_S_RFLAGS + i2];
   if (!(*f1 & (RC_RF_FALLEN | RC_RF_PENALIZED))) E.i[RC_S_TOUCHCNT + i1] += 1;
   if (!(*f2 & (RC_RF_FALLEN | RC_RF_PENALIZED))) E.i[RC_S_TOUCHCNT + i2] += 1;
-  const float normalThresh = 0.9999f, pushingThresh = 0.99995f;
-  Rand6 ru = E.rng.block((uint32_t)E.i[RC_S_ELAPSED], RC_SITE_ROBCOL, sa, sb, 0);
-  if (ru.u(0) > powf((*f1 & RC_RF_MIGHTPUSH) ? pushingThresh : normalThresh, (float)E.i[RC_S_TOUCHCNT + i1]) &&
+  /* thresholds 0.9999^n resp. 0.99995^n as exp(n ln t) */
+  const float lnNormal = -1.000050003e-04f, lnPushing = -5.000125004e-05f;
+  Rand6 ru = rng_block(E, (uint32_t)E.i[RC_S_ELAPSED], RC_SITE_ROBCOL, sa, sb, 0);
+  if (ru.u(0) > expf(((*f1 & RC_RF_MIGHTPUSH) ? lnPushing : lnNormal) * (float)E.i[RC_S_TOUCHCNT + i1]) &&
       !(*f1 & RC_RF_FALLEN)) {
     fall(E, i1, (*f1 & RC_RF_MIGHTPUSH) ? 1 : 0);
     E.i[RC_S_TOUCHCNT + i1] = 0;
   }
-  if (ru.u(1) > powf((*f2 & RC_RF_MIGHTPUSH) ? pushingThresh : normalThresh, (float)E.i[RC_S_TOUCHCNT + i2]) &&
+  if (ru.u(1) > expf(((*f2 & RC_RF_MIGHTPUSH) ? lnPushing : lnNormal) * (float)E.i[RC_S_TOUCHCNT + i2]) &&
       !(*f2 & RC_RF_FALLEN)) {
     fall(E, i2, (*f2 & RC_RF_MIGHTPUSH) ? 1 : 0);
     E.i[RC_S_TOUCHCNT + i2] = 0;
@@ -683,13 +714,13 @@ __device__ void cb_robot_collision(Env& E, int sa, int sb) {
   }
 }
 
-__device__ void cb_separate(Env& E, int sa, int sb) {
+__device__ void cb_separate(const Env E, int sa, int sb) {
   /* separate, (Robot, Robot) and (Robot, Goalpost): RoboCupEnvironment.py:1084-1094 */
   if (is_foot(sa)) { E.i[RC_S_RFLAGS + sa / 2] &= ~(RC_RF_TOUCHING | RC_RF_MIGHTPUSH); E.i[RC_S_TOUCHCNT + sa / 2] = 0; }
   if (is_foot(sb)) { E.i[RC_S_RFLAGS + sb / 2] &= ~(RC_RF_TOUCHING | RC_RF_MIGHTPUSH); E.i[RC_S_TOUCHCNT + sb / 2] = 0; }
 }
 
-__device__ void cb_goalpost_collision(Env& E, int foot, int post) {
+__device__ void cb_goalpost_collision(const Env E, int foot, int post) {
   /* post_solve, (Robot, Goalpost): RoboCupEnvironment.py:1097-1123 */
   if (!E.c->can_fall) return;
   int r = foot / 2;
@@ -697,12 +728,12 @@ __device__ void cb_goalpost_collision(Env& E, int foot, int post) {
   if (fl & RC_RF_FALLEN) { E.i[RC_S_TOUCHCNT + r] = 0; return; }
   if (!(fl & RC_RF_TOUCHING)) { E.i[RC_S_RFLAGS + r] = fl | RC_RF_TOUCHING; E.i[RC_S_TOUCHCNT + r] = 0; }
   E.i[RC_S_TOUCHCNT + r] += 1;
-  float thresh = powf(0.9998f, (float)E.i[RC_S_TOUCHCNT + r]);
+  float thresh = expf(-2.000200027e-04f * (float)E.i[RC_S_TOUCHCNT + r]); /* 0.9998^n */
   float u = rnd(E, (uint32_t)E.i[RC_S_ELAPSED], RC_SITE_POSTCOL, post, foot, 0);
   if (u > thresh) fall(E, r, 1);
 }
 
-__device__ void cb_ball_collision(Env& E, int foot) {
+__device__ void cb_ball_collision(const Env E, int foot) {
   /* begin, (Robot, Ball): RoboCupEnvironment.py:1126-1146 */
   int r = foot / 2;
   int owned = E.i[RC_S_BALLOWNED];
@@ -771,11 +802,11 @@ __device__ __forceinline__ float clamp01(float t) { return fminf(fmaxf(t, 0.f), 
 __device__ __forceinline__ V2 vlerp(V2 a, V2 b, float t) { return a * (1.f - t) + b * t; }
 
 /* Shape geometry relative to its own body: feet are the segments (-10, +-10)-(10, +-10) (Robot.py:24-27) */
-__device__ __forceinline__ void shape_local(const Env& E, int s, V2* oa, V2* ob) {
+__device__ __forceinline__ void shape_local(const Env E, int s, V2* oa, V2* ob) {
   if (is_foot(s)) {
     float ly = (s & 1) ? -ROB_LEN : ROB_LEN;
     float sn, cs;
-    sincosf(E.f[RC_S_ANG + s], &sn, &cs);
+    sincos_b(E.f[RC_S_ANG + s], &sn, &cs);
     *oa = v2(-ROB_LEN * cs - ly * sn, -ROB_LEN * sn + ly * cs);
     *ob = v2(ROB_LEN * cs - ly * sn, ROB_LEN * sn + ly * cs);
   } else {
@@ -787,7 +818,7 @@ __device__ __forceinline__ void shape_local(const Env& E, int s, V2* oa, V2* ob)
 /* Narrow phase in the frame of body a (origin = a's position, dab = position of b relative to a from
    the two-float coordinates), so that penetration depths of ~0.1 px are not lost in float32
    coordinates of ~500 px.  Contact points come out relative to a's position. */
-__device__ __noinline__ void narrowphase(const Env& E, int a, int b, V2 dab, Manifold* m) {
+__device__ __noinline__ void narrowphase(const Env E, int a, int b, V2 dab, Manifold* m) {
   V2 ata, atb, bta, btb;
   shape_local(E, a, &ata, &atb);
   shape_local(E, b, &bta, &btb);
@@ -853,7 +884,7 @@ __device__ __noinline__ void narrowphase(const Env& E, int a, int b, V2 dab, Man
 }
 
 /* cpSpaceCollideShapes + cpArbiterUpdate + begin callbacks for an AABB-overlapping pair i < j */
-__device__ __noinline__ void collide_pair(Env& E, int i, int j) {
+__device__ __noinline__ void collide_pair(const Env E, int i, int j) {
   int a = i, b = j;
   if (is_foot(a) && !is_foot(b)) { a = j; b = i; } /* cpCollide orders by primitive type */
   if (b == a + 1 && !(a & 1) && b < 20) {
@@ -917,7 +948,7 @@ struct BodyVel {
   float vx, vy, w;
 };
 
-__device__ __forceinline__ void load_body(const Env& E, int s, float* vx, float* vy, float* w, float* vbx, float* vby, float* wb) {
+__device__ __forceinline__ void load_body(const Env E, int s, float* vx, float* vy, float* w, float* vbx, float* vby, float* wb) {
   if (s < RC_NBODY) {
     *vx = E.f[RC_S_VX + s]; *vy = E.f[RC_S_VY + s]; *w = E.f[RC_S_W + s];
     *vbx = E.f[RC_S_VBX + s]; *vby = E.f[RC_S_VBY + s]; *wb = E.f[RC_S_WB + s];
@@ -927,7 +958,7 @@ __device__ __forceinline__ void load_body(const Env& E, int s, float* vx, float*
 }
 
 /* cpArbiterApplyImpulse for every active contact, in order (Gauss-Seidel): lane 0 */
-__device__ __noinline__ void contacts_iteration(Env& E) {
+__device__ __noinline__ void contacts_iteration(const Env E) {
   int nact = E.i[X_NACTIVE];
   for (int q = 0; q < nact; q++) {
     int key = E.i[RC_S_ARBKEY + E.i[X_ACTIVE + q]];
@@ -982,7 +1013,7 @@ __device__ __noinline__ void contacts_iteration(Env& E) {
   }
 }
 
-__device__ void space_step(Env& E) {
+__device__ __noinline__ void space_step(const Env E) {
   /* cpSpaceStep (Chipmunk2D 7.0.x), dt = 0.01 */
   const int lane = E.lane;
   const int P = E.c->P;
@@ -1135,7 +1166,7 @@ __device__ void space_step(Env& E) {
     __syncwarp();
   }
 #ifdef RC_DEBUG_PRINT
-  if (lane == 0 && nact && E.rng.env_id == RC_DEBUG_PRINT) {
+  if (lane == 0 && nact && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT) {
     for (int q = 0; q < nact; q++) {
       int k = E.i[X_ACTIVE + q];
       int key = E.i[RC_S_ARBKEY + k];
@@ -1242,15 +1273,15 @@ __device__ void space_step(Env& E) {
       }
       __syncwarp();
 #ifdef RC_DEBUG_PRINT
-      if (lane == 0 && E.rng.env_id == RC_DEBUG_PRINT && (it < 2))
+      if (lane == 0 && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT && (it < 2))
         for (int b = 4; b < 10; b++) printf("GPU it%d pre-contacts body %d v=(%.6f,%.6f) w=%.6f\n", it, b, E.f[RC_S_VX + b], E.f[RC_S_VY + b], E.f[RC_S_W + b]);
 #endif
       if (lane == 0) contacts_iteration(E);
       __syncwarp();
 #ifdef RC_DEBUG_PRINT
-      if (lane == 0 && E.rng.env_id == RC_DEBUG_PRINT && (it < 2))
+      if (lane == 0 && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT && (it < 2))
         for (int b = 4; b < 10; b++) printf("GPU it%d post-contacts body %d v=(%.6f,%.6f) w=%.6f\n", it, b, E.f[RC_S_VX + b], E.f[RC_S_VY + b], E.f[RC_S_W + b]);
-      if (isRobot && lane >= 2 && lane < 5 && E.rng.env_id == RC_DEBUG_PRINT && it < 2) printf("GPU it%d robot %d pivOn %d pivB=(%.6f,%.6f) rotBias=%.6f pivJ=(%.3f,%.3f) rotJ=%.3f\n", it, lane, (int)pivOn, pivBx, pivBy, rotBias, pivJx, pivJy, rotJ);
+      if (isRobot && lane >= 2 && lane < 5 && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT && it < 2) printf("GPU it%d robot %d pivOn %d pivB=(%.6f,%.6f) rotBias=%.6f pivJ=(%.3f,%.3f) rotJ=%.3f\n", it, lane, (int)pivOn, pivBx, pivBy, rotBias, pivJx, pivJy, rotJ);
 #endif
       if (isRobot) {
         lvx = E.f[RC_S_VX + L]; lvy = E.f[RC_S_VY + L]; lw = E.f[RC_S_W + L];
@@ -1321,7 +1352,7 @@ __device__ __forceinline__ int does_interact(float ax, float ay, bool ahas, floa
 }
 
 /* getFullState(agent): RoboCupEnvironment.py:1162-1188 -> one RC_FULL_WORDS record, lanes cooperate */
-__device__ void full_state_agent(const Env& E, int ag, float* dst /* global or shared */) {
+__device__ __noinline__ void full_state_agent(const Env E, int ag, float* dst /* global or shared */) {
   int lane = E.lane;
   int P = E.c->P;
   float team = (float)team_of(E, ag);
@@ -1336,9 +1367,9 @@ __device__ void full_state_agent(const Env& E, int ag, float* dst /* global or s
     float s, c;
     dst[RC_U_SELF + 0] = (p.x - W_ / 2) * STDNORM * team;
     dst[RC_U_SELF + 1] = (p.y - H_ / 2) * STDNORM * team;
-    sincosf(a + h, &s, &c);
+    sincos_b(a + h, &s, &c);
     dst[RC_U_SELF + 2] = c; dst[RC_U_SELF + 3] = s;
-    sincosf(h, &s, &c);
+    sincos_b(h, &s, &c);
     dst[RC_U_SELF + 4] = c; dst[RC_U_SELF + 5] = s;
     dst[RC_U_SELF + 6] = team;
     dst[RC_U_SELF + 7] = (E.i[RC_S_RFLAGS + ag] & (RC_RF_FALLEN | RC_RF_PENALIZED)) ? 1.f : 0.f;
@@ -1351,7 +1382,7 @@ __device__ void full_state_agent(const Env& E, int ag, float* dst /* global or s
       int r = k < ag ? k : k + 1;
       V2 q = robot_pos(E, r);
       float s, c;
-      sincosf(robot_angle(E, r), &s, &c);
+      sincos_b(robot_angle(E, r), &s, &c);
       o[0] = (q.x - W_ / 2) * STDNORM * team;
       o[1] = (q.y - H_ / 2) * STDNORM * team;
       o[2] = c; o[3] = s;
@@ -1364,7 +1395,7 @@ __device__ void full_state_agent(const Env& E, int ag, float* dst /* global or s
 }
 
 /* insert a row into one list of the staged record (Python list.insert semantics, capped) */
-__device__ void stage_insert(Env& E, int type, int at, const float* row) {
+__device__ __noinline__ void stage_insert(const Env E, int type, int at, const float* row) {
   const int off[6] = {RC_O_BALL, RC_O_ROBOT, RC_O_POST, RC_O_CROSS, RC_O_FCROSS, RC_O_LINE};
   const int cap[6] = {RC_CAP_BALL, RC_CAP_ROBOT, RC_CAP_POST, RC_CAP_CROSS, RC_CAP_FCROSS, RC_CAP_LINE};
   const int feat[6] = {RC_F_BALL, RC_F_ROBOT, RC_F_POST, RC_F_CROSS, RC_F_FCROSS, RC_F_LINE};
@@ -1380,7 +1411,7 @@ __device__ void stage_insert(Env& E, int type, int at, const float* row) {
   if (n < c) E.i[V_CNT + type] = n + 1;
 }
 
-__device__ __forceinline__ void polar_row(float* row, V2 p, float radius, float sizeMean, float t1, float t2, float team) {
+__device__ __noinline__ void polar_row(float* row, V2 p, float radius, float sizeMean, float t1, float t2, float team) {
   /* cutils.py:308-315: (scale(dist), cos, sin of atan2(y*team, x*team), size, tags * team) */
   float dist = len(p);
   float inv = dist > 0 ? 1.f / dist : 0.f;
@@ -1392,199 +1423,187 @@ __device__ __forceinline__ void polar_row(float* row, V2 p, float radius, float 
   row[5] = t2 * team;
 }
 
-/* getAgentVision of one observer (PARTIAL): builds the record in shared memory (V_STAGE) */
-__device__ void agent_vision(Env& E, int ag, uint32_t tick) {
+/* random false positives (RoboCupEnvironment.py:1279-1305): `hits` = the loop indices whose first draw
+   fired; they are rare and inserted in loop order.  Out of line: keeps the hot vision code small. */
+__device__ __noinline__ void false_positives(const Env E, int ag, uint32_t tick, unsigned hits, float team) {
+  const int lane = E.lane;
+  const float maxVis1 = (W_ * 0.8f) * (W_ * 0.8f);
+  while (hits) {
+    int i = __ffs(hits) - 1;
+    hits &= hits - 1;
+    if (lane == 0) {
+      Rand6 ru = rng_block(E, tick, RC_SITE_OBS_FP, ag, i, 0);
+      Rand6 r2 = rng_block(E, tick, RC_SITE_OBS_FP, ag, i, 1); /* k = 6, 7 */
+      int c = randint_from(ru.u(1), 0, 5);
+      float d = ru.u(2) * sqrtf(maxVis1);
+      float a = ru.u(3) * 2 * ROB_FOV - ROB_FOV;
+      V2 fp = rot(v2(d, 0), a);
+      float sz = 1.f - 0.4f * (ru.u(4) - 0.5f);
+      float closest = (ag == E.i[RC_S_CLOSEST] || ag == E.i[RC_S_CLOSEST + 1]) ? 1.f : 0.f;
+      float row[8];
+      if (c == 0) {
+        row[0] = fp.x * STDNORM2; row[1] = fp.y * STDNORM2; row[2] = (BALL_RADIUS * 2 * sz - BALL_RADIUS * 2) * 2.f;
+        row[3] = 0.f; row[4] = closest;
+        stage_insert(E, 0, E.i[V_CNT + 0], row);
+      } else if (c == 1) {
+        float s, cs;
+        sincos_b((ru.u(5) - 0.5f) * 2 * PI_F, &s, &cs);
+        row[0] = fp.x * STDNORM2; row[1] = fp.y * STDNORM2; row[2] = (ROB_TOTAL * sz - ROB_TOTAL) * 2.f;
+        row[3] = cs; row[4] = s;
+        row[5] = r2.u(0) > 0.5f ? -1.f : 1.f;
+        row[6] = r2.u(1) > 0.9f ? 1.f : 0.f;
+        int at = E.i[V_CNT + 1];
+        if (at < RC_CAP_ROBOT) { E.f[V_RAW + 3 * at] = fp.x; E.f[V_RAW + 3 * at + 1] = fp.y; E.f[V_RAW + 3 * at + 2] = 1.f; }
+        stage_insert(E, 1, at, row);
+      } else if (c <= 4) {
+        float t1 = (float)randint_from(ru.u(5), -1, 1), t2 = (float)randint_from(r2.u(0), -1, 1);
+        float rad0 = c == 2 ? POST_RADIUS : PEN_RADIUS;
+        polar_row(row, fp, rad0 * sz, rad0, t1, t2, team);
+        if (c == 4) {
+          float s, cs;
+          sincos_b(r2.u(1) * PI_F * 2, &s, &cs);
+          row[6] = cs; row[7] = -s;
+          stage_insert(E, 4, E.i[V_CNT + 3], row); /* inserted at len(crossDets) (reference behaviour) */
+        } else stage_insert(E, c, E.i[V_CNT + c], row);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+/* getAgentVision of one observer (PARTIAL): builds the record in shared memory (V_STAGE).
+   Point objects: lane = object (ball, 9 robot slots, 4 posts, 3 penalty crosses, 16 line crosses = 33,
+   so a second, usually empty, pass handles the last line cross); lines: lane = line. */
+__device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   const int lane = E.lane;
   const int P = E.c->P;
   const float magn = E.c->noise_mag, randB = E.c->rand_base;
   const bool realistic = E.c->noise_type == DYNENV_NOISE_REALISTIC;
-  const float team = (float)team_of(E, ag);
+  const int teamI = team_of(E, ag);
+  const float team = (float)teamI;
   const V2 pos = robot_pos(E, ag);
   const float headAngle = robot_angle(E, ag) + E.f[RC_S_HEAD + ag];
   float hs, hc;
-  sincosf(headAngle, &hs, &hc);
+  sincos_b(headAngle, &hs, &hc);
   /* FoV edge directions: (1,0) rotated by headAngle +- pi/4 */
   const float q = 0.70710678118654752f;
   const V2 vec1 = v2((hc - hs) * q, (hs + hc) * q), vec2 = v2((hc + hs) * q, (hs - hc) * q);
   /* _setup_vision(0.4, 0.8): environment_base.py:161-172 */
   const float maxVis0 = (W_ * 0.4f) * (W_ * 0.4f), maxVis1 = (W_ * 0.8f) * (W_ * 0.8f);
-  const int agFlag = (E.i[RC_S_RFLAGS + ag] & (RC_RF_FALLEN | RC_RF_PENALIZED)) ? 1 : 0;
-  /* clear the staged record */
+  const float agFlag = (E.i[RC_S_RFLAGS + ag] & (RC_RF_FALLEN | RC_RF_PENALIZED)) ? 1.f : 0.f;
+  const float closest = (ag == E.i[RC_S_CLOSEST] || ag == E.i[RC_S_CLOSEST + 1]) ? 1.f : 0.f;
+  const unsigned lt = (1u << lane) - 1;
   for (int w = lane; w < RC_OBS_WORDS; w += 32) E.f[V_STAGE + w] = 0.f;
   __syncwarp();
 
-  int nb = 0, nr = 0, np = 0, ncr = 0, nf = 0, nl = 0, nfRound0 = 0;
-  for (int round = 0; round < 2; round++) {
-    /* lane -> object.  round 0: ball, 9 robot slots, 4 posts, 3 penalty crosses, line crosses 0..14;
-       round 1: line cross 15, the 11 lines */
-    int kind; /* 0 ball 1 robot 2 post 3 cross 4 fcross 5 line -1 none */
-    int idx;
-    if (round == 0) {
-      if (lane == 0) { kind = 0; idx = 0; }
-      else if (lane < 10) { kind = 1; idx = lane - 1; if (idx >= P - 1) kind = -1; }
-      else if (lane < 14) { kind = 2; idx = lane - 10; }
-      else if (lane < 17) { kind = 3; idx = lane - 14; }
-      else { kind = 4; idx = lane - 17; }
-    } else {
-      if (lane == 0) { kind = 4; idx = 15; }
-      else if (lane < 12) { kind = 5; idx = lane - 1; }
-      else { kind = -1; idx = 0; }
-    }
-    int seen = S_NO;
-    bool has = false;
-    V2 p = v2(0, 0);
-    float radius = 0, ex0 = 0, ex1 = 0, ex2 = 0, maxDist = maxVis0;
-    V2 lp1 = v2(0, 0), lp2 = v2(0, 0), ldir = v2(0, 0); /* lines: end points and lp2 - lp1 */
-    if (kind >= 0 && kind <= 4) {
-      V2 pt;
-      if (kind == 0) { pt = ball_pos(E); radius = BALL_RADIUS * 2; ex0 = (float)(E.i[RC_S_BALLOWNED] * team_of(E, ag)); }
-      else if (kind == 1) {
+  int nb = 0, nr = 0, np = 0, ncr = 0, nf = 0;
+  unsigned robHas = 0; /* lanes 1..9 of pass 0 whose robot is inside the field of view */
+  for (int pass = 0; pass < 2; pass++) {
+    const int obj = pass * 32 + lane;
+    int kind = -1, idx = 0; /* 0 ball 1 robot 2 post 3 cross 4 line cross */
+    float radius = PEN_RADIUS, maxDist = maxVis0, ex0 = 0, ex1 = 0, ex2 = 0;
+    V2 pt = v2(0, 0);
+    if (obj == 0) {
+      kind = 0; pt = ball_pos(E); radius = BALL_RADIUS * 2; ex0 = (float)(E.i[RC_S_BALLOWNED] * teamI);
+    } else if (obj < 10) {
+      idx = obj - 1;
+      if (idx < P - 1) {
+        kind = 1;
         int r = idx < ag ? idx : idx + 1;
         pt = robot_pos(E, r); radius = ROB_TOTAL; maxDist = maxVis1;
         ex0 = robot_angle(E, r) - headAngle;
-        ex1 = (float)(team_of(E, ag) * team_of(E, r));
-        ex2 = (float)agFlag; /* the OBSERVER's fallen|penalized flag (reference behaviour) */
-      } else {
-        int mi = kind == 2 ? idx : (kind == 3 ? 4 + idx : 7 + idx);
-        pt = v2(g_marks[mi][0], g_marks[mi][1]);
-        ex0 = g_marks[mi][2]; ex1 = g_marks[mi][3];
-        radius = kind == 2 ? POST_RADIUS : PEN_RADIUS;
-        if (kind == 2) maxDist = maxVis1;
-        if (kind == 4) ex2 = 0.f - headAngle;
+        ex1 = (float)(teamI * team_of(E, r));
+        ex2 = agFlag; /* the OBSERVER's fallen|penalized flag (reference behaviour) */
       }
+    } else if (obj < 33) {
+      int mi = obj - 10;
+      kind = mi < 4 ? 2 : (mi < 7 ? 3 : 4);
+      idx = mi - (mi < 4 ? 0 : (mi < 7 ? 4 : 7));
+      float4 mk = *reinterpret_cast<const float4*>(g_marks[mi]);
+      pt = v2(mk.x, mk.y); ex0 = mk.z; ex1 = mk.w;
+      if (kind == 2) { radius = POST_RADIUS; maxDist = maxVis1; }
+      if (kind == 4) ex2 = -headAngle;
+    }
+    /* isSeenInArea, allowPartial (cutils.py:699-747) */
+    int seen = S_NO;
+    bool has = false;
+    V2 p = v2(0, 0);
+    if (kind >= 0) {
       pt = pt - pos;
-      /* isSeenInArea, allowPartial (cutils.py:699-747) */
       float dist1 = cross(vec1, pt), dist2 = cross(vec2, pt);
       if (dist1 < radius && dist2 > -radius) {
-        if (dist1 < -radius && dist2 > radius) seen = lensq(pt) < maxDist ? S_NORMAL : S_DISTANT;
-        else seen = S_PARTIAL;
+        seen = (dist1 < -radius && dist2 > radius) ? (lensq(pt) < maxDist ? S_NORMAL : S_DISTANT) : S_PARTIAL;
         p = rot_cs(pt, hc, -hs);
         has = true;
       }
-    } else if (kind == 5) {
-      /* isLineInArea (cutils.py:751-821) */
-      maxDist = maxVis1;
-      V2 p1 = v2(g_lines[idx][0], g_lines[idx][1]) - pos, p2 = v2(g_lines[idx][2], g_lines[idx][3]) - pos;
-      ex0 = g_lines[idx][4]; ex1 = g_lines[idx][5];
-      float dist11 = cross(vec1, p1), dist12 = cross(vec1, p2);
-      if (!(dist11 > 0 && dist12 > 0)) {
-        float dist21 = cross(vec2, p1), dist22 = cross(vec2, p2);
-        if (!(dist21 < 0 && dist22 < 0)) {
-          seen = S_NORMAL;
-          V2 pt1, pt2;
-          float t1 = 0.f, t2 = 1.f; /* line parameters of the clipped end points */
-          if (dist11 <= 0 && dist21 >= 0) pt1 = p1;
-          else {
-            float inter1 = cross(p1, vec1) / (cross(vec1, p2 - p1) + 1e-7f);
-            float inter2 = cross(p1, vec2) / (cross(vec2, p2 - p1) + 1e-7f);
-            float inter = (inter1 < 1 && inter2 < 1) ? fmaxf(inter1, inter2) : fminf(inter1, inter2);
-            pt1 = p1 + (p2 - p1) * inter;
-            t1 = inter;
-            seen = S_PARTIAL;
-          }
-          if (dist12 <= 0 && dist22 >= 0) pt2 = p2;
-          else {
-            float inter1 = cross(p2, vec1) / cross(vec1, p1 - p2);
-            float inter2 = cross(p2, vec2) / cross(vec2, p1 - p2);
-            float inter = (inter1 < 1 && inter2 < 1) ? fmaxf(inter1, inter2) : fminf(inter1, inter2);
-            pt2 = p2 + (p1 - p2) * inter;
-            t2 = 1.f - inter;
-            seen = S_PARTIAL;
-          }
-          if (lensq(pt1) > maxDist || lensq(pt2) > maxDist) seen = S_DISTANT;
-          lp1 = rot_cs(pt1, hc, -hs);
-          lp2 = rot_cs(pt2, hc, -hs);
-          /* lp2 - lp1 from the line's own direction: a clipped piece can be a fraction of a pixel
-             long, which the difference of two float32 end points (~300 px) cannot resolve */
-          ldir = rot_cs(p2 - p1, hc, -hs) * (t2 - t1);
-          if (lp1.x < 0 || lp2.x < 0) seen = S_NO;
-          has = true;
-        }
-      }
     }
-    /* publish the sightings the interaction tests read */
-    if (round == 0) {
-      if (kind == 1) { E.f[V_ROB + 3 * idx] = p.x; E.f[V_ROB + 3 * idx + 1] = p.y; E.f[V_ROB + 3 * idx + 2] = has ? 1.f : 0.f; }
+    if (pass == 1 && !__any_sync(FULLMASK, has)) break;
+    if (pass == 0) { /* publish the sightings the interaction tests read */
+      robHas = __ballot_sync(FULLMASK, kind == 1 && has);
+      if (kind == 1) { E.f[V_ROB + 3 * idx] = p.x; E.f[V_ROB + 3 * idx + 1] = p.y; }
       if (kind == 0) { E.f[V_BALL] = p.x; E.f[V_BALL + 1] = p.y; E.f[V_BALL + 2] = has ? 1.f : 0.f; }
       if (kind == 2) { E.f[V_POST + 3 * idx] = p.x; E.f[V_POST + 3 * idx + 1] = p.y; E.f[V_POST + 3 * idx + 2] = has ? 1.f : 0.f; }
       __syncwarp();
     }
-    /* interactions (RoboCupEnvironment.py:1227-1237): occlusion / proximity by the other robots */
+    /* interactions (RoboCupEnvironment.py:1227-1237): occlusion / proximity by the robots in view */
     int inter = I_NO;
-    if (kind >= 0 && kind <= 4 && has) {
-      for (int i = 0; i < P - 1; i++) {
-        if (kind == 1 && i == idx) continue;
-        int t = does_interact(E.f[V_ROB + 3 * i], E.f[V_ROB + 3 * i + 1], E.f[V_ROB + 3 * i + 2] != 0.f, p.x, p.y, true,
-                              ROB_TOTAL * 2, true);
-        inter = max(inter, t);
-      }
-      if (kind == 0) {
-        for (int k = 0; k < 4; k++)
-          inter = max(inter, does_interact(p.x, p.y, true, E.f[V_POST + 3 * k], E.f[V_POST + 3 * k + 1],
-                                           E.f[V_POST + 3 * k + 2] != 0.f, BALL_RADIUS * 8, false));
-      } else if (kind == 3) {
-        inter = max(inter, does_interact(E.f[V_BALL], E.f[V_BALL + 1], E.f[V_BALL + 2] != 0.f, p.x, p.y, true,
-                                         BALL_RADIUS * 4, false));
-      }
-    }
-    /* noise, false negatives, misclassification (cutils.py:417-468, 352-378) */
-    const int site = kind == 0 ? RC_SITE_OBS_BALL : kind == 1 ? RC_SITE_OBS_ROBOT : kind == 2 ? RC_SITE_OBS_POST
-                     : kind == 3 ? RC_SITE_OBS_CROSS : kind == 4 ? RC_SITE_OBS_FCROSS : RC_SITE_OBS_LINE;
-    if (kind >= 0 && kind <= 4) {
-      if (inter == I_OCCLUDE) seen = S_NO;
-      else if (seen != S_NO) {
-        Rand6 ru = E.rng.block(tick, site, ag, idx, 0);
-        V2 noiseVec = v2((ru.u(0) - 0.5f) * magn, (ru.u(1) - 0.5f) * magn);
-        if (!realistic) {
-          if (ru.u(2) < randB) seen = S_NO;
-          p = p + noiseVec;
-          radius *= (1.f - (ru.u(4) - 0.5f) * 0.2f);
-          if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn / 10.f;
-        } else {
-          float range = 0.25f + 3.75f * lensq(p) / maxDist;
-          float mult = range;
-          if (inter == I_NEARBY) mult = range * 2;
-          if (seen == S_DISTANT) mult = range * 3;
-          else if (seen == S_PARTIAL) mult = range * 4;
-          V2 newPos = p + v2(noiseVec.x * mult / 4, noiseVec.y * mult / 4);
-          /* |newPos| - |p| without cancellation: (2 p.d + d.d) / (|newPos| + |p|) */
-          V2 dsp = v2(noiseVec.x * mult / 4, noiseVec.y * mult / 4);
-          float lsum = len(newPos) + len(p);
-          float diff = lsum > 0 ? (2.f * dot(p, dsp) + dot(dsp, dsp)) / lsum : 0.f;
-          if (ru.u(2) < randB * mult) seen = S_NO;
-          if ((kind == 0 || kind == 3) && ru.u(3) < randB * mult / 2) seen = S_MISCLASS;
-          p = newPos;
-          radius *= 1.f + (ru.u(4) * 0.1f * diff);
-          if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn * mult / 180.f;
+    {
+      unsigned m = robHas;
+      const float R2 = (ROB_TOTAL * 2) * (ROB_TOTAL * 2);
+      const float lp = lensq(p);
+      while (m) {
+        int i = __ffs(m) - 2; /* lane -> robot slot */
+        m &= m - 1;
+        float ax = E.f[V_ROB + 3 * i], ay = E.f[V_ROB + 3 * i + 1];
+        if (has && !(kind == 1 && i == idx)) { /* cutils.doesInteract(robot, object, 35, canOcclude) */
+          float dx = ax - p.x, dy = ay - p.y;
+          float cr = ax * p.y - ay * p.x, la = ax * ax + ay * ay;
+          int t = (dx * dx + dy * dy < R2) ? I_NEARBY : I_NO;
+          if (cr * cr < R2 * la && la < lp) t = I_OCCLUDE;
+          inter = max(inter, t);
         }
       }
-    } else if (kind == 5 && seen != S_NO) {
-      Rand6 ru = E.rng.block(tick, site, ag, idx, 0);
-      V2 n1 = v2((ru.u(0) - 0.5f) * magn, (ru.u(1) - 0.5f) * magn);
-      V2 n2 = v2((ru.u(2) - 0.5f) * magn, (ru.u(3) - 0.5f) * magn);
+      if (has && kind == 0) { /* ball near a post */
+        for (int k = 0; k < 4; k++) {
+          float dx = p.x - E.f[V_POST + 3 * k], dy = p.y - E.f[V_POST + 3 * k + 1];
+          if (E.f[V_POST + 3 * k + 2] != 0.f && dx * dx + dy * dy < (BALL_RADIUS * 8) * (BALL_RADIUS * 8)) inter = max(inter, I_NEARBY);
+        }
+      } else if (has && kind == 3) { /* penalty cross near the ball */
+        float dx = p.x - E.f[V_BALL], dy = p.y - E.f[V_BALL + 1];
+        if (E.f[V_BALL + 2] != 0.f && dx * dx + dy * dy < (BALL_RADIUS * 4) * (BALL_RADIUS * 4)) inter = max(inter, I_NEARBY);
+      }
+    }
+    /* noise, false negatives, misclassification (cutils.py:417-468) */
+    if (inter == I_OCCLUDE) seen = S_NO;
+    else if (seen != S_NO) {
+      const int site = RC_SITE_OBS_BALL + kind;
+      Rand6 ru = rng_block(E, tick, site, ag, idx, 0);
+      V2 noiseVec = v2((ru.u(0) - 0.5f) * magn, (ru.u(1) - 0.5f) * magn);
       if (!realistic) {
-        if (ru.u(4) < randB) seen = S_NO;
-        lp1 = lp1 + n1;
-        lp2 = lp2 + n2;
-        ldir = ldir + (n2 - n1);
+        if (ru.u(2) < randB) seen = S_NO;
+        p = p + noiseVec;
+        radius *= (1.f - (ru.u(4) - 0.5f) * 0.2f);
+        if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn / 10.f;
       } else {
-        float m1 = 0.25f + 3.75f * lensq(lp1) / maxDist;
-        float m2 = 0.25f + 3.75f * lensq(lp2) / maxDist;
-        float m = (m1 + m2) * 0.5f;
-#ifdef RC_DEBUG_PRINT
-        if (E.rng.env_id == RC_DEBUG_PRINT && ag == 8 && E.i[RC_S_ELAPSED] % 50 == 0)
-          printf("GPU line %d lp1=(%.5f,%.5f) lp2=(%.5f,%.5f) m1=%.6f m2=%.6f n1=(%.6f,%.6f) n2=(%.6f,%.6f) u4=%.6f\n", idx, lp1.x, lp1.y, lp2.x, lp2.y, m1, m2, n1.x, n1.y, n2.x, n2.y, ru.u(4));
-#endif
-        if (ru.u(4) < randB * m) seen = S_NO;
-        V2 a1 = v2(n1.x * m1 / 2, n1.y * m1 / 2), a2 = v2(n2.x * m2 / 2, n2.y * m2 / 2);
-        lp1 = lp1 + a1;
-        lp2 = lp2 + a2;
-        ldir = ldir + (a2 - a1);
+        float range = 0.25f + 3.75f * lensq(p) / maxDist;
+        float mult = range;
+        if (inter == I_NEARBY) mult = range * 2;
+        if (seen == S_DISTANT) mult = range * 3;
+        else if (seen == S_PARTIAL) mult = range * 4;
+        /* |newPos| - |p| without cancellation: (2 p.d + d.d) / (|newPos| + |p|) */
+        V2 dsp = v2(noiseVec.x * mult / 4, noiseVec.y * mult / 4);
+        V2 newPos = p + dsp;
+        float lsum = len(newPos) + len(p);
+        float diff = lsum > 0 ? (2.f * dot(p, dsp) + dot(dsp, dsp)) / lsum : 0.f;
+        if (ru.u(2) < randB * mult) seen = S_NO;
+        if ((kind == 0 || kind == 3) && ru.u(3) < randB * mult / 2) seen = S_MISCLASS;
+        p = newPos;
+        radius *= 1.f + (ru.u(4) * 0.1f * diff);
+        if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn * mult / 180.f;
       }
     }
     /* list membership (RoboCupEnvironment.py:1254-1276) */
     const bool okStrict = seen != S_NO && seen != S_MISCLASS;
-    const unsigned lt = (1u << lane) - 1;
     unsigned mBall = __ballot_sync(FULLMASK, kind == 0 && okStrict);
     unsigned mBallMis = __ballot_sync(FULLMASK, kind == 0 && seen == S_MISCLASS);
     unsigned mRob = __ballot_sync(FULLMASK, kind == 1 && seen != S_NO);
@@ -1592,80 +1611,130 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
     unsigned mCross = __ballot_sync(FULLMASK, kind == 3 && okStrict);
     unsigned mCrossMis = __ballot_sync(FULLMASK, kind == 3 && seen == S_MISCLASS);
     unsigned mFc = __ballot_sync(FULLMASK, kind == 4 && okStrict);
-    unsigned mLine = __ballot_sync(FULLMASK, kind == 5 && seen != S_NO);
-    float row[8];
-    int rtype = -1, rrow = 0;
-    if (kind == 0 || kind == 3) {
-      bool asBall = (kind == 0 && okStrict) || (kind == 3 && seen == S_MISCLASS);
-      bool asCross = (kind == 3 && okStrict) || (kind == 0 && seen == S_MISCLASS);
-      if (asBall) {
-        rtype = 0;
-        rrow = kind == 0 ? 0 : __popc(mBall) + __popc(mCrossMis & lt);
-        row[0] = p.x * STDNORM2; row[1] = p.y * STDNORM2; row[2] = (radius - BALL_RADIUS * 2) * 2.f;
-        row[3] = kind == 0 ? ex0 : 0.f;
-        row[4] = (ag == E.i[RC_S_CLOSEST] || ag == E.i[RC_S_CLOSEST + 1]) ? 1.f : 0.f;
-      } else if (asCross) {
-        rtype = 3;
-        float t1 = ex0, t2 = ex1;
-        if (kind == 0) { /* a ball taken for a cross gets random tags (:1260) */
-          Rand6 rm = E.rng.block(tick, RC_SITE_OBS_MISCROSS, ag, 0, 0);
-          t1 = (float)randint_from(rm.u(0), -1, 1);
-          t2 = (float)randint_from(rm.u(1), -1, 1);
-          rrow = __popc(mCross);
-        } else rrow = __popc(mCross & lt);
-        polar_row(row, p, radius, PEN_RADIUS, t1, t2, team);
+    /* misclassified balls and crosses change lists (:1258-1263) */
+    int lkind = kind;
+    float t1 = ex0, t2 = ex1;
+    if (seen == S_MISCLASS) {
+      if (kind == 0) { /* a ball taken for a cross gets random tags */
+        Rand6 rm = rng_block(E, tick, RC_SITE_OBS_MISCROSS, ag, 0, 0);
+        t1 = (float)randint_from(rm.u(0), -1, 1);
+        t2 = (float)randint_from(rm.u(1), -1, 1);
+        lkind = 3;
+      } else { lkind = 0; ex0 = 0.f; }
+    }
+    if (seen != S_NO) {
+      if (lkind <= 1) { /* ball / robot rows: normalised position and size */
+        int rrow;
+        float* dst;
+        if (lkind == 0) {
+          rrow = kind == 0 ? 0 : __popc(mBall) + __popc(mCrossMis & lt);
+          dst = E.f + (V_STAGE + RC_O_BALL + rrow * RC_F_BALL);
+          dst[2] = (radius - BALL_RADIUS * 2) * 2.f; dst[3] = ex0; dst[4] = closest;
+        } else {
+          rrow = __popc(mRob & lt);
+          dst = E.f + (V_STAGE + RC_O_ROBOT + rrow * RC_F_ROBOT);
+          float s, c;
+          sincos_b(ex0, &s, &c);
+          dst[2] = (radius - ROB_TOTAL) * 2.f; dst[3] = c; dst[4] = s; dst[5] = ex1; dst[6] = ex2;
+          E.f[V_RAW + 3 * rrow] = p.x; E.f[V_RAW + 3 * rrow + 1] = p.y; E.f[V_RAW + 3 * rrow + 2] = seen == S_NORMAL ? 1.f : 0.f;
+        }
+        dst[0] = p.x * STDNORM2; dst[1] = p.y * STDNORM2;
+      } else { /* posts, crosses, line crosses: polar rows (cutils.py:308-315) */
+        int rrow, off, feat = 6;
+        if (lkind == 2) { rrow = __popc(mPost & lt); off = RC_O_POST; }
+        else if (lkind == 3) { rrow = kind == 0 ? __popc(mCross) : __popc(mCross & lt); off = RC_O_CROSS; }
+        else { rrow = nf + __popc(mFc & lt); off = RC_O_FCROSS; feat = RC_F_FCROSS; }
+        float* dst = E.f + (V_STAGE + off + rrow * feat);
+        float dist = len(p);
+        float inv = dist > 0 ? 1.f / dist : 0.f;
+        dst[0] = (dist * STDNORM - 0.5f) / 0.5f;
+        dst[1] = dist > 0 ? p.x * team * inv : 1.f;
+        dst[2] = dist > 0 ? p.y * team * inv : 0.f;
+        dst[3] = (radius - (lkind == 2 ? POST_RADIUS : PEN_RADIUS)) * 2.f;
+        dst[4] = t1 * team; dst[5] = t2 * team;
+        if (lkind == 4) {
+          float s, c;
+          sincos_b(ex2, &s, &c);
+          dst[6] = c; dst[7] = -s;
+        }
       }
-    } else if (kind == 1 && seen != S_NO) {
-      rtype = 1; rrow = __popc(mRob & lt);
-      float s, c;
-      sincosf(ex0, &s, &c);
-      row[0] = p.x * STDNORM2; row[1] = p.y * STDNORM2; row[2] = (radius - ROB_TOTAL) * 2.f;
-      row[3] = c; row[4] = s; row[5] = ex1; row[6] = ex2;
-      E.f[V_RAW + 3 * rrow] = p.x; E.f[V_RAW + 3 * rrow + 1] = p.y; E.f[V_RAW + 3 * rrow + 2] = seen == S_NORMAL ? 1.f : 0.f;
-    } else if (kind == 2 && seen != S_NO) {
-      rtype = 2; rrow = __popc(mPost & lt);
-      polar_row(row, p, radius, POST_RADIUS, ex0, ex1, team);
-    } else if (kind == 4 && okStrict) {
-      rtype = 4; rrow = nfRound0 + __popc(mFc & lt);
-      polar_row(row, p, radius, PEN_RADIUS, ex0, ex1, team);
-      float s, c;
-      sincosf(ex2, &s, &c);
-      row[6] = c; row[7] = -s;
-    } else if (kind == 5 && seen != S_NO) {
-      rtype = 5; rrow = __popc(mLine & lt);
-      /* normalizeLine: cutils.py:333-347 */
-      V2 d = ldir; /* = lp2 - lp1; |lp2 x lp1| = |d x lp1| */
-      float ld = len(d);
-      float dist = fabsf(cross(d, lp1)) / (ld + 1e-7f);
-      row[0] = (dist * STDNORM - 0.5f) / 0.5f;
-      row[1] = ld > 0 ? d.x / ld : 1.f;
-      row[2] = ld > 0 ? d.y / ld : 0.f;
-      row[3] = ex0; row[4] = ex1;
     }
-    if (rtype >= 0) {
-      const int off = rtype == 0 ? RC_O_BALL : rtype == 1 ? RC_O_ROBOT : rtype == 2 ? RC_O_POST : rtype == 3 ? RC_O_CROSS
-                      : rtype == 4 ? RC_O_FCROSS : RC_O_LINE;
-      const int feat = rtype == 0 ? RC_F_BALL : rtype == 1 ? RC_F_ROBOT : rtype == 4 ? RC_F_FCROSS : rtype == 5 ? RC_F_LINE : 6;
-      float* dst = E.f + V_STAGE + off + rrow * feat;
-#pragma unroll
-      for (int w = 0; w < 8; w++)
-        if (w < feat) dst[w] = row[w];
-    }
-    if (round == 0) {
+    if (pass == 0) {
       nb = __popc(mBall) + __popc(mCrossMis);
       nr = __popc(mRob);
       np = __popc(mPost);
       ncr = __popc(mCross) + __popc(mBallMis);
-      nfRound0 = __popc(mFc);
-      nf = nfRound0;
       /* seen flags (:1254-1255): robots by slot, ball strictly seen */
       if (kind == 1) E.i[V_STAGE + RC_O_ROBSEEN + idx] = seen != S_NO ? 1 : 0;
       if (lane == 0) E.i[V_STAGE + RC_O_BALLSEEN] = okStrict ? 1 : 0;
-    } else {
-      nf += __popc(mFc);
-      nl = __popc(mLine);
     }
-    __syncwarp();
+    nf += __popc(mFc);
+  }
+  /* lines: isLineInArea (cutils.py:751-821), addNoiseLine (:352-378), normalizeLine (:333-347) */
+  int nl;
+  {
+    int seen = S_NO;
+    V2 lp1 = v2(0, 0), ldir = v2(0, 0);
+    float tx = 0, ty = 0;
+    if (lane < 11) {
+      const float* ln = g_lines[lane];
+      V2 p1 = v2(ln[0], ln[1]) - pos, p2 = v2(ln[2], ln[3]) - pos;
+      tx = ln[4]; ty = ln[5];
+      float dist11 = cross(vec1, p1), dist12 = cross(vec1, p2);
+      float dist21 = cross(vec2, p1), dist22 = cross(vec2, p2);
+      if (!(dist11 > 0 && dist12 > 0) && !(dist21 < 0 && dist22 < 0)) {
+        seen = S_NORMAL;
+        V2 D = p2 - p1;
+        float t1 = 0.f, t2 = 1.f; /* line parameters of the clipped end points */
+        if (!(dist11 <= 0 && dist21 >= 0)) {
+          float inter1 = cross(p1, vec1) / (cross(vec1, D) + 1e-7f);
+          float inter2 = cross(p1, vec2) / (cross(vec2, D) + 1e-7f);
+          t1 = (inter1 < 1 && inter2 < 1) ? fmaxf(inter1, inter2) : fminf(inter1, inter2);
+          seen = S_PARTIAL;
+        }
+        if (!(dist12 <= 0 && dist22 >= 0)) {
+          float inter1 = cross(p2, vec1) / -cross(vec1, D);
+          float inter2 = cross(p2, vec2) / -cross(vec2, D);
+          t2 = 1.f - ((inter1 < 1 && inter2 < 1) ? fmaxf(inter1, inter2) : fminf(inter1, inter2));
+          seen = S_PARTIAL;
+        }
+        V2 pt1 = p1 + D * t1, pt2 = p2 - D * (1.f - t2);
+        if (lensq(pt1) > maxVis1 || lensq(pt2) > maxVis1) seen = S_DISTANT;
+        lp1 = rot_cs(pt1, hc, -hs);
+        V2 lp2 = rot_cs(pt2, hc, -hs);
+        /* lp2 - lp1 from the line's own direction: a clipped piece can be a fraction of a pixel long,
+           which the difference of two float32 end points (~300 px) cannot resolve */
+        ldir = rot_cs(D, hc, -hs) * (t2 - t1);
+        if (lp1.x < 0 || lp2.x < 0) seen = S_NO;
+        if (seen != S_NO) {
+          Rand6 ru = rng_block(E, tick, RC_SITE_OBS_LINE, ag, lane, 0);
+          V2 n1 = v2((ru.u(0) - 0.5f) * magn, (ru.u(1) - 0.5f) * magn);
+          V2 n2 = v2((ru.u(2) - 0.5f) * magn, (ru.u(3) - 0.5f) * magn);
+          if (!realistic) {
+            if (ru.u(4) < randB) seen = S_NO;
+            lp1 = lp1 + n1;
+            ldir = ldir + (n2 - n1);
+          } else {
+            float m1 = 0.25f + 3.75f * lensq(lp1) / maxVis1;
+            float m2 = 0.25f + 3.75f * lensq(lp2) / maxVis1;
+            if (ru.u(4) < randB * ((m1 + m2) * 0.5f)) seen = S_NO;
+            V2 a1 = v2(n1.x * m1 / 2, n1.y * m1 / 2), a2 = v2(n2.x * m2 / 2, n2.y * m2 / 2);
+            lp1 = lp1 + a1;
+            ldir = ldir + (a2 - a1);
+          }
+        }
+      }
+    }
+    unsigned mLine = __ballot_sync(FULLMASK, seen != S_NO);
+    nl = __popc(mLine);
+    if (seen != S_NO) {
+      float* dst = E.f + (V_STAGE + RC_O_LINE + __popc(mLine & lt) * RC_F_LINE);
+      float ld = len(ldir); /* ldir = lp2 - lp1; |lp2 x lp1| = |ldir x lp1| */
+      dst[0] = (fabsf(cross(ldir, lp1)) / (ld + 1e-7f) * STDNORM - 0.5f) / 0.5f;
+      dst[1] = ld > 0 ? ldir.x / ld : 1.f;
+      dst[2] = ld > 0 ? ldir.y / ld : 0.f;
+      dst[3] = tx; dst[4] = ty;
+    }
   }
   if (lane == 0) {
     E.i[V_STAGE + RC_O_NLANDMARKS] = nf + nl + ncr + np;
@@ -1673,84 +1742,36 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
     E.i[V_CNT + 3] = ncr; E.i[V_CNT + 4] = nf; E.i[V_CNT + 5] = nl;
   }
   __syncwarp();
-  /* random false positives (:1279-1305): ten draws, hits are rare and inserted in loop order */
+  /* random false positives (:1279-1305): ten draws, lane = loop index */
   {
-    Rand6 ru;
     bool hit = false;
-    if (lane < 10) {
-      ru = E.rng.block(tick, RC_SITE_OBS_FP, ag, lane, 0);
-      hit = ru.u(0) < randB;
-    }
+    if (lane < 10) hit = rng_block(E, tick, RC_SITE_OBS_FP, ag, lane, 0).u(0) < randB;
     unsigned hits = __ballot_sync(FULLMASK, hit);
-    while (hits) {
-      int i = __ffs(hits) - 1;
-      hits &= hits - 1;
-      if (lane == i) {
-        int c = randint_from(ru.u(1), 0, 5);
-        float d = ru.u(2) * sqrtf(maxVis1);
-        float a = ru.u(3) * 2 * ROB_FOV - ROB_FOV;
-        V2 fp = rot(v2(d, 0), a);
-        float sz = 1.f - 0.4f * (ru.u(4) - 0.5f);
-        Rand6 r2 = E.rng.block(tick, RC_SITE_OBS_FP, ag, lane, 1); /* k = 6, 7 */
-        float row[8];
-        if (c == 0) {
-          row[0] = fp.x * STDNORM2; row[1] = fp.y * STDNORM2; row[2] = (BALL_RADIUS * 2 * sz - BALL_RADIUS * 2) * 2.f;
-          row[3] = 0.f;
-          row[4] = (ag == E.i[RC_S_CLOSEST] || ag == E.i[RC_S_CLOSEST + 1]) ? 1.f : 0.f;
-          stage_insert(E, 0, E.i[V_CNT + 0], row);
-        } else if (c == 1) {
-          float ang = (ru.u(5) - 0.5f) * 2 * PI_F;
-          float s, cs;
-          sincosf(ang, &s, &cs);
-          row[0] = fp.x * STDNORM2; row[1] = fp.y * STDNORM2; row[2] = (ROB_TOTAL * sz - ROB_TOTAL) * 2.f;
-          row[3] = cs; row[4] = s;
-          row[5] = r2.u(0) > 0.5f ? -1.f : 1.f;
-          row[6] = r2.u(1) > 0.9f ? 1.f : 0.f;
-          int at = E.i[V_CNT + 1];
-          if (at < RC_CAP_ROBOT) { E.f[V_RAW + 3 * at] = fp.x; E.f[V_RAW + 3 * at + 1] = fp.y; E.f[V_RAW + 3 * at + 2] = 1.f; }
-          stage_insert(E, 1, at, row);
-        } else if (c <= 4) {
-          float t1 = (float)randint_from(ru.u(5), -1, 1), t2 = (float)randint_from(r2.u(0), -1, 1);
-          float rad0 = c == 2 ? POST_RADIUS : PEN_RADIUS;
-          polar_row(row, fp, rad0 * sz, rad0, t1, t2, team);
-          if (c == 4) {
-            float s, cs;
-            sincosf(r2.u(1) * PI_F * 2, &s, &cs);
-            row[6] = cs; row[7] = -s;
-            stage_insert(E, 4, E.i[V_CNT + 3], row); /* inserted at len(crossDets) (reference behaviour) */
-          } else stage_insert(E, c, E.i[V_CNT + c], row);
-        }
-      }
-      __syncwarp();
-    }
+    if (hits) false_positives(E, ag, tick, hits, team);
   }
   /* false-positive balls near robots (:1308-1316), lane = row of the robot list */
   if (realistic) {
     int nrNow = E.i[V_CNT + 1];
     bool create = false;
-    float row[5];
+    float bx = 0, by = 0, brad = 0;
     if (lane < nrNow && E.f[V_RAW + 3 * lane + 2] != 0.f) {
-      Rand6 ru = E.rng.block(tick, RC_SITE_OBS_FPBALL, ag, lane, 0);
+      Rand6 ru = rng_block(E, tick, RC_SITE_OBS_FPBALL, ag, lane, 0);
       V2 rp = v2(E.f[V_RAW + 3 * lane], E.f[V_RAW + 3 * lane + 1]);
       if (ru.u(0) < randB * 10 && len(rp) < 250.f) {
         create = true;
-        float ox = 2 * ru.u(2) - 1.f, oy = 2 * ru.u(3) - 1.f;
-        float rad = BALL_RADIUS * 2 * (1.f - 0.4f * (ru.u(4) - 0.5f));
-        row[0] = (rp.x + ox * ROB_TOTAL) * STDNORM2;
-        row[1] = (rp.y + oy * ROB_TOTAL) * STDNORM2;
-        row[2] = (rad - BALL_RADIUS * 2) * 2.f;
-        row[3] = 0.f;
-        row[4] = (ag == E.i[RC_S_CLOSEST] || ag == E.i[RC_S_CLOSEST + 1]) ? 1.f : 0.f;
+        bx = rp.x + (2 * ru.u(2) - 1.f) * ROB_TOTAL;
+        by = rp.y + (2 * ru.u(3) - 1.f) * ROB_TOTAL;
+        brad = BALL_RADIUS * 2 * (1.f - 0.4f * (ru.u(4) - 0.5f));
       }
     }
     unsigned cm = __ballot_sync(FULLMASK, create);
     if (cm) {
       int nbNow = E.i[V_CNT + 0];
       __syncwarp();
-      int at = nbNow + __popc(cm & ((1u << lane) - 1));
+      int at = nbNow + __popc(cm & lt);
       if (create && at < RC_CAP_BALL) {
-        float* dst = E.f + V_STAGE + RC_O_BALL + at * RC_F_BALL;
-        for (int w = 0; w < 5; w++) dst[w] = row[w];
+        float* dst = E.f + (V_STAGE + RC_O_BALL + at * RC_F_BALL);
+        dst[0] = bx * STDNORM2; dst[1] = by * STDNORM2; dst[2] = (brad - BALL_RADIUS * 2) * 2.f; dst[3] = 0.f; dst[4] = closest;
       }
       if (lane == 0) E.i[V_CNT + 0] = min(nbNow + __popc(cm), (int)RC_CAP_BALL);
       __syncwarp();
@@ -1767,7 +1788,7 @@ __device__ void agent_vision(Env& E, int ag, uint32_t tick) {
 }
 
 /* one observation tick of every agent; records go straight to HBM with coalesced stores */
-__device__ void observe_tick(Env& E, int t, uint32_t tick, float* obs_env, float* full_env) {
+__device__ __noinline__ void observe_tick(const Env E, int t, uint32_t tick, float* obs_env, float* full_env) {
   const int P = E.c->P;
   const int lane = E.lane;
   if (E.c->obs_type == DYNENV_OBS_FULL) {
@@ -1788,7 +1809,7 @@ __device__ void observe_tick(Env& E, int t, uint32_t tick, float* obs_env, float
 }
 
 /* ================================================================= reset (scene set-up) */
-__device__ void init_scene(Env& E) {
+__device__ __noinline__ void init_scene(const Env E) {
   /* RoboCupEnvironment.__init__ + _setup_scene (RoboCupEnvironment.py:42-63,239-336); lane 0 draws the
      scene, every lane clears the record first */
   const int lane = E.lane;
@@ -1796,7 +1817,6 @@ __device__ void init_scene(Env& E) {
   __syncwarp();
   for (int w = lane; w < RC_STATE_WORDS; w += 32) E.i[w] = 0;
   __syncwarp();
-  E.rng.episode = (uint32_t)episode;
   if (lane == 0) {
     const SimCfg& c = *E.c;
     E.i[RC_S_EPISODE] = episode;
@@ -1807,7 +1827,7 @@ __device__ void init_scene(Env& E) {
     int k = 0;
     Rand6 blk;
     auto U = [&]() {
-      if (k % 6 == 0) blk = E.rng.block(DYNENV_TICK_RESET, RC_SITE_RESET, 0, 0, k / 6);
+      if (k % 6 == 0) blk = rng_block(E, DYNENV_TICK_RESET, RC_SITE_RESET, 0, 0, k / 6);
       float u = blk.u(k % 6);
       k++;
       return u;
@@ -1883,13 +1903,13 @@ __device__ void init_scene(Env& E) {
 }
 
 /* info['Full State'] + info['Recon States'] (RoboCupEnvironment.py:511-512,1151-1161) */
-__device__ void fill_info(Env& E, float* info_env) {
+__device__ __noinline__ void fill_info(const Env E, float* info_env) {
   const int lane = E.lane;
   const int P = E.c->P;
   if (lane < P) {
     V2 p = robot_pos(E, lane);
     float s, c;
-    sincosf(robot_angle(E, lane), &s, &c);
+    sincos_b(robot_angle(E, lane), &s, &c);
     float* o = info_env + RC_I_STATE_ROBOTS + 6 * lane;
     o[0] = p.x * STDNORM2; o[1] = p.y * STDNORM2; o[2] = c; o[3] = s;
     o[4] = (float)team_of(E, lane);
@@ -1904,13 +1924,13 @@ __device__ void fill_info(Env& E, float* info_env) {
   for (int ag = 0; ag < P; ag++) full_state_agent(E, ag, info_env + RC_I_RECON + ag * RC_FULL_WORDS);
 }
 
-__device__ __forceinline__ void clear_step_scratch(Env& E) {
+__device__ __forceinline__ void clear_step_scratch(const Env E) {
   for (int w = X_REW + E.lane; w < X_NACTIVE + 1; w += 32) E.i[w] = 0;
   __syncwarp();
 }
 
 /* RoboCupEnvironment.step: RoboCupEnvironment.py:446-524 */
-__device__ void step_env(Env& E, const float* actions_env, float* obs_env, float* full_env, float* info_env) {
+__device__ __noinline__ void step_env(const Env E, const float* actions_env, float* obs_env, float* full_env, float* info_env) {
   const int lane = E.lane;
   const int P = E.c->P;
   clear_step_scratch(E);
@@ -1961,7 +1981,7 @@ __device__ void step_env(Env& E, const float* actions_env, float* obs_env, float
 }
 
 /* environment_base.reset: new scene + nTimeSteps copies of the initial observation (:205-224) */
-__device__ void reset_env(Env& E, float* obs_env, float* full_env, float* info_env, bool write_info) {
+__device__ __noinline__ void reset_env(const Env E, float* obs_env, float* full_env, float* info_env, bool write_info) {
   init_scene(E);
   clear_step_scratch(E);
   for (int t = 0; t < RC_NTICK; t++) observe_tick(E, t, DYNENV_TICK_RESETOBS | (uint32_t)t, obs_env, full_env);
