@@ -170,7 +170,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E = args.envs
-    sim = dynenv_b200.BatchedRoboCup(E, N_PLAYERS, dynenv_b200.ObservationType.PARTIAL, dynenv_b200.NoiseType.REALISTIC,
+    obs_type = dynenv_b200.ObservationType.FULL if args.debug_full_obs else dynenv_b200.ObservationType.PARTIAL
+    sim = dynenv_b200.BatchedRoboCup(E, N_PLAYERS, obs_type, dynenv_b200.NoiseType.REALISTIC,
                                      2.0, canFall=True, useObsRewards=True, auto_reset=True, seed=42, device=local,
                                      env_id_offset=rank * E)
     sim.reset()
@@ -275,6 +276,7 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--debug-full-obs", action="store_true", help="(profiling aid) FULL observations: physics and rules only")
     ap.add_argument("--cpu-steps", type=int, default=1500, help="env-steps per host thread of the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":

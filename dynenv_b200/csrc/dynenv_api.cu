@@ -59,13 +59,30 @@ __device__ __forceinline__ rc::Env make_env(int base, const SimCfg& cfg, int e, 
 }
 
 /*
- * One env step of every environment: all 50 substeps and 5 observation ticks in one launch.
- * grid = ceil(nEnvs / RC_WPC) CTAs of RC_WPC warps; warp w of CTA b owns environment b*RC_WPC + w.
+ * One env step = RC_NTICK x { rc_phys_kernel (10 substeps), rc_obs_kernel (one observation tick) } +
+ * rc_finish_kernel, all on the caller's stream.  Every kernel: grid = ceil(nEnvs / RC_WPC) CTAs of RC_WPC
+ * warps, warp w of CTA b owns environment b*RC_WPC + w, whose record it loads into its shared-memory slice
+ * and stores back (coalesced).  See rc_sim.cuh (phys_substeps) for why the phases are separate launches.
  */
 __global__ void __launch_bounds__(RC_WPC * 32)
-rc_step_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
-               float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info,
-               float* __restrict__ term_obs, float* __restrict__ term_full) {
+rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
+               int sub_b, int sub_e, int first) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * RC_WPC + warp;
+  stage_cfg(cfg);
+  if (e >= cfg.n_envs) return;
+  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = rc::g_smem + base;
+  load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
+  rc::Env E = make_env(base, cfg, e, lane);
+  rc::phys_substeps(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
+  store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
+}
+
+/* observation tick t of the step in flight (after substep 10 t + 9) */
+__global__ void __launch_bounds__(RC_WPC * 32)
+rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, int t, int subs_left,
+              float* __restrict__ obs, float* __restrict__ full, float* __restrict__ term_obs, float* __restrict__ term_full) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
@@ -76,15 +93,36 @@ rc_step_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
   rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
   const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
-  const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + (cfg.sub_end - cfg.sub_begin) >= rc::MAXTIME;
-  float* o = obs ? obs + e * obs_stride : nullptr;
-  float* f = full ? full + e * full_stride : nullptr;
+  /* a finishing episode's last observations go to the terminal buffers, its first ones (written by the
+     finish kernel after the reset) to `out` */
+  const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + subs_left >= rc::MAXTIME;
+  float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
+  float* f = finishing ? (term_full ? term_full + e * full_stride : nullptr) : (full ? full + e * full_stride : nullptr);
+  rc::observe_tick(E, t, (uint32_t)E.i[RC_S_ELAPSED], o, f);
+  /* only the processSeens sums changed */
+  __syncwarp();
+  uint32_t* g = state + (size_t)e * RC_STATE_WORDS;
+  for (int w = RC_S_STEP_LSUM + lane; w < RC_S_STEP_END; w += 32) g[w] = S[w];
+}
+
+/* rewards, info, done, episode statistics; finished environments are re-initialised (auto-reset) */
+__global__ void __launch_bounds__(RC_WPC * 32)
+rc_finish_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, float* __restrict__ obs,
+                 float* __restrict__ full, float* __restrict__ info) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * RC_WPC + warp;
+  stage_cfg(cfg);
+  if (e >= cfg.n_envs) return;
+  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = rc::g_smem + base;
+  load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
+  rc::Env E = make_env(base, cfg, e, lane);
+  const int P = cfg.P;
+  const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
   float* inf = info ? info + (size_t)e * RC_INFO_WORDS : nullptr;
-  /* a finishing episode's last observations go to the terminal buffers, its first ones to `out` */
-  float* so = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : o;
-  float* sf = finishing ? (term_full ? term_full + e * full_stride : nullptr) : f;
-  rc::step_env(E, actions + (size_t)e * P * 4, so, sf, inf);
-  if (finishing) rc::reset_env(E, o, f, inf, false);
+  rc::finish_step(E, inf);
+  if (cfg.auto_reset && E.i[RC_S_ELAPSED] >= rc::MAXTIME)
+    rc::reset_env(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr, inf, false);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
 }
 
@@ -206,13 +244,28 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
   const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
   const DynEnvRoboCupOut* t = static_cast<const DynEnvRoboCupOut*>(terminal_out);
   cudaSetDevice(h->cfg.device);
-  int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
-  size_t smem = ((size_t)rc::CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
-  rc_step_kernel<<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      h->sim, h->state, actions_dev, o->obs, o->full, o->info, t ? t->obs : nullptr, t ? t->full : nullptr);
-  h->last_launches = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
+  const size_t smem = ((size_t)rc::CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
+  int launches = 0;
+  /* blocks of substeps up to the next observation tick (every 10th substep) */
+  for (int b = h->sim.sub_begin; b < h->sim.sub_end;) {
+    int e = (b / 10 + 1) * 10;
+    if (e > h->sim.sub_end) e = h->sim.sub_end;
+    rc_phys_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, actions_dev, b, e, b == h->sim.sub_begin);
+    launches++;
+    if (e % 10 == 0) {
+      rc_obs_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
+                                                      t ? t->obs : nullptr, t ? t->full : nullptr);
+      launches++;
+    }
+    b = e;
+  }
+  rc_finish_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, o->obs, o->full, o->info);
+  launches++;
+  h->last_launches = launches;
   cudaError_t ce = cudaGetLastError();
-  if (ce != cudaSuccess) return cuda_fail(ce, "rc_step_kernel launch");
+  if (ce != cudaSuccess) return cuda_fail(ce, "rc step kernels launch");
   return DYNENV_OK;
 }
 

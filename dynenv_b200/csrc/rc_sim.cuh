@@ -48,18 +48,14 @@ enum { I_NO = 0, I_NEARBY = 1, I_OCCLUDE = 2 };
 
 /* ---- scratch layout (words after the state record) */
 enum {
-  X_REW = RC_STATE_WORDS,      /* F[10] robotRewards of this step     */
-  X_POSREW = X_REW + 10,       /* F[10] robotPosRewards               */
-  X_TEAMREW = X_POSREW + 10,   /* F[2]                                */
-  X_CURREW = X_TEAMREW + 2,    /* F[2] currReward of isBallOutOfField */
+  /* accumulators of the step in flight live in the record (they cross kernel launches) */
+  X_REW = RC_S_STEP_REW, X_POSREW = RC_S_STEP_POSREW, X_TEAMREW = RC_S_STEP_TEAMREW, X_DIAG = RC_S_STEP_DIAG,
+  X_LSUM = RC_S_STEP_LSUM, X_BSUM = RC_S_STEP_BSUM, X_RSEEN = RC_S_STEP_RSEEN,
+  X_CURREW = RC_STATE_WORDS,   /* F[2] currReward of isBallOutOfField */
   X_OLDBX = X_CURREW + 2,      /* F ball position before the rules moved it */
   X_OLDBY = X_OLDBX + 1,
-  X_DIAG = X_OLDBY + 1,        /* I RC_IF_* */
-  X_TOUCHED = X_DIAG + 1,      /* I bit k: cached pair k collided this substep */
-  X_LSUM = X_TOUCHED + 1,      /* I[10] sum of numLandMarks over ticks */
-  X_BSUM = X_LSUM + 10,        /* I[10] sum of ballsSeen               */
-  X_RSEEN = X_BSUM + 10,       /* I[10][9] sum of robotsSeen           */
-  X_NACTIVE = X_RSEEN + 90,    /* I */
+  X_TOUCHED = X_OLDBY + 1,     /* I bit k: cached pair k collided this substep */
+  X_NACTIVE = X_TOUCHED + 1,   /* I */
   X_ACTIVE = X_NACTIVE + 1,    /* I[RC_MAXACTIVE] index of the cached pair */
   X_ENVID = X_ACTIVE + RC_MAXACTIVE, /* I global environment id (RNG counter word 0) */
   X_UNION = (X_ENVID + 1 + 3) / 4 * 4,
@@ -887,12 +883,6 @@ __device__ __noinline__ void narrowphase(const Env E, int a, int b, V2 dab, Mani
 __device__ __noinline__ void collide_pair(const Env E, int i, int j) {
   int a = i, b = j;
   if (is_foot(a) && !is_foot(b)) { a = j; b = i; } /* cpCollide orders by primitive type */
-  if (b == a + 1 && !(a & 1) && b < 20) {
-    /* the two feet of one robot: their core segments are 20 apart (> 2 x 7.5) while the joints hold */
-    V2 d = pos_diff(E, b, a);
-    float da = __fadd_rn(__fsub_rn(E.f[RC_S_ANG + b], E.f[RC_S_ANG + a]), __fsub_rn(E.f[RC_S_ANGL + b], E.f[RC_S_ANGL + a]));
-    if (fabsf(d.x) + fabsf(d.y) < 2.f && fabsf(da) < 0.1f) return;
-  }
   Manifold m;
   V2 dab = pos_diff(E, b, a);
   narrowphase(E, a, b, dab, &m);
@@ -1013,12 +1003,174 @@ __device__ __noinline__ void contacts_iteration(const Env E) {
   }
 }
 
+/* ---- cold parts of space.step (pairs in contact): out of line, so that the contact-free substep --
+   the common case -- stays a short, instruction-cache resident piece of code */
+
+/* cached pairs that did not collide this substep: age, separate callbacks, expiry after 3 substeps
+   (cpSpaceArbiterSetFilter); lane = cached pair */
+__device__ __noinline__ void age_cached_pairs(const Env E) {
+  const int lane = E.lane;
+  int nArb = E.i[RC_S_NARB];
+  unsigned touched = (unsigned)E.i[X_TOUCHED];
+  int key = 0, con = 0;
+  float jn0 = 0, jt0 = 0, jn1 = 0, jt1 = 0;
+  bool have = lane < nArb;
+  bool keep = false, sep = false;
+  if (have) {
+    key = E.i[RC_S_ARBKEY + lane]; con = E.i[RC_S_ARBCON + lane];
+    jn0 = E.f[RC_S_ARBJN0 + lane]; jt0 = E.f[RC_S_ARBJT0 + lane];
+    jn1 = E.f[RC_S_ARBJN1 + lane]; jt1 = E.f[RC_S_ARBJT1 + lane];
+    keep = true;
+    if (!((touched >> lane) & 1)) {
+      int age = ((key >> 24) & 255) + 1;
+      int state = (key >> 16) & 255;
+      int a = key & 255, b = (key >> 8) & 255;
+      if (state != RC_ARB_CACHED) {
+        state = RC_ARB_CACHED;
+        sep = !(a == BALL); /* (Ball, Robot) and (Ball, Goalpost) have no separate handler */
+      }
+      key = a | (b << 8) | (state << 16) | (age << 24);
+      keep = age < 3;
+    }
+  }
+  unsigned sepmask = __ballot_sync(FULLMASK, sep);
+  unsigned keepmask = __ballot_sync(FULLMASK, keep);
+  if (sepmask && lane == 0) {
+    unsigned mk = sepmask;
+    while (mk) {
+      int k = __ffs(mk) - 1;
+      mk &= mk - 1;
+      int kk = E.i[RC_S_ARBKEY + k];
+      cb_separate(E, kk & 255, (kk >> 8) & 255);
+    }
+  }
+  __syncwarp();
+  int newIdx = __popc(keepmask & ((1u << lane) - 1));
+  if (keep) {
+    E.i[RC_S_ARBKEY + newIdx] = key; E.i[RC_S_ARBCON + newIdx] = con;
+    E.f[RC_S_ARBJN0 + newIdx] = jn0; E.f[RC_S_ARBJT0 + newIdx] = jt0;
+    E.f[RC_S_ARBJN1 + newIdx] = jn1; E.f[RC_S_ARBJT1 + newIdx] = jt1;
+  }
+  int nact = E.i[X_NACTIVE];
+  int myActive = lane < nact ? E.i[X_ACTIVE + lane] : 0;
+  int remapped = __shfl_sync(FULLMASK, newIdx, myActive);
+  __syncwarp();
+  if (lane < nact) E.i[X_ACTIVE + lane] = remapped;
+  if (lane == 0) E.i[RC_S_NARB] = __popc(keepmask);
+  if (have && lane >= __popc(keepmask)) { /* records stay canonical: unused slots are zero */
+    E.i[RC_S_ARBKEY + lane] = 0; E.i[RC_S_ARBCON + lane] = 0;
+    E.f[RC_S_ARBJN0 + lane] = 0.f; E.f[RC_S_ARBJT0 + lane] = 0.f;
+    E.f[RC_S_ARBJN1 + lane] = 0.f; E.f[RC_S_ARBJT1 + lane] = 0.f;
+  }
+  __syncwarp();
+}
+
+/* cpArbiterPreStep of the active contacts: lane = 2 * pair + contact */
+__device__ __noinline__ void prestep_contacts(const Env E, float biasCoef) {
+  const int lane = E.lane;
+  const int nact = E.i[X_NACTIVE];
+  const float slop = 0.1f;
+  int q = lane >> 1, c = lane & 1;
+  if (q < nact) {
+    int k = E.i[X_ACTIVE + q];
+    int key = E.i[RC_S_ARBKEY + k];
+    int ncon = E.i[RC_S_ARBCON + k] & 255;
+    if (c < ncon) {
+      int a = key & 255, b = (key >> 8) & 255;
+      V2 n = v2(E.f[X_ANX + q], E.f[X_ANY + q]);
+      V2 r1 = v2(E.f[X_CR1X + lane], E.f[X_CR1Y + lane]), r2 = v2(E.f[X_CR2X + lane], E.f[X_CR2Y + lane]);
+      float ami = body_minv(a), aii = body_iinv(a), bmi = body_minv(b), bii = body_iinv(b);
+      float r1cn = cross(r1, n), r2cn = cross(r2, n);
+      V2 t = v2(-n.y, n.x);
+      float r1ct = cross(r1, t), r2ct = cross(r2, t);
+      E.f[X_CNMASS + lane] = 1.f / (ami + aii * r1cn * r1cn + bmi + bii * r2cn * r2cn);
+      E.f[X_CTMASS + lane] = 1.f / (ami + aii * r1ct * r1ct + bmi + bii * r2ct * r2ct);
+      V2 bd = pos_diff(E, b, a);
+      float dist = dot(r2 - r1 + bd, n);
+      E.f[X_CBIAS + lane] = -biasCoef * fminf(0.f, dist + slop) / DT;
+      E.f[X_CJBIAS + lane] = 0.f;
+      float avx, avy, aw, bvx, bvy, bw, d0, d1, d2;
+      load_body(E, a, &avx, &avy, &aw, &d0, &d1, &d2);
+      load_body(E, b, &bvx, &bvy, &bw, &d0, &d1, &d2);
+      V2 vr = v2((bvx - r2.y * bw) - (avx - r1.y * aw), (bvy + r2.x * bw) - (avy + r1.x * aw));
+      E.f[X_CBOUNCE + lane] = dot(vr, n) * E.f[X_AE + q];
+    }
+  }
+  __syncwarp();
+}
+
+/* cached contact impulses re-applied in pair order (cpArbiterApplyCachedImpulse): lane 0 */
+__device__ __noinline__ void warm_start_contacts(const Env E, float dt_coef) {
+  if (E.lane == 0) {
+    const int nact = E.i[X_NACTIVE];
+    for (int q = 0; q < nact; q++) {
+      int k = E.i[X_ACTIVE + q];
+      int key = E.i[RC_S_ARBKEY + k];
+      if (((key >> 16) & 255) == RC_ARB_FIRST) continue;
+      int a = key & 255, b = (key >> 8) & 255;
+      int ncon = E.i[RC_S_ARBCON + k] & 255;
+      V2 n = v2(E.f[X_ANX + q], E.f[X_ANY + q]);
+      for (int c = 0; c < ncon; c++) {
+        int ci = 2 * q + c;
+        float jn = E.f[X_CJN + ci], jt = E.f[X_CJT + ci];
+        V2 j = v2(n.x * jn - n.y * jt, n.x * jt + n.y * jn) * dt_coef;
+        V2 r1 = v2(E.f[X_CR1X + ci], E.f[X_CR1Y + ci]), r2 = v2(E.f[X_CR2X + ci], E.f[X_CR2Y + ci]);
+        if (a < RC_NBODY) {
+          E.f[RC_S_VX + a] -= j.x * body_minv(a); E.f[RC_S_VY + a] -= j.y * body_minv(a);
+          E.f[RC_S_W + a] -= body_iinv(a) * cross(r1, j);
+        }
+        if (b < RC_NBODY) {
+          E.f[RC_S_VX + b] += j.x * body_minv(b); E.f[RC_S_VY + b] += j.y * body_minv(b);
+          E.f[RC_S_W + b] += body_iinv(b) * cross(r2, j);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+/* accumulated impulses back into the cached pairs, post-solve callbacks in pair order, deferred
+   space.add(joint) */
+__device__ __noinline__ void post_solve(const Env E) {
+  const int lane = E.lane;
+  const int nact = E.i[X_NACTIVE];
+  if (lane < nact) {
+    int k = E.i[X_ACTIVE + lane];
+    E.f[RC_S_ARBJN0 + k] = E.f[X_CJN + 2 * lane]; E.f[RC_S_ARBJT0 + k] = E.f[X_CJT + 2 * lane];
+    E.f[RC_S_ARBJN1 + k] = E.f[X_CJN + 2 * lane + 1]; E.f[RC_S_ARBJT1 + k] = E.f[X_CJT + 2 * lane + 1];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int q = 0; q < nact; q++) {
+      int key = E.i[RC_S_ARBKEY + E.i[X_ACTIVE + q]];
+      int a = key & 255, b = (key >> 8) & 255;
+      if (is_foot(a) && is_foot(b)) cb_robot_collision(E, a, b);
+      else if (a >= POST0 && is_foot(b)) cb_goalpost_collision(E, b, a);
+    }
+  }
+  __syncwarp();
+  if (lane < E.c->P) joint_add_now(E, lane);
+  __syncwarp();
+}
+
+/* candidate pairs of shape i (lanes j in `hits`), in ascending j: lane 0 */
+__device__ __noinline__ void collide_hits(const Env E, int i, unsigned hits) {
+  if (E.lane == 0) {
+    while (hits) {
+      int j = __ffs(hits) - 1;
+      hits &= hits - 1;
+      collide_pair(E, i, j);
+    }
+  }
+  __syncwarp();
+}
+
 __device__ __noinline__ void space_step(const Env E) {
   /* cpSpaceStep (Chipmunk2D 7.0.x), dt = 0.01 */
   const int lane = E.lane;
   const int P = E.c->P;
   const float dt = DT;
-  int prevStepped = E.i[RC_S_STEPPED];
+  const int prevStepped = E.i[RC_S_STEPPED];
   int nArb = E.i[RC_S_NARB];
   __syncwarp();
   if (lane == 0) {
@@ -1030,9 +1182,9 @@ __device__ __noinline__ void space_step(const Env E) {
     int key = E.i[RC_S_ARBKEY + lane];
     if (((key >> 16) & 255) == RC_ARB_FIRST) E.i[RC_S_ARBKEY + lane] = (key & ~0xff0000) | (RC_ARB_NORMAL << 16);
   }
-  /* integrate positions (cpBodyUpdatePosition), refresh shape geometry, bounding boxes in registers */
-  float bcx = 0, bcy = 0, bcr = 0; /* bounding circle of this lane's shape */
-  bool active = lane < NSHAPE && shape_active(E, lane);
+  /* integrate positions (cpBodyUpdatePosition), refresh shape geometry, bounding circles in registers */
+  float bcx = 0, bcy = 0, bcr = 0;
+  const bool active = lane < NSHAPE && shape_active(E, lane);
   if (lane <= BALL && active) {
     float px = E.f[RC_S_PX + lane], pxl = E.f[RC_S_PXL + lane];
     float py = E.f[RC_S_PY + lane], pyl = E.f[RC_S_PYL + lane];
@@ -1056,131 +1208,31 @@ __device__ __noinline__ void space_step(const Env E) {
   __syncwarp();
   /* collide: pairs in ascending (i, j) insertion order; lane j tests its bounding circle against shape i.
      (Chipmunk's bounding-box test is implied: shapes that touch have overlapping boxes; the margin
-     covers the float32 rounding of the absolute centres.) */
-  for (int i = 0; i <= BALL; i++) {
-    if (!shape_active(E, i)) continue;
-    float dx = __shfl_sync(FULLMASK, bcx, i) - bcx, dy = __shfl_sync(FULLMASK, bcy, i) - bcy;
-    float rr = __shfl_sync(FULLMASK, bcr, i) + bcr + 0.05f;
-    bool hit = active && lane > i && dx * dx + dy * dy < rr * rr;
-    unsigned hits = __ballot_sync(FULLMASK, hit);
-    if (hits) {
-      if (lane == 0) {
-        while (hits) {
-          int j = __ffs(hits) - 1;
-          hits &= hits - 1;
-          collide_pair(E, i, j);
-        }
-      }
-      __syncwarp();
+     covers the float32 rounding of the absolute centres.)  The two feet of one robot (j = i + 1, i even)
+     always pass this test; collide_pair rejects them cheaply while the joints hold. */
+  {
+    /* own-feet pairs only matter when the feet have come apart (kick) or turned against each other */
+    bool ownFeetApart = false;
+    if (lane < 2 * P && (lane & 1)) {
+      V2 d = pos_diff(E, lane, lane - 1);
+      float da = __fadd_rn(__fsub_rn(E.f[RC_S_ANG + lane], E.f[RC_S_ANG + lane - 1]), __fsub_rn(E.f[RC_S_ANGL + lane], E.f[RC_S_ANGL + lane - 1]));
+      ownFeetApart = !(fabsf(d.x) + fabsf(d.y) < 2.f && fabsf(da) < 0.1f);
+    }
+    const int nShapes = 2 * P;
+    for (int i = 0; i <= BALL; i++) {
+      if (i >= nShapes && i < BALL) continue;
+      float dx = __shfl_sync(FULLMASK, bcx, i) - bcx, dy = __shfl_sync(FULLMASK, bcy, i) - bcy;
+      float rr = __shfl_sync(FULLMASK, bcr, i) + bcr + 0.05f;
+      bool hit = active && lane > i && dx * dx + dy * dy < rr * rr;
+      if (hit && lane == i + 1 && (lane & 1) && lane < 20) hit = ownFeetApart;
+      unsigned hits = __ballot_sync(FULLMASK, hit);
+      if (hits) collide_hits(E, i, hits);
     }
   }
-  /* cached pairs that did not collide: age, separate callbacks, expiry after 3 substeps */
-  nArb = E.i[RC_S_NARB];
-  if (nArb) {
-    unsigned touched = (unsigned)E.i[X_TOUCHED];
-    int key = 0, con = 0;
-    float jn0 = 0, jt0 = 0, jn1 = 0, jt1 = 0;
-    bool have = lane < nArb;
-    bool keep = false, sep = false;
-    if (have) {
-      key = E.i[RC_S_ARBKEY + lane]; con = E.i[RC_S_ARBCON + lane];
-      jn0 = E.f[RC_S_ARBJN0 + lane]; jt0 = E.f[RC_S_ARBJT0 + lane];
-      jn1 = E.f[RC_S_ARBJN1 + lane]; jt1 = E.f[RC_S_ARBJT1 + lane];
-      keep = true;
-      if (!((touched >> lane) & 1)) {
-        int age = ((key >> 24) & 255) + 1;
-        int state = (key >> 16) & 255;
-        int a = key & 255, b = (key >> 8) & 255;
-        if (state != RC_ARB_CACHED) {
-          state = RC_ARB_CACHED;
-          sep = !(a == BALL); /* (Ball, Robot) and (Ball, Goalpost) have no separate handler */
-        }
-        key = a | (b << 8) | (state << 16) | (age << 24);
-        keep = age < 3;
-      }
-    }
-    unsigned sepmask = __ballot_sync(FULLMASK, sep);
-    unsigned keepmask = __ballot_sync(FULLMASK, keep);
-    if (sepmask) {
-      if (lane == 0) {
-        unsigned mk = sepmask;
-        while (mk) {
-          int k = __ffs(mk) - 1;
-          mk &= mk - 1;
-          int kk = E.i[RC_S_ARBKEY + k];
-          cb_separate(E, kk & 255, (kk >> 8) & 255);
-        }
-      }
-    }
-    __syncwarp();
-    int newIdx = __popc(keepmask & ((1u << lane) - 1));
-    if (keep) {
-      E.i[RC_S_ARBKEY + newIdx] = key; E.i[RC_S_ARBCON + newIdx] = con;
-      E.f[RC_S_ARBJN0 + newIdx] = jn0; E.f[RC_S_ARBJT0 + newIdx] = jt0;
-      E.f[RC_S_ARBJN1 + newIdx] = jn1; E.f[RC_S_ARBJT1 + newIdx] = jt1;
-    }
-    int nact = E.i[X_NACTIVE];
-    int myActive = lane < nact ? E.i[X_ACTIVE + lane] : 0;
-    int remapped = __shfl_sync(FULLMASK, newIdx, myActive);
-    __syncwarp();
-    if (lane < nact) E.i[X_ACTIVE + lane] = remapped;
-    if (lane == 0) E.i[RC_S_NARB] = __popc(keepmask);
-    if (have && lane >= __popc(keepmask)) { /* records stay canonical: unused slots are zero */
-      E.i[RC_S_ARBKEY + lane] = 0; E.i[RC_S_ARBCON + lane] = 0;
-      E.f[RC_S_ARBJN0 + lane] = 0.f; E.f[RC_S_ARBJT0 + lane] = 0.f;
-      E.f[RC_S_ARBJN1 + lane] = 0.f; E.f[RC_S_ARBJT1 + lane] = 0.f;
-    }
-    __syncwarp();
-  }
+  if (E.i[RC_S_NARB]) age_cached_pairs(E);
   const int nact = E.i[X_NACTIVE];
-  /* pre-step of the active contacts: lane = 2 * pair + contact */
-  const float slop = 0.1f;
   const float biasCoef = 6.1259606640e-02f; /* 1 - collisionBias^dt, collisionBias = 0.9^60 */
-  if (nact) {
-    int q = lane >> 1, c = lane & 1;
-    if (q < nact) {
-      int k = E.i[X_ACTIVE + q];
-      int key = E.i[RC_S_ARBKEY + k];
-      int ncon = E.i[RC_S_ARBCON + k] & 255;
-      if (c < ncon) {
-        int a = key & 255, b = (key >> 8) & 255;
-        V2 n = v2(E.f[X_ANX + q], E.f[X_ANY + q]);
-        V2 r1 = v2(E.f[X_CR1X + lane], E.f[X_CR1Y + lane]), r2 = v2(E.f[X_CR2X + lane], E.f[X_CR2Y + lane]);
-        float ami = body_minv(a), aii = body_iinv(a), bmi = body_minv(b), bii = body_iinv(b);
-        float r1cn = cross(r1, n), r2cn = cross(r2, n);
-        V2 t = v2(-n.y, n.x);
-        float r1ct = cross(r1, t), r2ct = cross(r2, t);
-        E.f[X_CNMASS + lane] = 1.f / (ami + aii * r1cn * r1cn + bmi + bii * r2cn * r2cn);
-        E.f[X_CTMASS + lane] = 1.f / (ami + aii * r1ct * r1ct + bmi + bii * r2ct * r2ct);
-        V2 bd = pos_diff(E, b, a);
-        float dist = dot(r2 - r1 + bd, n);
-        E.f[X_CBIAS + lane] = -biasCoef * fminf(0.f, dist + slop) / dt;
-        E.f[X_CJBIAS + lane] = 0.f;
-        float avx, avy, aw, bvx, bvy, bw, d0, d1, d2;
-        load_body(E, a, &avx, &avy, &aw, &d0, &d1, &d2);
-        load_body(E, b, &bvx, &bvy, &bw, &d0, &d1, &d2);
-        V2 vr = v2((bvx - r2.y * bw) - (avx - r1.y * aw), (bvy + r2.x * bw) - (avy + r1.x * aw));
-        E.f[X_CBOUNCE + lane] = dot(vr, n) * E.f[X_AE + q];
-      }
-    }
-    __syncwarp();
-  }
-#ifdef RC_DEBUG_PRINT
-  if (lane == 0 && nact && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT) {
-    for (int q = 0; q < nact; q++) {
-      int k = E.i[X_ACTIVE + q];
-      int key = E.i[RC_S_ARBKEY + k];
-      for (int c = 0; c < (E.i[RC_S_ARBCON + k] & 255); c++) {
-        int ci = 2 * q + c;
-        printf("GPU q%d (%d,%d) st%d c%d n=(%.7f,%.7f) r1=(%.6f,%.6f) r2=(%.6f,%.6f) nMass=%.4f tMass=%.4f bias=%.6f bounce=%.6f jn=%.3f jt=%.3f\n",
-               q, key & 255, (key >> 8) & 255, (key >> 16) & 255, c, E.f[X_ANX + q], E.f[X_ANY + q], E.f[X_CR1X + ci], E.f[X_CR1Y + ci],
-               E.f[X_CR2X + ci], E.f[X_CR2Y + ci], E.f[X_CNMASS + ci], E.f[X_CTMASS + ci], E.f[X_CBIAS + ci], E.f[X_CBOUNCE + ci],
-               E.f[X_CJN + ci], E.f[X_CJT + ci]);
-      }
-    }
-  }
-  __syncwarp();
-#endif
+  if (nact) prestep_contacts(E, biasCoef);
   /* joints pre-step (lane = robot): pivot with both anchors at the centres of gravity, rotary limit 0..0 */
   const int L = 2 * lane, R = 2 * lane + 1;
   const bool isRobot = lane < P;
@@ -1223,33 +1275,7 @@ __device__ __noinline__ void space_step(const Env E) {
   __syncwarp();
   /* warm start: cached contact impulses in pair order, then the joints */
   const float dt_coef = prevStepped ? 1.f : 0.f;
-  if (nact) {
-    if (lane == 0) {
-      for (int q = 0; q < nact; q++) {
-        int k = E.i[X_ACTIVE + q];
-        int key = E.i[RC_S_ARBKEY + k];
-        if (((key >> 16) & 255) == RC_ARB_FIRST) continue;
-        int a = key & 255, b = (key >> 8) & 255;
-        int ncon = E.i[RC_S_ARBCON + k] & 255;
-        V2 n = v2(E.f[X_ANX + q], E.f[X_ANY + q]);
-        for (int c = 0; c < ncon; c++) {
-          int ci = 2 * q + c;
-          float jn = E.f[X_CJN + ci], jt = E.f[X_CJT + ci];
-          V2 j = v2(n.x * jn - n.y * jt, n.x * jt + n.y * jn) * dt_coef;
-          V2 r1 = v2(E.f[X_CR1X + ci], E.f[X_CR1Y + ci]), r2 = v2(E.f[X_CR2X + ci], E.f[X_CR2Y + ci]);
-          if (a < RC_NBODY) {
-            E.f[RC_S_VX + a] -= j.x * body_minv(a); E.f[RC_S_VY + a] -= j.y * body_minv(a);
-            E.f[RC_S_W + a] -= body_iinv(a) * cross(r1, j);
-          }
-          if (b < RC_NBODY) {
-            E.f[RC_S_VX + b] += j.x * body_minv(b); E.f[RC_S_VY + b] += j.y * body_minv(b);
-            E.f[RC_S_W + b] += body_iinv(b) * cross(r2, j);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
+  if (nact) warm_start_contacts(E, dt_coef);
   float lvx = 0, lvy = 0, lw = 0, rvx = 0, rvy = 0, rw = 0;
   if (isRobot) {
     lvx = E.f[RC_S_VX + L]; lvy = E.f[RC_S_VY + L]; lw = E.f[RC_S_W + L];
@@ -1265,6 +1291,7 @@ __device__ __noinline__ void space_step(const Env E) {
   }
   /* solver: 10 iterations of {all contacts in order, then all joints}; without contacts the
      joints of different robots are independent and iterate in registers */
+#pragma unroll 1
   for (int it = 0; it < 10; it++) {
     if (nact) {
       if (isRobot) {
@@ -1272,37 +1299,26 @@ __device__ __noinline__ void space_step(const Env E) {
         E.f[RC_S_VX + R] = rvx; E.f[RC_S_VY + R] = rvy; E.f[RC_S_W + R] = rw;
       }
       __syncwarp();
-#ifdef RC_DEBUG_PRINT
-      if (lane == 0 && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT && (it < 2))
-        for (int b = 4; b < 10; b++) printf("GPU it%d pre-contacts body %d v=(%.6f,%.6f) w=%.6f\n", it, b, E.f[RC_S_VX + b], E.f[RC_S_VY + b], E.f[RC_S_W + b]);
-#endif
       if (lane == 0) contacts_iteration(E);
       __syncwarp();
-#ifdef RC_DEBUG_PRINT
-      if (lane == 0 && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT && (it < 2))
-        for (int b = 4; b < 10; b++) printf("GPU it%d post-contacts body %d v=(%.6f,%.6f) w=%.6f\n", it, b, E.f[RC_S_VX + b], E.f[RC_S_VY + b], E.f[RC_S_W + b]);
-      if (isRobot && lane >= 2 && lane < 5 && (uint32_t)E.i[X_ENVID] == RC_DEBUG_PRINT && it < 2) printf("GPU it%d robot %d pivOn %d pivB=(%.6f,%.6f) rotBias=%.6f pivJ=(%.3f,%.3f) rotJ=%.3f\n", it, lane, (int)pivOn, pivBx, pivBy, rotBias, pivJx, pivJy, rotJ);
-#endif
       if (isRobot) {
         lvx = E.f[RC_S_VX + L]; lvy = E.f[RC_S_VY + L]; lw = E.f[RC_S_W + L];
         rvx = E.f[RC_S_VX + R]; rvy = E.f[RC_S_VY + R]; rw = E.f[RC_S_W + R];
       }
     }
-    if (isRobot) {
-      if (pivOn) { /* cpPivotJoint applyImpulse, r1 = r2 = 0 */
-        float jx = pivK * (pivBx - (rvx - lvx)), jy = pivK * (pivBy - (rvy - lvy));
-        pivJx += jx; pivJy += jy;
-        lvx -= jx * FOOT_MINV; lvy -= jy * FOOT_MINV;
-        rvx += jx * FOOT_MINV; rvy += jy * FOOT_MINV;
-      }
-      if (rotBias != 0) { /* cpRotaryLimitJoint applyImpulse */
-        float j = -(rotBias + (rw - lw)) * rotISum;
-        float jOld = rotJ;
-        rotJ = rotBias < 0 ? fmaxf(jOld + j, 0.f) : fminf(jOld + j, 0.f);
-        j = rotJ - jOld;
-        lw -= j * FOOT_IINV;
-        rw += j * FOOT_IINV;
-      }
+    if (pivOn) { /* cpPivotJoint applyImpulse, r1 = r2 = 0 */
+      float jx = pivK * (pivBx - (rvx - lvx)), jy = pivK * (pivBy - (rvy - lvy));
+      pivJx += jx; pivJy += jy;
+      lvx -= jx * FOOT_MINV; lvy -= jy * FOOT_MINV;
+      rvx += jx * FOOT_MINV; rvy += jy * FOOT_MINV;
+    }
+    if (rotBias != 0) { /* cpRotaryLimitJoint applyImpulse */
+      float j = -(rotBias + (rw - lw)) * rotISum;
+      float jOld = rotJ;
+      rotJ = rotBias < 0 ? fmaxf(jOld + j, 0.f) : fminf(jOld + j, 0.f);
+      j = rotJ - jOld;
+      lw -= j * FOOT_IINV;
+      rw += j * FOOT_IINV;
     }
   }
   if (isRobot) {
@@ -1311,28 +1327,7 @@ __device__ __noinline__ void space_step(const Env E) {
     E.f[RC_S_PIVJX + lane] = pivJx; E.f[RC_S_PIVJY + lane] = pivJy; E.f[RC_S_ROTJ + lane] = rotJ;
   }
   __syncwarp();
-  if (nact) {
-    /* accumulated contact impulses back into the cached pairs */
-    int q = lane;
-    if (q < nact) {
-      int k = E.i[X_ACTIVE + q];
-      E.f[RC_S_ARBJN0 + k] = E.f[X_CJN + 2 * q]; E.f[RC_S_ARBJT0 + k] = E.f[X_CJT + 2 * q];
-      E.f[RC_S_ARBJN1 + k] = E.f[X_CJN + 2 * q + 1]; E.f[RC_S_ARBJT1 + k] = E.f[X_CJT + 2 * q + 1];
-    }
-    __syncwarp();
-    /* post-solve callbacks, active pairs in order; joints re-added from callbacks take effect now */
-    if (lane == 0) {
-      for (int q2 = 0; q2 < nact; q2++) {
-        int key = E.i[RC_S_ARBKEY + E.i[X_ACTIVE + q2]];
-        int a = key & 255, b = (key >> 8) & 255;
-        if (is_foot(a) && is_foot(b)) cb_robot_collision(E, a, b);
-        else if (a >= POST0 && is_foot(b)) cb_goalpost_collision(E, b, a);
-      }
-    }
-    __syncwarp();
-    if (isRobot) joint_add_now(E, lane);
-    __syncwarp();
-  }
+  if (nact) post_solve(E);
 }
 
 /* ================================================================= observations */
@@ -1925,23 +1920,28 @@ __device__ __noinline__ void fill_info(const Env E, float* info_env) {
 }
 
 __device__ __forceinline__ void clear_step_scratch(const Env E) {
-  for (int w = X_REW + E.lane; w < X_NACTIVE + 1; w += 32) E.i[w] = 0;
+  for (int w = RC_S_STEP_REW + E.lane; w < RC_S_STEP_END; w += 32) E.i[w] = 0;
   __syncwarp();
 }
 
-/* RoboCupEnvironment.step: RoboCupEnvironment.py:446-524 */
-__device__ __noinline__ void step_env(const Env E, const float* actions_env, float* obs_env, float* full_env, float* info_env) {
-  const int lane = E.lane;
-  const int P = E.c->P;
-  clear_step_scratch(E);
-  for (int sub = E.c->sub_begin; sub < E.c->sub_end; sub++) {
+/* RoboCupEnvironment.step (RoboCupEnvironment.py:446-524) is a sequence of launches: blocks of substeps
+   [b, e) that end at an observation tick, the tick's observations, and the finish.  The phases are
+   separate kernels because each one's hot code then fits the SM's instruction cache; fused into one
+   kernel the warps of an SM sit in different phases and the step is instruction-fetch bound. */
+__device__ __forceinline__ void phys_substeps(const Env E, const float* actions_env, int sub_b, int sub_e, bool first) {
+  if (first) clear_step_scratch(E);
+  for (int sub = sub_b; sub < sub_e; sub++) {
     robots_phase(E, sub, actions_env);
     ball_out_of_field(E);
     space_step(E);
-    if (lane == 0) E.i[RC_S_ELAPSED] += 1;
+    if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
     __syncwarp();
-    if (sub % 10 == 9) observe_tick(E, sub / 10, (uint32_t)E.i[RC_S_ELAPSED], obs_env, full_env);
   }
+}
+
+__device__ __forceinline__ void finish_step(const Env E, float* info_env) {
+  const int lane = E.lane;
+  const int P = E.c->P;
   /* processSeens (:1563-1575) and reward assembly (:499-509) */
   if (lane < P) {
     float obsRew = 0.f;

@@ -171,7 +171,18 @@ enum {
   RC_S_ANGL = RC_S_PYL + RC_NBODY,
   RC_S_INITXL = RC_S_ANGL + RC_NBODY,   /* F [RC_MAXP] */
   RC_S_INITYL = RC_S_INITXL + RC_MAXP,
-  RC_STATE_WORDS_RAW = RC_S_INITYL + RC_MAXP,
+  /* accumulators of the step in flight: a step is a sequence of kernel launches (substep blocks,
+     observation ticks, finish), which hand these over through the record.  Zeroed at the first
+     substep of a step; meaningless between steps (the oracle leaves them 0). */
+  RC_S_STEP_REW = RC_S_INITYL + RC_MAXP,        /* F [RC_MAXP] robotRewards so far            */
+  RC_S_STEP_POSREW = RC_S_STEP_REW + RC_MAXP,   /* F [RC_MAXP] robotPosRewards                */
+  RC_S_STEP_TEAMREW = RC_S_STEP_POSREW + RC_MAXP, /* F [2] teamRewards                        */
+  RC_S_STEP_DIAG = RC_S_STEP_TEAMREW + 2,       /* I RC_IF_* flags                            */
+  RC_S_STEP_LSUM = RC_S_STEP_DIAG + 1,          /* I [RC_MAXP] sum over ticks of numLandMarks */
+  RC_S_STEP_BSUM = RC_S_STEP_LSUM + RC_MAXP,    /* I [RC_MAXP] sum of ballsSeen               */
+  RC_S_STEP_RSEEN = RC_S_STEP_BSUM + RC_MAXP,   /* I [RC_MAXP][RC_MAXP-1] sum of robotsSeen   */
+  RC_S_STEP_END = RC_S_STEP_RSEEN + RC_MAXP * (RC_MAXP - 1),
+  RC_STATE_WORDS_RAW = RC_S_STEP_END,
   RC_STATE_WORDS = (RC_STATE_WORDS_RAW + 31) / 32 * 32 /* records start 128-byte aligned */
 };
 
