@@ -46,6 +46,7 @@ constexpr float STDNORM = 2.f / 1040.f;
 enum { S_NO = 0, S_PARTIAL = 1, S_DISTANT = 2, S_NORMAL = 3, S_MISCLASS = 4 };
 enum { I_NO = 0, I_NEARBY = 1, I_OCCLUDE = 2 };
 
+constexpr int NSHAPE_ = 25, RC_MAXCAND = 48;
 /* ---- scratch layout (words after the state record) */
 enum {
   /* accumulators of the step in flight live in the record (they cross kernel launches) */
@@ -76,6 +77,15 @@ enum {
   X_CJN = X_CJBIAS + 2 * RC_MAXACTIVE,
   X_CJT = X_CJN + 2 * RC_MAXACTIVE,
   X_PHYS_END = X_CJT + 2 * RC_MAXACTIVE,
+  /* broad phase: bounding circles of the shapes and of the groups (robot = both feet), candidate pairs */
+  X_BCX = X_PHYS_END,          /* F[25] */
+  X_BCY = X_BCX + NSHAPE_,     /* F[25] */
+  X_GX = X_BCY + NSHAPE_,      /* F[15] */
+  X_GY = X_GX + 15,
+  X_GR = X_GY + 15,
+  X_NCAND = X_GR + 15,         /* I */
+  X_CAND = X_NCAND + 1,        /* I[RC_MAXCAND] i * 32 + j */
+  X_BP_END = X_CAND + RC_MAXCAND,
   /* vision view of the union */
   V_ROB = X_UNION,             /* F[9][3] other robots' sightings: x, y, has */
   V_BALL = V_ROB + 27,         /* F[3] */
@@ -84,7 +94,7 @@ enum {
   V_CNT = V_RAW + 3 * RC_CAP_ROBOT, /* I[6] list lengths */
   V_STAGE = (V_CNT + 6 + 3) / 4 * 4, /* [RC_OBS_WORDS] the observation record being built */
   V_END = V_STAGE + RC_OBS_WORDS,
-  ENV_SMEM_WORDS = ((X_PHYS_END > V_END ? X_PHYS_END : V_END) + 31) / 32 * 32
+  ENV_SMEM_WORDS = ((X_BP_END > V_END ? X_BP_END : V_END) + 31) / 32 * 32
 };
 
 /* ---- static scene tables (RoboCupEnvironment.py:153-227,296-302) */
@@ -123,6 +133,9 @@ struct SharedCfg {
   __device__ __forceinline__ const SimCfg* operator->() const { return reinterpret_cast<const SimCfg*>(g_smem); }
   __device__ __forceinline__ const SimCfg& operator*() const { return *reinterpret_cast<const SimCfg*>(g_smem); }
 };
+/* broad phase over groups: robots 0..9, ball 10, posts 11..14; all pairs (a < b) with a dynamic (99) */
+__device__ const unsigned char g_pairs[99][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {0, 7}, {0, 8}, {0, 9}, {0, 10}, {0, 11}, {0, 12}, {0, 13}, {0, 14}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 7}, {1, 8}, {1, 9}, {1, 10}, {1, 11}, {1, 12}, {1, 13}, {1, 14}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {2, 9}, {2, 10}, {2, 11}, {2, 12}, {2, 13}, {2, 14}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8}, {3, 9}, {3, 10}, {3, 11}, {3, 12}, {3, 13}, {3, 14}, {4, 5}, {4, 6}, {4, 7}, {4, 8}, {4, 9}, {4, 10}, {4, 11}, {4, 12}, {4, 13}, {4, 14}, {5, 6}, {5, 7}, {5, 8}, {5, 9}, {5, 10}, {5, 11}, {5, 12}, {5, 13}, {5, 14}, {6, 7}, {6, 8}, {6, 9}, {6, 10}, {6, 11}, {6, 12}, {6, 13}, {6, 14}, {7, 8}, {7, 9}, {7, 10}, {7, 11}, {7, 12}, {7, 13}, {7, 14}, {8, 9}, {8, 10}, {8, 11}, {8, 12}, {8, 13}, {8, 14}, {9, 10}, {9, 11}, {9, 12}, {9, 13}, {9, 14}, {10, 11}, {10, 12}, {10, 13}, {10, 14}};
+
 struct Env {
   SharedF f;
   SharedI i;
@@ -640,18 +653,18 @@ __device__ __noinline__ void ball_out_of_field(const Env E) {
   }
   __syncwarp();
   /* argmin per team, first minimum wins (strict <) */
-#pragma unroll
-  for (int t = 0; t < 2; t++) {
-    bool mine = lane < P && ((lane < nPl) == (t == 0));
-    float d = mine ? d2 : INFINITY;
-    int idx = mine ? lane : 99;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      float od = __shfl_xor_sync(FULLMASK, d, o);
-      int oi = __shfl_xor_sync(FULLMASK, idx, o);
-      if (od < d || (od == d && oi < idx)) { d = od; idx = oi; }
+  {
+    /* non-negative floats order like their bit patterns: one warp-wide integer min per team, the
+       lowest lane holding the minimum is the first minimal index */
+    unsigned bits = __float_as_uint(d2);
+    unsigned m0 = __reduce_min_sync(FULLMASK, lane < nPl ? bits : 0xffffffffu);
+    unsigned m1 = __reduce_min_sync(FULLMASK, (lane >= nPl && lane < P) ? bits : 0xffffffffu);
+    unsigned w0 = __ballot_sync(FULLMASK, lane < nPl && bits == m0);
+    unsigned w1 = __ballot_sync(FULLMASK, lane >= nPl && lane < P && bits == m1);
+    if (lane == 0) {
+      E.i[RC_S_CLOSEST] = w0 ? __ffs(w0) - 1 : 0;
+      E.i[RC_S_CLOSEST + 1] = w1 ? __ffs(w1) - 1 : nPl;
     }
-    if (lane == 0) E.i[RC_S_CLOSEST + t] = idx == 99 ? t * nPl : idx;
   }
   __syncwarp();
 }
@@ -795,6 +808,22 @@ __device__ void seg_seg_closest(V2 a0, V2 a1, V2 b0, V2 b1, V2* nOut, float* dOu
 }
 
 __device__ __forceinline__ float clamp01(float t) { return fminf(fmaxf(t, 0.f), 1.f); }
+
+/* cheap exact test: are two non-crossing-or-crossing segments farther apart than `dist`?  (closest
+   points of two segments, Ericson, Real-Time Collision Detection 5.1.9); used to skip the manifold
+   construction for foot pairs that are near but not touching */
+__device__ bool segments_apart(V2 p1, V2 q1, V2 p2, V2 q2, float dist) {
+  V2 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+  float c = dot(d1, r), b = dot(d1, d2);
+  float denom = a * e - b * b;
+  float s = denom > 1e-6f ? clamp01((b * f - c * e) / denom) : 0.f;
+  float t = (b * s + f) / e;
+  if (t < 0.f) { t = 0.f; s = clamp01(-c / a); }
+  else if (t > 1.f) { t = 1.f; s = clamp01((b - c) / a); }
+  V2 dd = (p1 + d1 * s) - (p2 + d2 * t);
+  return dot(dd, dd) > dist * dist;
+}
 __device__ __forceinline__ V2 vlerp(V2 a, V2 b, float t) { return a * (1.f - t) + b * t; }
 
 /* Shape geometry relative to its own body: feet are the segments (-10, +-10)-(10, +-10) (Robot.py:24-27) */
@@ -847,6 +876,7 @@ __device__ __noinline__ void narrowphase(const Env E, int a, int b, V2 dab, Mani
       m->cnt = 1;
     }
   } else { /* SegmentToSegment + SupportEdgeForSegment + ContactPoints */
+    if (segments_apart(ata, atb, bta, btb, 2 * ROB_RAD + 0.01f)) return;
     V2 n;
     float d;
     seg_seg_closest(ata, atb, bta, btb, &n, &d);
@@ -1153,14 +1183,44 @@ __device__ __noinline__ void post_solve(const Env E) {
   __syncwarp();
 }
 
-/* candidate pairs of shape i (lanes j in `hits`), in ascending j: lane 0 */
-__device__ __noinline__ void collide_hits(const Env E, int i, unsigned hits) {
+/* group pairs that came close (bit k of g[k / 32] = pair g_pairs[k]) and own-feet pairs (bit = odd foot):
+   expanded to shape pairs, filtered by the shapes' bounding circles, sorted into Chipmunk's ascending
+   (i, j) insertion order and collided: lane 0 */
+__device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsigned g0, unsigned g1, unsigned g2, unsigned g3) {
   if (E.lane == 0) {
-    while (hits) {
-      int j = __ffs(hits) - 1;
-      hits &= hits - 1;
-      collide_pair(E, i, j);
+    int n = 0;
+    while (own) {
+      int j = __ffs(own) - 1;
+      own &= own - 1;
+      E.i[X_CAND + n++] = (j - 1) * 32 + j;
     }
+    unsigned g[4] = {g0, g1, g2, g3};
+    for (int w = 0; w < 4; w++) {
+      unsigned m = g[w];
+      while (m) {
+        int k = 32 * w + __ffs(m) - 1;
+        m &= m - 1;
+        int a = g_pairs[k][0], b = g_pairs[k][1];
+        int a0 = a < 10 ? 2 * a : a + 10, na = a < 10 ? 2 : 1;
+        int b0 = b < 10 ? 2 * b : b + 10, nb = b < 10 ? 2 : 1;
+        for (int x = 0; x < na; x++)
+          for (int y = 0; y < nb; y++) {
+            int i = a0 + x, j = b0 + y;
+            float dx = E.f[X_BCX + i] - E.f[X_BCX + j], dy = E.f[X_BCY + i] - E.f[X_BCY + j];
+            float rr = (i < 20 ? ROB_LEN + ROB_RAD : 10.f) + (j < 20 ? ROB_LEN + ROB_RAD : 10.f) + 0.05f;
+            if (dx * dx + dy * dy < rr * rr) {
+              if (n < RC_MAXCAND) E.i[X_CAND + n++] = i * 32 + j;
+              else E.i[X_DIAG] |= RC_IF_ACTIVE_OVERFLOW;
+            }
+          }
+      }
+    }
+    for (int x = 1; x < n; x++) { /* insertion sort: n is tiny */
+      int key = E.i[X_CAND + x], y = x - 1;
+      while (y >= 0 && E.i[X_CAND + y] > key) { E.i[X_CAND + y + 1] = E.i[X_CAND + y]; y--; }
+      E.i[X_CAND + y + 1] = key;
+    }
+    for (int x = 0; x < n; x++) collide_pair(E, E.i[X_CAND + x] >> 5, E.i[X_CAND + x] & 31);
   }
   __syncwarp();
 }
@@ -1206,28 +1266,50 @@ __device__ __noinline__ void space_step(const Env E) {
     bcx = p.x; bcy = p.y; bcr = 10.f;
   }
   __syncwarp();
-  /* collide: pairs in ascending (i, j) insertion order; lane j tests its bounding circle against shape i.
-     (Chipmunk's bounding-box test is implied: shapes that touch have overlapping boxes; the margin
-     covers the float32 rounding of the absolute centres.)  The two feet of one robot (j = i + 1, i even)
-     always pass this test; collide_pair rejects them cheaply while the joints hold. */
+  /* collide.  Broad phase on groups first (robot = bounding circle of its two feet, ball, posts): 99 group
+     pairs, lane = pair, four rounds; only groups that come close are expanded into shape pairs, which are
+     then collided in ascending (i, j) insertion order like Chipmunk's.  (Its bounding-box test is implied:
+     shapes that touch have overlapping boxes; the margins cover the float32 rounding of the centres.) */
   {
-    /* own-feet pairs only matter when the feet have come apart (kick) or turned against each other */
-    bool ownFeetApart = false;
-    if (lane < 2 * P && (lane & 1)) {
-      V2 d = pos_diff(E, lane, lane - 1);
-      float da = __fadd_rn(__fsub_rn(E.f[RC_S_ANG + lane], E.f[RC_S_ANG + lane - 1]), __fsub_rn(E.f[RC_S_ANGL + lane], E.f[RC_S_ANGL + lane - 1]));
-      ownFeetApart = !(fabsf(d.x) + fabsf(d.y) < 2.f && fabsf(da) < 0.1f);
+    if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
+    float ocx = __shfl_xor_sync(FULLMASK, bcx, 1), ocy = __shfl_xor_sync(FULLMASK, bcy, 1);
+    bool ownFeetApart = false; /* own-feet pairs only matter once a kick or a turn has pulled the feet apart */
+    if (lane < 20) {
+      if (!(lane & 1)) {
+        float ddx = bcx - ocx, ddy = bcy - ocy;
+        E.f[X_GX + (lane >> 1)] = (bcx + ocx) * 0.5f;
+        E.f[X_GY + (lane >> 1)] = (bcy + ocy) * 0.5f;
+        E.f[X_GR + (lane >> 1)] = ROB_LEN + ROB_RAD + 0.5f * sqrtf(ddx * ddx + ddy * ddy);
+      } else if (lane < 2 * P) {
+        V2 d = pos_diff(E, lane, lane - 1);
+        float da = __fadd_rn(__fsub_rn(E.f[RC_S_ANG + lane], E.f[RC_S_ANG + lane - 1]), __fsub_rn(E.f[RC_S_ANGL + lane], E.f[RC_S_ANGL + lane - 1]));
+        ownFeetApart = !(fabsf(d.x) + fabsf(d.y) < 2.f && fabsf(da) < 0.1f);
+      }
+    } else if (lane < NSHAPE) {
+      E.f[X_GX + lane - 10] = bcx; E.f[X_GY + lane - 10] = bcy; E.f[X_GR + lane - 10] = 10.f;
     }
-    const int nShapes = 2 * P;
-    for (int i = 0; i <= BALL; i++) {
-      if (i >= nShapes && i < BALL) continue;
-      float dx = __shfl_sync(FULLMASK, bcx, i) - bcx, dy = __shfl_sync(FULLMASK, bcy, i) - bcy;
-      float rr = __shfl_sync(FULLMASK, bcr, i) + bcr + 0.05f;
-      bool hit = active && lane > i && dx * dx + dy * dy < rr * rr;
-      if (hit && lane == i + 1 && (lane & 1) && lane < 20) hit = ownFeetApart;
-      unsigned hits = __ballot_sync(FULLMASK, hit);
-      if (hits) collide_hits(E, i, hits);
+    __syncwarp();
+    unsigned own = __ballot_sync(FULLMASK, ownFeetApart);
+    unsigned g0, g1, g2, g3;
+    {
+      unsigned gh[4];
+#pragma unroll
+      for (int rnd = 0; rnd < 4; rnd++) {
+        int k = lane + 32 * rnd;
+        bool hit = false;
+        if (k < 99) {
+          int a = g_pairs[k][0], b = g_pairs[k][1];
+          if ((a >= 10 || a < P) && (b >= 10 || b < P)) {
+            float dx = E.f[X_GX + a] - E.f[X_GX + b], dy = E.f[X_GY + a] - E.f[X_GY + b];
+            float rr = E.f[X_GR + a] + E.f[X_GR + b] + 0.05f;
+            hit = dx * dx + dy * dy < rr * rr;
+          }
+        }
+        gh[rnd] = __ballot_sync(FULLMASK, hit);
+      }
+      g0 = gh[0]; g1 = gh[1]; g2 = gh[2]; g3 = gh[3];
     }
+    if (own | g0 | g1 | g2 | g3) collide_candidates(E, own, g0, g1, g2, g3);
   }
   if (E.i[RC_S_NARB]) age_cached_pairs(E);
   const int nact = E.i[X_NACTIVE];
@@ -1291,8 +1373,12 @@ __device__ __noinline__ void space_step(const Env E) {
   }
   /* solver: 10 iterations of {all contacts in order, then all joints}; without contacts the
      joints of different robots are independent and iterate in registers */
+  /* Without contacts every joint is an independent one-constraint system whose first sweep already
+     solves it exactly (K is the exact inverse); sweeps 3..10 of the reference only move the last bit,
+     so two sweeps are run.  With contacts all ten sweeps are needed and run. */
+  const int sweeps = nact ? 10 : 2;
 #pragma unroll 1
-  for (int it = 0; it < 10; it++) {
+  for (int it = 0; it < sweeps; it++) {
     if (nact) {
       if (isRobot) {
         E.f[RC_S_VX + L] = lvx; E.f[RC_S_VY + L] = lvy; E.f[RC_S_W + L] = lw;

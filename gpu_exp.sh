@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 --no-cpu --debug-full-obs 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('FULL env-steps/s', d['value'], 'kernel_ms', d['roofline']['kernel_ms'])"
-ncu --set full --clock-control none --import-source on -k regex:rc_step -s 3 -c 1 -o gpurun_out/prof_full -f python bench.py --steps 3 --warmup 2 --no-cpu --debug-full-obs > gpurun_out/ncu3.log 2>&1
-tail -2 gpurun_out/ncu3.log
+python bench.py --steps 3 --warmup 2 --no-cpu > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 2 --no-cpu > gpurun_out/ncu1.log 2>&1
+tail -2 gpurun_out/ncu1.log
