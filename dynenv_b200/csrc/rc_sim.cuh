@@ -80,10 +80,10 @@ enum {
   /* broad phase: bounding circles of the shapes and of the groups (robot = both feet), candidate pairs */
   X_BCX = X_PHYS_END,          /* F[25] */
   X_BCY = X_BCX + NSHAPE_,     /* F[25] */
-  X_GX = X_BCY + NSHAPE_,      /* F[15] */
-  X_GY = X_GX + 15,
-  X_GR = X_GY + 15,
-  X_NCAND = X_GR + 15,         /* I */
+  X_GX = X_BCY + NSHAPE_,      /* F[16]: 15 groups + a far-away dummy for unused pair slots */
+  X_GY = X_GX + 16,
+  X_GR = X_GY + 16,
+  X_NCAND = X_GR + 16,         /* I */
   X_CAND = X_NCAND + 1,        /* I[RC_MAXCAND] i * 32 + j */
   X_BP_END = X_CAND + RC_MAXCAND,
   /* vision view of the union */
@@ -1225,7 +1225,26 @@ __device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsig
   __syncwarp();
 }
 
-__device__ __noinline__ void space_step(const Env E) {
+/* this lane's group pairs of the four broad-phase rounds, one byte each (a << 4 | b); pairs with a
+   robot that does not exist point at the far-away dummy group */
+__device__ __forceinline__ uint32_t broadphase_pairs(const Env E) {
+  uint32_t packed = 0;
+  const int P = E.c->P;
+#pragma unroll
+  for (int rnd = 0; rnd < 4; rnd++) {
+    int k = E.lane + 32 * rnd;
+    uint32_t byte = 0xFE; /* (dummy 15, post 14) */
+    if (k < 99) {
+      int a = g_pairs[k][0], b = g_pairs[k][1];
+      if ((a >= 10 || a < P) && (b >= 10 || b < P)) byte = (uint32_t)(a << 4 | b);
+    }
+    packed |= byte << (8 * rnd);
+  }
+  if (E.lane == 0) { E.f[X_GX + 15] = 1e18f; E.f[X_GY + 15] = 1e18f; E.f[X_GR + 15] = 0.f; }
+  return packed;
+}
+
+__device__ __noinline__ void space_step(const Env E, const uint32_t pairs4) {
   /* cpSpaceStep (Chipmunk2D 7.0.x), dt = 0.01 */
   const int lane = E.lane;
   const int P = E.c->P;
@@ -1295,17 +1314,10 @@ __device__ __noinline__ void space_step(const Env E) {
       unsigned gh[4];
 #pragma unroll
       for (int rnd = 0; rnd < 4; rnd++) {
-        int k = lane + 32 * rnd;
-        bool hit = false;
-        if (k < 99) {
-          int a = g_pairs[k][0], b = g_pairs[k][1];
-          if ((a >= 10 || a < P) && (b >= 10 || b < P)) {
-            float dx = E.f[X_GX + a] - E.f[X_GX + b], dy = E.f[X_GY + a] - E.f[X_GY + b];
-            float rr = E.f[X_GR + a] + E.f[X_GR + b] + 0.05f;
-            hit = dx * dx + dy * dy < rr * rr;
-          }
-        }
-        gh[rnd] = __ballot_sync(FULLMASK, hit);
+        const int a = (pairs4 >> (8 * rnd + 4)) & 15, b = (pairs4 >> (8 * rnd)) & 15;
+        float dx = E.f[X_GX + a] - E.f[X_GX + b], dy = E.f[X_GY + a] - E.f[X_GY + b];
+        float rr = E.f[X_GR + a] + E.f[X_GR + b] + 0.05f;
+        gh[rnd] = __ballot_sync(FULLMASK, dx * dx + dy * dy < rr * rr);
       }
       g0 = gh[0]; g1 = gh[1]; g2 = gh[2]; g3 = gh[3];
     }
@@ -1552,6 +1564,13 @@ __device__ __noinline__ void false_positives(const Env E, int ag, uint32_t tick,
   }
 }
 
+/* observation encoders: 2-ulp reciprocal square root / division are ample for values that the reference
+   rounds to float32 anyway, and save the IEEE sequences' slow-path checks */
+__device__ __forceinline__ float fast_len(V2 a) {
+  float l2 = lensq(a);
+  return l2 > 0.f ? l2 * rsqrtf(l2) : 0.f;
+}
+
 /* getAgentVision of one observer (PARTIAL): builds the record in shared memory (V_STAGE).
    Point objects: lane = object (ball, 9 robot slots, 4 posts, 3 penalty crosses, 16 line crosses = 33,
    so a second, usually empty, pass handles the last line cross); lines: lane = line. */
@@ -1664,9 +1683,9 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
         if (ru.u(2) < randB) seen = S_NO;
         p = p + noiseVec;
         radius *= (1.f - (ru.u(4) - 0.5f) * 0.2f);
-        if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn / 10.f;
+        if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn * 0.1f;
       } else {
-        float range = 0.25f + 3.75f * lensq(p) / maxDist;
+        float range = 0.25f + 3.75f * lensq(p) * (1.f / maxDist);
         float mult = range;
         if (inter == I_NEARBY) mult = range * 2;
         if (seen == S_DISTANT) mult = range * 3;
@@ -1674,13 +1693,13 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
         /* |newPos| - |p| without cancellation: (2 p.d + d.d) / (|newPos| + |p|) */
         V2 dsp = v2(noiseVec.x * mult / 4, noiseVec.y * mult / 4);
         V2 newPos = p + dsp;
-        float lsum = len(newPos) + len(p);
-        float diff = lsum > 0 ? (2.f * dot(p, dsp) + dot(dsp, dsp)) / lsum : 0.f;
+        float lsum = fast_len(newPos) + fast_len(p);
+        float diff = lsum > 0 ? __fdividef(2.f * dot(p, dsp) + dot(dsp, dsp), lsum) : 0.f;
         if (ru.u(2) < randB * mult) seen = S_NO;
         if ((kind == 0 || kind == 3) && ru.u(3) < randB * mult / 2) seen = S_MISCLASS;
         p = newPos;
         radius *= 1.f + (ru.u(4) * 0.1f * diff);
-        if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn * mult / 180.f;
+        if (kind == 4) ex2 += (ru.u(5) - 0.5f) * magn * mult * (1.f / 180.f);
       }
     }
     /* list membership (RoboCupEnvironment.py:1254-1276) */
@@ -1726,9 +1745,10 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
         else if (lkind == 3) { rrow = kind == 0 ? __popc(mCross) : __popc(mCross & lt); off = RC_O_CROSS; }
         else { rrow = nf + __popc(mFc & lt); off = RC_O_FCROSS; feat = RC_F_FCROSS; }
         float* dst = E.f + (V_STAGE + off + rrow * feat);
-        float dist = len(p);
-        float inv = dist > 0 ? 1.f / dist : 0.f;
-        dst[0] = (dist * STDNORM - 0.5f) / 0.5f;
+        float l2 = lensq(p);
+        float inv = l2 > 0 ? rsqrtf(l2) : 0.f;
+        float dist = l2 * inv;
+        dst[0] = (dist * STDNORM - 0.5f) * 2.f;
         dst[1] = dist > 0 ? p.x * team * inv : 1.f;
         dst[2] = dist > 0 ? p.y * team * inv : 0.f;
         dst[3] = (radius - (lkind == 2 ? POST_RADIUS : PEN_RADIUS)) * 2.f;
@@ -1751,6 +1771,11 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
     }
     nf += __popc(mFc);
   }
+  /* one Philox evaluation serves three consumers: lanes 0..10 the noise of line `lane`, lanes 11..20 the
+     test draw of false-positive loop index lane - 11, lanes 21..31 the false-positive ball of robot row
+     lane - 21 (every draw is addressed by its consumer, include/dynenv_rng.h) */
+  const Rand6 rmix = rng_block(E, tick, lane < 11 ? RC_SITE_OBS_LINE : (lane < 21 ? RC_SITE_OBS_FP : RC_SITE_OBS_FPBALL), ag,
+                               lane < 11 ? lane : (lane < 21 ? lane - 11 : lane - 21), 0);
   /* lines: isLineInArea (cutils.py:751-821), addNoiseLine (:352-378), normalizeLine (:333-347) */
   int nl;
   {
@@ -1788,7 +1813,7 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
         ldir = rot_cs(D, hc, -hs) * (t2 - t1);
         if (lp1.x < 0 || lp2.x < 0) seen = S_NO;
         if (seen != S_NO) {
-          Rand6 ru = rng_block(E, tick, RC_SITE_OBS_LINE, ag, lane, 0);
+          const Rand6& ru = rmix;
           V2 n1 = v2((ru.u(0) - 0.5f) * magn, (ru.u(1) - 0.5f) * magn);
           V2 n2 = v2((ru.u(2) - 0.5f) * magn, (ru.u(3) - 0.5f) * magn);
           if (!realistic) {
@@ -1796,8 +1821,8 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
             lp1 = lp1 + n1;
             ldir = ldir + (n2 - n1);
           } else {
-            float m1 = 0.25f + 3.75f * lensq(lp1) / maxVis1;
-            float m2 = 0.25f + 3.75f * lensq(lp2) / maxVis1;
+            float m1 = 0.25f + 3.75f * lensq(lp1) * (1.f / maxVis1);
+            float m2 = 0.25f + 3.75f * lensq(lp2) * (1.f / maxVis1);
             if (ru.u(4) < randB * ((m1 + m2) * 0.5f)) seen = S_NO;
             V2 a1 = v2(n1.x * m1 / 2, n1.y * m1 / 2), a2 = v2(n2.x * m2 / 2, n2.y * m2 / 2);
             lp1 = lp1 + a1;
@@ -1810,10 +1835,11 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
     nl = __popc(mLine);
     if (seen != S_NO) {
       float* dst = E.f + (V_STAGE + RC_O_LINE + __popc(mLine & lt) * RC_F_LINE);
-      float ld = len(ldir); /* ldir = lp2 - lp1; |lp2 x lp1| = |ldir x lp1| */
-      dst[0] = (fabsf(cross(ldir, lp1)) / (ld + 1e-7f) * STDNORM - 0.5f) / 0.5f;
-      dst[1] = ld > 0 ? ldir.x / ld : 1.f;
-      dst[2] = ld > 0 ? ldir.y / ld : 0.f;
+      float ld = fast_len(ldir); /* ldir = lp2 - lp1; |lp2 x lp1| = |ldir x lp1| */
+      float ild = ld > 0 ? __fdividef(1.f, ld) : 0.f;
+      dst[0] = (__fdividef(fabsf(cross(ldir, lp1)), ld + 1e-7f) * STDNORM - 0.5f) * 2.f;
+      dst[1] = ld > 0 ? ldir.x * ild : 1.f;
+      dst[2] = ld > 0 ? ldir.y * ild : 0.f;
       dst[3] = tx; dst[4] = ty;
     }
   }
@@ -1825,37 +1851,40 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   __syncwarp();
   /* random false positives (:1279-1305): ten draws, lane = loop index */
   {
-    bool hit = false;
-    if (lane < 10) hit = rng_block(E, tick, RC_SITE_OBS_FP, ag, lane, 0).u(0) < randB;
-    unsigned hits = __ballot_sync(FULLMASK, hit);
+    unsigned hits = __ballot_sync(FULLMASK, lane >= 11 && lane < 21 && rmix.u(0) < randB) >> 11;
     if (hits) false_positives(E, ag, tick, hits, team);
   }
-  /* false-positive balls near robots (:1308-1316), lane = row of the robot list */
+  /* false-positive balls near robots (:1308-1316): lane 21 + k = row k of the robot list (a 12th row, which
+     needs three false-positive robots, takes a second round with its own draw) */
   if (realistic) {
-    int nrNow = E.i[V_CNT + 1];
-    bool create = false;
-    float bx = 0, by = 0, brad = 0;
-    if (lane < nrNow && E.f[V_RAW + 3 * lane + 2] != 0.f) {
-      Rand6 ru = rng_block(E, tick, RC_SITE_OBS_FPBALL, ag, lane, 0);
-      V2 rp = v2(E.f[V_RAW + 3 * lane], E.f[V_RAW + 3 * lane + 1]);
-      if (ru.u(0) < randB * 10 && len(rp) < 250.f) {
-        create = true;
-        bx = rp.x + (2 * ru.u(2) - 1.f) * ROB_TOTAL;
-        by = rp.y + (2 * ru.u(3) - 1.f) * ROB_TOTAL;
-        brad = BALL_RADIUS * 2 * (1.f - 0.4f * (ru.u(4) - 0.5f));
+    const int nrNow = E.i[V_CNT + 1];
+    for (int row0 = 0; row0 < nrNow; row0 += 11) {
+      const int row = row0 + lane - 21;
+      bool create = false;
+      float bx = 0, by = 0, brad = 0;
+      if (lane >= 21 && row < nrNow && E.f[V_RAW + 3 * row + 2] != 0.f) {
+        Rand6 ru = rmix;
+        if (row0) ru = rng_block(E, tick, RC_SITE_OBS_FPBALL, ag, row, 0);
+        V2 rp = v2(E.f[V_RAW + 3 * row], E.f[V_RAW + 3 * row + 1]);
+        if (ru.u(0) < randB * 10 && lensq(rp) < 250.f * 250.f) {
+          create = true;
+          bx = rp.x + (2 * ru.u(2) - 1.f) * ROB_TOTAL;
+          by = rp.y + (2 * ru.u(3) - 1.f) * ROB_TOTAL;
+          brad = BALL_RADIUS * 2 * (1.f - 0.4f * (ru.u(4) - 0.5f));
+        }
       }
-    }
-    unsigned cm = __ballot_sync(FULLMASK, create);
-    if (cm) {
-      int nbNow = E.i[V_CNT + 0];
-      __syncwarp();
-      int at = nbNow + __popc(cm & lt);
-      if (create && at < RC_CAP_BALL) {
-        float* dst = E.f + (V_STAGE + RC_O_BALL + at * RC_F_BALL);
-        dst[0] = bx * STDNORM2; dst[1] = by * STDNORM2; dst[2] = (brad - BALL_RADIUS * 2) * 2.f; dst[3] = 0.f; dst[4] = closest;
+      unsigned cm = __ballot_sync(FULLMASK, create);
+      if (cm) {
+        int nbNow = E.i[V_CNT + 0];
+        __syncwarp();
+        int at = nbNow + __popc(cm & lt);
+        if (create && at < RC_CAP_BALL) {
+          float* dst = E.f + (V_STAGE + RC_O_BALL + at * RC_F_BALL);
+          dst[0] = bx * STDNORM2; dst[1] = by * STDNORM2; dst[2] = (brad - BALL_RADIUS * 2) * 2.f; dst[3] = 0.f; dst[4] = closest;
+        }
+        if (lane == 0) E.i[V_CNT + 0] = min(nbNow + __popc(cm), (int)RC_CAP_BALL);
+        __syncwarp();
       }
-      if (lane == 0) E.i[V_CNT + 0] = min(nbNow + __popc(cm), (int)RC_CAP_BALL);
-      __syncwarp();
     }
   }
   if (lane < 6) E.i[V_STAGE + RC_O_COUNTS + lane] = E.i[V_CNT + lane];
@@ -2016,10 +2045,11 @@ __device__ __forceinline__ void clear_step_scratch(const Env E) {
    kernel the warps of an SM sit in different phases and the step is instruction-fetch bound. */
 __device__ __forceinline__ void phys_substeps(const Env E, const float* actions_env, int sub_b, int sub_e, bool first) {
   if (first) clear_step_scratch(E);
+  const uint32_t pairs4 = broadphase_pairs(E);
   for (int sub = sub_b; sub < sub_e; sub++) {
     robots_phase(E, sub, actions_env);
     ball_out_of_field(E);
-    space_step(E);
+    space_step(E, pairs4);
     if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
     __syncwarp();
   }

@@ -13,10 +13,10 @@ out = subprocess.run("cd /tmp/cub && nvdisasm -c *.cubin", shell=True, capture_o
 funcs, n, insec = [], 0, False
 for ln in out:
     if ln.startswith('//---') and '.text.' in ln:
-        insec = 'rc_step_kernel' in ln
+        insec = os.environ.get('KERNEL','rc_phys_kernel') in ln
         n = 0
         if insec:
-            funcs.append((0, 'rc_step_kernel'))
+            funcs.append((0, os.environ.get('KERNEL','rc_phys_kernel')))
         continue
     if ln.startswith('//---'):
         insec = False
