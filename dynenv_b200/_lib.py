@@ -6,7 +6,7 @@ import os
 from . import layout as L
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libdynenv_b200.so")
+LIB_PATH = os.environ.get("DYNENV_B200_LIB") or os.path.join(_DIR, "libdynenv_b200.so")
 _LIB = None
 
 EXPORTS = ["dynenv_abi_version", "dynenv_last_error", "dynenv_create", "dynenv_destroy", "dynenv_state_words",

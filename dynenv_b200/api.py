@@ -1,0 +1,266 @@
+"""Drop-in API of the reference for the rollout path (host side, Python like the reference's):
+
+  RoboCupEnvironment(nPlayers, render, observationType, noiseType, noiseMagnitude, obs_space_cast, allowHeadTurn)
+      .step(actions) .reset() .set_random_seed(seed) .observation_space .action_space ...
+      (DynEnv/RoboCupEnvironment.py:23-64,446-524; environment_base.py:190-224)
+  make_dyn_env(env, num_envs, num_players, render, observationType, noiseType, noiseMagnitude,
+               use_continuous_actions) -> (vec_env, name)                     (DynEnv/__init__.py:6-25)
+  BatchedVecEnv: the VecEnv calls the learner uses (step / step_async / step_wait / reset / get_attr /
+      env_method / seed / close; DynEnv/utils/base_vec_env.py:57-233, subproc_vec_env.py:50-175) over ONE
+      batched simulator instead of one process per environment.
+
+Same names, argument meaning and error behaviour.  The simulation itself runs in the CUDA library; these
+classes only validate, launch and convert formats."""
+import numpy as np
+
+from . import layout as L
+from . import reference_format as RF
+from . import spaces as S
+from .enums import DynEnvType, NoiseType, ObservationType
+
+_ACT_HI = (5, 3, 3, 7)
+
+
+def validate_robocup_actions(actions, nAgents, allowHeadTurn):
+    """The checks of RoboCupEnvironment.step / processAction (:461-463, :543-550), same messages."""
+    actions = np.asarray(actions)
+    if actions.shape != (nAgents, 4):
+        raise Exception("Error: There must be %d actions of length 4" % nAgents)
+    a = actions.astype(np.float64)
+    move, turn, kick, head = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+    if ((move < 0) | (move > 4)).any() or ((turn < 0) | (turn > 2)).any() or ((kick < 0) | (kick > 2)).any():
+        raise Exception("Error: Robot motion commands must be between 0 and 4, 0 and 2 and 0 and 2")
+    if allowHeadTurn:
+        if (np.abs(head) > 3).any():
+            raise Exception("Error: Head turn commands must be between -3 and +3")
+    elif ((head < 0) | (head > 6)).any():
+        raise Exception("Error: Head turn commands must be between 0 and 6")
+    return a.astype(np.float32)
+
+
+def robocup_spaces(observationType, allowHeadTurn, mean=2.0):
+    """action_space / observation_space as the reference builds them (:338-430)"""
+    Box, Dict, Tuple, MultiBinary, MultiDiscrete = S.Box, S.Dict, S.Tuple, S.MultiBinary, S.MultiDiscrete
+    action = Tuple((MultiDiscrete([5, 3, 3]), Box(low=-3, high=3, shape=(1,)))) if allowHeadTurn else \
+        Tuple((MultiDiscrete([5, 3, 3, 7]),))
+    pos_xy = Box(-mean * 2, +mean * 2, shape=(2,))
+    pos_radial = Box(-1, +1, shape=(3,))
+    team = Box(-1, 1, shape=(1,))
+    radius = Box(-mean * 2, +mean * 2, shape=(1,))
+    line = Dict({"position": pos_radial, "type": Box(-1, +1, shape=(2,))})
+    cross = Dict({"position": pos_radial, "radius": radius, "type": Box(-1, +1, shape=(2,))})
+    fcross = Dict({"position": pos_radial, "radius": radius, "type": Box(-1, +1, shape=(2,)), "angle": Box(-1, +1, shape=(2,))})
+    self_space = Dict({"position": pos_xy, "orientation": Box(-1, 1, shape=(4,)), "team": team,
+                       "penalized or penalized": MultiBinary(1)})
+    if observationType == ObservationType.FULL:
+        ball = Dict({"position": pos_xy, "team": team, "closest": MultiBinary(1)})
+        robot = Dict({"position": pos_xy, "orientation": Box(-1, 1, shape=(2,)), "team": team,
+                      "penalized or penalized": MultiBinary(1)})
+        obs = Tuple([Tuple([ball, robot]), Tuple([self_space, ])])
+    elif observationType == ObservationType.IMAGE:
+        obs = Box(0, 1, shape=(4, 480, 640))
+    else:
+        ball = Dict({"position": pos_xy, "radius": radius, "team": team, "closest": MultiBinary(1)})
+        robot = Dict({"position": pos_xy, "radius": radius, "orientation": Box(-1, 1, shape=(2,)), "team": team,
+                      "penalized or penalized": MultiBinary(1)})
+        obs = Tuple([Tuple([ball, robot]), Tuple([cross, cross, fcross, line])])
+    return action, obs
+
+
+class _Agent(object):
+    """what callers read from `env.agents[i]` (Robot.py:58-88): identity only; the state lives on the device"""
+
+    def __init__(self, idx, nPlayers):
+        self.id = idx
+        self.team = 1 if idx < nPlayers else -1
+
+
+class RoboCupEnvironment(object):
+    """One RoboCup environment with the reference's interface, simulated on the GPU (batch of one).
+    Class-level toggles as in RoboCupEnvironment.py:18-21."""
+    randomInit = False
+    deterministicTurn = False
+    canFall = True
+    useObsRewards = True
+
+    def __init__(self, nPlayers, render=False, observationType=ObservationType.PARTIAL, noiseType=NoiseType.REALISTIC,
+                 noiseMagnitude=2, obs_space_cast=False, allowHeadTurn=False, seed=0, device=0):
+        if noiseMagnitude < 0 or noiseMagnitude > 5:  # environment_base.py:162-164 (which prints and exits)
+            raise ValueError("Error: The noise magnitude must be between 0 and 5!")
+        if render:
+            raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+        if ObservationType(observationType) == ObservationType.IMAGE:
+            raise NotImplementedError("IMAGE observations are not built yet (the reference's own step() raises "
+                                      "TypeError in IMAGE mode, RoboCupEnvironment.py:1571)")
+        from .batched import BatchedRoboCup
+        self.observationType = ObservationType(observationType)
+        self.noiseType = NoiseType(noiseType)
+        self.noiseMagnitude = noiseMagnitude
+        self.allowHeadTurn = allowHeadTurn
+        self.obs_space_cast = obs_space_cast
+        self.maxPlayers = 5
+        self.nPlayers = min(nPlayers, self.maxPlayers)
+        self.nTimeSteps, self.stepIterCnt, self.maxTime = L.RC_NTICK, L.RC_SUBSTEPS, 12000
+        self.stepNum = self.maxTime / self.stepIterCnt
+        self.W, self.H = 1040, 740
+        self.mean = 2.0  # `2.0 if ObservationType.PARTIAL else 1.0` is always 2.0 (RoboCupEnvironment.py:67)
+        self.renderMode, self.agentVisID = False, None
+        self.elapsed = 0
+        self.agents = [_Agent(i, self.nPlayers) for i in range(2 * self.nPlayers)]
+        self.action_space, self.observation_space = robocup_spaces(self.observationType, allowHeadTurn, self.mean)
+        self._sim = BatchedRoboCup(1, nPlayers, self.observationType, self.noiseType, noiseMagnitude, allowHeadTurn,
+                                   randomInit=type(self).randomInit, deterministicTurn=type(self).deterministicTurn,
+                                   canFall=type(self).canFall, useObsRewards=type(self).useObsRewards, seed=seed, device=device)
+        self._full = self.observationType == ObservationType.FULL
+        self._last = None
+        self.reset()
+
+    # ---- the reference's calls
+    def set_random_seed(self, seed):
+        """seeds the generator; like the reference (environment_base.py:190-193) it does not reset"""
+        self._sim.set_random_seed(seed)
+
+    setRandomSeed = set_random_seed  # README.md:139 spelling
+
+    def reset(self):
+        self._last = RF.host_views(self._sim.reset(), self._full)
+        self.elapsed = 0
+        return RF.observations(self._last, 0, 2 * self.nPlayers, self._full)
+
+    def step(self, actions):
+        import torch
+        a = validate_robocup_actions(actions, 2 * self.nPlayers, self.allowHeadTurn)
+        out = self._sim.step(torch.from_numpy(a[None]).to(self._sim.device))
+        v = self._last = RF.host_views(out, self._full)
+        P = 2 * self.nPlayers
+        self.elapsed += self.stepIterCnt
+        return RF.observations(v, 0, P, self._full), v["rewards"][0, :P].astype(np.float64), bool(v["done"][0]), \
+            RF.info_dict(v, 0, P)
+
+    def getFullState(self, robot=None):
+        v, P = self._last, 2 * self.nPlayers
+        if robot is None:
+            return [np.array(v["state_robots"][0, :P]), np.array(v["state_ball"][0])]
+        a = robot.id if hasattr(robot, "id") else int(robot)
+        return (np.array(v["recon_ball"][0, a][None]), np.array(v["recon_self"][0, a][None]), np.array(v["recon_others"][0, a, :P - 1]))
+
+    def get_agent_locs(self):
+        return [self.getFullState(agent)[1][:, [0, 1, 2, 3, 4, 5]] for agent in self.agents]
+
+    def get_full_obs(self):
+        return [([o[0], o[2]], [o[1], ], (1, 1, 1)) for o in (self.getFullState(r) for r in self.agents)]
+
+    def get_class_specific_args(self):
+        return [self.allowHeadTurn]
+
+    def render(self):
+        raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+
+    def close(self):
+        self._sim.close()
+
+
+class BatchedVecEnv(object):
+    """VecEnv over one batched simulator: `num_envs` environments, auto-reset on done with
+    info['terminal_observation'] (utils/subproc_vec_env.py:17-23).  `step()` returns the reference's host
+    format (object ndarray [nEnvs, nTime, nAgents, 3], rewards [nEnvs, nAgents], dones, infos); at large
+    batch sizes use `step_tensors()`, which leaves everything on the device."""
+
+    def __init__(self, num_envs, nPlayers, observationType, noiseType, noiseMagnitude, allowHeadTurn=False, seed=0,
+                 device=0, env_id_offset=0, **toggles):
+        from .batched import BatchedRoboCup
+        self.num_envs = int(num_envs)
+        self.nPlayers = min(nPlayers, 5)
+        self.nAgents = 2 * self.nPlayers
+        self.allowHeadTurn = allowHeadTurn
+        self.observationType = ObservationType(observationType)
+        self._full = self.observationType == ObservationType.FULL
+        self.action_space, self.observation_space = robocup_spaces(self.observationType, allowHeadTurn)
+        self.sim = BatchedRoboCup(self.num_envs, nPlayers, observationType, noiseType, noiseMagnitude, allowHeadTurn,
+                                  auto_reset=True, terminal_outputs=True, seed=seed, device=device,
+                                  env_id_offset=env_id_offset, **toggles)
+        self._actions = None
+        self._attrs = dict(nPlayers=self.nPlayers, nTimeSteps=L.RC_NTICK, stepIterCnt=L.RC_SUBSTEPS, maxTime=12000,
+                           stepNum=12000 / L.RC_SUBSTEPS, observationType=self.observationType, renderMode=False,
+                           agentVisID=None, action_space=self.action_space, observation_space=self.observation_space)
+
+    # ---- device-resident fast path
+    def step_tensors(self, actions):
+        """actions: float32 CUDA tensor [num_envs, nAgents, 4]; returns (out, terminal) RoboCupOutputs views"""
+        return self.sim.step(actions), self.sim.terminal
+
+    # ---- VecEnv calls
+    def reset(self):
+        v = RF.host_views(self.sim.reset(), self._full)
+        return self._stack([RF.observations(v, e, self.nAgents, self._full) for e in range(self.num_envs)])
+
+    def step_async(self, actions):
+        self._actions = actions
+
+    def step_wait(self):
+        import torch
+        a = np.asarray(self._actions)
+        if a.shape != (self.num_envs, self.nAgents, 4):
+            raise Exception("Error: There must be %d actions of length 4" % self.nAgents)
+        a = np.stack([validate_robocup_actions(a[e], self.nAgents, self.allowHeadTurn) for e in range(self.num_envs)])
+        out = self.sim.step(torch.from_numpy(a).to(self.sim.device))
+        v = RF.host_views(out, self._full)
+        dones = v["done"].astype(bool)
+        tv = RF.host_views(self.sim.terminal, self._full, np.nonzero(dones)[0]) if dones.any() else None
+        obs, infos, k = [], [], 0
+        for e in range(self.num_envs):
+            info = RF.info_dict(v, e, self.nAgents)
+            if dones[e]:
+                # obs/full of the finished step were routed to the terminal buffers by the kernel
+                tvv = dict(tv)
+                info["terminal_observation"] = RF.observations(tvv, k, self.nAgents, self._full)
+                k += 1
+            obs.append(RF.observations(v, e, self.nAgents, self._full))
+            infos.append(info)
+        return self._stack(obs), v["rewards"][:, :self.nAgents].astype(np.float64), dones, tuple(infos)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    @staticmethod
+    def _stack(obs):
+        """_flatten_obs (subproc_vec_env.py:178-201): object array [nEnvs, nTime, nAgents, 3]"""
+        nE, nT, nA = len(obs), len(obs[0]), len(obs[0][0])
+        arr = np.empty((nE, nT, nA, 3), dtype=object)
+        for e in range(nE):
+            for t in range(nT):
+                for a in range(nA):
+                    for k in range(3):
+                        arr[e, t, a, k] = obs[e][t][a][k]
+        return arr
+
+    def seed(self, seed=None):
+        if seed is not None:
+            self.sim.set_random_seed(seed)  # global env ids keep the per-env streams distinct
+
+    def get_attr(self, attr_name, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [self._attrs[attr_name]] * n
+
+    def env_method(self, method_name, *args, **kwargs):
+        if method_name == "get_agent_locs":
+            rs = self.sim.out.recon_self.detach().cpu().numpy()
+            return [[rs[e, a][None][:, [0, 1, 2, 3, 4, 5]] for a in range(self.nAgents)] for e in range(self.num_envs)]
+        raise AttributeError(method_name)
+
+    def close(self):
+        self.sim.close()
+
+
+def make_dyn_env(env, num_envs, num_players, render, observationType, noiseType, noiseMagnitude,
+                 use_continuous_actions, seed=0, device=0):
+    """DynEnv.make_dyn_env (DynEnv/__init__.py:6-25): same arguments, same return (vec_env, name)."""
+    if render:
+        raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+    if env is DynEnvType.ROBO_CUP:
+        return BatchedVecEnv(num_envs, num_players, observationType, noiseType, noiseMagnitude,
+                             allowHeadTurn=use_continuous_actions, seed=seed, device=device), "RoboCup"
+    if env is DynEnvType.DRIVE:
+        raise NotImplementedError("DrivingEnvironment is not built yet (DESIGN.md, scope)")
+    raise ValueError

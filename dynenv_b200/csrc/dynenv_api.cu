@@ -15,7 +15,13 @@ using namespace dynenv;
 
 namespace {
 
-constexpr int RC_WPC = 4; /* environments (warps) per CTA */
+#ifndef RC_WPC_
+#define RC_WPC_ 4
+#endif
+#ifndef RC_MINB_
+#define RC_MINB_ 8 /* 64 registers per thread: 8 CTAs = 32 warps per SM (measured best, profiles/) */
+#endif
+constexpr int RC_WPC = RC_WPC_; /* environments (warps) per CTA */
 
 thread_local std::string g_err;
 
@@ -64,7 +70,7 @@ __device__ __forceinline__ rc::Env make_env(int base, const SimCfg& cfg, int e, 
  * warps, warp w of CTA b owns environment b*RC_WPC + w, whose record it loads into its shared-memory slice
  * and stores back (coalesced).  See rc_sim.cuh (phys_substeps) for why the phases are separate launches.
  */
-__global__ void __launch_bounds__(RC_WPC * 32)
+__global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
                int sub_b, int sub_e, int first) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,7 +86,7 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
 }
 
 /* observation tick t of the step in flight (after substep 10 t + 9) */
-__global__ void __launch_bounds__(RC_WPC * 32)
+__global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, int t, int subs_left,
               float* __restrict__ obs, float* __restrict__ full, float* __restrict__ term_obs, float* __restrict__ term_full) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,7 +112,7 @@ rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, 
 }
 
 /* rewards, info, done, episode statistics; finished environments are re-initialised (auto-reset) */
-__global__ void __launch_bounds__(RC_WPC * 32)
+__global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_finish_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, float* __restrict__ obs,
                  float* __restrict__ full, float* __restrict__ info) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,7 +132,7 @@ rc_finish_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ stat
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
 }
 
-__global__ void __launch_bounds__(RC_WPC * 32)
+__global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const uint8_t* __restrict__ mask,
                 float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -1,0 +1,91 @@
+"""GPU: the drop-in classes (formats, auto-reset, errors) and shard independence."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_single_env_drop_in_full():
+    import dynenv_b200
+    from dynenv_b200.api import RoboCupEnvironment
+    RoboCupEnvironment.canFall = False
+    try:
+        env = RoboCupEnvironment(nPlayers=1, observationType=dynenv_b200.ObservationType.FULL, noiseMagnitude=0)
+    finally:
+        RoboCupEnvironment.canFall = True
+    obs = env.reset()
+    assert len(obs) == 5 and len(obs[0]) == 2
+    (ball, others), (self_,), ones = obs[0][0]
+    assert ball.shape == (1, 4) and others.shape == (1, 6) and self_.shape == (1, 8) and ones == (1, 1, 1)
+    assert ball.dtype == np.float32
+    obs, rew, fin, info = env.step(np.array([[1, 0, 0, 3], [2, 1, 0, 3]]))
+    assert rew.shape == (2,) and rew.dtype == np.float64 and fin is False
+    assert info["Full State"][0].shape == (2, 6) and info["Full State"][1].shape == (3,)
+    assert len(info["Recon States"]) == 2 and env.elapsed == 50
+    locs = env.get_agent_locs()
+    assert len(locs) == 2 and locs[0].shape == (1, 6)
+    with pytest.raises(Exception, match="There must be 2 actions"):
+        env.step(np.zeros((3, 4)))
+    with pytest.raises(Exception, match="Robot motion commands"):
+        env.step(np.array([[7, 0, 0, 3], [0, 0, 0, 3]]))
+    env.setRandomSeed(5)
+    env.close()
+
+
+def test_single_env_partial_format():
+    import dynenv_b200
+    env = dynenv_b200.RoboCupEnvironment(nPlayers=2, noiseMagnitude=2)
+    obs = env.reset()
+    (balls, robots), (posts, crosses, fcs, lines), (nl, rs, bs) = obs[4][1]
+    for arr, f in ((balls, 5), (robots, 7), (posts, 6), (crosses, 6), (fcs, 8), (lines, 5)):
+        assert arr.dtype == np.float32 and (arr.shape == (0,) or arr.shape[1] == f)
+    assert rs.shape == (3,) and rs.dtype == np.uint8 and isinstance(bs, bool) and isinstance(nl, int)
+    obs, rew, fin, info = env.step(np.array([[3, 0, 0, 3]] * 4))
+    assert len(obs) == 5 and len(obs[0]) == 4 and rew.shape == (4,)
+
+
+def test_vec_env_auto_reset_and_terminal_observation():
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    venv, name = dynenv_b200.make_dyn_env(dynenv_b200.DynEnvType.ROBO_CUP, 3, 2, False, dynenv_b200.ObservationType.PARTIAL,
+                                          dynenv_b200.NoiseType.REALISTIC, 1.0, False)
+    assert name == "RoboCup" and venv.num_envs == 3
+    obs = venv.reset()
+    assert obs.shape == (3, 5, 4, 3)
+    # move environment 1 to the last step of its episode
+    st = venv.sim.get_state()
+    st[1, L.RC_S_ELAPSED] = 12000 - 50
+    venv.sim.set_state(st)
+    a = np.tile(np.array([1, 0, 0, 3]), (3, 4, 1))
+    obs, rew, dones, infos = venv.step(a)
+    assert obs.shape == (3, 5, 4, 3) and rew.shape == (3, 4) and dones.tolist() == [False, True, False]
+    assert "terminal_observation" in infos[1] and "terminal_observation" not in infos[0]
+    assert "episode_r" in infos[1] and len(infos[1]["episode_g"]) == 2
+    st = venv.sim.get_state().cpu().numpy()
+    assert st[1, L.RC_S_ELAPSED] == 0 and st[1, L.RC_S_EPISODE] == 2 and st[0, L.RC_S_ELAPSED] == 50
+    assert venv.get_attr("nTimeSteps") == [5, 5, 5]
+    assert len(venv.env_method("get_agent_locs")) == 3
+    with pytest.raises(Exception, match="There must be 4 actions"):
+        venv.step(np.zeros((3, 5, 4)))
+    venv.close()
+
+
+def test_results_do_not_depend_on_sharding():
+    """global env ids feed the RNG: 8 environments on one handle == 2 handles x 4 (what 2 GPUs would run)"""
+    import torch
+    import dynenv_b200
+    kw = dict(nPlayers=3, noiseMagnitude=2.0, canFall=True, seed=11)
+    whole = dynenv_b200.BatchedRoboCup(8, env_id_offset=0, **kw)
+    parts = [dynenv_b200.BatchedRoboCup(4, env_id_offset=o, **kw) for o in (0, 4)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    g = torch.Generator().manual_seed(3)
+    for _ in range(6):
+        a = (torch.rand((8, 6, 4), generator=g) * torch.tensor([5, 3, 3, 7])).floor().cuda()
+        ow = whole.step(a)
+        op = [p.step(a[4 * k:4 * k + 4].contiguous()) for k, p in enumerate(parts)]
+        assert torch.equal(ow.obs, torch.cat([o.obs for o in op]))
+        assert torch.equal(ow.info, torch.cat([o.info for o in op]))
+    assert torch.equal(whole.get_state(), torch.cat([p.get_state() for p in parts]))
