@@ -40,6 +40,15 @@ def algorithmic_bytes_per_env_step():
     return 4 * (2 * L.RC_STATE_WORDS + P * 4 + L.RC_NTICK * P * L.RC_OBS_WORDS + L.RC_INFO_WORDS)
 
 
+def kernel_bytes_per_env():
+    """algorithmic HBM bytes per environment of ONE launch of each kernel class"""
+    from dynenv_b200 import layout as L
+    rec = 4 * L.RC_STATE_WORDS
+    return {"phys": 2 * rec + 4 * P * 4,                                   # record in + out, actions
+            "obs": rec + 4 * P * L.RC_OBS_WORDS + 4 * (L.RC_S_STEP_END - L.RC_S_STEP_LSUM),  # record in, 10 records out
+            "finish": 2 * rec + 4 * L.RC_INFO_WORDS}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -132,7 +141,7 @@ def run_reference(args):
     if rank != 0:
         return
     # each "step" = every host thread advancing a bounded sample of env-steps of the same workload
-    per_step = 200
+    per_step = 1000
     for _ in range(max(1, min(args.warmup, 2))):
         cpu_env_steps_per_s(50)
     t_total, n_total, threads = 0.0, 0, 0
@@ -192,6 +201,8 @@ def run_gpu(args):
     for w in range(args.warmup):
         sim.step(pool[w % n_pool])
     barrier()
+    sim.debug_timing(True)
+    kms = {"phys": [0.0, 0], "obs": [0.0, 0], "finish": [0.0, 0]}
     sampler = ClockSampler(local)
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -203,8 +214,13 @@ def run_gpu(args):
         sim.step(pool[s % n_pool])
         evs[s][1].record(stream)
         launches += sim.last_launch_count()
+        if s % 4 == 3 or s == args.steps - 1:  # per-kernel durations (waits for that step; every 4th only)
+            for k, (ms, n) in sim.last_kernel_ms().items():
+                kms[k][0] += ms
+                kms[k][1] += n
     t_end.record(stream)
     barrier()
+    sim.debug_timing(False)
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
@@ -238,7 +254,12 @@ def run_gpu(args):
         value = total_envs * args.steps / (ms_total * 1e-3)
         e2e = total_envs * args.steps / (ms_e2e * 1e-3)
         bytes_launch = algorithmic_bytes_per_env_step() * E
-        achieved = bytes_launch / (kernel_ms * 1e-3) / 1e9
+        kb = kernel_bytes_per_env()
+        per_launch = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kms.items()}  # ms per launch
+        per_step = {k: per_launch[k] * (5 if k != "finish" else 1) for k in per_launch}
+        dom = max(per_step, key=per_step.get)  # dominant kernel class of the step
+        achieved = kb[dom] * E / (per_launch[dom] * 1e-3) / 1e9 if per_launch[dom] else 0.0
+        step_gbs = bytes_launch / (kernel_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -251,8 +272,12 @@ def run_gpu(args):
                         "note": "observations stay device-resident for the learner; rewards + done return to the host"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                             "kernel": "rc_step_kernel", "kernel_ms": kernel_ms,
-                             "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(),
+                             "kernel": "rc_%s_kernel" % dom, "kernel_ms_per_launch": per_launch[dom],
+                             "algorithmic_bytes_per_launch": kb[dom] * E,
+                             "launch_ms": per_launch, "share_of_step": {k: v / max(sum(per_step.values()), 1e-9) for k, v in per_step.items()},
+                             "step": {"ms": kernel_ms, "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(),
+                                      "achieved_gbs": step_gbs, "frac": step_gbs / peaks["hbm_gbs"]},
+                             "note": "the step is instruction-issue bound (FP32/INT pipes), not HBM bound; see DESIGN.md section 4",
                              "fp32": {"flop_per_env_step": FLOP_PER_ENV_STEP,
                                       "achieved_tflops": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12,
                                       "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
@@ -277,7 +302,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--debug-full-obs", action="store_true", help="(profiling aid) FULL observations: physics and rules only")
-    ap.add_argument("--cpu-steps", type=int, default=1500, help="env-steps per host thread of the cpu_baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=20000, help="env-steps per host thread of the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -138,6 +138,15 @@ class BatchedRoboCup(object):
         _lib.check(self._lib.dynenv_step(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
         return self.out
 
+    def debug_timing(self, enable=True):
+        _lib.check(self._lib.dynenv_debug_timing(self._h, int(bool(enable))))
+
+    def last_kernel_ms(self):
+        """{'phys': (ms, launches), 'obs': ..., 'finish': ...} of the last step (needs debug_timing(True))"""
+        ms, n = (C.c_float * 3)(), (C.c_int * 3)()
+        _lib.check(self._lib.dynenv_last_kernel_ms(self._h, ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("phys", "obs", "finish"))}
+
     def debug_substep_range(self, begin, end):
         _lib.check(self._lib.dynenv_debug_substep_range(self._h, int(begin), int(end)))
 

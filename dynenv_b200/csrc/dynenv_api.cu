@@ -153,12 +153,18 @@ rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state
 
 }  // namespace
 
+constexpr int MAX_TIMED = 16; /* launches of one step */
 struct DynEnvHandle_s {
   DynEnvConfig cfg;
   SimCfg sim;
   uint32_t* state;
   int state_words;
   int last_launches;
+  /* optional per-launch timing (dynenv_debug_timing): events bracketing every launch of the last step */
+  int timing;
+  cudaEvent_t ev[MAX_TIMED + 1];
+  int ev_class[MAX_TIMED]; /* 0 substep block, 1 observation tick, 2 finish */
+  int n_timed;
 };
 
 extern "C" {
@@ -207,6 +213,8 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   s.sub_end = RC_SUBSTEPS;
   h->state_words = RC_STATE_WORDS;
   h->last_launches = 0;
+  h->timing = 0;
+  h->n_timed = 0;
   size_t bytes = (size_t)cfg->n_envs * h->state_words * sizeof(uint32_t);
   if ((ce = cudaMalloc(&h->state, bytes)) != cudaSuccess) {
     delete h;
@@ -225,6 +233,8 @@ int dynenv_destroy(DynEnvHandle h) {
   if (!h) return DYNENV_OK;
   cudaSetDevice(h->cfg.device);
   cudaFree(h->state);
+  if (h->timing)
+    for (int k = 0; k <= MAX_TIMED; k++) cudaEventDestroy(h->ev[k]);
   delete h;
   return DYNENV_OK;
 }
@@ -254,21 +264,32 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
   const int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
   const size_t smem = ((size_t)rc::CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
   int launches = 0;
+  h->n_timed = 0;
+  auto mark = [&](int cls) { /* event after launch number `launches` (and one before the first) */
+    if (!h->timing || launches > MAX_TIMED) return;
+    if (cls >= 0) h->ev_class[launches - 1] = cls;
+    cudaEventRecord(h->ev[launches], st);
+    h->n_timed = launches;
+  };
+  mark(-1);
   /* blocks of substeps up to the next observation tick (every 10th substep) */
   for (int b = h->sim.sub_begin; b < h->sim.sub_end;) {
     int e = (b / 10 + 1) * 10;
     if (e > h->sim.sub_end) e = h->sim.sub_end;
     rc_phys_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, actions_dev, b, e, b == h->sim.sub_begin);
     launches++;
+    mark(0);
     if (e % 10 == 0) {
       rc_obs_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
                                                       t ? t->obs : nullptr, t ? t->full : nullptr);
       launches++;
+      mark(1);
     }
     b = e;
   }
   rc_finish_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, o->obs, o->full, o->info);
   launches++;
+  mark(2);
   h->last_launches = launches;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "rc step kernels launch");
@@ -302,6 +323,34 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream) {
 }
 
 int dynenv_last_launch_count(DynEnvHandle h) { return h ? h->last_launches : 0; }
+
+int dynenv_debug_timing(DynEnvHandle h, int enable) {
+  if (!h) return fail(DYNENV_E_INVALID, "null handle");
+  cudaSetDevice(h->cfg.device);
+  if (enable && !h->timing)
+    for (int k = 0; k <= MAX_TIMED; k++) cudaEventCreate(&h->ev[k]);
+  if (!enable && h->timing)
+    for (int k = 0; k <= MAX_TIMED; k++) cudaEventDestroy(h->ev[k]);
+  h->timing = enable ? 1 : 0;
+  h->n_timed = 0;
+  return DYNENV_OK;
+}
+
+int dynenv_last_kernel_ms(DynEnvHandle h, float* ms3, int* launches3) {
+  if (!h || !ms3 || !launches3) return fail(DYNENV_E_INVALID, "null argument");
+  for (int k = 0; k < 3; k++) { ms3[k] = 0.f; launches3[k] = 0; }
+  if (!h->timing || h->n_timed == 0) return DYNENV_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaError_t ce = cudaEventSynchronize(h->ev[h->n_timed]);
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaEventSynchronize");
+  for (int k = 0; k < h->n_timed; k++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]);
+    ms3[h->ev_class[k]] += ms;
+    launches3[h->ev_class[k]] += 1;
+  }
+  return DYNENV_OK;
+}
 
 int dynenv_debug_substep_range(DynEnvHandle h, int begin, int end) {
   if (!h || begin < 0 || end > RC_SUBSTEPS || begin > end) return fail(DYNENV_E_INVALID, "bad substep range");

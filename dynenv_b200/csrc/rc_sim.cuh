@@ -46,7 +46,7 @@ constexpr float STDNORM = 2.f / 1040.f;
 enum { S_NO = 0, S_PARTIAL = 1, S_DISTANT = 2, S_NORMAL = 3, S_MISCLASS = 4 };
 enum { I_NO = 0, I_NEARBY = 1, I_OCCLUDE = 2 };
 
-constexpr int NSHAPE_ = 25, RC_MAXCAND = 48;
+constexpr int NSHAPE_ = 25, RC_MAXCAND = 64;
 /* ---- scratch layout (words after the state record) */
 enum {
   /* accumulators of the step in flight live in the record (they cross kernel launches) */
@@ -1183,11 +1183,26 @@ __device__ __noinline__ void post_solve(const Env E) {
   __syncwarp();
 }
 
+/* do two shapes (cached world geometry) come within their radii + margin?  lane-parallel filter in front
+   of the serial narrow phase; the margin covers the float32 rounding of the absolute coordinates */
+__device__ bool shapes_touch(const Env E, int i, int j) {
+  V2 ia, ib, ja, jb;
+  shape_geom(E, i, &ia, &ib);
+  shape_geom(E, j, &ja, &jb);
+  const float m = 0.02f;
+  if (is_foot(i) && is_foot(j)) return !segments_apart(ia, ib, ja, jb, 2 * ROB_RAD + m);
+  if (!is_foot(i) && !is_foot(j)) return lensq(ia - ja) < (20.f + m) * (20.f + m);
+  V2 c = is_foot(i) ? ja : ia;
+  V2 sa = is_foot(i) ? ia : ja, sb = is_foot(i) ? ib : jb;
+  return lensq(c - closest_on_seg(c, sa, sb)) < (10.f + ROB_RAD + m) * (10.f + ROB_RAD + m);
+}
+
 /* group pairs that came close (bit k of g[k / 32] = pair g_pairs[k]) and own-feet pairs (bit = odd foot):
-   expanded to shape pairs, filtered by the shapes' bounding circles, sorted into Chipmunk's ascending
-   (i, j) insertion order and collided: lane 0 */
+   expanded to shape pairs (lane 0), tested exactly in parallel (lane = candidate), and the touching ones
+   collided in Chipmunk's ascending (i, j) insertion order (lane 0) */
 __device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsigned g0, unsigned g1, unsigned g2, unsigned g3) {
-  if (E.lane == 0) {
+  const int lane = E.lane;
+  if (lane == 0) {
     int n = 0;
     while (own) {
       int j = __ffs(own) - 1;
@@ -1208,19 +1223,35 @@ __device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsig
             int i = a0 + x, j = b0 + y;
             float dx = E.f[X_BCX + i] - E.f[X_BCX + j], dy = E.f[X_BCY + i] - E.f[X_BCY + j];
             float rr = (i < 20 ? ROB_LEN + ROB_RAD : 10.f) + (j < 20 ? ROB_LEN + ROB_RAD : 10.f) + 0.05f;
-            if (dx * dx + dy * dy < rr * rr) {
+            if (dx * dx + dy * dy < rr * rr) { /* bounding circles of the two shapes */
               if (n < RC_MAXCAND) E.i[X_CAND + n++] = i * 32 + j;
               else E.i[X_DIAG] |= RC_IF_ACTIVE_OVERFLOW;
             }
           }
       }
     }
-    for (int x = 1; x < n; x++) { /* insertion sort: n is tiny */
+    E.i[X_NCAND] = n;
+  }
+  __syncwarp();
+  const int n = E.i[X_NCAND];
+  int kept = 0;
+  for (int base = 0; base < n; base += 32) {
+    int c = base + lane;
+    int key = c < n ? E.i[X_CAND + c] : 0;
+    bool touch = c < n && shapes_touch(E, key >> 5, key & 31);
+    unsigned km = __ballot_sync(FULLMASK, touch);
+    __syncwarp();
+    if (touch) E.i[X_CAND + kept + __popc(km & ((1u << lane) - 1))] = key; /* kept + rank <= c: no overwrite of unread keys */
+    kept += __popc(km);
+    __syncwarp();
+  }
+  if (lane == 0 && kept) {
+    for (int x = 1; x < kept; x++) { /* insertion sort: tiny */
       int key = E.i[X_CAND + x], y = x - 1;
       while (y >= 0 && E.i[X_CAND + y] > key) { E.i[X_CAND + y + 1] = E.i[X_CAND + y]; y--; }
       E.i[X_CAND + y + 1] = key;
     }
-    for (int x = 0; x < n; x++) collide_pair(E, E.i[X_CAND + x] >> 5, E.i[X_CAND + x] & 31);
+    for (int x = 0; x < kept; x++) collide_pair(E, E.i[X_CAND + x] >> 5, E.i[X_CAND + x] & 31);
   }
   __syncwarp();
 }

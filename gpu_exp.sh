@@ -1,4 +1,4 @@
 #!/bin/bash
-for f in tools/tmp/variants/lib_w4_b1.so tools/tmp/variants/lib_w4_b6.so tools/tmp/variants/lib_w4_b8.so tools/tmp/variants/lib_w8_b1.so tools/tmp/variants/lib_w8_b3.so tools/tmp/variants/lib_w8_b4.so tools/tmp/variants/lib_w2_b10.so; do
-DYNENV_B200_LIB=$PWD/$f python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$f', 'env-steps/s', int(d['value']), 'kernel_ms', round(d['roofline']['kernel_ms'],2))"
-done
+mkdir -p gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:rc_phys -s 110 -c 1 -o gpurun_out/prof_phys_late -f python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/ncu2.log 2>&1
+tail -2 gpurun_out/ncu2.log

@@ -292,6 +292,13 @@ int dynenv_set_seed(DynEnvHandle h, uint64_t seed);
 int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream);
 int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);
 
+/* Measurement aid: with timing enabled, every launch of the following dynenv_step calls is bracketed by
+   CUDA events on the caller's stream; dynenv_last_kernel_ms waits for the last step's launches and returns
+   the summed duration (ms) and the launch count per kernel class: [0] substep blocks (rc_phys_kernel),
+   [1] observation ticks (rc_obs_kernel), [2] finish (rc_finish_kernel). */
+int dynenv_debug_timing(DynEnvHandle h, int enable);
+int dynenv_last_kernel_ms(DynEnvHandle h, float* ms3, int* launches3);
+
 /* number of kernels launched by the last dynenv_step / dynenv_reset call on this handle */
 int dynenv_last_launch_count(DynEnvHandle h);
 
