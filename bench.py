@@ -260,6 +260,13 @@ def run_gpu(args):
         dom = max(per_step, key=per_step.get)  # dominant kernel class of the step
         achieved = kb[dom] * E / (per_launch[dom] * 1e-3) / 1e9 if per_launch[dom] else 0.0
         step_gbs = bytes_launch / (kernel_ms * 1e-3) / 1e9
+        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("rc_%s_kernel" % dom)
+            if tr:
+                traffic = tr["dram_bytes_per_launch"] * E / tr["envs"]
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -271,7 +278,7 @@ def run_gpu(args):
                         "d2h_bytes_per_step": E * P * 4 + E * 4,
                         "note": "observations stay device-resident for the learner; rewards + done return to the host"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+                             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
                              "kernel": "rc_%s_kernel" % dom, "kernel_ms_per_launch": per_launch[dom],
                              "algorithmic_bytes_per_launch": kb[dom] * E,
                              "launch_ms": per_launch, "share_of_step": {k: v / max(sum(per_step.values()), 1e-9) for k, v in per_step.items()},
