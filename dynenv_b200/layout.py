@@ -92,3 +92,46 @@ def rc_int_mask():
             for k in range(off, off + cnt):
                 mask[k] = True
     return mask
+
+
+# ---------------------------------------------------------------- Driving state record
+_NC, _NPD, _NO, _NDA = C["DRV_MAXCARS"], C["DRV_MAXPED"], C["DRV_MAXOBS"], C["DRV_MAXARB"]
+DRV_FIELDS = {
+    "cpx": (C["DRV_S_CPX"], _NC, "f"), "cpy": (C["DRV_S_CPY"], _NC, "f"), "cang": (C["DRV_S_CANG"], _NC, "f"),
+    "cvx": (C["DRV_S_CVX"], _NC, "f"), "cvy": (C["DRV_S_CVY"], _NC, "f"), "cw": (C["DRV_S_CW"], _NC, "f"),
+    "cvbx": (C["DRV_S_CVBX"], _NC, "f"), "cvby": (C["DRV_S_CVBY"], _NC, "f"), "cwb": (C["DRV_S_CWB"], _NC, "f"),
+    "cdirx": (C["DRV_S_CDIRX"], _NC, "f"), "cdiry": (C["DRV_S_CDIRY"], _NC, "f"),
+    "cprevx": (C["DRV_S_CPREVX"], _NC, "f"), "cprevy": (C["DRV_S_CPREVY"], _NC, "f"),
+    "cgoalx": (C["DRV_S_CGOALX"], _NC, "f"), "cgoaly": (C["DRV_S_CGOALY"], _NC, "f"),
+    "ctype": (C["DRV_S_CTYPE"], _NC, "i"), "cteam": (C["DRV_S_CTEAM"], _NC, "i"), "cflags": (C["DRV_S_CFLAGS"], _NC, "i"),
+    "clane": (C["DRV_S_CLANE"], _NC, "i"),
+    "ppx": (C["DRV_S_PPX"], _NPD, "f"), "ppy": (C["DRV_S_PPY"], _NPD, "f"), "pvx": (C["DRV_S_PVX"], _NPD, "f"),
+    "pvy": (C["DRV_S_PVY"], _NPD, "f"), "pvbx": (C["DRV_S_PVBX"], _NPD, "f"), "pvby": (C["DRV_S_PVBY"], _NPD, "f"),
+    "pmoving": (C["DRV_S_PMOVING"], _NPD, "f"), "pspeed": (C["DRV_S_PSPEED"], _NPD, "i"), "pflags": (C["DRV_S_PFLAGS"], _NPD, "i"),
+    "opx": (C["DRV_S_OPX"], _NO, "f"), "opy": (C["DRV_S_OPY"], _NO, "f"),
+    "elapsed": (C["DRV_S_ELAPSED"], 1, "i"), "episode": (C["DRV_S_EPISODE"], 1, "i"), "allFinished": (C["DRV_S_ALLFIN"], 1, "i"),
+    "nPed": (C["DRV_S_NPED"], 1, "i"), "nObs": (C["DRV_S_NOBS"], 1, "i"), "stepped": (C["DRV_S_STEPPED"], 1, "i"),
+    "episodeRewards": (C["DRV_S_EPR"], _NC, "f"), "episodePosRewards": (C["DRV_S_EPPR"], _NC, "f"),
+    "nArb": (C["DRV_S_NARB"], 1, "i"), "arbKey": (C["DRV_S_ARBKEY"], _NDA, "i"), "arbCon": (C["DRV_S_ARBCON"], _NDA, "i"),
+    "arbJn0": (C["DRV_S_ARBJN0"], _NDA, "f"), "arbJt0": (C["DRV_S_ARBJT0"], _NDA, "f"),
+    "arbJn1": (C["DRV_S_ARBJN1"], _NDA, "f"), "arbJt1": (C["DRV_S_ARBJT1"], _NDA, "f"),
+    "cpxLo": (C["DRV_S_CPXL"], _NC, "f"), "cpyLo": (C["DRV_S_CPYL"], _NC, "f"), "cangLo": (C["DRV_S_CANGL"], _NC, "f"),
+    "ppxLo": (C["DRV_S_PPXL"], _NPD, "f"), "ppyLo": (C["DRV_S_PPYL"], _NPD, "f"),
+}
+DRV_SPLIT = {"cpx": "cpxLo", "cpy": "cpyLo", "cang": "cangLo", "ppx": "ppxLo", "ppy": "ppyLo"}
+DRV_INT_EXTRA = [C["DRV_S_STEP_DIAG"]]
+
+
+def int_mask(fields, n_words, extra=()):
+    mask = [False] * n_words
+    for off, cnt, kind in fields.values():
+        if kind == "i":
+            for k in range(off, off + cnt):
+                mask[k] = True
+    for k in extra:
+        mask[k] = True
+    return mask
+
+
+def drv_int_mask():
+    return int_mask(DRV_FIELDS, C["DRV_STATE_WORDS"], DRV_INT_EXTRA)

@@ -264,6 +264,145 @@ typedef struct DynEnvRoboCupOut {
   float* info;  /* [E][RC_INFO_WORDS]       rewards, done, episode stats, full/recon state     */
 } DynEnvRoboCupOut;
 
+/* ======================================================================= Driving
+ * DrivingEnvironment (DrivingEnvironment.py:20-56): N cars (boxes), up to 20 pedestrians (circles), up to
+ * 20 obstacles and 4 buildings (static boxes), two roads.  Shape ids follow the reference's insertion
+ * order (_setup_scene :58-63): buildings 0..3, cars 4..13, pedestrians 14..33, obstacles 34..53. */
+#define DRV_MAXCARS 10
+#define DRV_MAXPED 20
+#define DRV_MAXOBS 20
+#define DRV_NBUILD 4
+#define DRV_SUBSTEPS 10
+#define DRV_MAXARB 32
+#define DRV_MAXACTIVE 16
+#define DRV_SHAPE_CAR0 4
+#define DRV_SHAPE_PED0 14
+#define DRV_SHAPE_OBS0 34
+#define DRV_NSHAPE 54
+#define DRV_NLANEROWS 6     /* getCarLaneDistances rows: 4 (road 0) + 2 (road 1) */
+/* observation capacities per observer (after false positives) */
+#define DRV_CAP_CAR 14
+#define DRV_CAP_OBS 24
+#define DRV_CAP_PED 28
+#define DRV_CAP_LANE 10
+#define DRV_F_CAR 7
+#define DRV_F_OBS 6
+#define DRV_F_PED 2
+#define DRV_F_LANE 4
+#define DRV_F_SELF 9
+
+enum {
+  /* cars, arrays of DRV_MAXCARS (Car.py:15-52) */
+  DRV_S_CPX = 0,                              /* F position (hi word, see DRV_S_CPXL)  */
+  DRV_S_CPY = DRV_S_CPX + DRV_MAXCARS,
+  DRV_S_CANG = DRV_S_CPY + DRV_MAXCARS,       /* F angle                               */
+  DRV_S_CVX = DRV_S_CANG + DRV_MAXCARS,       /* F velocity                            */
+  DRV_S_CVY = DRV_S_CVX + DRV_MAXCARS,
+  DRV_S_CW = DRV_S_CVY + DRV_MAXCARS,         /* F angular velocity                    */
+  DRV_S_CVBX = DRV_S_CW + DRV_MAXCARS,        /* F bias velocity                       */
+  DRV_S_CVBY = DRV_S_CVBX + DRV_MAXCARS,
+  DRV_S_CWB = DRV_S_CVBY + DRV_MAXCARS,
+  DRV_S_CDIRX = DRV_S_CWB + DRV_MAXCARS,      /* F car.direction                       */
+  DRV_S_CDIRY = DRV_S_CDIRX + DRV_MAXCARS,
+  DRV_S_CPREVX = DRV_S_CDIRY + DRV_MAXCARS,   /* F prevPos                             */
+  DRV_S_CPREVY = DRV_S_CPREVX + DRV_MAXCARS,
+  DRV_S_CGOALX = DRV_S_CPREVY + DRV_MAXCARS,  /* F goal                                */
+  DRV_S_CGOALY = DRV_S_CGOALX + DRV_MAXCARS,
+  DRV_S_CTYPE = DRV_S_CGOALY + DRV_MAXCARS,   /* I type 0..3 (mass, size, power)       */
+  DRV_S_CTEAM = DRV_S_CTYPE + DRV_MAXCARS,    /* I                                     */
+  DRV_S_CFLAGS = DRV_S_CTEAM + DRV_MAXCARS,   /* I DRV_CF_*                            */
+  DRV_S_CLANE = DRV_S_CFLAGS + DRV_MAXCARS,   /* I car.position (LanePosition)         */
+  /* pedestrians, arrays of DRV_MAXPED (Pedestrian.py:21-37) */
+  DRV_S_PPX = DRV_S_CLANE + DRV_MAXCARS,
+  DRV_S_PPY = DRV_S_PPX + DRV_MAXPED,
+  DRV_S_PVX = DRV_S_PPY + DRV_MAXPED,
+  DRV_S_PVY = DRV_S_PVX + DRV_MAXPED,
+  DRV_S_PVBX = DRV_S_PVY + DRV_MAXPED,
+  DRV_S_PVBY = DRV_S_PVBX + DRV_MAXPED,
+  DRV_S_PMOVING = DRV_S_PVBY + DRV_MAXPED,    /* F moving (ms left)                    */
+  DRV_S_PSPEED = DRV_S_PMOVING + DRV_MAXPED,  /* I speed 3..6                          */
+  DRV_S_PFLAGS = DRV_S_PSPEED + DRV_MAXPED,   /* I DRV_PF_*                            */
+  /* obstacles, arrays of DRV_MAXOBS (half extents 10 x 10) */
+  DRV_S_OPX = DRV_S_PFLAGS + DRV_MAXPED,
+  DRV_S_OPY = DRV_S_OPX + DRV_MAXOBS,
+  /* environment scalars */
+  DRV_S_ELAPSED = DRV_S_OPY + DRV_MAXOBS,     /* I */
+  DRV_S_EPISODE = DRV_S_ELAPSED + 1,          /* I */
+  DRV_S_ALLFIN = DRV_S_EPISODE + 1,           /* I allFinished */
+  DRV_S_NPED = DRV_S_ALLFIN + 1,              /* I */
+  DRV_S_NOBS = DRV_S_NPED + 1,                /* I */
+  DRV_S_STEPPED = DRV_S_NOBS + 1,             /* I */
+  DRV_S_EPR = DRV_S_STEPPED + 1,              /* F [DRV_MAXCARS] episodeRewards    */
+  DRV_S_EPPR = DRV_S_EPR + DRV_MAXCARS,       /* F [DRV_MAXCARS] episodePosRewards */
+  /* cached contact pairs that involve a car (pedestrian-pedestrian and pedestrian-obstacle pairs are
+     ignored by the reference's handlers and never stored) */
+  DRV_S_NARB = DRV_S_EPPR + DRV_MAXCARS,
+  DRV_S_ARBKEY = DRV_S_NARB + 1,              /* I a | b<<8 | state<<16 | age<<24 */
+  DRV_S_ARBCON = DRV_S_ARBKEY + DRV_MAXARB,   /* I ncontacts | hash0<<8 | hash1<<16 */
+  DRV_S_ARBJN0 = DRV_S_ARBCON + DRV_MAXARB,
+  DRV_S_ARBJT0 = DRV_S_ARBJN0 + DRV_MAXARB,
+  DRV_S_ARBJN1 = DRV_S_ARBJT0 + DRV_MAXARB,
+  DRV_S_ARBJT1 = DRV_S_ARBJN1 + DRV_MAXARB,
+  /* low-order words of the two-float coordinates */
+  DRV_S_CPXL = DRV_S_ARBJT1 + DRV_MAXARB,
+  DRV_S_CPYL = DRV_S_CPXL + DRV_MAXCARS,
+  DRV_S_CANGL = DRV_S_CPYL + DRV_MAXCARS,
+  DRV_S_PPXL = DRV_S_CANGL + DRV_MAXCARS,
+  DRV_S_PPYL = DRV_S_PPXL + DRV_MAXPED,
+  /* accumulators of the step in flight */
+  DRV_S_STEP_REW = DRV_S_PPYL + DRV_MAXPED,       /* F [DRV_MAXCARS] carRewards    */
+  DRV_S_STEP_POSREW = DRV_S_STEP_REW + DRV_MAXCARS,
+  DRV_S_STEP_TEAMREW = DRV_S_STEP_POSREW + DRV_MAXCARS,
+  DRV_S_STEP_DIAG = DRV_S_STEP_TEAMREW + 1,
+  DRV_S_STEP_END = DRV_S_STEP_DIAG + 1,
+  DRV_STATE_WORDS_RAW = DRV_S_STEP_END,
+  DRV_STATE_WORDS = (DRV_STATE_WORDS_RAW + 31) / 32 * 32
+};
+#define DRV_CF_FINISHED 1
+#define DRV_CF_CRASHED 2
+#define DRV_PF_DEAD 1
+#define DRV_PF_CROSSING 2
+#define DRV_PF_BEGINCROSSING 4
+#define DRV_PF_SIDE 8
+#define DRV_PF_ROAD 16     /* 0: the vertical road, 1: the horizontal one */
+
+/* PARTIAL observation record per (env, observer): obs[E][N][DRV_OBS_WORDS]
+ * ((cars, obstacles, pedestrians), (self, lanes), (1,1,1)) of getAgentVision (DrivingEnvironment.py:960-977);
+ * FULL observations (get_full_obs :121-124) use the same record: cars = the other cars, obstacles rows hold
+ * 4 floats, lanes rows 5 floats (DRV_F_LANE_FULL), no noise. */
+#define DRV_F_LANE_FULL 5
+enum {
+  DRV_O_SELF = 0,                                           /* F [DRV_F_SELF]              */
+  DRV_O_CAR = DRV_O_SELF + DRV_F_SELF + 3,                  /* F [DRV_CAP_CAR][DRV_F_CAR]  */
+  DRV_O_OBS = DRV_O_CAR + DRV_CAP_CAR * DRV_F_CAR,          /* F [DRV_CAP_OBS][DRV_F_OBS]  */
+  DRV_O_PED = DRV_O_OBS + DRV_CAP_OBS * DRV_F_OBS,          /* F [DRV_CAP_PED][DRV_F_PED]  */
+  DRV_O_LANE = DRV_O_PED + DRV_CAP_PED * DRV_F_PED,         /* F [DRV_CAP_LANE][DRV_F_LANE_FULL] */
+  DRV_O_COUNTS = DRV_O_LANE + DRV_CAP_LANE * DRV_F_LANE_FULL, /* I [4] cars, obstacles, pedestrians, lanes */
+  DRV_OBS_WORDS_RAW = DRV_O_COUNTS + 4,
+  DRV_OBS_WORDS = (DRV_OBS_WORDS_RAW + 31) / 32 * 32
+};
+/* per-environment result record: info[E][DRV_INFO_WORDS] */
+enum {
+  DRV_I_REWARDS = 0,                         /* F [DRV_MAXCARS] carRewards */
+  DRV_I_DONE = DRV_I_REWARDS + DRV_MAXCARS,  /* I */
+  DRV_I_EPR = DRV_I_DONE + 1,                /* F [DRV_MAXCARS] */
+  DRV_I_EPPR = DRV_I_EPR + DRV_MAXCARS,
+  DRV_I_EPG = DRV_I_EPPR + DRV_MAXCARS,      /* I [2] finished-and-not-crashed, crashed */
+  DRV_I_FLAGS = DRV_I_EPG + 2,               /* I diagnostics (RC_IF_*) */
+  DRV_I_STATE_CARS = DRV_I_FLAGS + 1,        /* F [DRV_MAXCARS][7] info['Full State'][0] */
+  DRV_I_STATE_OBS = DRV_I_STATE_CARS + DRV_MAXCARS * 7, /* F [DRV_MAXOBS][4] */
+  DRV_I_STATE_PED = DRV_I_STATE_OBS + DRV_MAXOBS * 4,   /* F [DRV_MAXPED][2] */
+  DRV_I_NOBS = DRV_I_STATE_PED + DRV_MAXPED * 2,        /* I */
+  DRV_I_NPED = DRV_I_NOBS + 1,                          /* I */
+  DRV_INFO_WORDS_RAW = DRV_I_NPED + 1,
+  DRV_INFO_WORDS = (DRV_INFO_WORDS_RAW + 31) / 32 * 32
+};
+
+typedef struct DynEnvDrivingOut {
+  float* obs;   /* [E][N][DRV_OBS_WORDS] */
+  float* info;  /* [E][DRV_INFO_WORDS]   */
+} DynEnvDrivingOut;
+
 /* ---- entry points */
 int dynenv_abi_version(void);
 const char* dynenv_last_error(void);

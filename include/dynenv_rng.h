@@ -45,4 +45,18 @@
 #define RC_SITE_OBS_FP 24       /* b = loop index 0..9; k: 0 test, 1 class, 2 distance, 3 angle, 4.. class draws (:1279-1305) */
 #define RC_SITE_OBS_FPBALL 25   /* b = row in the robot list; k: 0 test, 1 drop test, 2,3 offset, 4 size (:1308-1316) */
 
+
+/* Driving sites */
+#define DRV_SITE_RESET 32      /* k: draws of _create_agents / _create_pedestrians / _create_obstacles in call order (DrivingEnvironment.py:76-98,527-584) */
+#define DRV_SITE_PEDMOVE 33    /* a = pedestrian; k: 0 duration, 1 speed, 2 crossing chance, 3 crossing speed (:470-500) */
+/* observation sites: a = observer, b = entity index.  addNoiseRect (cutils.py:479-542): k 0,1 position, 2 false negative,
+   3 misclassification, 4 angle; addNoiseLane (:380-413): k 0 distance, 1 angle, 2 false negative */
+#define DRV_SITE_OBS_SELF 40
+#define DRV_SITE_OBS_CAR 41
+#define DRV_SITE_OBS_PED 42
+#define DRV_SITE_OBS_OBST 43
+#define DRV_SITE_OBS_LANE 44
+#define DRV_SITE_OBS_FP 45     /* b = loop index; k: 0 test, 1 class, 2 distance, 3 direction, 4 object angle, 5.. class draws (:828-874) */
+#define DRV_SITE_OBS_FPPED 46  /* b = row of the car list; k: 0 test, 1, 2 offset (:877-882) */
+
 #endif

@@ -156,6 +156,134 @@ class RcOracle(object):
         self._lib.rc_load_state(self._h, w.ctypes.data)
 
 
+class DrvAgentObs(C.Structure):
+    _fields_ = [("self_", _arr(C.c_double, L.DRV_F_SELF)), ("car", _arr(C.c_double, L.DRV_CAP_CAR, L.DRV_F_CAR)),
+                ("obs", _arr(C.c_double, L.DRV_CAP_OBS, L.DRV_F_OBS)), ("ped", _arr(C.c_double, L.DRV_CAP_PED, L.DRV_F_PED)),
+                ("lane", _arr(C.c_double, L.DRV_CAP_LANE, L.DRV_F_LANE_FULL)), ("counts", _arr(C.c_int32, 4))]
+
+
+class DrvStepOut(C.Structure):
+    _fields_ = [("agent", DrvAgentObs * L.DRV_MAXCARS), ("rewards", _arr(C.c_double, L.DRV_MAXCARS)), ("done", C.c_int32),
+                ("episode_r", _arr(C.c_double, L.DRV_MAXCARS)), ("episode_p_r", _arr(C.c_double, L.DRV_MAXCARS)),
+                ("episode_g", _arr(C.c_int32, 2)), ("state_cars", _arr(C.c_double, L.DRV_MAXCARS, 7)),
+                ("state_obs", _arr(C.c_double, L.DRV_MAXOBS, 4)), ("state_ped", _arr(C.c_double, L.DRV_MAXPED, 2)),
+                ("nobs", C.c_int32), ("nped", C.c_int32)]
+
+    def to_dict(self):
+        out = {}
+        ag = self.agent
+        for name, key in (("self_", "self"), ("car", "car"), ("obs", "obs"), ("ped", "ped"), ("lane", "lane"), ("counts", "counts")):
+            out[key] = np.stack([np.ctypeslib.as_array(getattr(ag[i], name)).copy() for i in range(L.DRV_MAXCARS)])
+        for name, _ in self._fields_[1:]:
+            v = getattr(self, name)
+            out[name] = int(v) if isinstance(v, int) else np.ctypeslib.as_array(v).copy()
+        return out
+
+
+class DrvOracle(object):
+    """One Driving environment of the CPU oracle (oracle/drv_oracle.c)."""
+
+    def __init__(self, nPlayers, obsType=1, noiseType=1, noiseMagnitude=2.0, continuous=False, flags=0, seed=0, env_id=0):
+        lb = self._lib = lib()
+        lb.drv_create.restype = C.c_void_p
+        lb.drv_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint, C.c_uint64, C.c_uint32]
+        for name in ("drv_destroy", "drv_reset"):
+            getattr(lb, name).argtypes = [C.c_void_p]
+            getattr(lb, name).restype = None
+        lb.drv_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        for name in ("drv_tape_pos", "drv_tape_underflow", "drv_arb_overflow"):
+            getattr(lb, name).argtypes = [C.c_void_p]
+            getattr(lb, name).restype = C.c_int
+        lb.drv_store_state.argtypes = [C.c_void_p, C.c_void_p]
+        lb.drv_load_state.argtypes = [C.c_void_p, C.c_void_p]
+        lb.drv_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lb.drv_reset_obs.argtypes = [C.c_void_p, C.c_void_p]
+        lb.drv_debug_substep_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        assert lb.drv_stepout_size() == C.sizeof(DrvStepOut), (lb.drv_stepout_size(), C.sizeof(DrvStepOut))
+        self._h = lb.drv_create(int(nPlayers), int(obsType), int(noiseType), float(noiseMagnitude), int(bool(continuous)),
+                                int(flags), int(seed), int(env_id))
+        self.N = min(int(nPlayers), L.DRV_MAXCARS)
+        self._tape = None
+        self._out = DrvStepOut()
+
+    def __del__(self):
+        try:
+            self._lib.drv_destroy(self._h)
+        except Exception:
+            pass
+
+    def set_tape(self, tape):
+        if tape is None:
+            self._tape = None
+            self._lib.drv_set_tape(self._h, None, 0)
+        else:
+            self._tape = np.ascontiguousarray(tape, dtype=np.float64)
+            self._lib.drv_set_tape(self._h, self._tape.ctypes.data, len(self._tape))
+
+    def tape_pos(self):
+        return self._lib.drv_tape_pos(self._h)
+
+    def tape_underflow(self):
+        return bool(self._lib.drv_tape_underflow(self._h))
+
+    def arb_overflow(self):
+        return bool(self._lib.drv_arb_overflow(self._h))
+
+    def debug_substep_range(self, begin, end):
+        self._lib.drv_debug_substep_range(self._h, int(begin), int(end))
+
+    def reset(self):
+        self._lib.drv_reset(self._h)
+
+    def reset_obs(self):
+        self._lib.drv_reset_obs(self._h, C.byref(self._out))
+        return self._out.to_dict()
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.N, 2)
+        self._lib.drv_step(self._h, a.ctypes.data, C.byref(self._out))
+        return self._out.to_dict()
+
+    def get_state(self):
+        w = np.zeros(L.DRV_STATE_WORDS, dtype=np.float64)
+        self._lib.drv_store_state(self._h, w.ctypes.data)
+        return w
+
+    def set_state(self, words):
+        w = np.ascontiguousarray(words, dtype=np.float64)
+        assert w.shape == (L.DRV_STATE_WORDS,)
+        self._lib.drv_load_state(self._h, w.ctypes.data)
+
+
+def drv_words_to_f32_record(words):
+    """Driving: float64 word list -> uint32 record (two-float coordinates split into hi + lo)"""
+    w = np.array(words, dtype=np.float64)
+    for hi, lo in L.DRV_SPLIT.items():
+        (oh, cnt, _), (ol, _, _) = L.DRV_FIELDS[hi], L.DRV_FIELDS[lo]
+        v = w[..., oh:oh + cnt] + w[..., ol:ol + cnt]
+        h = v.astype(np.float32).astype(np.float64)
+        w[..., oh:oh + cnt] = h
+        w[..., ol:ol + cnt] = v - h
+    mask = np.array(L.drv_int_mask())
+    rec = np.zeros(w.shape, dtype=np.uint32)
+    rec[..., mask] = w[..., mask].astype(np.int64).astype(np.int32).view(np.uint32)
+    rec[..., ~mask] = w[..., ~mask].astype(np.float32).view(np.uint32)
+    return rec
+
+
+def drv_f32_record_to_words(rec):
+    r = np.asarray(rec, dtype=np.uint32)
+    mask = np.array(L.drv_int_mask())
+    w = np.zeros(r.shape, dtype=np.float64)
+    w[..., mask] = r[..., mask].view(np.int32).astype(np.float64)
+    w[..., ~mask] = r[..., ~mask].view(np.float32).astype(np.float64)
+    for hi, lo in L.DRV_SPLIT.items():
+        (oh, cnt, _), (ol, _, _) = L.DRV_FIELDS[hi], L.DRV_FIELDS[lo]
+        w[..., oh:oh + cnt] += w[..., ol:ol + cnt]
+        w[..., ol:ol + cnt] = 0
+    return w
+
+
 def pad_words(words):
     """float64 word lists of an older (shorter) record layout -> current width (new fields are zero)."""
     w = np.asarray(words, dtype=np.float64)

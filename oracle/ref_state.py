@@ -216,3 +216,107 @@ def robocup_set_state(env, w, ns):
         sp.cached_arbiters[(arb.a.index, arb.b.index)] = arb
         if st == 0:  # FIRST: was active in the previous substep
             sp.arbiters.append(arb)
+
+
+# ---------------------------------------------------------------- Driving
+DF = L.DRV_FIELDS
+
+
+def _drv_shape_id(env, shape):
+    """shim shape -> C-ABI shape id (buildings 0..3, cars 4..13, pedestrians 14..33, obstacles 34..53)"""
+    for k, b in enumerate(env.buildings):
+        if shape is b.shape:
+            return k
+    for k, c in enumerate(env.agents):
+        if shape is c.shape:
+            return L.DRV_SHAPE_CAR0 + k
+    for k, p in enumerate(env.pedestrians):
+        if shape is p.shape:
+            return L.DRV_SHAPE_PED0 + k
+    for k, o in enumerate(env.obstacles):
+        if shape is o.shape:
+            return L.DRV_SHAPE_OBS0 + k
+    raise KeyError(shape)
+
+
+def _drv_hash(h):
+    if h == 0:
+        return 0
+    (_, v1), (_, v2) = h
+    return 1 + v1 + 4 * v2
+
+
+def driving_get_state(env, episode=1):
+    w = np.zeros(L.DRV_STATE_WORDS, dtype=np.float64)
+    for i, c in enumerate(env.agents):
+        b = c.shape.body
+        for name, val in (("cpx", b._px), ("cpy", b._py), ("cang", b._a), ("cvx", b._vx), ("cvy", b._vy), ("cw", b._w),
+                          ("cvbx", b._vbx), ("cvby", b._vby), ("cwb", b._wb), ("cdirx", c.direction.x), ("cdiry", c.direction.y),
+                          ("cprevx", c.prevPos[0]), ("cprevy", c.prevPos[1]), ("cgoalx", c.goal[0]), ("cgoaly", c.goal[1]),
+                          ("ctype", c.type), ("cteam", c.team),
+                          ("cflags", (L.DRV_CF_FINISHED if c.finished else 0) | (L.DRV_CF_CRASHED if c.crashed else 0)),
+                          ("clane", int(c.position))):
+            w[DF[name][0] + i] = val
+    for i, p in enumerate(env.pedestrians):
+        b = p.shape.body
+        road = 0 if p.direction == env.roads[0].direction else 1
+        for name, val in (("ppx", b._px), ("ppy", b._py), ("pvx", b._vx), ("pvy", b._vy), ("pvbx", b._vbx), ("pvby", b._vby),
+                          ("pmoving", p.moving), ("pspeed", p.speed),
+                          ("pflags", (L.DRV_PF_DEAD if p.dead else 0) | (L.DRV_PF_CROSSING if p.crossing else 0)
+                           | (L.DRV_PF_BEGINCROSSING if p.beginCrossing else 0) | (L.DRV_PF_SIDE if p.side else 0)
+                           | (L.DRV_PF_ROAD if road else 0))):
+            w[DF[name][0] + i] = val
+    for i, o in enumerate(env.obstacles):
+        w[DF["opx"][0] + i], w[DF["opy"][0] + i] = o.shape.body._px, o.shape.body._py
+    N = len(env.agents)
+    w[DF["episodeRewards"][0]:DF["episodeRewards"][0] + N] = env.episodeRewards
+    w[DF["episodePosRewards"][0]:DF["episodePosRewards"][0] + N] = env.episodePosRewards
+    for name, val in (("elapsed", env.elapsed), ("episode", episode), ("allFinished", int(env.allFinished)),
+                      ("nPed", len(env.pedestrians)), ("nObs", len(env.obstacles)),
+                      ("stepped", 1 if env.space.curr_dt != 0.0 else 0)):
+        w[DF[name][0]] = val
+    # only pairs that involve a car are state: the others are ignored by the handlers (no contacts, no callbacks)
+    arbs = [a for a in env.space.cached_arbiters.values()
+            if any(L.DRV_SHAPE_CAR0 <= _drv_shape_id(env, s) < L.DRV_SHAPE_PED0 for s in (a.a, a.b))]
+    assert len(arbs) <= L.DRV_MAXARB
+    w[DF["nArb"][0]] = len(arbs)
+    for k, arb in enumerate(arbs):
+        a, b = _drv_shape_id(env, arb.a), _drv_shape_id(env, arb.b)
+        age = env.space.stamp - arb.stamp
+        w[DF["arbKey"][0] + k] = a | (b << 8) | (arb.state << 16) | (age << 24)
+        hs = [_drv_hash(c.hash) for c in arb.contacts] + [0, 0]
+        w[DF["arbCon"][0] + k] = len(arb.contacts) | (hs[0] << 8) | (hs[1] << 16)
+        for ci, c in enumerate(arb.contacts[:2]):
+            w[DF["arbJn%d" % ci][0] + k] = c.jnAcc
+            w[DF["arbJt%d" % ci][0] + k] = c.jtAcc
+    return w
+
+
+def driving_set_state(env, w, ns):
+    """Injects positions / velocities / flags of cars and pedestrians into a freshly reset reference env (same
+    scene: types, goals, counts are taken from the env itself); clears the arbiter cache."""
+    w = [float(v) for v in w]
+    Vec2d = ns.pymunk.Vec2d
+    friction_car = ns.cutils.friction_car
+    friction_car_crashed = ns.cutils.friction_car_crashed
+    for i, c in enumerate(env.agents):
+        b = c.shape.body
+        b._px, b._py, b._a = w[DF["cpx"][0] + i], w[DF["cpy"][0] + i], w[DF["cang"][0] + i]
+        b._vx, b._vy, b._w = w[DF["cvx"][0] + i], w[DF["cvy"][0] + i], w[DF["cw"][0] + i]
+        b._vbx = b._vby = b._wb = 0.0
+        c.direction = Vec2d(w[DF["cdirx"][0] + i], w[DF["cdiry"][0] + i])
+        c.prevPos = Vec2d(w[DF["cprevx"][0] + i], w[DF["cprevy"][0] + i])
+        fl = int(w[DF["cflags"][0] + i])
+        c.finished, c.crashed = bool(fl & L.DRV_CF_FINISHED), bool(fl & L.DRV_CF_CRASHED)
+        b.velocity_func = friction_car_crashed if c.finished else friction_car
+        c.shape.cache_bb()
+    for i, p in enumerate(env.pedestrians):
+        b = p.shape.body
+        b._px, b._py = w[DF["ppx"][0] + i], w[DF["ppy"][0] + i]
+        b._vx, b._vy = w[DF["pvx"][0] + i], w[DF["pvy"][0] + i]
+        p.moving = w[DF["pmoving"][0] + i]
+        fl = int(w[DF["pflags"][0] + i])
+        p.crossing, p.beginCrossing, p.side = bool(fl & L.DRV_PF_CROSSING), bool(fl & L.DRV_PF_BEGINCROSSING), 1 if fl & L.DRV_PF_SIDE else 0
+        p.shape.cache_bb()
+    env.space.cached_arbiters.clear()
+    env.space.arbiters = []
