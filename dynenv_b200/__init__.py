@@ -8,7 +8,7 @@ from .enums import DynEnvType, NoiseType, ObservationType  # noqa: F401
 
 def __getattr__(name):
     # torch is imported lazily so that `import dynenv_b200.layout` stays light (oracle, fixtures)
-    if name in ("BatchedRoboCup", "RoboCupOutputs"):
+    if name in ("BatchedRoboCup", "RoboCupOutputs", "BatchedDriving", "DrivingOutputs"):
         from . import batched
         return getattr(batched, name)
     if name in ("RoboCupEnvironment", "make_dyn_env", "BatchedVecEnv"):

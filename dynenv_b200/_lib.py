@@ -26,6 +26,10 @@ class DynEnvRoboCupOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("full", C.c_void_p), ("info", C.c_void_p)]
 
 
+class DynEnvDrivingOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("info", C.c_void_p)]
+
+
 class DynEnvError(Exception):
     def __init__(self, code, msg):
         Exception.__init__(self, msg)

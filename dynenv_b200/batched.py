@@ -164,3 +164,87 @@ class BatchedRoboCup(object):
         assert st.shape == (self.nEnvs, self.state_words) and st.element_size() == 4
         _lib.check(self._lib.dynenv_set_state(self._h, st.data_ptr(), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()  # `st` may be a temporary
+
+
+# ---------------------------------------------------------------------------------------------- Driving
+_DRV_TYPES = [("car", L.DRV_O_CAR, L.DRV_CAP_CAR, L.DRV_F_CAR), ("obs", L.DRV_O_OBS, L.DRV_CAP_OBS, L.DRV_F_OBS),
+              ("ped", L.DRV_O_PED, L.DRV_CAP_PED, L.DRV_F_PED), ("lane", L.DRV_O_LANE, L.DRV_CAP_LANE, L.DRV_F_LANE_FULL)]
+
+
+class DrivingOutputs(object):
+    """Named views of one set of Driving output buffers (no copies): per (env, car) the padded-with-counts
+    record of include/dynenv_b200.h (DRV_O_*), per env the result record (DRV_I_*)."""
+
+    def __init__(self, nEnvs, N, device):
+        self.N = N
+        self.record = torch.zeros((nEnvs, N, L.DRV_OBS_WORDS), dtype=torch.float32, device=device)
+        self.info = torch.zeros((nEnvs, L.DRV_INFO_WORDS), dtype=torch.float32, device=device)
+        self.c_struct = _lib.DynEnvDrivingOut(self.record.data_ptr(), self.info.data_ptr())
+        rec_i, info_i = self.record.view(torch.int32), self.info.view(torch.int32)
+        self.self_ = self.record[..., L.DRV_O_SELF:L.DRV_O_SELF + L.DRV_F_SELF]
+        for name, off, cap, feat in _DRV_TYPES:
+            setattr(self, name, self.record[..., off:off + cap * feat].unflatten(-1, (cap, feat)))
+        self.counts = rec_i[..., L.DRV_O_COUNTS:L.DRV_O_COUNTS + 4]
+        self.rewards = self.info[:, L.DRV_I_REWARDS:L.DRV_I_REWARDS + N]
+        self.done = info_i[:, L.DRV_I_DONE]
+        self.diag = info_i[:, L.DRV_I_FLAGS]
+        self.episode_r = self.info[:, L.DRV_I_EPR:L.DRV_I_EPR + N]
+        self.episode_p_r = self.info[:, L.DRV_I_EPPR:L.DRV_I_EPPR + N]
+        self.episode_g = info_i[:, L.DRV_I_EPG:L.DRV_I_EPG + 2]
+        self.state_cars = self.info[:, L.DRV_I_STATE_CARS:L.DRV_I_STATE_CARS + L.DRV_MAXCARS * 7].unflatten(-1, (L.DRV_MAXCARS, 7))[:, :N]
+        self.state_obs = self.info[:, L.DRV_I_STATE_OBS:L.DRV_I_STATE_OBS + L.DRV_MAXOBS * 4].unflatten(-1, (L.DRV_MAXOBS, 4))
+        self.state_ped = self.info[:, L.DRV_I_STATE_PED:L.DRV_I_STATE_PED + L.DRV_MAXPED * 2].unflatten(-1, (L.DRV_MAXPED, 2))
+        self.n_obs = info_i[:, L.DRV_I_NOBS]
+        self.n_ped = info_i[:, L.DRV_I_NPED]
+
+
+class BatchedDriving(object):
+    """nEnvs Driving environments on one GPU (reference: DynEnv/DrivingEnvironment.py:20-56 per env,
+    DynEnv/__init__.py:6-25 for the batch).  continuousActions=True takes acc = action[0], steer = action[1]
+    (the reference's own continuous branch raises UnboundLocalError, DrivingEnvironment.py:360-368)."""
+
+    nTimeSteps = 1
+    stepIterCnt = L.DRV_SUBSTEPS
+
+    def __init__(self, nEnvs, nPlayers, observationType=ObservationType.PARTIAL, noiseType=NoiseType.REALISTIC,
+                 noiseMagnitude=2.0, continuousActions=False, auto_reset=False, seed=0, device=0, env_id_offset=0,
+                 terminal_outputs=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dynenv_b200 needs a CUDA device (no CPU fallback)")
+        self._lib = _lib.lib()
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.nEnvs = int(nEnvs)
+        self.nPlayers = self.N = min(int(nPlayers), L.DRV_MAXCARS)
+        self.obs_type = int(observationType)
+        cfg = _lib.DynEnvConfig(L.DYNENV_ABI_VERSION, L.DYNENV_KIND_DRIVING, self.nEnvs, int(nPlayers), self.obs_type,
+                                int(noiseType), float(noiseMagnitude), int(bool(continuousActions)),
+                                L.DYNENV_FLAG_AUTO_RESET if auto_reset else 0,
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset), self.device.index or 0)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.dynenv_create(C.byref(cfg), C.byref(self._h)))
+        self.state_words = self._lib.dynenv_state_words(self._h)
+        with torch.cuda.device(self.device):
+            self.out = DrivingOutputs(self.nEnvs, self.N, self.device)
+            self.terminal = DrivingOutputs(self.nEnvs, self.N, self.device) if terminal_outputs else None
+
+    close = BatchedRoboCup.close
+    __del__ = BatchedRoboCup.__del__
+    _stream = BatchedRoboCup._stream
+    set_random_seed = BatchedRoboCup.set_random_seed
+    reset = BatchedRoboCup.reset
+    debug_timing = BatchedRoboCup.debug_timing
+    last_kernel_ms = BatchedRoboCup.last_kernel_ms
+    debug_substep_range = BatchedRoboCup.debug_substep_range
+    last_launch_count = BatchedRoboCup.last_launch_count
+    get_state = BatchedRoboCup.get_state
+    set_state = BatchedRoboCup.set_state
+
+    def step(self, actions):
+        """actions: float32 CUDA tensor [nEnvs, nCars, 2] (acceleration, steering)."""
+        if actions.shape != (self.nEnvs, self.N, 2):
+            raise Exception("Error: There must be 2 actions for every car")  # DrivingEnvironment.py:262-263
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
+        _lib.check(self._lib.dynenv_step(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
+        return self.out

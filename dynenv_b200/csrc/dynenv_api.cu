@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 
+#include "drv_sim.cuh"
 #include "rc_sim.cuh"
 
 using namespace dynenv;
@@ -35,22 +36,24 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 /* coalesced copy of one environment's state record between HBM and the warp's shared memory */
+template <int WORDS = RC_STATE_WORDS>
 __device__ __forceinline__ void load_record(uint32_t* S, const uint32_t* g, int lane) {
   const uint4* src = reinterpret_cast<const uint4*>(g);
   uint4* dst = reinterpret_cast<uint4*>(S);
-  for (int w = lane; w < RC_STATE_WORDS / 4; w += 32) dst[w] = src[w];
+  for (int w = lane; w < WORDS / 4; w += 32) dst[w] = src[w];
   __syncwarp();
 }
+template <int WORDS = RC_STATE_WORDS>
 __device__ __forceinline__ void store_record(uint32_t* g, const uint32_t* S, int lane) {
   __syncwarp();
   const uint4* src = reinterpret_cast<const uint4*>(S);
   uint4* dst = reinterpret_cast<uint4*>(g);
-  for (int w = lane; w < RC_STATE_WORDS / 4; w += 32) dst[w] = src[w];
+  for (int w = lane; w < WORDS / 4; w += 32) dst[w] = src[w];
 }
 
 /* the kernel parameter block -> shared memory, where every function of the simulation reads it */
 __device__ __forceinline__ void stage_cfg(const SimCfg& cfg) {
-  if (threadIdx.x < sizeof(SimCfg) / 4) rc::g_smem[threadIdx.x] = reinterpret_cast<const uint32_t*>(&cfg)[threadIdx.x];
+  if (threadIdx.x < sizeof(SimCfg) / 4) g_smem[threadIdx.x] = reinterpret_cast<const uint32_t*>(&cfg)[threadIdx.x];
   __syncthreads();
 }
 
@@ -77,8 +80,8 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
-  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
-  uint32_t* S = rc::g_smem + base;
+  const int base = CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
   rc::phys_substeps(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
@@ -93,8 +96,8 @@ rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, 
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
-  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
-  uint32_t* S = rc::g_smem + base;
+  const int base = CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
@@ -119,8 +122,8 @@ rc_finish_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ stat
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
-  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
-  uint32_t* S = rc::g_smem + base;
+  const int base = CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
@@ -140,8 +143,8 @@ rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state
   stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
   if (mask && !mask[e]) return;
-  const int base = rc::CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
-  uint32_t* S = rc::g_smem + base;
+  const int base = CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
@@ -149,6 +152,81 @@ rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state
   rc::reset_env(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr,
                 info ? info + (size_t)e * RC_INFO_WORDS : nullptr, true);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
+}
+
+/* ------------------------------------------------------------------------------------------- Driving
+ * One env step = drv_phys_kernel (10 substeps) + drv_obs_kernel (the observation of every car, rewards, info,
+ * done, auto-reset), same warp-per-environment layout as the RoboCup kernels. */
+#ifndef DRV_WPC_
+#define DRV_WPC_ 4
+#endif
+#ifndef DRV_MINB_
+#define DRV_MINB_ 4
+#endif
+constexpr int DRV_WPC = DRV_WPC_;
+
+__device__ __forceinline__ drv::Env make_drv_env(int base, const SimCfg& cfg, int e, int lane) {
+  drv::Env E;
+  E.f.base = base;
+  E.i.base = base;
+  E.lane = lane;
+  if (lane == 0) E.i[drv::X_ENVID] = (int)(cfg.env_id_offset + (uint32_t)e);
+  __syncwarp();
+  return E;
+}
+
+__global__ void __launch_bounds__(DRV_WPC * 32, DRV_MINB_)
+drv_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
+                int sub_b, int sub_e, int first) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * DRV_WPC + warp;
+  stage_cfg(cfg);
+  if (e >= cfg.n_envs) return;
+  const int base = CFG_WORDS + warp * drv::ENV_SMEM_WORDS;
+  uint32_t* S = g_smem + base;
+  load_record<DRV_STATE_WORDS>(S, state + (size_t)e * DRV_STATE_WORDS, lane);
+  drv::Env E = make_drv_env(base, cfg, e, lane);
+  drv::phys_substeps(E, actions + (size_t)e * cfg.P * 2, sub_b, sub_e, first != 0);
+  store_record<DRV_STATE_WORDS>(state + (size_t)e * DRV_STATE_WORDS, S, lane);
+}
+
+/* observation after the last substep (DrivingEnvironment.py:290-294), then rewards / info / done (:299-322);
+   a finishing episode's observation goes to the terminal buffer and the environment is re-initialised */
+__global__ void __launch_bounds__(DRV_WPC * 32, DRV_MINB_)
+drv_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, int observe, float* __restrict__ obs,
+               float* __restrict__ info, float* __restrict__ term_obs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * DRV_WPC + warp;
+  stage_cfg(cfg);
+  if (e >= cfg.n_envs) return;
+  const int base = CFG_WORDS + warp * drv::ENV_SMEM_WORDS;
+  uint32_t* S = g_smem + base;
+  load_record<DRV_STATE_WORDS>(S, state + (size_t)e * DRV_STATE_WORDS, lane);
+  drv::Env E = make_drv_env(base, cfg, e, lane);
+  const size_t obs_stride = (size_t)cfg.P * DRV_OBS_WORDS;
+  const bool finishing = cfg.auto_reset && E.i[DRV_S_ELAPSED] >= drv::MAXTIME;
+  float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
+  if (observe) drv::observe(E, (uint32_t)E.i[DRV_S_ELAPSED], o);
+  float* inf = info ? info + (size_t)e * DRV_INFO_WORDS : nullptr;
+  drv::finish_step(E, inf);
+  if (finishing) drv::reset_env(E, obs ? obs + e * obs_stride : nullptr, inf, false);
+  store_record<DRV_STATE_WORDS>(state + (size_t)e * DRV_STATE_WORDS, S, lane);
+}
+
+__global__ void __launch_bounds__(DRV_WPC * 32, DRV_MINB_)
+drv_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const uint8_t* __restrict__ mask,
+                 float* __restrict__ obs, float* __restrict__ info) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * DRV_WPC + warp;
+  stage_cfg(cfg);
+  if (e >= cfg.n_envs) return;
+  if (mask && !mask[e]) return;
+  const int base = CFG_WORDS + warp * drv::ENV_SMEM_WORDS;
+  uint32_t* S = g_smem + base;
+  load_record<DRV_STATE_WORDS>(S, state + (size_t)e * DRV_STATE_WORDS, lane);
+  drv::Env E = make_drv_env(base, cfg, e, lane);
+  drv::reset_env(E, obs ? obs + (size_t)e * cfg.P * DRV_OBS_WORDS : nullptr, info ? info + (size_t)e * DRV_INFO_WORDS : nullptr, true);
+  store_record<DRV_STATE_WORDS>(state + (size_t)e * DRV_STATE_WORDS, S, lane);
 }
 
 }  // namespace
@@ -179,7 +257,9 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   if (cfg->n_players <= 0) return fail(DYNENV_E_INVALID, "n_players must be positive");
   if (cfg->noise_magnitude < 0 || cfg->noise_magnitude > 5)
     return fail(DYNENV_E_INVALID, "Error: The noise magnitude must be between 0 and 5!"); /* environment_base.py:162-164 */
-  if (cfg->kind != DYNENV_KIND_ROBOCUP) return fail(DYNENV_E_UNSUPPORTED, "only DYNENV_KIND_ROBOCUP is built so far");
+  if (cfg->kind != DYNENV_KIND_ROBOCUP && cfg->kind != DYNENV_KIND_DRIVING) return fail(DYNENV_E_INVALID, "unknown environment kind");
+  if (cfg->kind == DYNENV_KIND_DRIVING && cfg->obs_type == DYNENV_OBS_IMAGE)
+    return fail(DYNENV_E_INVALID, "Image observation type is not supported for this environment"); /* DrivingEnvironment.py:33-35 */
   if (cfg->obs_type != DYNENV_OBS_FULL && cfg->obs_type != DYNENV_OBS_PARTIAL)
     return fail(DYNENV_E_UNSUPPORTED, "observation type not built (FULL and PARTIAL are)");
   int ndev = 0;
@@ -194,8 +274,10 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   h->cfg = *cfg;
   SimCfg& s = h->sim;
   s.n_envs = cfg->n_envs;
-  s.n_players = cfg->n_players > 5 ? 5 : cfg->n_players; /* environment_base.py:56-57 */
-  s.P = 2 * s.n_players;
+  const bool driving = cfg->kind == DYNENV_KIND_DRIVING;
+  const int maxPlayers = driving ? DRV_MAXCARS : 5;
+  s.n_players = cfg->n_players > maxPlayers ? maxPlayers : cfg->n_players; /* environment_base.py:56-57 */
+  s.P = driving ? s.n_players : 2 * s.n_players;
   s.obs_type = cfg->obs_type;
   s.noise_type = cfg->noise_type;
   s.continuous = cfg->continuous;
@@ -210,8 +292,8 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   s.seed_hi = (uint32_t)(cfg->seed >> 32);
   s.env_id_offset = (uint32_t)cfg->env_id_offset;
   s.sub_begin = 0;
-  s.sub_end = RC_SUBSTEPS;
-  h->state_words = RC_STATE_WORDS;
+  s.sub_end = driving ? DRV_SUBSTEPS : RC_SUBSTEPS;
+  h->state_words = driving ? (int)DRV_STATE_WORDS : (int)RC_STATE_WORDS;
   h->last_launches = 0;
   h->timing = 0;
   h->n_timed = 0;
@@ -243,10 +325,20 @@ int dynenv_state_words(DynEnvHandle h) { return h ? h->state_words : DYNENV_E_IN
 
 int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* stream) {
   if (!h || !out) return fail(DYNENV_E_INVALID, "null argument");
-  const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
   cudaSetDevice(h->cfg.device);
+  if (h->cfg.kind == DYNENV_KIND_DRIVING) {
+    const DynEnvDrivingOut* d = static_cast<const DynEnvDrivingOut*>(out);
+    const int dgrid = (h->sim.n_envs + DRV_WPC - 1) / DRV_WPC;
+    const size_t dsmem = ((size_t)CFG_WORDS + (size_t)DRV_WPC * drv::ENV_SMEM_WORDS) * sizeof(uint32_t);
+    drv_reset_kernel<<<dgrid, DRV_WPC * 32, dsmem, static_cast<cudaStream_t>(stream)>>>(h->sim, h->state, env_mask_dev, d->obs, d->info);
+    h->last_launches = 1;
+    cudaError_t de = cudaGetLastError();
+    if (de != cudaSuccess) return cuda_fail(de, "drv_reset_kernel launch");
+    return DYNENV_OK;
+  }
+  const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
   int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
-  size_t smem = ((size_t)rc::CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
+  size_t smem = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
   rc_reset_kernel<<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(h->sim, h->state, env_mask_dev, o->obs,
                                                                                    o->full, o->info);
   h->last_launches = 1;
@@ -257,12 +349,29 @@ int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* s
 
 int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* terminal_out, void* stream) {
   if (!h || !out || !actions_dev) return fail(DYNENV_E_INVALID, "null argument");
-  const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
-  const DynEnvRoboCupOut* t = static_cast<const DynEnvRoboCupOut*>(terminal_out);
   cudaSetDevice(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->cfg.kind == DYNENV_KIND_DRIVING) {
+    const DynEnvDrivingOut* d = static_cast<const DynEnvDrivingOut*>(out);
+    const DynEnvDrivingOut* dt = static_cast<const DynEnvDrivingOut*>(terminal_out);
+    const int dgrid = (h->sim.n_envs + DRV_WPC - 1) / DRV_WPC;
+    const size_t dsmem = ((size_t)CFG_WORDS + (size_t)DRV_WPC * drv::ENV_SMEM_WORDS) * sizeof(uint32_t);
+    h->n_timed = 0;
+    if (h->timing) cudaEventRecord(h->ev[0], st);
+    drv_phys_kernel<<<dgrid, DRV_WPC * 32, dsmem, st>>>(h->sim, h->state, actions_dev, h->sim.sub_begin, h->sim.sub_end, 1);
+    if (h->timing) { cudaEventRecord(h->ev[1], st); h->ev_class[0] = 0; }
+    drv_obs_kernel<<<dgrid, DRV_WPC * 32, dsmem, st>>>(h->sim, h->state, h->sim.sub_end == DRV_SUBSTEPS, d->obs, d->info,
+                                                       dt ? dt->obs : nullptr);
+    if (h->timing) { cudaEventRecord(h->ev[2], st); h->ev_class[1] = 1; h->n_timed = 2; }
+    h->last_launches = 2;
+    cudaError_t de = cudaGetLastError();
+    if (de != cudaSuccess) return cuda_fail(de, "drv step kernels launch");
+    return DYNENV_OK;
+  }
+  const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
+  const DynEnvRoboCupOut* t = static_cast<const DynEnvRoboCupOut*>(terminal_out);
   const int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
-  const size_t smem = ((size_t)rc::CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
+  const size_t smem = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
   int launches = 0;
   h->n_timed = 0;
   auto mark = [&](int cls) { /* event after launch number `launches` (and one before the first) */
@@ -353,7 +462,8 @@ int dynenv_last_kernel_ms(DynEnvHandle h, float* ms3, int* launches3) {
 }
 
 int dynenv_debug_substep_range(DynEnvHandle h, int begin, int end) {
-  if (!h || begin < 0 || end > RC_SUBSTEPS || begin > end) return fail(DYNENV_E_INVALID, "bad substep range");
+  if (!h || begin < 0 || end > (h->cfg.kind == DYNENV_KIND_DRIVING ? DRV_SUBSTEPS : RC_SUBSTEPS) || begin > end)
+    return fail(DYNENV_E_INVALID, "bad substep range");
   h->sim.sub_begin = begin;
   h->sim.sub_end = end;
   return DYNENV_OK;

@@ -107,6 +107,37 @@ struct Rand6 {
   }
 };
 
+/* The CTA's dynamic shared memory: [0, CFG_WORDS) a copy of the SimCfg, then one ENV_SMEM_WORDS slice
+   per warp.  Everything is addressed through this symbol so that the compiler emits LDS/STS (a pointer
+   handed to a non-inlined function would degrade to generic loads). */
+extern __shared__ __align__(16) uint32_t g_smem[];
+constexpr int CFG_WORDS = 32;
+static_assert(sizeof(SimCfg) <= CFG_WORDS * 4, "SimCfg must fit its shared-memory slot");
+
+struct SharedF { /* this warp's slice viewed as float */
+  int base;
+  __device__ __forceinline__ float& operator[](int k) const { return reinterpret_cast<float*>(g_smem)[base + k]; }
+  __device__ __forceinline__ float* operator+(int k) const { return reinterpret_cast<float*>(g_smem) + base + k; }
+};
+struct SharedI { /* ... and as int */
+  int base;
+  __device__ __forceinline__ int& operator[](int k) const { return reinterpret_cast<int*>(g_smem)[base + k]; }
+};
+struct SharedCfg {
+  __device__ __forceinline__ const SimCfg* operator->() const { return reinterpret_cast<const SimCfg*>(g_smem); }
+  __device__ __forceinline__ const SimCfg& operator*() const { return *reinterpret_cast<const SimCfg*>(g_smem); }
+};
+/* Two-float coordinates (hi + lo, include/dynenv_b200.h): accumulate d into (hi, lo) without losing
+   the bits that do not fit hi (Knuth two-sum + renormalisation) */
+__device__ __forceinline__ void two_add(float& hi, float& lo, float d) {
+  float s = __fadd_rn(hi, d);
+  float bb = __fsub_rn(s, hi);
+  float err = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(d, bb));
+  lo = __fadd_rn(lo, err);
+  float h2 = __fadd_rn(s, lo);
+  lo = __fsub_rn(lo, __fsub_rn(h2, s));
+  hi = h2;
+}
 /* random.randint(lo, hi) from a uniform, as the oracle derives it (oracle/ref_loader.py) */
 __device__ __forceinline__ int randint_from(float u, int lo, int hi) { return lo + (int)(u * (float)(hi - lo + 1)); }
 

@@ -113,26 +113,6 @@ __device__ const float g_lines[11][6] = {
     {70, 480, 130, 480, 1, -0.37f}, {130, 260, 130, 480, 0.87f, 0},  {910, 260, 970, 260, -1, 0.37f},
     {910, 480, 970, 480, -1, -0.37f}, {910, 260, 910, 480, -0.87f, 0}};
 
-/* The CTA's dynamic shared memory: [0, CFG_WORDS) a copy of the SimCfg, then one ENV_SMEM_WORDS slice
-   per warp.  Everything is addressed through this symbol so that the compiler emits LDS/STS (a pointer
-   handed to a non-inlined function would degrade to generic loads). */
-extern __shared__ __align__(16) uint32_t g_smem[];
-constexpr int CFG_WORDS = 32;
-static_assert(sizeof(SimCfg) <= CFG_WORDS * 4, "SimCfg must fit its shared-memory slot");
-
-struct SharedF { /* this warp's slice viewed as float */
-  int base;
-  __device__ __forceinline__ float& operator[](int k) const { return reinterpret_cast<float*>(g_smem)[base + k]; }
-  __device__ __forceinline__ float* operator+(int k) const { return reinterpret_cast<float*>(g_smem) + base + k; }
-};
-struct SharedI { /* ... and as int */
-  int base;
-  __device__ __forceinline__ int& operator[](int k) const { return reinterpret_cast<int*>(g_smem)[base + k]; }
-};
-struct SharedCfg {
-  __device__ __forceinline__ const SimCfg* operator->() const { return reinterpret_cast<const SimCfg*>(g_smem); }
-  __device__ __forceinline__ const SimCfg& operator*() const { return *reinterpret_cast<const SimCfg*>(g_smem); }
-};
 /* broad phase over groups: robots 0..9, ball 10, posts 11..14; all pairs (a < b) with a dynamic (99) */
 __device__ const unsigned char g_pairs[99][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {0, 7}, {0, 8}, {0, 9}, {0, 10}, {0, 11}, {0, 12}, {0, 13}, {0, 14}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 7}, {1, 8}, {1, 9}, {1, 10}, {1, 11}, {1, 12}, {1, 13}, {1, 14}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {2, 9}, {2, 10}, {2, 11}, {2, 12}, {2, 13}, {2, 14}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8}, {3, 9}, {3, 10}, {3, 11}, {3, 12}, {3, 13}, {3, 14}, {4, 5}, {4, 6}, {4, 7}, {4, 8}, {4, 9}, {4, 10}, {4, 11}, {4, 12}, {4, 13}, {4, 14}, {5, 6}, {5, 7}, {5, 8}, {5, 9}, {5, 10}, {5, 11}, {5, 12}, {5, 13}, {5, 14}, {6, 7}, {6, 8}, {6, 9}, {6, 10}, {6, 11}, {6, 12}, {6, 13}, {6, 14}, {7, 8}, {7, 9}, {7, 10}, {7, 11}, {7, 12}, {7, 13}, {7, 14}, {8, 9}, {8, 10}, {8, 11}, {8, 12}, {8, 13}, {8, 14}, {9, 10}, {9, 11}, {9, 12}, {9, 13}, {9, 14}, {10, 11}, {10, 12}, {10, 13}, {10, 14}};
 
@@ -160,17 +140,6 @@ __device__ __forceinline__ bool shape_active(const Env E, int s) { return s >= 2
 __device__ __forceinline__ V2 body_pos(const Env E, int s) { /* hi words: float32 view */
   if (s < RC_NBODY) return v2(E.f[RC_S_PX + s], E.f[RC_S_PY + s]);
   return post_pos(s - POST0);
-}
-/* Two-float coordinates (hi + lo, include/dynenv_b200.h): accumulate d into (hi, lo) without losing
-   the bits that do not fit hi (Knuth two-sum + renormalisation) */
-__device__ __forceinline__ void two_add(float& hi, float& lo, float d) {
-  float s = __fadd_rn(hi, d);
-  float bb = __fsub_rn(s, hi);
-  float err = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(d, bb));
-  lo = __fadd_rn(lo, err);
-  float h2 = __fadd_rn(s, lo);
-  lo = __fsub_rn(lo, __fsub_rn(h2, s));
-  hi = h2;
 }
 /* position of body b relative to body a, from both words: exact where it matters (close bodies) */
 __device__ __forceinline__ V2 pos_diff(const Env E, int b, int a) {

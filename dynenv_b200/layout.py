@@ -118,7 +118,9 @@ DRV_FIELDS = {
     "cpxLo": (C["DRV_S_CPXL"], _NC, "f"), "cpyLo": (C["DRV_S_CPYL"], _NC, "f"), "cangLo": (C["DRV_S_CANGL"], _NC, "f"),
     "ppxLo": (C["DRV_S_PPXL"], _NPD, "f"), "ppyLo": (C["DRV_S_PPYL"], _NPD, "f"),
 }
-DRV_SPLIT = {"cpx": "cpxLo", "cpy": "cpyLo", "cang": "cangLo", "ppx": "ppxLo", "ppy": "ppyLo"}
+DRV_SPLIT = {"cpx": "cpxLo", "cpy": "cpyLo", "ppx": "ppxLo", "ppy": "ppyLo"}
+# float64 fields stored as two 32-bit words: high-word field -> low-word field
+DRV_DOUBLE = {"cang": "cangLo"}
 DRV_INT_EXTRA = [C["DRV_S_STEP_DIAG"]]
 
 

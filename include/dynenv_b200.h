@@ -295,7 +295,7 @@ enum {
   /* cars, arrays of DRV_MAXCARS (Car.py:15-52) */
   DRV_S_CPX = 0,                              /* F position (hi word, see DRV_S_CPXL)  */
   DRV_S_CPY = DRV_S_CPX + DRV_MAXCARS,
-  DRV_S_CANG = DRV_S_CPY + DRV_MAXCARS,       /* F angle                               */
+  DRV_S_CANG = DRV_S_CPY + DRV_MAXCARS,       /* I angle: HIGH 32 bits of the float64 (low: DRV_S_CANGL) */
   DRV_S_CVX = DRV_S_CANG + DRV_MAXCARS,       /* F velocity                            */
   DRV_S_CVY = DRV_S_CVX + DRV_MAXCARS,
   DRV_S_CW = DRV_S_CVY + DRV_MAXCARS,         /* F angular velocity                    */
@@ -346,7 +346,7 @@ enum {
   /* low-order words of the two-float coordinates */
   DRV_S_CPXL = DRV_S_ARBJT1 + DRV_MAXARB,
   DRV_S_CPYL = DRV_S_CPXL + DRV_MAXCARS,
-  DRV_S_CANGL = DRV_S_CPYL + DRV_MAXCARS,
+  DRV_S_CANGL = DRV_S_CPYL + DRV_MAXCARS,     /* I low 32 bits of the float64 car angles */
   DRV_S_PPXL = DRV_S_CANGL + DRV_MAXCARS,
   DRV_S_PPYL = DRV_S_PPXL + DRV_MAXPED,
   /* accumulators of the step in flight */

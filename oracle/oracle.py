@@ -256,7 +256,8 @@ class DrvOracle(object):
 
 
 def drv_words_to_f32_record(words):
-    """Driving: float64 word list -> uint32 record (two-float coordinates split into hi + lo)"""
+    """Driving: float64 word list -> uint32 record (two-float coordinates split into hi + lo, float64 car angles
+    into their high / low 32 bits)"""
     w = np.array(words, dtype=np.float64)
     for hi, lo in L.DRV_SPLIT.items():
         (oh, cnt, _), (ol, _, _) = L.DRV_FIELDS[hi], L.DRV_FIELDS[lo]
@@ -268,6 +269,11 @@ def drv_words_to_f32_record(words):
     rec = np.zeros(w.shape, dtype=np.uint32)
     rec[..., mask] = w[..., mask].astype(np.int64).astype(np.int32).view(np.uint32)
     rec[..., ~mask] = w[..., ~mask].astype(np.float32).view(np.uint32)
+    for hi, lo in L.DRV_DOUBLE.items():
+        (oh, cnt, _), (ol, _, _) = L.DRV_FIELDS[hi], L.DRV_FIELDS[lo]
+        bits = np.ascontiguousarray(w[..., oh:oh + cnt] + w[..., ol:ol + cnt]).view(np.uint64)
+        rec[..., oh:oh + cnt] = (bits >> np.uint64(32)).astype(np.uint32)
+        rec[..., ol:ol + cnt] = (bits & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     return rec
 
 
@@ -280,6 +286,11 @@ def drv_f32_record_to_words(rec):
     for hi, lo in L.DRV_SPLIT.items():
         (oh, cnt, _), (ol, _, _) = L.DRV_FIELDS[hi], L.DRV_FIELDS[lo]
         w[..., oh:oh + cnt] += w[..., ol:ol + cnt]
+        w[..., ol:ol + cnt] = 0
+    for hi, lo in L.DRV_DOUBLE.items():
+        (oh, cnt, _), (ol, _, _) = L.DRV_FIELDS[hi], L.DRV_FIELDS[lo]
+        bits = (r[..., oh:oh + cnt].astype(np.uint64) << np.uint64(32)) | r[..., ol:ol + cnt].astype(np.uint64)
+        w[..., oh:oh + cnt] = np.ascontiguousarray(bits).view(np.float64)
         w[..., ol:ol + cnt] = 0
     return w
 

@@ -22,7 +22,7 @@ def load_golden(name, prefix="robocup_"):
     from oracle.oracle import pad_words
     g = dict(np.load(os.path.join(GOLDEN, "%s%s.npz" % (prefix, name))))
     for k in ("state0", "states", "state_reset"):
-        if k in g:
+        if k in g and prefix == "robocup_":
             g[k] = pad_words(g[k])
     return g
 
@@ -139,4 +139,81 @@ def compare_step(cfg, sim_out, gpu_state_words, outs, oracle_words, tol=1e-4):
                 got = g[k][e]
                 if rel_err(got, ref) > max(tol, LINE_TOL if k == "line" else 0):
                     bad.append((e, k, rel_err(got, ref)))
+    return bad
+
+
+# ---------------------------------------------------------------- Driving: GPU <-> oracle comparison
+DRV_OBS_KEYS = ["self", "car", "obs", "ped", "lane"]
+# warm-start impulses are compared by the velocity they stand for (lightest car: 1200)
+DRV_IMPULSE_SCALE = {"arbJn0": 1.0 / 1200, "arbJt0": 1.0 / 1200, "arbJn1": 1.0 / 1200, "arbJt1": 1.0 / 1200}
+
+
+def drv_golden_cfg(g):
+    c = g["cfg"]
+    return dict(nPlayers=int(c[0]), obsType=int(c[1]), noiseType=int(c[2]), noiseMag=float(c[3]), continuous=bool(c[4]))
+
+
+def drv_oracle_step_batch(cfg, recs, actions, seed, env_id0=0):
+    """CPU oracle (Philox mode), one step from each Driving state record (uint32 [N, W]); actions [N, nCars, 2]."""
+    from oracle.oracle import DrvOracle, drv_f32_record_to_words
+    outs, after = [], []
+    for i in range(len(recs)):
+        orc = DrvOracle(cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"], cfg["continuous"], seed=seed,
+                        env_id=env_id0 + i)
+        orc.set_state(drv_f32_record_to_words(recs[i]))
+        outs.append(orc.step(actions[i]))
+        after.append(orc.get_state())
+        assert not orc.arb_overflow()
+    return outs, np.array(after)
+
+
+def drv_compare_obs(e, g, o, N, tol, bad):
+    if not np.array_equal(g["counts"][e][:N], o["counts"][:N]):
+        bad.append((e, "counts", (g["counts"][e][:N].tolist(), o["counts"][:N].tolist())))
+        return
+    for k in DRV_OBS_KEYS:
+        err = rel_err(g[k][e][:N], o[k][:N])
+        if err > tol:
+            bad.append((e, k, err))
+
+
+def drv_compare_step(cfg, sim_out, gpu_state_words, outs, oracle_words, tol=1e-4):
+    """One batched GPU Driving step against per-env oracle results: integer / flag / count fields equal, floats
+    within tol * (1 + |ref|).  Returns a list of (env, what, detail) mismatches."""
+    N = min(cfg["nPlayers"], L.DRV_MAXCARS)
+    bad = []
+    g = {"self": sim_out.self_}
+    for k in DRV_OBS_KEYS[1:] + ["counts", "rewards", "done", "diag", "state_cars", "state_obs", "state_ped", "n_obs", "n_ped",
+                                 "episode_r", "episode_p_r", "episode_g"]:
+        g[k] = getattr(sim_out, k)
+    g = {k: v.detach().cpu().numpy() for k, v in g.items()}
+    for e, o in enumerate(outs):
+        if g["diag"][e] != 0:
+            bad.append((e, "diag", int(g["diag"][e])))
+        ws, wo = gpu_state_words[e], oracle_words[e]
+        for name, (off, cnt, kind) in L.DRV_FIELDS.items():
+            a, b = ws[off:off + cnt], wo[off:off + cnt]
+            if name in DRV_IMPULSE_SCALE:
+                a, b = a * DRV_IMPULSE_SCALE[name], b * DRV_IMPULSE_SCALE[name]
+            if kind == "i":
+                if not np.array_equal(a, b):
+                    bad.append((e, "state." + name, (a.tolist(), b.tolist())))
+            elif rel_err(a, b) > tol:
+                bad.append((e, "state." + name, rel_err(a, b)))
+        if rel_err(g["rewards"][e], o["rewards"][:N]) > tol:
+            bad.append((e, "rewards", rel_err(g["rewards"][e], o["rewards"][:N])))
+        if bool(g["done"][e]) != bool(o["done"]):
+            bad.append((e, "done", None))
+        if o["done"]:
+            for k in ("episode_r", "episode_p_r"):
+                if rel_err(g[k][e], o[k][:N]) > tol * 10:
+                    bad.append((e, k, rel_err(g[k][e], o[k][:N])))
+            if not np.array_equal(g["episode_g"][e], o["episode_g"]):
+                bad.append((e, "episode_g", None))
+        for k, ref in (("state_cars", o["state_cars"][:N]), ("state_obs", o["state_obs"]), ("state_ped", o["state_ped"])):
+            if rel_err(g[k][e], ref) > tol:
+                bad.append((e, k, rel_err(g[k][e], ref)))
+        if int(g["n_obs"][e]) != int(o["nobs"]) or int(g["n_ped"][e]) != int(o["nped"]):
+            bad.append((e, "n_obs/n_ped", None))
+        drv_compare_obs(e, g, o, N, tol, bad)
     return bad

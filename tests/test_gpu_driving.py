@@ -1,0 +1,81 @@
+"""GPU parity of the Driving path (run on the B200 box, `-m gpu`): the CUDA kernels, called through the C ABI,
+against the CPU oracle (oracle/drv_oracle.c) on the same inputs and the same Philox draws: integer / flag / count
+fields exactly, continuous values within 1e-4 relative (the kernels compute in float32, the oracle in float64).
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from helpers import drv_compare_step, drv_golden_cfg, drv_oracle_step_batch, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+NAMES = golden_names("driving_")
+
+
+def _sim(cfg, n, seed, **kw):
+    import dynenv_b200
+    return dynenv_b200.BatchedDriving(n, cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"],
+                                      continuousActions=cfg["continuous"], seed=seed, **kw)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_one_step_from_golden_states(name):
+    """every step of every golden scenario, each started from the reference's own previous state"""
+    import torch
+    from oracle.oracle import drv_f32_record_to_words, drv_words_to_f32_record
+    g = load_golden(name, "driving_")
+    cfg = drv_golden_cfg(g)
+    words = np.concatenate([g["state0"][None], g["states"][:-1]], 0)
+    recs = drv_words_to_f32_record(words)
+    seed = 2000 + len(name)
+    sim = _sim(cfg, len(recs), seed)
+    sim.set_state(torch.from_numpy(recs.view(np.int32)))
+    out = sim.step(torch.from_numpy(np.ascontiguousarray(g["actions"], dtype=np.float32)).cuda())
+    torch.cuda.synchronize()
+    assert sim.last_launch_count() == 2  # substeps + observation/finish
+    gw = drv_f32_record_to_words(sim.get_state().cpu().numpy().view(np.uint32))
+    outs, ow = drv_oracle_step_batch(cfg, recs, g["actions"], seed)
+    bad = drv_compare_step(cfg, out, gw, outs, ow, TOL)
+    assert not bad, bad[:12]
+
+
+@pytest.mark.parametrize("nPlayers,obs,noise,mag,cont", [
+    (10, 1, 1, 2.0, False), (10, 1, 0, 3.0, True), (4, 0, 1, 0.0, False), (7, 1, 1, 5.0, True)])
+def test_rollout_states(nPlayers, obs, noise, mag, cont):
+    """device reset + random play; every few steps the GPU state is handed to the oracle and one step is compared"""
+    import torch
+    from dynenv_b200 import layout as L
+    from oracle.oracle import DrvOracle, drv_f32_record_to_words
+    cfg = dict(nPlayers=nPlayers, obsType=obs, noiseType=noise, noiseMag=mag, continuous=cont)
+    n, seed, N = 48, 91, nPlayers
+    sim = _sim(cfg, n, seed)
+    out = sim.reset()
+    torch.cuda.synchronize()
+    st = drv_f32_record_to_words(sim.get_state().cpu().numpy().view(np.uint32))
+    counts0 = out.counts.cpu().numpy()
+    for e in range(0, n, 7):  # reset parity: the oracle draws the same scene and the same first observation
+        orc = DrvOracle(nPlayers, obs, noise, mag, cont, seed=seed, env_id=e)
+        orc.reset()
+        w = orc.get_state()
+        for name, (off, cnt, kind) in L.DRV_FIELDS.items():
+            assert np.allclose(st[e, off:off + cnt], w[off:off + cnt], rtol=1e-6, atol=1e-4), (e, name)
+        o = orc.reset_obs()
+        assert np.array_equal(counts0[e], o["counts"][:N]), (e, counts0[e].tolist(), o["counts"][:N].tolist())
+    rng = np.random.default_rng(6)
+    total_bad = []
+    for step in range(40):
+        a = rng.uniform(-3, 3, (n, N, 2)).astype(np.float32) if cont else rng.integers(0, 3, (n, N, 2)).astype(np.float32)
+        if step % 5 == 4:
+            recs = sim.get_state().cpu().numpy().view(np.uint32)
+            out = sim.step(torch.from_numpy(a).cuda())
+            torch.cuda.synchronize()
+            gw = drv_f32_record_to_words(sim.get_state().cpu().numpy().view(np.uint32))
+            outs, ow = drv_oracle_step_batch(cfg, recs, a, seed)
+            total_bad += [(step,) + b for b in drv_compare_step(cfg, out, gw, outs, ow, TOL)]
+        else:
+            sim.step(torch.from_numpy(a).cuda())
+    # 8 compared steps x n environments; float32 ties at the reference's hard thresholds may split a few
+    envs_bad = set((b[0], b[1]) for b in total_bad)
+    assert len(envs_bad) <= (8 * n) // 50, total_bad[:12]
+    hard = [b for b in total_bad if b[2] in ("diag", "done", "state.elapsed", "state.episode")]
+    assert not hard, hard[:10]
