@@ -2,7 +2,10 @@
 """Benchmark of the rollout hot path: env-steps/s of RoboCup 5v5 (50 substeps + 5 observation ticks x 10
 observers per env-step), PARTIAL observation, REALISTIC noise magnitude 2 (BASELINE.json configs[1]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference] [--workload robocup|driving]
+
+`--workload driving` measures BASELINE.json configs[2] instead (DrivingEnvironment, 10 cars, PARTIAL, continuous
+actions, REALISTIC noise 2: 10 substeps + 1 observation x 10 observers per env-step); the default is configs[1].
 
 One process per GPU (torchrun for N > 1); environments are sharded by contiguous env-id range with no
 data-path collective (weak scaling: E environments per GPU).  Prints ONE JSON line on rank 0.
@@ -24,29 +27,103 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "env-steps/sec (RoboCup 5v5, 50 substeps)"
 UNIT = "env-steps/s"
-WORKLOAD = "RoboCup 5v5 PARTIAL REALISTIC noise 2, canFall, auto-reset"
-N_PLAYERS = 5
-P = 2 * N_PLAYERS
-FLOP_PER_ENV_STEP = 1.0e6  # SURVEY.md 8d contract figure
+FLOP_PER_ENV_STEP = 1.0e6  # SURVEY.md 8d contract figure (both workloads)
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
-def algorithmic_bytes_per_env_step():
-    """step-boundary HBM traffic of one env-step: state record in + out, actions in,
-    5 x 10 observation records, result record."""
-    from dynenv_b200 import layout as L
-    return 4 * (2 * L.RC_STATE_WORDS + P * 4 + L.RC_NTICK * P * L.RC_OBS_WORDS + L.RC_INFO_WORDS)
+class RoboCupWorkload(object):
+    """BASELINE.json configs[1]"""
+    name = "robocup"
+    metric = "env-steps/sec (RoboCup 5v5, 50 substeps)"
+    workload = "RoboCup 5v5 PARTIAL REALISTIC noise 2, canFall, auto-reset"
+    P, act = 10, 4
+    launches_per_step = {"phys": 5, "obs": 5, "finish": 1}
+    prefix = "rc"
+
+    def make_sim(self, E, local, rank, full=False):
+        import dynenv_b200
+        obs_type = dynenv_b200.ObservationType.FULL if full else dynenv_b200.ObservationType.PARTIAL
+        return dynenv_b200.BatchedRoboCup(E, 5, obs_type, dynenv_b200.NoiseType.REALISTIC, 2.0, canFall=True,
+                                          useObsRewards=True, auto_reset=True, seed=42, device=local, env_id_offset=rank * E)
+
+    def make_actions(self, E, g, dev):
+        """int uniform move [0,5) turn [0,3) kick [0,3) head [0,7)"""
+        import torch
+        hi = torch.tensor([5, 3, 3, 7], device=dev)
+        return (torch.rand((E, self.P, 4), generator=g, device=dev) * hi).floor().contiguous()
+
+    def config(self, L):
+        return {"substeps": L.RC_SUBSTEPS, "obs_ticks": L.RC_NTICK, "observers": self.P}
+
+    def algorithmic_bytes_per_env_step(self):
+        """step-boundary HBM traffic of one env-step: state record in + out, actions in,
+        5 x 10 observation records, result record."""
+        from dynenv_b200 import layout as L
+        return 4 * (2 * L.RC_STATE_WORDS + self.P * 4 + L.RC_NTICK * self.P * L.RC_OBS_WORDS + L.RC_INFO_WORDS)
+
+    def kernel_bytes_per_env(self):
+        """algorithmic HBM bytes per environment of ONE launch of each kernel class"""
+        from dynenv_b200 import layout as L
+        rec = 4 * L.RC_STATE_WORDS
+        return {"phys": 2 * rec + 4 * self.P * 4,                                   # record in + out, actions
+                "obs": rec + 4 * self.P * L.RC_OBS_WORDS + 4 * (L.RC_S_STEP_END - L.RC_S_STEP_LSUM),  # record in, 10 records out
+                "finish": 2 * rec + 4 * L.RC_INFO_WORDS}
+
+    def cpu_env(self, i):
+        from oracle import oracle as O
+        env = O.RcOracle(5, 1, 1, 2.0, False, seed=42, env_id=i)
+        return env, env._lib.rc_step
+
+    def cpu_actions(self, rng, n_steps):
+        return np.stack([rng.integers(0, 5, (n_steps, self.P)), rng.integers(0, 3, (n_steps, self.P)),
+                         rng.integers(0, 3, (n_steps, self.P)), rng.integers(0, 7, (n_steps, self.P))], -1).astype(np.float64)
 
 
-def kernel_bytes_per_env():
-    """algorithmic HBM bytes per environment of ONE launch of each kernel class"""
-    from dynenv_b200 import layout as L
-    rec = 4 * L.RC_STATE_WORDS
-    return {"phys": 2 * rec + 4 * P * 4,                                   # record in + out, actions
-            "obs": rec + 4 * P * L.RC_OBS_WORDS + 4 * (L.RC_S_STEP_END - L.RC_S_STEP_LSUM),  # record in, 10 records out
-            "finish": 2 * rec + 4 * L.RC_INFO_WORDS}
+class DrivingWorkload(object):
+    """BASELINE.json configs[2]"""
+    name = "driving"
+    metric = "env-steps/sec (Driving 10 cars, 10 substeps)"
+    workload = "Driving 10 cars PARTIAL continuous actions REALISTIC noise 2, auto-reset"
+    P, act = 10, 2
+    launches_per_step = {"phys": 1, "obs": 1, "finish": 0}
+    prefix = "drv"
+
+    def make_sim(self, E, local, rank, full=False):
+        import dynenv_b200
+        obs_type = dynenv_b200.ObservationType.FULL if full else dynenv_b200.ObservationType.PARTIAL
+        return dynenv_b200.BatchedDriving(E, 10, obs_type, dynenv_b200.NoiseType.REALISTIC, 2.0, continuousActions=True,
+                                          auto_reset=True, seed=42, device=local, env_id_offset=rank * E)
+
+    def make_actions(self, E, g, dev):
+        """float uniform [-3, 3) acceleration and steering"""
+        import torch
+        return (torch.rand((E, self.P, 2), generator=g, device=dev) * 6.0 - 3.0).contiguous()
+
+    def config(self, L):
+        return {"substeps": L.DRV_SUBSTEPS, "obs_ticks": 1, "observers": self.P}
+
+    def algorithmic_bytes_per_env_step(self):
+        from dynenv_b200 import layout as L
+        return 4 * (2 * L.DRV_STATE_WORDS + self.P * 2 + self.P * L.DRV_OBS_WORDS + L.DRV_INFO_WORDS)
+
+    def kernel_bytes_per_env(self):
+        from dynenv_b200 import layout as L
+        rec = 4 * L.DRV_STATE_WORDS
+        return {"phys": 2 * rec + 4 * self.P * 2,
+                "obs": 2 * rec + 4 * self.P * L.DRV_OBS_WORDS + 4 * L.DRV_INFO_WORDS,  # record in + out, 10 records, result record
+                "finish": 0}
+
+    def cpu_env(self, i):
+        from oracle import oracle as O
+        env = O.DrvOracle(10, 1, 1, 2.0, True, seed=42, env_id=i)
+        return env, env._lib.drv_step
+
+    def cpu_actions(self, rng, n_steps):
+        return rng.uniform(-3, 3, (n_steps, self.P, 2))
+
+
+WORKLOADS = {"robocup": RoboCupWorkload, "driving": DrivingWorkload}
 
 
 def measured_peaks():
@@ -104,7 +181,7 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_env_steps_per_s(n_steps, threads=None):
+def cpu_env_steps_per_s(wl, n_steps, threads=None):
     """the C oracle, one environment per host thread (ctypes releases the GIL), all threads stepping
     n_steps env-steps; returns (env-steps/s over all threads, threads)"""
     import ctypes as C
@@ -115,17 +192,17 @@ def cpu_env_steps_per_s(n_steps, threads=None):
     barrier = threading.Barrier(threads)
 
     def work(i):
-        env = O.RcOracle(N_PLAYERS, 1, 1, 2.0, False, seed=42, env_id=i)
+        env, step_fn = wl.cpu_env(i)
         env.reset()
         rng = np.random.default_rng(1234 + i)
-        acts = np.stack([rng.integers(0, 5, (n_steps, P)), rng.integers(0, 3, (n_steps, P)),
-                         rng.integers(0, 3, (n_steps, P)), rng.integers(0, 7, (n_steps, P))], -1).astype(np.float64)
-        acts = np.ascontiguousarray(acts)
+        acts = np.ascontiguousarray(wl.cpu_actions(rng, n_steps), dtype=np.float64)
         ref = C.byref(env._out)
         barrier.wait()
         t0 = time.perf_counter()
         for s in range(n_steps):
-            env._lib.rc_step(env._h, acts[s].ctypes.data, ref)
+            step_fn(env._h, acts[s].ctypes.data, ref)
+            if env._out.done:  # the vec-env's auto-reset (utils/subproc_vec_env.py:17-23)
+                env.reset()
         out[i] = time.perf_counter() - t0
 
     ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
@@ -140,13 +217,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]()
+    METRIC, WORKLOAD = wl.metric, wl.workload
     # each "step" = every host thread advancing a bounded sample of env-steps of the same workload
     per_step = 1000
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_env_steps_per_s(50)
+        cpu_env_steps_per_s(wl, 50)
     t_total, n_total, threads = 0.0, 0, 0
     for _ in range(args.steps):
-        rate, threads, dt = cpu_env_steps_per_s(per_step)
+        rate, threads, dt = cpu_env_steps_per_s(wl, per_step)
         t_total += dt
         n_total += threads * per_step
     value = n_total / t_total
@@ -179,17 +258,15 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E = args.envs
-    obs_type = dynenv_b200.ObservationType.FULL if args.debug_full_obs else dynenv_b200.ObservationType.PARTIAL
-    sim = dynenv_b200.BatchedRoboCup(E, N_PLAYERS, obs_type, dynenv_b200.NoiseType.REALISTIC,
-                                     2.0, canFall=True, useObsRewards=True, auto_reset=True, seed=42, device=local,
-                                     env_id_offset=rank * E)
+    wl = WORKLOADS[args.workload]()
+    METRIC, WORKLOAD, P = wl.metric, wl.workload, wl.P
+    sim = wl.make_sim(E, local, rank, full=args.debug_full_obs)
     sim.reset()
-    # synthetic actions: int uniform move [0,5) turn [0,3) kick [0,3) head [0,7), generator seed 1234
+    # synthetic actions, generator seed 1234
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
-    n_pool = 4
-    hi = torch.tensor([5, 3, 3, 7], device=dev)
-    pool = [(torch.rand((E, P, 4), generator=g, device=dev) * hi).floor().contiguous() for _ in range(n_pool)]
+    n_pool = min(args.steps + args.warmup, 128)  # fresh uniform actions every step (a short cycle would bias the play)
+    pool = [wl.make_actions(E, g, dev) for _ in range(n_pool)]
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -200,6 +277,7 @@ def run_gpu(args):
 
     for w in range(args.warmup):
         sim.step(pool[w % n_pool])
+    pool = pool[args.warmup % n_pool:] + pool[:args.warmup % n_pool]
     barrier()
     sim.debug_timing(True)
     kms = {"phys": [0.0, 0], "obs": [0.0, 0], "finish": [0.0, 0]}
@@ -227,8 +305,9 @@ def run_gpu(args):
     diag = int(sim.out.diag.max().item())
 
     # end to end through the host-facing call: pinned host actions in, rewards + done out, every step
-    h_act = [p.cpu().pin_memory() for p in pool]
-    d_act = torch.empty((E, P, 4), device=dev)
+    h_act = [p.cpu().pin_memory() for p in pool[:min(n_pool, 32)]]
+    n_pool = len(h_act)
+    d_act = torch.empty((E, P, wl.act), device=dev)
     h_rew = torch.empty((E, P), dtype=torch.float32).pin_memory()
     h_done = torch.empty((E,), dtype=torch.int32).pin_memory()
     barrier()
@@ -253,16 +332,16 @@ def run_gpu(args):
         total_envs = E * world
         value = total_envs * args.steps / (ms_total * 1e-3)
         e2e = total_envs * args.steps / (ms_e2e * 1e-3)
-        bytes_launch = algorithmic_bytes_per_env_step() * E
-        kb = kernel_bytes_per_env()
+        bytes_launch = wl.algorithmic_bytes_per_env_step() * E
+        kb = wl.kernel_bytes_per_env()
         per_launch = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kms.items()}  # ms per launch
-        per_step = {k: per_launch[k] * (5 if k != "finish" else 1) for k in per_launch}
+        per_step = {k: per_launch[k] * wl.launches_per_step[k] for k in per_launch}
         dom = max(per_step, key=per_step.get)  # dominant kernel class of the step
         achieved = kb[dom] * E / (per_launch[dom] * 1e-3) / 1e9 if per_launch[dom] else 0.0
         step_gbs = bytes_launch / (kernel_ms * 1e-3) / 1e9
         traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("rc_%s_kernel" % dom)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s_%s_kernel" % (wl.prefix, dom))
             if tr:
                 traffic = tr["dram_bytes_per_launch"] * E / tr["envs"]
         except Exception:
@@ -270,19 +349,19 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "envs_per_gpu": E, "envs_total": total_envs, "substeps": L.RC_SUBSTEPS,
-                           "obs_ticks": L.RC_NTICK, "observers": P,
-                           "l2": "state + outputs per step (%.1f GB) exceed the 126 MB L2" % (bytes_launch / 1e9)},
+                "config": dict({"workload": WORKLOAD, "envs_per_gpu": E, "envs_total": total_envs,
+                                "l2": "state + outputs per step (%.1f GB) exceed the 126 MB L2" % (bytes_launch / 1e9)},
+                               **wl.config(L)),
                 "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * P * 4 * 4,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * P * wl.act * 4,
                         "d2h_bytes_per_step": E * P * 4 + E * 4,
                         "note": "observations stay device-resident for the learner; rewards + done return to the host"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
-                             "kernel": "rc_%s_kernel" % dom, "kernel_ms_per_launch": per_launch[dom],
+                             "kernel": "%s_%s_kernel" % (wl.prefix, dom), "kernel_ms_per_launch": per_launch[dom],
                              "algorithmic_bytes_per_launch": kb[dom] * E,
                              "launch_ms": per_launch, "share_of_step": {k: v / max(sum(per_step.values()), 1e-9) for k, v in per_step.items()},
-                             "step": {"ms": kernel_ms, "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(),
+                             "step": {"ms": kernel_ms, "algorithmic_bytes_per_env_step": wl.algorithmic_bytes_per_env_step(),
                                       "achieved_gbs": step_gbs, "frac": step_gbs / peaks["hbm_gbs"]},
                              "note": "the step is instruction-issue bound (FP32/INT pipes), not HBM bound; see DESIGN.md section 4",
                              "fp32": {"flop_per_env_step": FLOP_PER_ENV_STEP,
@@ -291,7 +370,7 @@ def run_gpu(args):
                                       "frac": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12 / FP32_NOMINAL_TFLOPS}},
                 "diag_flags": diag}
         if not args.no_cpu and world == 1:
-            rate, threads, dt = cpu_env_steps_per_s(args.cpu_steps)
+            rate, threads, dt = cpu_env_steps_per_s(wl, args.cpu_steps)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d host threads x %d env-steps of the same workload (%.1f s), C restatement "
                                               "of the reference" % (threads, args.cpu_steps, dt)}
@@ -307,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="robocup", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--debug-full-obs", action="store_true", help="(profiling aid) FULL observations: physics and rules only")
     ap.add_argument("--cpu-steps", type=int, default=20000, help="env-steps per host thread of the cpu_baseline sample")

@@ -11,7 +11,7 @@ def __getattr__(name):
     if name in ("BatchedRoboCup", "RoboCupOutputs", "BatchedDriving", "DrivingOutputs"):
         from . import batched
         return getattr(batched, name)
-    if name in ("RoboCupEnvironment", "make_dyn_env", "BatchedVecEnv"):
+    if name in ("RoboCupEnvironment", "DrivingEnvironment", "make_dyn_env", "BatchedVecEnv"):
         from . import api
         return getattr(api, name)
     raise AttributeError(name)

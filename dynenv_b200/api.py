@@ -3,6 +3,8 @@
   RoboCupEnvironment(nPlayers, render, observationType, noiseType, noiseMagnitude, obs_space_cast, allowHeadTurn)
       .step(actions) .reset() .set_random_seed(seed) .observation_space .action_space ...
       (DynEnv/RoboCupEnvironment.py:23-64,446-524; environment_base.py:190-224)
+  DrivingEnvironment(nPlayers, render, observationType, noiseType, noiseMagnitude, obs_space_cast, continuousActions)
+      (DynEnv/DrivingEnvironment.py:20-56,248-322)
   make_dyn_env(env, num_envs, num_players, render, observationType, noiseType, noiseMagnitude,
                use_continuous_actions) -> (vec_env, name)                     (DynEnv/__init__.py:6-25)
   BatchedVecEnv: the VecEnv calls the learner uses (step / step_async / step_wait / reset / get_attr /
@@ -160,6 +162,117 @@ class RoboCupEnvironment(object):
         self._sim.close()
 
 
+def validate_driving_actions(actions, nAgents, continuousActions):
+    """The checks of DrivingEnvironment.step / processAction (:261-263, :364-367), same messages.  With
+    continuousActions the reference itself raises UnboundLocalError (:360-368); here acc = action[0], steer = action[1]."""
+    actions = np.asarray(actions)
+    if actions.shape != (nAgents, 2):
+        raise Exception("Error: There must be 2 actions for every car")
+    a = actions.astype(np.float64)
+    acc, steer = (a[:, 0], a[:, 1]) if continuousActions else (a[:, 0] - 1, (a[:, 1] - 1) * 2)
+    if (np.abs(acc) > 3).any():
+        raise Exception("Error: Acceleration must be between +/-3")
+    if (np.abs(steer) > 3).any():
+        raise Exception("Error: Steering must be between +/-3")
+    return a.astype(np.float32)
+
+
+def driving_spaces(observationType, continuousActions, mean=5.0):
+    """action_space / observation_space as the reference builds them (DrivingEnvironment.py:170-230)"""
+    Box, Dict, Tuple, MultiBinary, MultiDiscrete = S.Box, S.Dict, S.Tuple, S.MultiBinary, S.MultiDiscrete
+    action = Tuple((Box(-3, +3, shape=(2,)),)) if continuousActions else Tuple((MultiDiscrete([3, 3]),))
+    pos_xy = Box(-mean * 2, +mean * 2, shape=(2,))
+    width_height = Box(-10, 10, shape=(2,))
+    orientation = Box(-1, 1, shape=(2,))
+    type_ = Box(-1, 1, shape=(1,))
+    self_space = Dict({"position": pos_xy, "orientation": orientation, "width_height": width_height, "goal_position": pos_xy,
+                       "finished": MultiBinary(1)})
+    car_space = Dict({"position": pos_xy, "orientation": orientation, "width_height": width_height, "finished": MultiBinary(1)})
+    pedestrian_space = Dict({"position": pos_xy})
+    if observationType == ObservationType.FULL:
+        lane_space = Dict({"points": Box(-mean * 2, mean * 2, shape=(4,)), "type": type_})
+        obstacle_space = Dict({"position": pos_xy, "width_height": width_height})
+    else:
+        lane_space = Dict({"signed_distance": Box(-mean * 2, mean * 2, shape=(1,)), "orientation": orientation, "type": type_})
+        obstacle_space = Dict({"position": pos_xy, "orientation": orientation, "width_height": width_height})
+    return action, Tuple([Tuple([car_space, obstacle_space, pedestrian_space]), Tuple([self_space, lane_space])])
+
+
+class DrivingEnvironment(object):
+    """One Driving environment with the reference's interface (DrivingEnvironment.py:20-56), simulated on the GPU
+    (batch of one)."""
+
+    def __init__(self, nPlayers, render=False, observationType=ObservationType.PARTIAL, noiseType=NoiseType.REALISTIC,
+                 noiseMagnitude=2, obs_space_cast=False, continuousActions=False, seed=0, device=0):
+        if noiseMagnitude < 0 or noiseMagnitude > 5:  # environment_base.py:162-164 (which prints and exits)
+            raise ValueError("Error: The noise magnitude must be between 0 and 5!")
+        if render:
+            raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+        if ObservationType(observationType) == ObservationType.IMAGE:  # DrivingEnvironment.py:33-35 (prints and exits)
+            raise ValueError("Image observation type is not supported for this environment")
+        from .batched import BatchedDriving
+        self.observationType = ObservationType(observationType)
+        self.noiseType = NoiseType(noiseType)
+        self.noiseMagnitude = noiseMagnitude
+        self.continuousActions = continuousActions
+        self.obs_space_cast = obs_space_cast
+        self.maxPlayers = 10
+        self.nPlayers = min(nPlayers, self.maxPlayers)
+        self.nTimeSteps, self.stepIterCnt, self.maxTime = 1, L.DRV_SUBSTEPS, 6000
+        self.stepNum = self.maxTime / self.stepIterCnt
+        self.W, self.H = 1750, 1000
+        self.mean = 5.0
+        self.renderMode, self.agentVisID = False, None
+        self.elapsed = 0
+        self.agents = [_Agent(i, self.nPlayers) for i in range(self.nPlayers)]
+        self.action_space, self.observation_space = driving_spaces(self.observationType, continuousActions, self.mean)
+        self._sim = BatchedDriving(1, nPlayers, self.observationType, self.noiseType, noiseMagnitude, continuousActions,
+                                   seed=seed, device=device)
+        self._full = self.observationType == ObservationType.FULL
+        self._last = None
+        self.reset()
+
+    def set_random_seed(self, seed):
+        """seeds the generator; like the reference (environment_base.py:190-193) it does not reset"""
+        self._sim.set_random_seed(seed)
+
+    setRandomSeed = set_random_seed  # README.md:139 spelling
+
+    def reset(self):
+        self._last = RF.drv_host_views(self._sim.reset())
+        self.elapsed = 0
+        return RF.drv_observations(self._last, 0, self.nPlayers, self._full)
+
+    def step(self, actions):
+        import torch
+        a = validate_driving_actions(actions, self.nPlayers, self.continuousActions)
+        out = self._sim.step(torch.from_numpy(a[None]).to(self._sim.device))
+        v = self._last = RF.drv_host_views(out)
+        N = self.nPlayers
+        self.elapsed += self.stepIterCnt
+        return RF.drv_observations(v, 0, N, self._full), v["rewards"][0, :N].astype(np.float64), bool(v["done"][0]), \
+            RF.drv_info_dict(v, 0, N)
+
+    def getFullState(self, agent=None):
+        a = None if agent is None else (agent.id if hasattr(agent, "id") else int(agent))
+        return RF.drv_full_state(self._last, 0, self.nPlayers, a)
+
+    def get_agent_locs(self):
+        return [self.getFullState(agent)[0][:, [0, 1, 2, 3]] for agent in self.agents]
+
+    def get_full_obs(self):
+        return [([o[1], o[2], o[3]], [o[0], o[4]], (1, 1, 1)) for o in (self.getFullState(car) for car in self.agents)]
+
+    def get_class_specific_args(self):
+        return [self.continuousActions]
+
+    def render(self):
+        raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+
+    def close(self):
+        self._sim.close()
+
+
 class BatchedVecEnv(object):
     """VecEnv over one batched simulator: `num_envs` environments, auto-reset on done with
     info['terminal_observation'] (utils/subproc_vec_env.py:17-23).  `step()` returns the reference's host
@@ -167,22 +280,49 @@ class BatchedVecEnv(object):
     batch sizes use `step_tensors()`, which leaves everything on the device."""
 
     def __init__(self, num_envs, nPlayers, observationType, noiseType, noiseMagnitude, allowHeadTurn=False, seed=0,
-                 device=0, env_id_offset=0, **toggles):
-        from .batched import BatchedRoboCup
+                 device=0, env_id_offset=0, env=DynEnvType.ROBO_CUP, **toggles):
+        from .batched import BatchedDriving, BatchedRoboCup
         self.num_envs = int(num_envs)
-        self.nPlayers = min(nPlayers, 5)
-        self.nAgents = 2 * self.nPlayers
-        self.allowHeadTurn = allowHeadTurn
+        self.driving = env is DynEnvType.DRIVE
+        self.allowHeadTurn = allowHeadTurn  # RoboCup: allowHeadTurn, Driving: continuousActions (make_dyn_env)
         self.observationType = ObservationType(observationType)
         self._full = self.observationType == ObservationType.FULL
-        self.action_space, self.observation_space = robocup_spaces(self.observationType, allowHeadTurn)
-        self.sim = BatchedRoboCup(self.num_envs, nPlayers, observationType, noiseType, noiseMagnitude, allowHeadTurn,
-                                  auto_reset=True, terminal_outputs=True, seed=seed, device=device,
-                                  env_id_offset=env_id_offset, **toggles)
+        if self.driving:
+            self.nPlayers = self.nAgents = min(nPlayers, 10)
+            self.nAct = 2
+            self.action_space, self.observation_space = driving_spaces(self.observationType, allowHeadTurn)
+            self.sim = BatchedDriving(self.num_envs, nPlayers, observationType, noiseType, noiseMagnitude, allowHeadTurn,
+                                      auto_reset=True, terminal_outputs=True, seed=seed, device=device,
+                                      env_id_offset=env_id_offset)
+            nT, nSub, maxT = 1, L.DRV_SUBSTEPS, 6000
+        else:
+            self.nPlayers = min(nPlayers, 5)
+            self.nAgents = 2 * self.nPlayers
+            self.nAct = 4
+            self.action_space, self.observation_space = robocup_spaces(self.observationType, allowHeadTurn)
+            self.sim = BatchedRoboCup(self.num_envs, nPlayers, observationType, noiseType, noiseMagnitude, allowHeadTurn,
+                                      auto_reset=True, terminal_outputs=True, seed=seed, device=device,
+                                      env_id_offset=env_id_offset, **toggles)
+            nT, nSub, maxT = L.RC_NTICK, L.RC_SUBSTEPS, 12000
         self._actions = None
-        self._attrs = dict(nPlayers=self.nPlayers, nTimeSteps=L.RC_NTICK, stepIterCnt=L.RC_SUBSTEPS, maxTime=12000,
-                           stepNum=12000 / L.RC_SUBSTEPS, observationType=self.observationType, renderMode=False,
+        self._attrs = dict(nPlayers=self.nPlayers, nTimeSteps=nT, stepIterCnt=nSub, maxTime=maxT,
+                           stepNum=maxT / nSub, observationType=self.observationType, renderMode=False,
                            agentVisID=None, action_space=self.action_space, observation_space=self.observation_space)
+
+    # ---- format adapters (RoboCup / Driving)
+    def _views(self, out, env_ids=None):
+        return RF.drv_host_views(out, env_ids) if self.driving else RF.host_views(out, self._full, env_ids)
+
+    def _obs(self, v, e):
+        return RF.drv_observations(v, e, self.nAgents, self._full) if self.driving else RF.observations(v, e, self.nAgents, self._full)
+
+    def _info(self, v, e):
+        return RF.drv_info_dict(v, e, self.nAgents) if self.driving else RF.info_dict(v, e, self.nAgents)
+
+    def _validate(self, a):
+        if self.driving:
+            return validate_driving_actions(a, self.nAgents, self.allowHeadTurn)
+        return validate_robocup_actions(a, self.nAgents, self.allowHeadTurn)
 
     # ---- device-resident fast path
     def step_tensors(self, actions):
@@ -191,8 +331,8 @@ class BatchedVecEnv(object):
 
     # ---- VecEnv calls
     def reset(self):
-        v = RF.host_views(self.sim.reset(), self._full)
-        return self._stack([RF.observations(v, e, self.nAgents, self._full) for e in range(self.num_envs)])
+        v = self._views(self.sim.reset())
+        return self._stack([self._obs(v, e) for e in range(self.num_envs)])
 
     def step_async(self, actions):
         self._actions = actions
@@ -200,22 +340,22 @@ class BatchedVecEnv(object):
     def step_wait(self):
         import torch
         a = np.asarray(self._actions)
-        if a.shape != (self.num_envs, self.nAgents, 4):
-            raise Exception("Error: There must be %d actions of length 4" % self.nAgents)
-        a = np.stack([validate_robocup_actions(a[e], self.nAgents, self.allowHeadTurn) for e in range(self.num_envs)])
+        if a.shape != (self.num_envs, self.nAgents, self.nAct):
+            raise Exception("Error: There must be 2 actions for every car" if self.driving else
+                            "Error: There must be %d actions of length 4" % self.nAgents)
+        a = np.stack([self._validate(a[e]) for e in range(self.num_envs)])
         out = self.sim.step(torch.from_numpy(a).to(self.sim.device))
-        v = RF.host_views(out, self._full)
+        v = self._views(out)
         dones = v["done"].astype(bool)
-        tv = RF.host_views(self.sim.terminal, self._full, np.nonzero(dones)[0]) if dones.any() else None
+        tv = self._views(self.sim.terminal, np.nonzero(dones)[0]) if dones.any() else None
         obs, infos, k = [], [], 0
         for e in range(self.num_envs):
-            info = RF.info_dict(v, e, self.nAgents)
+            info = self._info(v, e)
             if dones[e]:
                 # obs/full of the finished step were routed to the terminal buffers by the kernel
-                tvv = dict(tv)
-                info["terminal_observation"] = RF.observations(tvv, k, self.nAgents, self._full)
+                info["terminal_observation"] = self._obs(dict(tv), k)
                 k += 1
-            obs.append(RF.observations(v, e, self.nAgents, self._full))
+            obs.append(self._obs(v, e))
             infos.append(info)
         return self._stack(obs), v["rewards"][:, :self.nAgents].astype(np.float64), dones, tuple(infos)
 
@@ -244,6 +384,9 @@ class BatchedVecEnv(object):
         return [self._attrs[attr_name]] * n
 
     def env_method(self, method_name, *args, **kwargs):
+        if method_name == "get_agent_locs" and self.driving:  # DrivingEnvironment.py:126-127
+            sc = self.sim.out.state_cars.detach().cpu().numpy()
+            return [[sc[e, a][None][:, [0, 1, 2, 3]] for a in range(self.nAgents)] for e in range(self.num_envs)]
         if method_name == "get_agent_locs":
             rs = self.sim.out.recon_self.detach().cpu().numpy()
             return [[rs[e, a][None][:, [0, 1, 2, 3, 4, 5]] for a in range(self.nAgents)] for e in range(self.num_envs)]
@@ -262,5 +405,6 @@ def make_dyn_env(env, num_envs, num_players, render, observationType, noiseType,
         return BatchedVecEnv(num_envs, num_players, observationType, noiseType, noiseMagnitude,
                              allowHeadTurn=use_continuous_actions, seed=seed, device=device), "RoboCup"
     if env is DynEnvType.DRIVE:
-        raise NotImplementedError("DrivingEnvironment is not built yet (DESIGN.md, scope)")
+        return BatchedVecEnv(num_envs, num_players, observationType, noiseType, noiseMagnitude,
+                             allowHeadTurn=use_continuous_actions, seed=seed, device=device, env=DynEnvType.DRIVE), "Driving"
     raise ValueError

@@ -194,6 +194,7 @@ class DrivingOutputs(object):
         self.state_cars = self.info[:, L.DRV_I_STATE_CARS:L.DRV_I_STATE_CARS + L.DRV_MAXCARS * 7].unflatten(-1, (L.DRV_MAXCARS, 7))[:, :N]
         self.state_obs = self.info[:, L.DRV_I_STATE_OBS:L.DRV_I_STATE_OBS + L.DRV_MAXOBS * 4].unflatten(-1, (L.DRV_MAXOBS, 4))
         self.state_ped = self.info[:, L.DRV_I_STATE_PED:L.DRV_I_STATE_PED + L.DRV_MAXPED * 2].unflatten(-1, (L.DRV_MAXPED, 2))
+        self.goals = self.info[:, L.DRV_I_GOALS:L.DRV_I_GOALS + L.DRV_MAXCARS * 2].unflatten(-1, (L.DRV_MAXCARS, 2))[:, :N]
         self.n_obs = info_i[:, L.DRV_I_NOBS]
         self.n_ped = info_i[:, L.DRV_I_NPED]
 

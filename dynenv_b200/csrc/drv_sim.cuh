@@ -34,7 +34,7 @@ constexpr float MAXVIS0 = (W_ * 0.4f) * (W_ * 0.4f), MAXVIS1 = (W_ * 0.6f) * (W_
 constexpr float ANGLE_NOISE = PI_F / 180.f; /* cutils.py:203 */
 constexpr float NORMX = 10.f / W_, NORMY = 10.f / H_, NORMW = 1.f / 7.5f, NORMH = 1.f / 15.f;
 constexpr float SNORMX = 0.5f / (W_ + 100.f), SNORMY = 0.5f / (H_ + 100.f), SNORMW = 1.f / 15.f, SNORMH = 1.f / 25.f;
-constexpr int NCAND = 64;
+constexpr int NCAND = 32; /* bounding-box overlapping pairs per substep: one per lane */
 constexpr int NOCC = 34; /* possible occluders of one observer: cars 0..9, obstacles 10..29, buildings 30..33 */
 constexpr int NRESET_BLOCKS = 48;
 
@@ -387,198 +387,13 @@ __device__ void cb_car_hit(const Env E, int ci) {
   car_crash(E, ci);
 }
 
-/* ================================================================= narrow phase (serial) */
-struct Box { /* vertices CCW (-h,-w), (h,-w), (h,w), (-h,w) and plane normals (plane i: edge v[i-1] -> v[i]) */
-  V2 v[4], n[4];
-};
-__device__ __forceinline__ void make_box(V2 ctr, float c, float s, float hx, float hy, Box* b) {
-  const float lx[4] = {-hx, hx, hx, -hx}, ly[4] = {-hy, -hy, hy, hy};
-#pragma unroll
-  for (int i = 0; i < 4; i++) b->v[i] = v2(ctr.x + lx[i] * c - ly[i] * s, ctr.y + lx[i] * s + ly[i] * c);
-  b->n[0] = v2(-c, -s); b->n[1] = v2(s, -c); b->n[2] = v2(c, s); b->n[3] = v2(-s, c);
-}
-/* box of shape s centred at `ctr` (cars: orientation from the substep's cos / sin table) */
-__device__ __forceinline__ void shape_box(const Env E, int s, V2 ctr, Box* b) {
-  if (is_car(s)) {
-    int i = s - DRV_SHAPE_CAR0, t = E.i[DRV_S_CTYPE + i];
-    make_box(ctr, E.f[X_CC + i], E.f[X_CS + i], car_length(t), car_width(t), b);
-  } else if (s < DRV_NBUILD) make_box(ctr, 1.f, 0.f, BUILD_W, BUILD_H, b);
-  else make_box(ctr, 1.f, 0.f, OBST_HALF, OBST_HALF, b);
-}
+/* ================================================================= narrow phase helpers */
 __device__ __forceinline__ float clamp01(float t) { return fminf(fmaxf(t, 0.f), 1.f); }
 __device__ __forceinline__ V2 vlerp(V2 a, V2 b, float t) { return a * (1.f - t) + b * t; }
 __device__ __forceinline__ V2 closest_on_seg(V2 p, V2 a, V2 b) {
   V2 d = b - a;
   float t = clamp01(dot(d, p - a) / lensq(d));
   return a + d * t;
-}
-struct Manifold {
-  V2 n, p1[2], p2[2];
-  int hash[2], cnt;
-};
-/* SupportEdgeForPoly: the edge of the box that faces direction n; vertex indices are the feature hashes */
-__device__ void support_edge(const Box* s, V2 n, V2* pa, int* ha, V2* pb, int* hb) {
-  int i1 = 0;
-  float best = -3.0e38f;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    float d = dot(s->v[i], n);
-    if (d > best) { best = d; i1 = i; }
-  }
-  int i0 = (i1 + 3) & 3, i2 = (i1 + 1) & 3;
-  if (dot(n, s->n[i1]) > dot(n, s->n[i2])) { *pa = s->v[i0]; *ha = i0; *pb = s->v[i1]; *hb = i1; }
-  else { *pa = s->v[i1]; *ha = i1; *pb = s->v[i2]; *hb = i2; }
-}
-/* box - box: minimum-penetration axis among both boxes' edge normals, then Chipmunk's ContactPoints */
-__device__ __noinline__ void collide_box_box(const Box* A, const Box* B, Manifold* m) {
-  float best = -3.0e38f;
-  V2 bn = v2(1.f, 0.f);
-  for (int i = 0; i < 4; i++) {
-    V2 ax = A->n[(i + 1) & 3];
-    float mn = 3.0e38f, mx = -3.0e38f;
-    for (int q = 0; q < 4; q++) { mn = fminf(mn, dot(ax, B->v[q])); mx = fmaxf(mx, dot(ax, A->v[q])); }
-    if (mn - mx > best) { best = mn - mx; bn = ax; }
-  }
-  for (int i = 0; i < 4; i++) {
-    V2 ax = B->n[(i + 1) & 3];
-    float mn = 3.0e38f, mx = -3.0e38f;
-    for (int q = 0; q < 4; q++) { mn = fminf(mn, dot(ax, A->v[q])); mx = fmaxf(mx, dot(ax, B->v[q])); }
-    if (mn - mx > best) { best = mn - mx; bn = v2(-ax.x, -ax.y); }
-  }
-  m->cnt = 0;
-  if (!(best <= 0.f)) return;
-  V2 n = bn;
-  m->n = n;
-  V2 e1a, e1b, e2a, e2b;
-  int h1a, h1b, h2a, h2b;
-  support_edge(A, n, &e1a, &h1a, &e1b, &h1b);
-  support_edge(B, v2(-n.x, -n.y), &e2a, &h2a, &e2b, &h2b);
-  float d_e1_a = cross(e1a, n), d_e1_b = cross(e1b, n), d_e2_a = cross(e2a, n), d_e2_b = cross(e2b, n);
-  float e1_denom = 1.f / (d_e1_b - d_e1_a + 1.1754944e-38f), e2_denom = 1.f / (d_e2_b - d_e2_a + 1.1754944e-38f);
-  int cnt = 0;
-  {
-    V2 p1 = vlerp(e1a, e1b, clamp01((d_e2_b - d_e1_a) * e1_denom));
-    V2 p2 = vlerp(e2a, e2b, clamp01((d_e1_a - d_e2_a) * e2_denom));
-    if (dot(p2 - p1, n) <= 0.f) { m->p1[cnt] = p1; m->p2[cnt] = p2; m->hash[cnt] = 1 + h1a + 4 * h2b; cnt++; }
-  }
-  {
-    V2 p1 = vlerp(e1a, e1b, clamp01((d_e2_a - d_e1_a) * e1_denom));
-    V2 p2 = vlerp(e2a, e2b, clamp01((d_e1_b - d_e2_a) * e2_denom));
-    if (dot(p2 - p1, n) <= 0.f) { m->p1[cnt] = p1; m->p2[cnt] = p2; m->hash[cnt] = 1 + h1b + 4 * h2a; cnt++; }
-  }
-  m->cnt = cnt;
-}
-/* circle at the origin (a) - box (b): CircleToPoly */
-__device__ __noinline__ void collide_circle_box(float cr, const Box* P, Manifold* m) {
-  const V2 c = v2(0.f, 0.f);
-  bool inside = true;
-  for (int i = 0; i < 4; i++) {
-    V2 a = P->v[i], b = P->v[(i + 1) & 3];
-    if ((b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x) < 0.f) { inside = false; break; }
-  }
-  float d;
-  V2 pb, n;
-  if (inside) {
-    float best = -3.0e38f;
-    int bi = 0;
-    for (int i = 0; i < 4; i++) {
-      float q = dot(c - P->v[i], P->n[i]);
-      if (q > best) { best = q; bi = i; }
-    }
-    n = v2(-P->n[bi].x, -P->n[bi].y);
-    pb = closest_on_seg(c, P->v[(bi + 3) & 3], P->v[bi]);
-    d = best;
-  } else {
-    d = 3.0e38f;
-    pb = c;
-    for (int i = 0; i < 4; i++) {
-      /* closest point of edge v[i-1] -> v[i] to the origin; inside the edge it is the foot of the perpendicular,
-         taken along the edge's plane normal: for an axis-aligned box the off-axis component then vanishes like
-         in float64 instead of carrying the rounding of a + d t (1e-7, which a fast car turns into a spurious
-         impulse and spin) */
-      V2 a = P->v[(i + 3) & 3], b = P->v[i];
-      V2 dv = b - a;
-      float t = -dot(dv, a) / lensq(dv);
-      V2 q = t <= 0.f ? a : (t >= 1.f ? b : P->n[i] * dot(P->n[i], a));
-      float dd = len(q);
-      if (dd < d) { d = dd; pb = q; }
-    }
-    n = d > 0.f ? v2((pb.x - c.x) / d, (pb.y - c.y) / d) : v2(1.f, 0.f);
-  }
-  m->cnt = 0;
-  if (d <= cr) {
-    m->n = n;
-    m->p1[0] = c + n * cr;
-    m->p2[0] = pb;
-    m->hash[0] = 0;
-    m->cnt = 1;
-  }
-}
-
-/* cpSpaceCollideShapes + cpArbiterUpdate + begin callbacks for a bounding-box overlapping pair i < j
-   (insertion order), at least one of them a car; geometry in the frame centred at body a */
-__device__ __noinline__ void collide_pair(const Env E, int i, int j) {
-  int a = i, b = j;
-  if (!is_ped(a) && is_ped(b)) { a = j; b = i; } /* cpCollide orders by primitive type: circle first */
-  Manifold m;
-  V2 dab = pos_diff(E, b, a);
-  Box B;
-  shape_box(E, b, dab, &B);
-  if (is_ped(a)) collide_circle_box(PED_R, &B, &m);
-  else {
-    Box A;
-    shape_box(E, a, v2(0.f, 0.f), &A);
-    collide_box_box(&A, &B, &m);
-  }
-  if (m.cnt == 0) return;
-  int nArb = E.i[DRV_S_NARB];
-  int key16 = a | (b << 8);
-  int k = 0;
-  for (; k < nArb; k++)
-    if ((E.i[DRV_S_ARBKEY + k] & 0xffff) == key16) break;
-  if (k == nArb) {
-    if (nArb >= DRV_MAXARB) { E.i[X_DIAG] |= RC_IF_ARB_OVERFLOW; return; }
-    E.i[DRV_S_NARB] = nArb + 1;
-    E.i[DRV_S_ARBKEY + k] = key16 | (RC_ARB_FIRST << 16);
-    E.i[DRV_S_ARBCON + k] = 0;
-    E.f[DRV_S_ARBJN0 + k] = 0.f; E.f[DRV_S_ARBJT0 + k] = 0.f; E.f[DRV_S_ARBJN1 + k] = 0.f; E.f[DRV_S_ARBJT1 + k] = 0.f;
-  }
-  int state = (E.i[DRV_S_ARBKEY + k] >> 16) & 255;
-  if (state == RC_ARB_CACHED) state = RC_ARB_FIRST;
-  if (state == RC_ARB_FIRST) { /* begin callbacks */
-    if (is_car(a) && is_car(b)) cb_car_crash(E, a - DRV_SHAPE_CAR0, b - DRV_SHAPE_CAR0);
-    else if (is_ped(a)) { if (!cb_ped_hit(E, b - DRV_SHAPE_CAR0, a - DRV_SHAPE_PED0)) state = RC_ARB_IGNORE; }
-    else cb_car_hit(E, (is_car(a) ? a : b) - DRV_SHAPE_CAR0);
-  }
-  E.i[DRV_S_ARBKEY + k] = key16 | (state << 16); /* age = 0 */
-  E.i[X_TOUCHED] |= 1 << k;
-  if (state == RC_ARB_IGNORE) {
-    E.i[DRV_S_ARBCON + k] = 0;
-    E.f[DRV_S_ARBJN0 + k] = 0.f; E.f[DRV_S_ARBJN1 + k] = 0.f;
-    return;
-  }
-  int nact = E.i[X_NACTIVE];
-  if (nact >= DRV_MAXACTIVE) { E.i[X_DIAG] |= RC_IF_ACTIVE_OVERFLOW; return; }
-  /* contacts: anchors relative to the bodies, impulses carried over by feature hash */
-  int con = E.i[DRV_S_ARBCON + k];
-  int oldN = con & 255, oh0 = (con >> 8) & 255, oh1 = (con >> 16) & 255;
-  float ojn0 = E.f[DRV_S_ARBJN0 + k], ojn1 = E.f[DRV_S_ARBJN1 + k];
-  for (int c = 0; c < 2; c++) {
-    int ci = 2 * nact + c;
-    float jn = 0.f;
-    if (c < m.cnt) {
-      if (oldN > 0 && m.hash[c] == oh0) jn = ojn0;
-      if (oldN > 1 && m.hash[c] == oh1) jn = ojn1;
-      E.f[X_CR1X + ci] = m.p1[c].x; E.f[X_CR1Y + ci] = m.p1[c].y;
-      E.f[X_CR2X + ci] = m.p2[c].x - dab.x; E.f[X_CR2Y + ci] = m.p2[c].y - dab.y;
-    }
-    E.f[X_CJN + ci] = jn;
-  }
-  E.i[DRV_S_ARBCON + k] = m.cnt | (m.hash[0] << 8) | ((m.cnt > 1 ? m.hash[1] : 0) << 16);
-  E.f[X_ANX + nact] = m.n.x;
-  E.f[X_ANY + nact] = m.n.y;
-  E.i[X_ACTIVE + nact] = k;
-  E.i[X_NACTIVE] = nact + 1;
 }
 
 /* ================================================================= space.step */
@@ -695,36 +510,6 @@ __device__ __noinline__ void age_cached_pairs(const Env E) {
   __syncwarp();
 }
 
-/* cpArbiterPreStep of the active contacts: lane = 2 * pair + contact */
-__device__ __noinline__ void prestep_contacts(const Env E) {
-  const int lane = E.lane;
-  const int nact = E.i[X_NACTIVE];
-  const float slop = 0.1f;
-  const float biasCoef = 6.1259606640e-02f; /* 1 - collisionBias^dt, collisionBias = 0.9^60 */
-  int q = lane >> 1, c = lane & 1;
-  if (q < nact) {
-    int k = E.i[X_ACTIVE + q];
-    int key = E.i[DRV_S_ARBKEY + k];
-    int ncon = E.i[DRV_S_ARBCON + k] & 255;
-    if (c < ncon) {
-      int a = key & 255, b = (key >> 8) & 255;
-      V2 n = v2(E.f[X_ANX + q], E.f[X_ANY + q]);
-      V2 r1 = v2(E.f[X_CR1X + lane], E.f[X_CR1Y + lane]), r2 = v2(E.f[X_CR2X + lane], E.f[X_CR2Y + lane]);
-      float ami = body_minv(E, a), aii = body_iinv(E, a), bmi = body_minv(E, b), bii = body_iinv(E, b);
-      float r1cn = cross(r1, n), r2cn = cross(r2, n);
-      E.f[X_CNMASS + lane] = 1.f / (ami + aii * r1cn * r1cn + bmi + bii * r2cn * r2cn);
-      V2 bd = pos_diff(E, b, a);
-      float dist = dot(r2 - r1 + bd, n);
-      E.f[X_CBIAS + lane] = -biasCoef * fminf(0.f, dist + slop) / DT;
-      E.f[X_CJBIAS + lane] = 0.f;
-      BodyV A = load_body(E, a), B = load_body(E, b);
-      V2 vr = v2((B.vx - r2.y * B.w) - (A.vx - r1.y * A.w), (B.vy + r2.x * B.w) - (A.vy + r1.x * A.w));
-      E.f[X_CBOUNCE + lane] = dot(vr, n) * (0.05f * 0.05f); /* every shape: elasticity 0.05 */
-    }
-  }
-  __syncwarp();
-}
-
 /* cached contact impulses re-applied in pair order (cpArbiterApplyCachedImpulse): lane 0 */
 __device__ __noinline__ void warm_start_contacts(const Env E, float dt_coef) {
   if (E.lane == 0) {
@@ -752,8 +537,8 @@ __device__ __noinline__ void warm_start_contacts(const Env E, float dt_coef) {
   __syncwarp();
 }
 
-/* shape pairs whose bounding boxes overlap (X_BPMASK), collided in Chipmunk's ascending (i, j) insertion order */
-__device__ __noinline__ void collide_candidates(const Env E) {
+/* shape pairs whose bounding boxes overlap (X_BPMASK) -> X_CAND, in Chipmunk's ascending (i, j) insertion order */
+__device__ __forceinline__ void build_candidates(const Env E) {
   const int lane = E.lane;
   const int N = E.c->P;
   int m0 = E.i[X_BPMASK + lane], m1 = E.i[X_BPMASK + 32 + lane];
@@ -795,11 +580,6 @@ __device__ __noinline__ void collide_candidates(const Env E) {
     }
   }
   __syncwarp();
-  if (lane == 0) {
-    const int n = E.i[X_NCAND];
-    for (int x = 0; x < n; x++) collide_pair(E, E.i[X_CAND + x] >> 6, E.i[X_CAND + x] & 63);
-  }
-  __syncwarp();
 }
 
 __device__ __forceinline__ void friction(float m, float fr, float rfr, float& x, float& y, float& theta) {
@@ -810,6 +590,373 @@ __device__ __forceinline__ void friction(float m, float fr, float rfr, float& x,
   x = fabsf(x) < factor ? 0.f : x - a0;
   y = fabsf(y) < factor ? 0.f : y - a1;
   theta = fabsf(theta) < rotFactor ? 0.f : theta - (theta > 0.f ? rotFactor : -rotFactor);
+}
+
+/* ---- narrow phase in registers: one candidate pair per lane, everything unrolled (no local memory) */
+struct BoxR { /* vertices CCW (-h,-w), (h,-w), (h,w), (-h,w); plane normal i belongs to edge v[i-1] -> v[i] */
+  V2 v0, v1, v2, v3;
+  float c, s;
+};
+__device__ __forceinline__ BoxR make_boxr(V2 ctr, float c, float s, float hx, float hy) {
+  BoxR b;
+  b.v0 = v2(ctr.x + -hx * c - -hy * s, ctr.y + -hx * s + -hy * c);
+  b.v1 = v2(ctr.x + hx * c - -hy * s, ctr.y + hx * s + -hy * c);
+  b.v2 = v2(ctr.x + hx * c - hy * s, ctr.y + hx * s + hy * c);
+  b.v3 = v2(ctr.x + -hx * c - hy * s, ctr.y + -hx * s + hy * c);
+  b.c = c; b.s = s;
+  return b;
+}
+__device__ __forceinline__ V2 bvert(const BoxR& b, int i) { return i == 0 ? b.v0 : (i == 1 ? b.v1 : (i == 2 ? b.v2 : b.v3)); }
+__device__ __forceinline__ V2 bnorm(const BoxR& b, int i) {
+  return i == 0 ? v2(-b.c, -b.s) : (i == 1 ? v2(b.s, -b.c) : (i == 2 ? v2(b.c, b.s) : v2(-b.s, b.c)));
+}
+__device__ __forceinline__ BoxR shape_boxr(const Env E, int s, V2 ctr) {
+  if (is_car(s)) {
+    int i = s - DRV_SHAPE_CAR0, t = E.i[DRV_S_CTYPE + i];
+    return make_boxr(ctr, E.f[X_CC + i], E.f[X_CS + i], car_length(t), car_width(t));
+  }
+  if (s < DRV_NBUILD) return make_boxr(ctr, 1.f, 0.f, BUILD_W, BUILD_H);
+  return make_boxr(ctr, 1.f, 0.f, OBST_HALF, OBST_HALF);
+}
+struct ManR {
+  float nx, ny;
+  V2 p1a, p2a, p1b, p2b; /* contact 0 / 1 */
+  int h0, h1, cnt;
+};
+__device__ __forceinline__ void sat_axis(V2 ax, const BoxR& own, const BoxR& other, float sign, float& best, V2& bn) {
+  float mn = fminf(fminf(dot(ax, other.v0), dot(ax, other.v1)), fminf(dot(ax, other.v2), dot(ax, other.v3)));
+  float mx = fmaxf(fmaxf(dot(ax, own.v0), dot(ax, own.v1)), fmaxf(dot(ax, own.v2), dot(ax, own.v3)));
+  if (mn - mx > best) { best = mn - mx; bn = v2(ax.x * sign, ax.y * sign); }
+}
+__device__ __forceinline__ void support_edge_r(const BoxR& s, V2 n, V2* pa, int* ha, V2* pb, int* hb) {
+  int i1 = 0;
+  float best = dot(s.v0, n), d;
+  d = dot(s.v1, n); if (d > best) { best = d; i1 = 1; }
+  d = dot(s.v2, n); if (d > best) { best = d; i1 = 2; }
+  d = dot(s.v3, n); if (d > best) { best = d; i1 = 3; }
+  int i0 = (i1 + 3) & 3, i2 = (i1 + 1) & 3;
+  if (dot(n, bnorm(s, i1)) > dot(n, bnorm(s, i2))) { *pa = bvert(s, i0); *ha = i0; *pb = bvert(s, i1); *hb = i1; }
+  else { *pa = bvert(s, i1); *ha = i1; *pb = bvert(s, i2); *hb = i2; }
+}
+/* box - box: minimum-penetration axis among both boxes' edge normals, then Chipmunk's ContactPoints */
+__device__ __forceinline__ void box_box_r(const BoxR& A, const BoxR& B, ManR* m) {
+  float best = -3.0e38f;
+  V2 bn = v2(1.f, 0.f);
+  sat_axis(bnorm(A, 1), A, B, 1.f, best, bn); sat_axis(bnorm(A, 2), A, B, 1.f, best, bn);
+  sat_axis(bnorm(A, 3), A, B, 1.f, best, bn); sat_axis(bnorm(A, 0), A, B, 1.f, best, bn);
+  sat_axis(bnorm(B, 1), B, A, -1.f, best, bn); sat_axis(bnorm(B, 2), B, A, -1.f, best, bn);
+  sat_axis(bnorm(B, 3), B, A, -1.f, best, bn); sat_axis(bnorm(B, 0), B, A, -1.f, best, bn);
+  m->cnt = 0;
+  if (!(best <= 0.f)) return;
+  V2 n = bn;
+  m->nx = n.x; m->ny = n.y;
+  V2 e1a, e1b, e2a, e2b;
+  int h1a, h1b, h2a, h2b;
+  support_edge_r(A, n, &e1a, &h1a, &e1b, &h1b);
+  support_edge_r(B, v2(-n.x, -n.y), &e2a, &h2a, &e2b, &h2b);
+  float d_e1_a = cross(e1a, n), d_e1_b = cross(e1b, n), d_e2_a = cross(e2a, n), d_e2_b = cross(e2b, n);
+  float e1_denom = 1.f / (d_e1_b - d_e1_a + 1.1754944e-38f), e2_denom = 1.f / (d_e2_b - d_e2_a + 1.1754944e-38f);
+  int cnt = 0;
+  {
+    V2 p1 = vlerp(e1a, e1b, clamp01((d_e2_b - d_e1_a) * e1_denom));
+    V2 p2 = vlerp(e2a, e2b, clamp01((d_e1_a - d_e2_a) * e2_denom));
+    if (dot(p2 - p1, n) <= 0.f) { m->p1a = p1; m->p2a = p2; m->h0 = 1 + h1a + 4 * h2b; cnt = 1; }
+  }
+  {
+    V2 p1 = vlerp(e1a, e1b, clamp01((d_e2_a - d_e1_a) * e1_denom));
+    V2 p2 = vlerp(e2a, e2b, clamp01((d_e1_b - d_e2_a) * e2_denom));
+    if (dot(p2 - p1, n) <= 0.f) {
+      int h = 1 + h1b + 4 * h2a;
+      if (cnt == 0) { m->p1a = p1; m->p2a = p2; m->h0 = h; }
+      else { m->p1b = p1; m->p2b = p2; m->h1 = h; }
+      cnt++;
+    }
+  }
+  m->cnt = cnt;
+}
+/* closest point of edge a -> b (plane normal nrm) to the origin; inside the edge it is the foot of the perpendicular,
+   taken along the plane normal: for an axis-aligned box the off-axis component then vanishes like in float64 instead
+   of carrying the rounding of a + d t (1e-7, which a fast car turns into a spurious impulse and spin) */
+__device__ __forceinline__ V2 edge_closest(V2 a, V2 b, V2 nrm) {
+  V2 dv = b - a;
+  float t = -dot(dv, a) / lensq(dv);
+  return t <= 0.f ? a : (t >= 1.f ? b : nrm * dot(nrm, a));
+}
+/* circle of radius cr at the origin (a) - box (b): CircleToPoly */
+__device__ __forceinline__ void circle_box_r(float cr, const BoxR& P, ManR* m) {
+  /* inside: the centre is on the inner side of every edge */
+  bool inside = !(cross(P.v1 - P.v0, v2(-P.v0.x, -P.v0.y)) < 0.f) && !(cross(P.v2 - P.v1, v2(-P.v1.x, -P.v1.y)) < 0.f) &&
+                !(cross(P.v3 - P.v2, v2(-P.v2.x, -P.v2.y)) < 0.f) && !(cross(P.v0 - P.v3, v2(-P.v3.x, -P.v3.y)) < 0.f);
+  float d;
+  V2 pb, n;
+  if (inside) {
+    float best = -dot(P.v0, bnorm(P, 0)), q;
+    int bi = 0;
+    q = -dot(P.v1, bnorm(P, 1)); if (q > best) { best = q; bi = 1; }
+    q = -dot(P.v2, bnorm(P, 2)); if (q > best) { best = q; bi = 2; }
+    q = -dot(P.v3, bnorm(P, 3)); if (q > best) { best = q; bi = 3; }
+    V2 nb = bnorm(P, bi);
+    n = v2(-nb.x, -nb.y);
+    pb = closest_on_seg(v2(0.f, 0.f), bvert(P, (bi + 3) & 3), bvert(P, bi));
+    d = best;
+  } else {
+    V2 q = edge_closest(P.v3, P.v0, bnorm(P, 0));
+    d = len(q); pb = q;
+    float dd;
+    q = edge_closest(P.v0, P.v1, bnorm(P, 1)); dd = len(q); if (dd < d) { d = dd; pb = q; }
+    q = edge_closest(P.v1, P.v2, bnorm(P, 2)); dd = len(q); if (dd < d) { d = dd; pb = q; }
+    q = edge_closest(P.v2, P.v3, bnorm(P, 3)); dd = len(q); if (dd < d) { d = dd; pb = q; }
+    n = d > 0.f ? v2(pb.x / d, pb.y / d) : v2(1.f, 0.f);
+  }
+  m->cnt = 0;
+  if (d <= cr) {
+    m->nx = n.x; m->ny = n.y;
+    m->p1a = n * cr;
+    m->p2a = pb;
+    m->h0 = 0;
+    m->cnt = 1;
+  }
+}
+
+__device__ __forceinline__ void friction_phase(const Env E, bool isCar, bool isPed) {
+  /* velocity update through the friction callbacks: cars (cutils.py:78-85), dead pedestrians (:88-90); live
+     pedestrians have the default update (nothing to do without forces) */
+  const int lane = E.lane;
+  if (isCar) {
+    const int i = lane;
+    float x = E.f[DRV_S_CVX + i], y = E.f[DRV_S_CVY + i], th = E.f[DRV_S_CW + i];
+    const bool fin = E.i[DRV_S_CFLAGS + i] & DRV_CF_FINISHED;
+    friction(car_mass(E.i[DRV_S_CTYPE + i]), fin ? 5e-4f : 5e-5f, fin ? 2e-5f : 1e-5f, x, y, th);
+    E.f[DRV_S_CVX + i] = x; E.f[DRV_S_CVY + i] = y; E.f[DRV_S_CW + i] = th;
+  } else if (isPed && (E.i[DRV_S_PFLAGS + lane - 10] & DRV_PF_DEAD)) {
+    const int i = lane - 10;
+    float x = E.f[DRV_S_PVX + i], y = E.f[DRV_S_PVY + i], th = 0.f;
+    friction(90.f, 5e-2f, 2e-4f, x, y, th);
+    E.f[DRV_S_PVX + i] = x; E.f[DRV_S_PVY + i] = y;
+  }
+  __syncwarp();
+}
+
+/* The collision half of cpSpaceStep for an environment with bounding-box overlapping pairs or cached pairs:
+   narrow phase (lane = candidate pair), cpArbiterUpdate, begin callbacks (serial, in pair order), ageing of the
+   cached pairs, pre-step, the friction velocity update, warm start and the 10 solver iterations.  Pairs that share
+   no dynamic body are independent systems and iterate in the registers of their lane; otherwise the contacts are
+   solved in pair order on lane 0 (Gauss-Seidel like the reference). */
+__device__ __noinline__ void contacts_substep(const Env E, int prevStepped, bool haveCand, bool isCar, bool isPed) {
+  const int lane = E.lane;
+  const unsigned lt = (1u << lane) - 1;
+  int ncand = 0;
+  if (haveCand) {
+    build_candidates(E);
+    ncand = E.i[X_NCAND];
+  }
+  /* ---- narrow phase */
+  ManR m;
+  m.cnt = 0; m.nx = m.ny = 0.f; m.h0 = m.h1 = 0;
+  m.p1a = m.p2a = m.p1b = m.p2b = v2(0.f, 0.f);
+  int a = 0, b = 0;
+  V2 dab = v2(0.f, 0.f);
+  if (lane < ncand) {
+    const int key = E.i[X_CAND + lane];
+    a = key >> 6; b = key & 63;
+    if (!is_ped(a) && is_ped(b)) { int t = a; a = b; b = t; } /* cpCollide orders by primitive type: circle first */
+    dab = pos_diff(E, b, a);
+    BoxR B = shape_boxr(E, b, dab);
+    if (is_ped(a)) circle_box_r(PED_R, B, &m);
+    else {
+      BoxR A = shape_boxr(E, a, v2(0.f, 0.f));
+      box_box_r(A, B, &m);
+    }
+  }
+  bool hit = m.cnt > 0;
+  const int nArb0 = E.i[DRV_S_NARB];
+  if (!__any_sync(FULLMASK, hit) && nArb0 == 0) {
+    friction_phase(E, isCar, isPed);
+    return;
+  }
+  /* ---- cpArbiterUpdate: find or create the cached pair */
+  const int key16 = a | (b << 8);
+  int k = -1;
+  if (hit)
+    for (int kk = 0; kk < nArb0; kk++)
+      if ((E.i[DRV_S_ARBKEY + kk] & 0xffff) == key16) { k = kk; break; }
+  const bool isNew = hit && k < 0;
+  const unsigned newMask = __ballot_sync(FULLMASK, isNew);
+  if (isNew) {
+    k = nArb0 + __popc(newMask & lt);
+    if (k >= DRV_MAXARB) { hit = false; E.i[X_DIAG] |= RC_IF_ARB_OVERFLOW; }
+  }
+  int state = RC_ARB_FIRST, oldCon = 0;
+  float ojn0 = 0.f, ojn1 = 0.f;
+  if (hit && !isNew) {
+    state = (E.i[DRV_S_ARBKEY + k] >> 16) & 255;
+    if (state == RC_ARB_CACHED) state = RC_ARB_FIRST;
+    oldCon = E.i[DRV_S_ARBCON + k];
+    ojn0 = E.f[DRV_S_ARBJN0 + k]; ojn1 = E.f[DRV_S_ARBJN1 + k];
+  }
+  __syncwarp();
+  if (lane == 0) E.i[DRV_S_NARB] = min(nArb0 + __popc(newMask), DRV_MAXARB);
+  /* ---- begin callbacks of first-touch pairs, in pair order (rare) */
+  unsigned firstMask = __ballot_sync(FULLMASK, hit && state == RC_ARB_FIRST);
+  unsigned ignoreMask = 0;
+  while (firstMask) {
+    const int src = __ffs(firstMask) - 1;
+    firstMask &= firstMask - 1;
+    const int aa = __shfl_sync(FULLMASK, a, src), bb = __shfl_sync(FULLMASK, b, src);
+    int ign = 0;
+    if (lane == 0) {
+      if (is_car(aa) && is_car(bb)) cb_car_crash(E, aa - DRV_SHAPE_CAR0, bb - DRV_SHAPE_CAR0);
+      else if (is_ped(aa)) ign = cb_ped_hit(E, bb - DRV_SHAPE_CAR0, aa - DRV_SHAPE_PED0) ? 0 : 1;
+      else cb_car_hit(E, (is_car(aa) ? aa : bb) - DRV_SHAPE_CAR0);
+    }
+    ign = __shfl_sync(FULLMASK, ign, 0);
+    if (ign) ignoreMask |= 1u << src;
+    __syncwarp();
+  }
+  if (hit && ((ignoreMask >> lane) & 1)) state = RC_ARB_IGNORE;
+  /* ---- cached-pair records, active list (pair order = lane order) */
+  bool act = hit && state != RC_ARB_IGNORE;
+  unsigned actMask = __ballot_sync(FULLMASK, act);
+  int q = __popc(actMask & lt);
+  if (act && q >= DRV_MAXACTIVE) { act = false; E.i[X_DIAG] |= RC_IF_ACTIVE_OVERFLOW; }
+  actMask = __ballot_sync(FULLMASK, act);
+  const int nact = __popc(actMask);
+  const unsigned touched = __reduce_or_sync(FULLMASK, hit ? (1u << k) : 0u);
+  float jn0 = 0.f, jn1 = 0.f;
+  if (hit) {
+    E.i[DRV_S_ARBKEY + k] = key16 | (state << 16); /* age = 0 */
+    if (act) {
+      const int oldN = oldCon & 255, oh0 = (oldCon >> 8) & 255, oh1 = (oldCon >> 16) & 255;
+      if (oldN > 0 && m.h0 == oh0) jn0 = ojn0;
+      if (oldN > 1 && m.h0 == oh1) jn0 = ojn1;
+      if (m.cnt > 1) {
+        if (oldN > 0 && m.h1 == oh0) jn1 = ojn0;
+        if (oldN > 1 && m.h1 == oh1) jn1 = ojn1;
+      }
+      E.i[DRV_S_ARBCON + k] = m.cnt | (m.h0 << 8) | ((m.cnt > 1 ? m.h1 : 0) << 16);
+      E.i[X_ACTIVE + q] = k;
+    } else {
+      E.i[DRV_S_ARBCON + k] = 0;
+      E.f[DRV_S_ARBJN0 + k] = 0.f; E.f[DRV_S_ARBJN1 + k] = 0.f;
+    }
+    if (isNew) { E.f[DRV_S_ARBJT0 + k] = 0.f; E.f[DRV_S_ARBJT1 + k] = 0.f; }
+  }
+  if (lane == 0) { E.i[X_TOUCHED] = (int)touched; E.i[X_NACTIVE] = nact; }
+  __syncwarp();
+  age_cached_pairs(E);
+  if (nact == 0) {
+    friction_phase(E, isCar, isPed);
+    return;
+  }
+  if (act) k = E.i[X_ACTIVE + q];
+  /* ---- cpArbiterPreStep (velocities before the friction update) */
+  const float slop = 0.1f;
+  const float biasCoef = 6.1259606640e-02f; /* 1 - collisionBias^dt, collisionBias = 0.9^60 */
+  const V2 n = v2(m.nx, m.ny);
+  const V2 r1a = m.p1a, r2a = m.p2a - dab, r1b = m.p1b, r2b = m.p2b - dab;
+  float ami = 0.f, aii = 0.f, bmi = 0.f, bii = 0.f;
+  float nMass0 = 0.f, nMass1 = 0.f, bias0 = 0.f, bias1 = 0.f, bounce0 = 0.f, bounce1 = 0.f;
+  if (act) {
+    ami = body_minv(E, a); aii = body_iinv(E, a); bmi = body_minv(E, b); bii = body_iinv(E, b);
+    BodyV A = load_body(E, a), B = load_body(E, b);
+    {
+      float r1cn = cross(r1a, n), r2cn = cross(r2a, n);
+      nMass0 = 1.f / (ami + aii * r1cn * r1cn + bmi + bii * r2cn * r2cn);
+      bias0 = -biasCoef * fminf(0.f, dot(r2a - r1a + dab, n) + slop) / DT;
+      V2 vr = v2((B.vx - r2a.y * B.w) - (A.vx - r1a.y * A.w), (B.vy + r2a.x * B.w) - (A.vy + r1a.x * A.w));
+      bounce0 = dot(vr, n) * (0.05f * 0.05f); /* every shape: elasticity 0.05 */
+    }
+    if (m.cnt > 1) {
+      float r1cn = cross(r1b, n), r2cn = cross(r2b, n);
+      nMass1 = 1.f / (ami + aii * r1cn * r1cn + bmi + bii * r2cn * r2cn);
+      bias1 = -biasCoef * fminf(0.f, dot(r2b - r1b + dab, n) + slop) / DT;
+      V2 vr = v2((B.vx - r2b.y * B.w) - (A.vx - r1b.y * A.w), (B.vy + r2b.x * B.w) - (A.vy + r1b.x * A.w));
+      bounce1 = dot(vr, n) * (0.05f * 0.05f);
+    }
+  }
+  /* do two active pairs share a dynamic body? */
+  bool conflict = false;
+  {
+    const bool aDyn = a >= DRV_SHAPE_CAR0 && a < DRV_SHAPE_OBS0, bDyn = b >= DRV_SHAPE_CAR0 && b < DRV_SHAPE_OBS0;
+    unsigned mm = actMask;
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const int aj = __shfl_sync(FULLMASK, a, src), bj = __shfl_sync(FULLMASK, b, src);
+      if (act && src != lane && ((aDyn && (a == aj || a == bj)) || (bDyn && (b == aj || b == bj)))) conflict = true;
+    }
+    conflict = __any_sync(FULLMASK, conflict);
+  }
+  __syncwarp();
+  friction_phase(E, isCar, isPed);
+  const float dt_coef = prevStepped ? 1.f : 0.f;
+  if (!conflict) {
+    if (act) {
+      BodyV A = load_body(E, a), B = load_body(E, b);
+      if (state != RC_ARB_FIRST) { /* cpArbiterApplyCachedImpulse */
+        V2 j = n * (jn0 * dt_coef);
+        A.vx -= j.x * ami; A.vy -= j.y * ami; A.w -= aii * cross(r1a, j);
+        B.vx += j.x * bmi; B.vy += j.y * bmi; B.w += bii * cross(r2a, j);
+        if (m.cnt > 1) {
+          j = n * (jn1 * dt_coef);
+          A.vx -= j.x * ami; A.vy -= j.y * ami; A.w -= aii * cross(r1b, j);
+          B.vx += j.x * bmi; B.vy += j.y * bmi; B.w += bii * cross(r2b, j);
+        }
+      }
+      float jb0 = 0.f, jb1 = 0.f;
+#pragma unroll 1
+      for (int it = 0; it < 10; it++) { /* cpArbiterApplyImpulse; shape friction is 0: no tangential impulse */
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          if (c == 1 && m.cnt < 2) break;
+          const V2 r1 = c ? r1b : r1a, r2 = c ? r2b : r2a;
+          const float nMass = c ? nMass1 : nMass0, bias = c ? bias1 : bias0, bounce = c ? bounce1 : bounce0;
+          float& jBiasAcc = c ? jb1 : jb0;
+          float& jnAccR = c ? jn1 : jn0;
+          V2 vb1 = v2(A.vbx - r1.y * A.wb, A.vby + r1.x * A.wb);
+          V2 vb2 = v2(B.vbx - r2.y * B.wb, B.vby + r2.x * B.wb);
+          V2 vr = v2((B.vx - r2.y * B.w) - (A.vx - r1.y * A.w), (B.vy + r2.x * B.w) - (A.vy + r1.x * A.w));
+          float vbn = dot(vb2 - vb1, n), vrn = dot(vr, n);
+          float jbn = (bias - vbn) * nMass, jbnOld = jBiasAcc;
+          jBiasAcc = fmaxf(jbnOld + jbn, 0.f);
+          float jn = -(bounce + vrn) * nMass, jnOld = jnAccR;
+          jnAccR = fmaxf(jnOld + jn, 0.f);
+          V2 jb = n * (jBiasAcc - jbnOld);
+          A.vbx -= jb.x * ami; A.vby -= jb.y * ami; A.wb -= aii * cross(r1, jb);
+          B.vbx += jb.x * bmi; B.vby += jb.y * bmi; B.wb += bii * cross(r2, jb);
+          V2 j = n * (jnAccR - jnOld);
+          A.vx -= j.x * ami; A.vy -= j.y * ami; A.w -= aii * cross(r1, j);
+          B.vx += j.x * bmi; B.vy += j.y * bmi; B.w += bii * cross(r2, j);
+        }
+      }
+      store_body(E, a, A);
+      store_body(E, b, B);
+    }
+  } else {
+    /* shared bodies: the reference's Gauss-Seidel order on lane 0 */
+    if (act) {
+      E.f[X_ANX + q] = n.x; E.f[X_ANY + q] = n.y;
+      const int c0 = 2 * q, c1 = 2 * q + 1;
+      E.f[X_CR1X + c0] = r1a.x; E.f[X_CR1Y + c0] = r1a.y; E.f[X_CR2X + c0] = r2a.x; E.f[X_CR2Y + c0] = r2a.y;
+      E.f[X_CR1X + c1] = r1b.x; E.f[X_CR1Y + c1] = r1b.y; E.f[X_CR2X + c1] = r2b.x; E.f[X_CR2Y + c1] = r2b.y;
+      E.f[X_CNMASS + c0] = nMass0; E.f[X_CNMASS + c1] = nMass1;
+      E.f[X_CBIAS + c0] = bias0; E.f[X_CBIAS + c1] = bias1;
+      E.f[X_CBOUNCE + c0] = bounce0; E.f[X_CBOUNCE + c1] = bounce1;
+      E.f[X_CJBIAS + c0] = 0.f; E.f[X_CJBIAS + c1] = 0.f;
+      E.f[X_CJN + c0] = jn0; E.f[X_CJN + c1] = jn1;
+    }
+    __syncwarp();
+    warm_start_contacts(E, dt_coef);
+    if (lane == 0)
+      for (int it = 0; it < 10; it++) contacts_iteration(E);
+    __syncwarp();
+    if (act) { jn0 = E.f[X_CJN + 2 * q]; jn1 = E.f[X_CJN + 2 * q + 1]; }
+  }
+  if (act) { /* accumulated impulses back into the cached pairs */
+    E.f[DRV_S_ARBJN0 + k] = jn0;
+    E.f[DRV_S_ARBJN1 + k] = m.cnt > 1 ? jn1 : 0.f;
+  }
+  __syncwarp();
 }
 
 __device__ __noinline__ void space_step(const Env E) {
@@ -832,6 +979,7 @@ __device__ __noinline__ void space_step(const Env E) {
   /* integrate positions (cpBodyUpdatePosition); bounding boxes of this lane's two shapes in registers:
      round 0 = shape `lane` (buildings 0..3, cars 4..13, pedestrians 0..17), round 1 = shape 32 + lane */
   const bool isCar = lane < N, isPed = lane >= 10 && lane - 10 < nPed;
+  bool atRest = false; /* this lane's body did not move in this substep and has no velocity */
   if (isCar) {
     const int i = lane;
     float px = E.f[DRV_S_CPX + i], pxl = E.f[DRV_S_CPXL + i], py = E.f[DRV_S_CPY + i], pyl = E.f[DRV_S_CPYL + i];
@@ -840,6 +988,8 @@ __device__ __noinline__ void space_step(const Env E) {
     two_add(py, pyl, __fmul_rn(E.f[DRV_S_CVY + i] + E.f[DRV_S_CVBY + i], DT));
     const float wsum = E.f[DRV_S_CW + i] + E.f[DRV_S_CWB + i];
     if (wsum != 0.f) { an += (double)wsum * 0.01; store_ang(E, i, an); }
+    atRest = E.f[DRV_S_CVX + i] == 0.f && E.f[DRV_S_CVY + i] == 0.f && E.f[DRV_S_CW + i] == 0.f && E.f[DRV_S_CVBX + i] == 0.f &&
+             E.f[DRV_S_CVBY + i] == 0.f && E.f[DRV_S_CWB + i] == 0.f;
     E.f[DRV_S_CPX + i] = px; E.f[DRV_S_CPXL + i] = pxl; E.f[DRV_S_CPY + i] = py; E.f[DRV_S_CPYL + i] = pyl;
     E.f[DRV_S_CVBX + i] = 0.f; E.f[DRV_S_CVBY + i] = 0.f; E.f[DRV_S_CWB + i] = 0.f;
     float sn, cs;
@@ -854,6 +1004,7 @@ __device__ __noinline__ void space_step(const Env E) {
     float px = E.f[DRV_S_PPX + i], pxl = E.f[DRV_S_PPXL + i], py = E.f[DRV_S_PPY + i], pyl = E.f[DRV_S_PPYL + i];
     two_add(px, pxl, __fmul_rn(E.f[DRV_S_PVX + i] + E.f[DRV_S_PVBX + i], DT));
     two_add(py, pyl, __fmul_rn(E.f[DRV_S_PVY + i] + E.f[DRV_S_PVBY + i], DT));
+    atRest = E.f[DRV_S_PVX + i] == 0.f && E.f[DRV_S_PVY + i] == 0.f && E.f[DRV_S_PVBX + i] == 0.f && E.f[DRV_S_PVBY + i] == 0.f;
     E.f[DRV_S_PPX + i] = px; E.f[DRV_S_PPXL + i] = pxl; E.f[DRV_S_PPY + i] = py; E.f[DRV_S_PPYL + i] = pyl;
     E.f[DRV_S_PVBX + i] = 0.f; E.f[DRV_S_PVBY + i] = 0.f;
   }
@@ -861,6 +1012,11 @@ __device__ __noinline__ void space_step(const Env E) {
   /* broad phase: every shape against the N cars (Chipmunk's bounding-box test; the margin covers the float32
      rounding of the absolute coordinates, the narrow phase decides exactly) */
   {
+    /* bit per dynamic body (cars 0..9, pedestrians 10..29): at rest.  Pairs of resting bodies are exactly where they
+       were in the previous substep and their contacts carry no impulse: if that holds for every overlapping pair and
+       every cached pair, the collision half of this substep changes nothing and is skipped. */
+    const unsigned restMask = __ballot_sync(FULLMASK, atRest);
+    bool pairsRest = true;
     int mask[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
@@ -885,43 +1041,34 @@ __device__ __noinline__ void space_step(const Env E) {
         if (ov && (selfCar == 99 || i < selfCar)) m |= 1 << i;
       }
       mask[r] = m;
+      if (m) {
+        const int ownBit = s - DRV_SHAPE_CAR0; /* cars 4..13 -> 0..9, pedestrians 14..33 -> 10..29 */
+        const bool ownDyn = s >= DRV_SHAPE_CAR0 && s < DRV_SHAPE_OBS0;
+        if ((ownDyn && !((restMask >> ownBit) & 1)) || (m & ~restMask & 0x3ff)) pairsRest = false;
+      }
     }
-    if (__any_sync(FULLMASK, (mask[0] | mask[1]) != 0)) {
-      E.i[X_BPMASK + lane] = mask[0];
-      E.i[X_BPMASK + 32 + lane] = mask[1];
-      __syncwarp();
-      collide_candidates(E);
+    const bool haveCand = __any_sync(FULLMASK, (mask[0] | mask[1]) != 0);
+    bool skip = false;
+    if (haveCand || nArb) {
+      if (lane < nArb) { /* cached pairs: touched in the previous substep, no stored impulse, both bodies at rest */
+        const int key = E.i[DRV_S_ARBKEY + lane];
+        const int a = key & 255, b = (key >> 8) & 255;
+        const bool aOk = !(a >= DRV_SHAPE_CAR0 && a < DRV_SHAPE_OBS0) || ((restMask >> (a - DRV_SHAPE_CAR0)) & 1);
+        const bool bOk = !(b >= DRV_SHAPE_CAR0 && b < DRV_SHAPE_OBS0) || ((restMask >> (b - DRV_SHAPE_CAR0)) & 1);
+        const int st = (key >> 16) & 0xffff; /* state | age << 8 */
+        if (!(aOk && bOk && (st == RC_ARB_NORMAL || st == RC_ARB_IGNORE) && E.f[DRV_S_ARBJN0 + lane] == 0.f && E.f[DRV_S_ARBJN1 + lane] == 0.f))
+          pairsRest = false;
+      }
+      skip = __all_sync(FULLMASK, pairsRest);
     }
-  }
-  if (E.i[DRV_S_NARB]) age_cached_pairs(E);
-  const int nact = E.i[X_NACTIVE];
-  if (nact) prestep_contacts(E);
-  /* velocity update through the friction callbacks: cars (cutils.py:78-85), dead pedestrians (:88-90); live
-     pedestrians have the default update (nothing to do without forces) */
-  if (isCar) {
-    const int i = lane;
-    float x = E.f[DRV_S_CVX + i], y = E.f[DRV_S_CVY + i], th = E.f[DRV_S_CW + i];
-    const bool fin = E.i[DRV_S_CFLAGS + i] & DRV_CF_FINISHED;
-    friction(car_mass(E.i[DRV_S_CTYPE + i]), fin ? 5e-4f : 5e-5f, fin ? 2e-5f : 1e-5f, x, y, th);
-    E.f[DRV_S_CVX + i] = x; E.f[DRV_S_CVY + i] = y; E.f[DRV_S_CW + i] = th;
-  } else if (isPed && (E.i[DRV_S_PFLAGS + lane - 10] & DRV_PF_DEAD)) {
-    const int i = lane - 10;
-    float x = E.f[DRV_S_PVX + i], y = E.f[DRV_S_PVY + i], th = 0.f;
-    friction(90.f, 5e-2f, 2e-4f, x, y, th);
-    E.f[DRV_S_PVX + i] = x; E.f[DRV_S_PVY + i] = y;
-  }
-  __syncwarp();
-  if (nact) {
-    warm_start_contacts(E, prevStepped ? 1.f : 0.f);
-    if (lane == 0)
-      for (int it = 0; it < 10; it++) contacts_iteration(E);
-    __syncwarp();
-    if (lane < nact) { /* accumulated impulses back into the cached pairs */
-      int k = E.i[X_ACTIVE + lane];
-      E.f[DRV_S_ARBJN0 + k] = E.f[X_CJN + 2 * lane];
-      E.f[DRV_S_ARBJN1 + k] = (E.i[DRV_S_ARBCON + k] & 255) > 1 ? E.f[X_CJN + 2 * lane + 1] : 0.f;
-    }
-    __syncwarp();
+    if ((haveCand || nArb) && !skip) {
+      if (haveCand) {
+        E.i[X_BPMASK + lane] = mask[0];
+        E.i[X_BPMASK + 32 + lane] = mask[1];
+        __syncwarp();
+      }
+      contacts_substep(E, prevStepped, haveCand, isCar, isPed);
+    } else friction_phase(E, isCar, isPed);
   }
 }
 
@@ -962,6 +1109,22 @@ __device__ __forceinline__ float wrap_pi(float a) {
   return a;
 }
 
+/* atan2 to ~2e-7 rad in ~25 instructions (atan2f costs ~75): octant reduction, then Cephes' atanf scheme -- a second
+   reduction to |t| <= tan(pi/8) and a 4-term odd polynomial */
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+  const bool big = a > 0.41421356237309503f;
+  const float t = big ? __fdividef(a - 1.f, a + 1.f) : a;
+  const float z = t * t;
+  float r = fmaf(fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f), z * t, t);
+  if (big) r += 0.78539816339744831f;
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (x < 0.f) r = 3.14159265358979324f - r;
+  return copysignf(r, y);
+}
+
 /* cutils.doesInteractPoly (cutils.py:643-696, canOcclude = True) of a point-like sighting at p1 (angle ang1 in the
    observer frame) against occluder o, whose view-block data the observer's pass has put into shared memory */
 __device__ __forceinline__ int interact_poly(const Env E, float p1x, float p1y, float ang1, int o, float radius) {
@@ -995,7 +1158,7 @@ __device__ __forceinline__ void occluder_store(const Env E, int o, V2 p, V2 tr, 
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     cr[k] = v2(tr.x + sx[k] * hx, tr.y + sy[k] * hy);
-    ang[k] = wrap_pi(atan2f(cr[k].y, cr[k].x) - ang2);
+    ang[k] = wrap_pi(fast_atan2(cr[k].y, cr[k].x) - ang2);
     dist[k] = lensq(cr[k]);
   }
   int mn = 0, mx = 0, cl = 0;
@@ -1083,6 +1246,7 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   B = A;
   float angA = 0.f, angB = 0.f;
   bool listA = false, listB = false;
+  int nFree; /* slot-A lanes without a car / obstacle: the first four of them take the buildings' view-block data */
   {
     bool have = false;
     float x = 0, xl = 0, y = 0, yl = 0, hx = OBST_HALF, hy = OBST_HALF;
@@ -1097,21 +1261,29 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
     } else if (lane < 30) {
       if (lane - 10 < nObs) { have = true; x = E.f[DRV_S_OPX + lane - 10]; y = E.f[DRV_S_OPY + lane - 10]; }
     }
-    if (have) {
+    const unsigned freeMask = __ballot_sync(FULLMASK, !have);
+    nFree = __popc(freeMask);
+    const int bld = have ? -1 : __popc(freeMask & ((1u << lane) - 1));
+    const bool isBuild = !have && bld < DRV_NBUILD;
+    if (isBuild) { V2 bp = build_pos(bld); x = bp.x; y = bp.y; hx = BUILD_W; hy = BUILD_H; }
+    if (have || isBuild) {
       V2 tr = v2(__fadd_rn(__fsub_rn(x, ox), __fsub_rn(xl, oxl)), __fadd_rn(__fsub_rn(y, oy), __fsub_rn(yl, oyl)));
       float dist = lensq(tr);
-      if (dist <= MAXVIS0) {
+      const bool seen = isBuild || dist <= MAXVIS0; /* buildings: isSeenInRadius with maxDist 2e7 */
+      V2 p = v2(tr.x * ca + tr.y * sa, -tr.x * sa + tr.y * ca);
+      const float ang = fast_atan2(p.y, p.x);
+      if (have && seen) {
         A.seen = dist <= MAXVIS1 ? S_NORMAL : S_DISTANT;
-        A.px = tr.x * ca + tr.y * sa; A.py = -tr.x * sa + tr.y * ca;
-        if (lane < 10) {
-          sincos_d(__dsub_rn(load_ang(E, lane), oa), &A.s, &A.c);
-        } else { A.c = ca; A.s = -sa; }
+        A.px = p.x; A.py = p.y;
+        if (lane < 10) sincos_d(__dsub_rn(load_ang(E, lane), oa), &A.s, &A.c);
+        else { A.c = ca; A.s = -sa; }
         A.w = hy; A.h = hx;
-        angA = atan2f(A.py, A.px);
+        angA = ang;
         listA = true;
       }
-      occluder_store(E, lane, v2(A.px, A.py), tr, hx, hy, angA, listA);
-    } else if (lane < 30) E.i[V_OK + lane] = 0;
+      occluder_store(E, isBuild ? 30 + bld : lane, p, tr, hx, hy, ang, seen);
+    }
+    if (!have && lane < 30) E.i[V_OK + lane] = 0;
   }
   if (lane < 20) {
     if (lane < nPed) {
@@ -1122,15 +1294,16 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
         B.seen = dist <= MAXVIS1 ? S_NORMAL : S_DISTANT;
         B.px = tr.x * ca + tr.y * sa; B.py = -tr.x * sa + tr.y * ca;
         B.c = ca; B.s = -sa;
-        angB = atan2f(B.py, B.px);
+        angB = fast_atan2(B.py, B.px);
         listB = true;
       }
     }
-  } else if (lane < 24) {
+  }
+  if (nFree < DRV_NBUILD && lane >= 20 + nFree && lane < 24) { /* 10 cars and 20 obstacles: the remaining buildings */
     V2 bp = build_pos(lane - 20);
     V2 tr = v2(__fsub_rn(__fsub_rn(bp.x, ox), oxl), __fsub_rn(__fsub_rn(bp.y, oy), oyl));
     V2 p = v2(tr.x * ca + tr.y * sa, -tr.x * sa + tr.y * ca);
-    occluder_store(E, 30 + lane - 20, p, tr, BUILD_W, BUILD_H, atan2f(p.y, p.x), true);
+    occluder_store(E, 30 + lane - 20, p, tr, BUILD_W, BUILD_H, fast_atan2(p.y, p.x), true);
   }
   __syncwarp();
   /* ---- occlusion by buildings (:785-792): occluded sightings leave their lists */
@@ -1408,6 +1581,8 @@ __device__ __noinline__ void fill_info(const Env E, float* info_env) {
     float r7[7];
     car_row(E, lane, r7);
     for (int k = 0; k < 7; k++) info_env[DRV_I_STATE_CARS + lane * 7 + k] = r7[k];
+    info_env[DRV_I_GOALS + 2 * lane] = normalize_(E.f[DRV_S_CGOALX + lane], SNORMX, 0.f);
+    info_env[DRV_I_GOALS + 2 * lane + 1] = normalize_(E.f[DRV_S_CGOALY + lane], SNORMY, 0.f);
   }
   if (lane < nObs) {
     float* o = info_env + DRV_I_STATE_OBS + lane * 4;

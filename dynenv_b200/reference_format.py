@@ -71,3 +71,74 @@ def host_views(out, full, env_ids=None):
             t = t[env_ids]
         v[k] = t.detach().cpu().numpy()
     return v
+
+
+# ---------------------------------------------------------------------------------------------- Driving
+# DrivingEnvironment.getAgentVision returns ((cars[.,7], obstacles[.,6], pedestrians[.,2]), (self[1,9], lanes[.,4]), (1,1,1))
+# (DrivingEnvironment.py:960-977); get_full_obs ([others[N-1,7], obstacles[.,4], pedestrians[.,2]], [self[1,9], lanes[8,5]], (1,1,1))
+# (:121-124).  Inputs: numpy copies of the views of `DrivingOutputs`.
+DRV_VIEW_KEYS = ["self_", "car", "obs", "ped", "lane", "counts", "rewards", "done", "state_cars", "state_obs", "state_ped", "n_obs",
+                 "n_ped", "goals", "episode_r", "episode_p_r", "episode_g"]
+
+
+def drv_host_views(out, env_ids=None):
+    v = {}
+    for k in DRV_VIEW_KEYS:
+        t = getattr(out, k)
+        if env_ids is not None:
+            t = t[env_ids]
+        v[k] = t.detach().cpu().numpy()
+    return v
+
+
+def drv_lanes_full():
+    """the constant lane rows of getFullState (DrivingEnvironment.py:690-696), including the reference's negative
+    Python index: row i holds the geometry of lane offset (i - nLanes) mod (2 nLanes + 1) - nLanes"""
+    rows = []
+    snx, sny = 0.5 / 1800.0, 0.5 / 1100.0
+    for (nL, p0, p1, nrm) in ((2, (875.0, 0.0), (875.0, 1000.0), (-1.0, 0.0)), (1, (0.0, 500.0), (1750.0, 500.0), (0.0, 1.0))):
+        cnt = 2 * nL + 1
+        for i in range(-nL, nL + 1):
+            off = ((i - nL) % cnt) - nL
+            l0 = (p0[0] + nrm[0] * off * 35.0, p0[1] + nrm[1] * off * 35.0)
+            l1 = (p1[0] + nrm[0] * off * 35.0, p1[1] + nrm[1] * off * 35.0)
+            rows.append([l0[0] * snx * 2, l0[1] * sny * 2, l1[0] * snx * 2, l1[1] * sny * 2,
+                         1 if abs(i) == nL else (-1 if i == 0 else 0)])
+    return np.array(rows, dtype=np.float32)
+
+
+def drv_observations(views, e, N, full):
+    """[[obs of car 0, ... car N-1]] (nTimeSteps = 1)"""
+    out = []
+    for a in range(N):
+        c = views["counts"][e, a]
+        cars = _rows(views["car"][e, a], int(c[0]))
+        obst = _rows(views["obs"][e, a][:, :4] if full else views["obs"][e, a], int(c[1]))
+        peds = _rows(views["ped"][e, a], int(c[2]))
+        lanes = _rows(views["lane"][e, a] if full else views["lane"][e, a][:, :4], int(c[3]))
+        self_ = np.array(views["self_"][e, a][None], dtype=np.float32)
+        if full:
+            out.append(([cars, obst, peds], [self_, lanes], (1, 1, 1)))
+        else:
+            out.append(((cars, obst, peds), (self_, lanes), (1, 1, 1)))
+    return [out]
+
+
+def drv_full_state(views, e, N, agent=None):
+    """getFullState(agent) (DrivingEnvironment.py:686-747)"""
+    cars = np.array(views["state_cars"][e, :N], dtype=np.float32)
+    tail = [_rows(views["state_obs"][e], int(views["n_obs"][e])), _rows(views["state_ped"][e], int(views["n_ped"][e])), drv_lanes_full()]
+    if agent is None:
+        return [cars] + tail
+    self_ = np.concatenate([cars[agent, :6], views["goals"][e, agent], cars[agent, 6:7]]).astype(np.float32)[None]
+    return [self_, np.delete(cars, agent, axis=0)] + tail
+
+
+def drv_info_dict(views, e, N):
+    info = {"Full State": drv_full_state(views, e, N), "Recon States": [drv_full_state(views, e, N, a) for a in range(N)]}
+    if bool(views["done"][e]):  # DrivingEnvironment.py:310-316
+        info["episode_r"] = np.array(views["episode_r"][e, :N], dtype=np.float64)
+        info["episode_p_r"] = np.array(views["episode_p_r"][e, :N], dtype=np.float64)
+        info["episode_o_r"] = [0, ] * N
+        info["episode_g"] = [int(views["episode_g"][e, 0]), int(views["episode_g"][e, 1])]
+    return info

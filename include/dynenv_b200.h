@@ -394,7 +394,9 @@ enum {
   DRV_I_STATE_PED = DRV_I_STATE_OBS + DRV_MAXOBS * 4,   /* F [DRV_MAXPED][2] */
   DRV_I_NOBS = DRV_I_STATE_PED + DRV_MAXPED * 2,        /* I */
   DRV_I_NPED = DRV_I_NOBS + 1,                          /* I */
-  DRV_INFO_WORDS_RAW = DRV_I_NPED + 1,
+  DRV_I_GOALS = DRV_I_NPED + 1,                         /* F [DRV_MAXCARS][2] goals, normalised like the state rows
+                                                           (the self row of info['Recon States']) */
+  DRV_INFO_WORDS_RAW = DRV_I_GOALS + DRV_MAXCARS * 2,
   DRV_INFO_WORDS = (DRV_INFO_WORDS_RAW + 31) / 32 * 32
 };
 

@@ -282,7 +282,8 @@ def drv_f32_record_to_words(rec):
     mask = np.array(L.drv_int_mask())
     w = np.zeros(r.shape, dtype=np.float64)
     w[..., mask] = r[..., mask].view(np.int32).astype(np.float64)
-    w[..., ~mask] = r[..., ~mask].view(np.float32).astype(np.float64)
+    with np.errstate(invalid="ignore"):  # the float64 angle words are not float32 numbers; they are overwritten below
+        w[..., ~mask] = r[..., ~mask].view(np.float32).astype(np.float64)
     for hi, lo in L.DRV_SPLIT.items():
         (oh, cnt, _), (ol, _, _) = L.DRV_FIELDS[hi], L.DRV_FIELDS[lo]
         w[..., oh:oh + cnt] += w[..., ol:ol + cnt]

@@ -89,3 +89,73 @@ def test_results_do_not_depend_on_sharding():
         assert torch.equal(ow.obs, torch.cat([o.obs for o in op]))
         assert torch.equal(ow.info, torch.cat([o.info for o in op]))
     assert torch.equal(whole.get_state(), torch.cat([p.get_state() for p in parts]))
+
+
+def test_driving_single_env_drop_in():
+    import dynenv_b200
+    env = dynenv_b200.DrivingEnvironment(nPlayers=4, noiseMagnitude=2)
+    obs = env.reset()
+    assert len(obs) == 1 and len(obs[0]) == 4
+    (cars, obst, peds), (self_, lanes), ones = obs[0][0]
+    assert self_.shape == (1, 9) and self_.dtype == np.float32 and ones == (1, 1, 1)
+    for arr, f in ((cars, 7), (obst, 6), (peds, 2), (lanes, 4)):
+        assert arr.dtype == np.float32 and (arr.shape == (0,) or arr.shape[1] == f)
+    obs, rew, fin, info = env.step(np.array([[2, 1], [2, 1], [0, 2], [1, 0]]))
+    assert rew.shape == (4,) and rew.dtype == np.float64 and fin is False and env.elapsed == 10
+    fs = info["Full State"]
+    assert fs[0].shape == (4, 7) and fs[1].shape[1] == 4 and fs[2].shape[1] == 2 and fs[3].shape == (8, 5)
+    rs = info["Recon States"]
+    assert len(rs) == 4 and rs[0][0].shape == (1, 9) and rs[0][1].shape == (3, 7)
+    assert np.allclose(rs[1][0][0, :6], fs[0][1, :6]) and rs[1][0][0, 8] == fs[0][1, 6]
+    assert env.get_agent_locs()[0].shape == (1, 4)
+    with pytest.raises(Exception, match="2 actions for every car"):
+        env.step(np.zeros((3, 2)))
+    with pytest.raises(Exception, match="Acceleration must be between"):
+        env.step(np.array([[9, 1]] * 4))
+    env.close()
+    # FULL observations: ([others, obstacles, pedestrians], [self, lanes], (1, 1, 1))
+    env = dynenv_b200.DrivingEnvironment(nPlayers=3, observationType=dynenv_b200.ObservationType.FULL, noiseMagnitude=0)
+    (others, obst, peds), (self_, lanes), _ = env.reset()[0][2]
+    assert others.shape == (2, 7) and obst.shape[1] == 4 and lanes.shape == (8, 5) and self_.shape == (1, 9)
+    assert np.allclose(lanes, env.getFullState()[3])
+    env.close()
+
+
+def test_driving_vec_env_auto_reset():
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    venv, name = dynenv_b200.make_dyn_env(dynenv_b200.DynEnvType.DRIVE, 3, 5, False, dynenv_b200.ObservationType.PARTIAL,
+                                          dynenv_b200.NoiseType.REALISTIC, 1.0, True)
+    assert name == "Driving" and venv.num_envs == 3
+    obs = venv.reset()
+    assert obs.shape == (3, 1, 5, 3)
+    st = venv.sim.get_state()
+    st[2, L.DRV_S_ELAPSED] = 6000 - 10
+    venv.sim.set_state(st)
+    a = np.random.default_rng(0).uniform(-3, 3, (3, 5, 2))
+    obs, rew, dones, infos = venv.step(a)
+    assert obs.shape == (3, 1, 5, 3) and rew.shape == (3, 5) and dones.tolist() == [False, False, True]
+    assert "terminal_observation" in infos[2] and "episode_r" in infos[2] and infos[2]["episode_o_r"] == [0] * 5
+    st = venv.sim.get_state().cpu().numpy()
+    assert st[2, L.DRV_S_ELAPSED] == 0 and st[2, L.DRV_S_EPISODE] == 2 and st[0, L.DRV_S_ELAPSED] == 10
+    assert venv.get_attr("nTimeSteps") == [1, 1, 1] and len(venv.env_method("get_agent_locs")) == 3
+    venv.close()
+
+
+def test_driving_results_do_not_depend_on_sharding():
+    import torch
+    import dynenv_b200
+    kw = dict(nPlayers=6, noiseMagnitude=2.0, continuousActions=True, seed=13)
+    whole = dynenv_b200.BatchedDriving(8, env_id_offset=0, **kw)
+    parts = [dynenv_b200.BatchedDriving(4, env_id_offset=o, **kw) for o in (0, 4)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    g = torch.Generator().manual_seed(4)
+    for _ in range(8):
+        a = (torch.rand((8, 6, 2), generator=g) * 6 - 3).cuda()
+        ow = whole.step(a)
+        op = [p.step(a[4 * k:4 * k + 4].contiguous()) for k, p in enumerate(parts)]
+        assert torch.equal(ow.record, torch.cat([o.record for o in op]))
+        assert torch.equal(ow.info, torch.cat([o.info for o in op]))
+    assert torch.equal(whole.get_state(), torch.cat([p.get_state() for p in parts]))

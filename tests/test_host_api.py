@@ -113,3 +113,51 @@ def test_no_device_fails_loudly():
     with pytest.raises(RuntimeError):
         import dynenv_b200
         dynenv_b200.BatchedRoboCup(2, 5)
+
+
+def test_driving_validation_and_spaces():
+    ok = np.array([[2, 0], [1, 1], [0, 2]])
+    assert api.validate_driving_actions(ok, 3, False).dtype == np.float32
+    with pytest.raises(Exception, match="2 actions for every car"):
+        api.validate_driving_actions(np.zeros((2, 2)), 3, False)
+    with pytest.raises(Exception, match="Acceleration must be between"):
+        api.validate_driving_actions(np.array([[5, 1]] * 3), 3, False)
+    with pytest.raises(Exception, match="Steering must be between"):
+        api.validate_driving_actions(np.array([[0.5, -3.5]] * 3), 3, True)
+    act, obs = api.driving_spaces(ObservationType.PARTIAL, False)
+    assert list(act.spaces[0].nvec) == [3, 3]
+    assert set(obs.spaces[1].spaces[1].spaces) == {"signed_distance", "orientation", "type"}
+    act, obs = api.driving_spaces(ObservationType.FULL, True)
+    assert act.spaces[0].shape == (2,) and set(obs.spaces[0].spaces[1].spaces) == {"position", "width_height"}
+
+
+def test_driving_reference_format():
+    """ragged Driving observations and info from padded records (host logic only)"""
+    rng = np.random.default_rng(1)
+    E, N = 2, 4
+    v = {"self_": rng.normal(size=(E, N, L.DRV_F_SELF)).astype(np.float32),
+         "car": rng.normal(size=(E, N, L.DRV_CAP_CAR, L.DRV_F_CAR)).astype(np.float32),
+         "obs": rng.normal(size=(E, N, L.DRV_CAP_OBS, L.DRV_F_OBS)).astype(np.float32),
+         "ped": rng.normal(size=(E, N, L.DRV_CAP_PED, L.DRV_F_PED)).astype(np.float32),
+         "lane": rng.normal(size=(E, N, L.DRV_CAP_LANE, L.DRV_F_LANE_FULL)).astype(np.float32),
+         "counts": rng.integers(0, 5, (E, N, 4)).astype(np.int32), "rewards": rng.normal(size=(E, N)).astype(np.float32),
+         "done": np.array([0, 1], np.int32), "state_cars": rng.normal(size=(E, N, 7)).astype(np.float32),
+         "state_obs": rng.normal(size=(E, L.DRV_MAXOBS, 4)).astype(np.float32),
+         "state_ped": rng.normal(size=(E, L.DRV_MAXPED, 2)).astype(np.float32), "n_obs": np.array([11, 0], np.int32),
+         "n_ped": np.array([13, 20], np.int32), "goals": rng.normal(size=(E, N, 2)).astype(np.float32),
+         "episode_r": rng.normal(size=(E, N)).astype(np.float32), "episode_p_r": rng.normal(size=(E, N)).astype(np.float32),
+         "episode_g": np.array([[0, 0], [1, 3]], np.int32)}
+    v["counts"][0, 1] = [3, 0, 2, 6]
+    obs = RF.drv_observations(v, 0, N, full=False)
+    assert len(obs) == 1 and len(obs[0]) == N
+    (cars, obst, peds), (self_, lanes), ones = obs[0][1]
+    assert cars.shape == (3, 7) and obst.shape == (0,) and peds.shape == (2, 2) and lanes.shape == (6, 4) and self_.shape == (1, 9)
+    assert np.array_equal(lanes, v["lane"][0, 1, :6, :4]) and ones == (1, 1, 1)
+    info = RF.drv_info_dict(v, 1, N)
+    assert info["Full State"][0].shape == (N, 7) and info["Full State"][1].shape == (0,) and info["Full State"][2].shape == (20, 2)
+    assert info["Full State"][3].shape == (8, 5) and info["episode_g"] == [1, 3] and info["episode_o_r"] == [0] * N
+    rs = info["Recon States"][2]
+    assert rs[0].shape == (1, 9) and rs[1].shape == (N - 1, 7) and np.array_equal(rs[0][0, 6:8], v["goals"][1, 2])
+    assert "episode_r" not in RF.drv_info_dict(v, 0, N)
+    lanes = RF.drv_lanes_full()  # the reference's negative-index quirk: type tags of row i, geometry of another lane line
+    assert lanes[:, 4].tolist() == [1, 0, -1, 0, 1, 1, -1, 1]
