@@ -94,6 +94,20 @@ class RcStepOut(C.Structure):
         return out
 
 
+class RcRawVision(C.Structure):
+    _fields_ = [("ball", _arr(C.c_double, L.RC_CAP_BALL, 3)), ("robot", _arr(C.c_double, L.RC_CAP_ROBOT, 3)),
+                ("post", _arr(C.c_double, L.RC_CAP_POST, 3)), ("cross", _arr(C.c_double, L.RC_CAP_CROSS, 3)),
+                ("fcross", _arr(C.c_double, L.RC_CAP_FCROSS, 3)), ("line", _arr(C.c_double, L.RC_CAP_LINE, 4)),
+                ("circle", _arr(C.c_double, 4)), ("counts", _arr(C.c_int32, L.RC_NTYPES)), ("pad", _arr(C.c_int32, 2))]
+
+    def to_dict(self):
+        return {name: np.ctypeslib.as_array(getattr(self, name)).copy() for name, _ in self._fields_ if name != "pad"}
+
+
+class RcRawOut(C.Structure):
+    _fields_ = [("v", (RcRawVision * _P) * _T)]
+
+
 class RcOracle(object):
     """One RoboCup environment of the CPU oracle."""
 
@@ -132,6 +146,15 @@ class RcOracle(object):
 
     def arb_overflow(self):
         return bool(self._lib.rc_arb_overflow(self._h))
+
+    def capture_raw(self, enable=True):
+        """the following reset_obs() / step() calls also record the raw detection lists (raw_vision())"""
+        assert self._lib.rc_rawout_size() == C.sizeof(RcRawOut)
+        self._raw = RcRawOut() if enable else None
+        self._lib.rc_set_raw_out(C.c_void_p(self._h), C.byref(self._raw) if enable else None)
+
+    def raw_vision(self, t, agent):
+        return self._raw.v[t][agent].to_dict()
 
     def reset(self):
         self._lib.rc_reset(self._h)

@@ -140,6 +140,7 @@ struct RcEnv {
   int active[RC_MAXARB], nActive;
   int arbOverflow;
   int subBegin, subEnd; /* debugging aid: substeps run by rc_step (0 = unset -> 0..RC_SUBSTEPS) */
+  struct RcRawOut* rawOut; /* optional: raw detection lists of every observation (IMAGE raster oracle) */
 };
 typedef struct RcEnv RcEnv;
 
@@ -1240,6 +1241,18 @@ static void list_insert(Det* l, int* n, int cap, int at, Det d) {
   if (*n < cap) (*n)++;
 }
 
+/* the detection lists of one getAgentVision call as the IMAGE branch draws them (RoboCupEnvironment.py:1318-1467):
+   positions and sizes in the observer's head frame, before the float32 encoders */
+typedef struct RcRawVision {
+  double ball[RC_CAP_BALL][3], robot[RC_CAP_ROBOT][3], post[RC_CAP_POST][3], cross[RC_CAP_CROSS][3],
+      fcross[RC_CAP_FCROSS][3]; /* x, y, size */
+  double line[RC_CAP_LINE][4];  /* x1, y1, x2, y2 */
+  double circle[4];             /* seen (SightingType != NoSighting), x, y, radius */
+  int32_t counts[RC_NTYPES];
+  int32_t pad[2];
+} RcRawVision;
+typedef struct RcRawOut { RcRawVision v[RC_NTICK][RC_MAXP]; } RcRawOut;
+
 typedef struct {
   int counts[RC_NTYPES];
   int numLandMarks;
@@ -1253,7 +1266,7 @@ typedef struct {
   double line[RC_CAP_LINE][RC_F_LINE];
 } AgentObs;
 
-static void agent_vision(RcEnv* e, int ag, uint32_t tick, AgentObs* out) {
+static void agent_vision(RcEnv* e, int ag, uint32_t tick, AgentObs* out, RcRawVision* raw) {
   /* RoboCupEnvironment.py:1192-1316,1536-1561 */
   memset(out, 0, sizeof(*out));
   Robot* agent = &e->rob[ag];
@@ -1463,6 +1476,21 @@ static void agent_vision(RcEnv* e, int ag, uint32_t tick, AgentObs* out) {
     out->line[q][4] = ln->ty;
   }
   out->counts[0] = nb; out->counts[1] = nr; out->counts[2] = np; out->counts[3] = ncr; out->counts[4] = nf; out->counts[5] = nl;
+  if (raw) {
+    memset(raw, 0, sizeof(*raw));
+    for (int k = 0; k < nb; k++) { raw->ball[k][0] = balls[k].p.x; raw->ball[k][1] = balls[k].p.y; raw->ball[k][2] = balls[k].radius; }
+    for (int k = 0; k < nr; k++) { raw->robot[k][0] = robs[k].p.x; raw->robot[k][1] = robs[k].p.y; raw->robot[k][2] = robs[k].radius; }
+    for (int k = 0; k < np; k++) { raw->post[k][0] = posts[k].p.x; raw->post[k][1] = posts[k].p.y; raw->post[k][2] = posts[k].radius; }
+    for (int k = 0; k < ncr; k++) { raw->cross[k][0] = crosses[k].p.x; raw->cross[k][1] = crosses[k].p.y; raw->cross[k][2] = crosses[k].radius; }
+    for (int k = 0; k < nf; k++) { raw->fcross[k][0] = fcs[k].p.x; raw->fcross[k][1] = fcs[k].p.y; raw->fcross[k][2] = fcs[k].radius; }
+    for (int q = 0; q < nl; q++) {
+      const LineSight* ln = &lineDets[lineKeep[q]];
+      raw->line[q][0] = ln->p1.x; raw->line[q][1] = ln->p1.y; raw->line[q][2] = ln->p2.x; raw->line[q][3] = ln->p2.y;
+    }
+    raw->circle[0] = circleDet.seen != S_NO;
+    if (circleDet.seen != S_NO) { raw->circle[1] = circleDet.p.x; raw->circle[2] = circleDet.p.y; raw->circle[3] = circleDet.radius; }
+    for (int k = 0; k < RC_NTYPES; k++) raw->counts[k] = out->counts[k];
+  }
 }
 
 /* getFullState(agent): RoboCupEnvironment.py:1162-1188 */
@@ -1526,6 +1554,8 @@ typedef struct RcStepOut {
 } RcStepOut;
 
 int rc_stepout_size(void) { return (int)sizeof(RcStepOut); }
+int rc_rawout_size(void) { return (int)sizeof(RcRawOut); }
+void rc_set_raw_out(RcEnv* e, RcRawOut* out) { e->rawOut = out; }
 
 RcEnv* rc_create(int nPlayers, int obsType, int noiseType, double noiseMag, int allowHeadTurn, unsigned flags,
                  uint64_t seed, uint32_t env_id) {
@@ -1578,7 +1608,9 @@ void rc_reset(RcEnv* e) {
   int nP = e->nPlayers, oT = e->obsType, nT = e->noiseType, aH = e->allowHeadTurn;
   double nM = e->noiseMag;
   int f0 = e->randomInit, f1 = e->deterministicTurn, f2 = e->canFall, f3 = e->useObsRewards;
+  struct RcRawOut* rawOut = e->rawOut;
   memset(e, 0, sizeof(*e));
+  e->rawOut = rawOut;
   e->rng = g; e->nPlayers = nP; e->P = 2 * nP; e->obsType = oT; e->noiseType = nT; e->allowHeadTurn = aH;
   e->noiseMag = nM; e->randBase = 0.01 * nM;
   e->randomInit = f0; e->deterministicTurn = f1; e->canFall = f2; e->useObsRewards = f3;
@@ -1757,7 +1789,7 @@ static void fill_obs_tick(RcEnv* e, int t, uint32_t tick, RcStepOut* out) {
       full_state_agent(e, r, out->full_ball[t][r], out->full_self[t][r], &out->full_others[t][r][0][0]);
     } else {
       AgentObs ao;
-      agent_vision(e, r, tick, &ao);
+      agent_vision(e, r, tick, &ao, e->rawOut ? &e->rawOut->v[t][r] : NULL);
       memcpy(out->ball[t][r], ao.ball, sizeof(ao.ball));
       memcpy(out->robot[t][r], ao.robot, sizeof(ao.robot));
       memcpy(out->post[t][r], ao.post, sizeof(ao.post));
