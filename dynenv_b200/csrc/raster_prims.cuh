@@ -1,0 +1,348 @@
+/*
+ * Rasterisation primitives of the IMAGE observation (RoboCupEnvironment.py:1318-1467): the pixel sets of
+ * cv2.line / cv2.polylines / cv2.rectangle(filled) / cv2.circle(filled) with lineType LINE_8, shift 0, on a
+ * 480 x 640 single-bit plane (20 uint32 words per row, bit x % 32 of word x / 32 = pixel x).
+ *
+ * The reference calls OpenCV (an external dependency, imgproc/src/drawing.cpp of OpenCV 4.x); what is restated here is
+ * its published integer algorithms -- clipLine, the 8-connected line iterator, the fixed-point Line2, FillConvexPoly,
+ * ThickLine with round caps, PolyLine, and the midpoint Circle -- so that the planes are bit-identical to cv2's
+ * (tests/test_raster_prims.py compares them with the installed cv2 on random primitives, including far-off-image
+ * coordinates).  Host + device code: the CUDA raster kernel draws into shared memory with atomicOr, the CPU test
+ * compiles the same functions with g++.
+ */
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define RP_FN __host__ __device__ inline
+#else
+#define RP_FN inline
+#endif
+
+namespace raster {
+
+constexpr int IMG_W = 640, IMG_H = 480, WORDS_PER_ROW = IMG_W / 32, PLANE_WORDS = IMG_H * WORDS_PER_ROW;
+constexpr int XY_SHIFT = 16;
+constexpr int64_t XY_ONE = (int64_t)1 << XY_SHIFT;
+
+struct P2 { /* cv::Point2l */
+  int64_t x, y;
+};
+
+RP_FN void or_word(uint32_t* p, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  atomicOr(p, m);
+#else
+  *p |= m;
+#endif
+}
+/* ICV_HLINE on row y for columns x1..x2 inclusive, both already inside the image (callers clip like OpenCV) */
+RP_FN void hline(uint32_t* plane, int y, int x1, int x2) {
+  if (x1 > x2) return;
+  uint32_t* row = plane + y * WORDS_PER_ROW;
+  const int w1 = x1 >> 5, w2 = x2 >> 5;
+  const uint32_t m1 = 0xffffffffu << (x1 & 31), m2 = 0xffffffffu >> (31 - (x2 & 31));
+  if (w1 == w2) { or_word(row + w1, m1 & m2); return; }
+  or_word(row + w1, m1);
+  for (int w = w1 + 1; w < w2; w++) or_word(row + w, 0xffffffffu);
+  or_word(row + w2, m2);
+}
+RP_FN void put_point(uint32_t* plane, int64_t x, int64_t y) {
+  if (x >= 0 && x < IMG_W && y >= 0 && y < IMG_H) or_word(plane + (int)y * WORDS_PER_ROW + ((int)x >> 5), 1u << ((int)x & 31));
+}
+
+/* cv::clipLine(Size2l, Point2l&, Point2l&) */
+RP_FN bool clip_line(int64_t width, int64_t height, P2& pt1, P2& pt2) {
+  const int64_t right = width - 1, bottom = height - 1;
+  if (width <= 0 || height <= 0) return false;
+  int64_t &x1 = pt1.x, &y1 = pt1.y, &x2 = pt2.x, &y2 = pt2.y;
+  int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+  int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+  if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+    int64_t a;
+    if (c1 & 12) {
+      a = c1 < 8 ? 0 : bottom;
+      x1 += (int64_t)((double)(a - y1) * (x2 - x1) / (y2 - y1));
+      y1 = a;
+      c1 = (x1 < 0) + (x1 > right) * 2;
+    }
+    if (c2 & 12) {
+      a = c2 < 8 ? 0 : bottom;
+      x2 += (int64_t)((double)(a - y2) * (x2 - x1) / (y2 - y1));
+      y2 = a;
+      c2 = (x2 < 0) + (x2 > right) * 2;
+    }
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      if (c1) {
+        a = c1 == 1 ? 0 : right;
+        y1 += (int64_t)((double)(a - x1) * (y2 - y1) / (x2 - x1));
+        x1 = a;
+        c1 = 0;
+      }
+      if (c2) {
+        a = c2 == 1 ? 0 : right;
+        y2 += (int64_t)((double)(a - x2) * (y2 - y1) / (x2 - x1));
+        x2 = a;
+        c2 = 0;
+      }
+    }
+  }
+  return (c1 | c2) == 0;
+}
+
+/* Line(): cv::LineIterator, 8-connected, left to right, after clipping to the image */
+RP_FN void line_thin(uint32_t* plane, P2 pt1, P2 pt2) {
+  if ((uint64_t)pt1.x >= (uint64_t)IMG_W || (uint64_t)pt2.x >= (uint64_t)IMG_W || (uint64_t)pt1.y >= (uint64_t)IMG_H ||
+      (uint64_t)pt2.y >= (uint64_t)IMG_H) {
+    if (!clip_line(IMG_W, IMG_H, pt1, pt2)) return;
+  }
+  int delta_x = 1, delta_y = 1;
+  int dx = (int)(pt2.x - pt1.x), dy = (int)(pt2.y - pt1.y);
+  if (dx < 0) { dx = -dx; dy = -dy; pt1 = pt2; } /* leftToRight */
+  if (dy < 0) { dy = -dy; delta_y = -1; }
+  const bool vert = dy > dx;
+  if (vert) { int t = dx; dx = dy; dy = t; t = delta_x; delta_x = delta_y; delta_y = t; }
+  int err = dx - (dy + dy);
+  const int plusDelta = dx + dx, minusDelta = -(dy + dy);
+  int minusShift = delta_x, plusShift = 0, minusStep = 0, plusStep = delta_y;
+  const int count = dx + 1;
+  if (vert) { int t = plusStep; plusStep = plusShift; plusShift = t; t = minusStep; minusStep = minusShift; minusShift = t; }
+  int x = (int)pt1.x, y = (int)pt1.y;
+  for (int i = 0; i < count; i++) {
+    put_point(plane, x, y);
+    const int mask = err < 0 ? -1 : 0;
+    err += minusDelta + (plusDelta & mask);
+    x += minusShift + (plusShift & mask);
+    y += minusStep + (plusStep & mask);
+  }
+}
+
+/* Line2(): line between fixed-point (XY_SHIFT) end points */
+RP_FN void line2(uint32_t* plane, P2 pt1, P2 pt2) {
+  if (!clip_line((int64_t)IMG_W << XY_SHIFT, (int64_t)IMG_H << XY_SHIFT, pt1, pt2)) return;
+  int64_t dx = pt2.x - pt1.x, dy = pt2.y - pt1.y;
+  int64_t j = dx < 0 ? -1 : 0;
+  const int64_t ax = (dx ^ j) - j;
+  int64_t i = dy < 0 ? -1 : 0;
+  const int64_t ay = (dy ^ i) - i;
+  int64_t x_step, y_step;
+  int ecount;
+  if (ax > ay) {
+    dy = (dy ^ j) - j;
+    pt1.x ^= pt2.x & j; pt2.x ^= pt1.x & j; pt1.x ^= pt2.x & j;
+    pt1.y ^= pt2.y & j; pt2.y ^= pt1.y & j; pt1.y ^= pt2.y & j;
+    x_step = XY_ONE;
+    y_step = (dy << XY_SHIFT) / (ax | 1);
+    ecount = (int)((pt2.x - pt1.x) >> XY_SHIFT);
+  } else {
+    dx = (dx ^ i) - i;
+    pt1.x ^= pt2.x & i; pt2.x ^= pt1.x & i; pt1.x ^= pt2.x & i;
+    pt1.y ^= pt2.y & i; pt2.y ^= pt1.y & i; pt1.y ^= pt2.y & i;
+    x_step = (dx << XY_SHIFT) / (ay | 1);
+    y_step = XY_ONE;
+    ecount = (int)((pt2.y - pt1.y) >> XY_SHIFT);
+  }
+  pt1.x += (XY_ONE >> 1);
+  pt1.y += (XY_ONE >> 1);
+  put_point(plane, (pt2.x + (XY_ONE >> 1)) >> XY_SHIFT, (pt2.y + (XY_ONE >> 1)) >> XY_SHIFT);
+  if (ax > ay) {
+    pt1.x >>= XY_SHIFT;
+    while (ecount >= 0) {
+      put_point(plane, pt1.x, pt1.y >> XY_SHIFT);
+      pt1.x++;
+      pt1.y += y_step;
+      ecount--;
+    }
+  } else {
+    pt1.y >>= XY_SHIFT;
+    while (ecount >= 0) {
+      put_point(plane, pt1.x >> XY_SHIFT, pt1.y);
+      pt1.x += x_step;
+      pt1.y++;
+      ecount--;
+    }
+  }
+}
+
+/* FillConvexPoly() for 4 vertices, line_type LINE_8; `shift` = 0 (integer vertices) or XY_SHIFT */
+RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift) {
+  const int npts = 4;
+  struct Edge { int idx, di; int64_t x, dx; int ye; } edge[2];
+  const int delta = 1 << shift >> 1;
+  int i, y, imin = 0;
+  int edges = npts;
+  int64_t xmin, xmax, ymin, ymax;
+  const int delta1 = (int)(XY_ONE >> 1), delta2 = (int)(XY_ONE >> 1);
+  P2 p0 = v[npts - 1];
+  p0.x <<= XY_SHIFT - shift;
+  p0.y <<= XY_SHIFT - shift;
+  xmin = xmax = v[0].x;
+  ymin = ymax = v[0].y;
+  for (i = 0; i < npts; i++) {
+    P2 p = v[i];
+    if (p.y < ymin) { ymin = p.y; imin = i; }
+    ymax = ymax > p.y ? ymax : p.y;
+    xmax = xmax > p.x ? xmax : p.x;
+    xmin = xmin < p.x ? xmin : p.x;
+    p.x <<= XY_SHIFT - shift;
+    p.y <<= XY_SHIFT - shift;
+    if (shift == 0) {
+      P2 a, b;
+      a.x = p0.x >> XY_SHIFT; a.y = p0.y >> XY_SHIFT; b.x = p.x >> XY_SHIFT; b.y = p.y >> XY_SHIFT;
+      line_thin(plane, a, b);
+    } else line2(plane, p0, p);
+    p0 = p;
+  }
+  xmin = (xmin + delta) >> shift;
+  xmax = (xmax + delta) >> shift;
+  ymin = (ymin + delta) >> shift;
+  ymax = (ymax + delta) >> shift;
+  if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= IMG_W || (int)ymin >= IMG_H) return;
+  ymax = ymax < IMG_H - 1 ? ymax : IMG_H - 1;
+  edge[0].idx = edge[1].idx = imin;
+  edge[0].ye = edge[1].ye = y = (int)ymin;
+  edge[0].di = 1;
+  edge[1].di = npts - 1;
+  edge[0].x = edge[1].x = -XY_ONE;
+  edge[0].dx = edge[1].dx = 0;
+  do {
+    for (i = 0; i < 2; i++) {
+      if (y >= edge[i].ye) {
+        int idx0 = edge[i].idx, di = edge[i].di;
+        int idx = idx0 + di;
+        if (idx >= npts) idx -= npts;
+        int ty = 0;
+        for (; edges-- > 0;) {
+          ty = (int)((v[idx].y + delta) >> shift);
+          if (ty > y) {
+            int64_t xs = v[idx0].x, xe = v[idx].x;
+            if (shift != XY_SHIFT) { xs <<= XY_SHIFT - shift; xe <<= XY_SHIFT - shift; }
+            edge[i].ye = ty;
+            edge[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+            edge[i].x = xs;
+            edge[i].idx = idx;
+            break;
+          }
+          idx0 = idx;
+          idx += di;
+          if (idx >= npts) idx -= npts;
+        }
+      }
+    }
+    if (edges < 0) break;
+    if (y >= 0) {
+      int left = 0, right = 1;
+      if (edge[0].x > edge[1].x) { left = 1; right = 0; }
+      int xx1 = (int)((edge[left].x + delta1) >> XY_SHIFT);
+      int xx2 = (int)((edge[right].x + delta2) >> XY_SHIFT);
+      if (xx2 >= 0 && xx1 < IMG_W) {
+        if (xx1 < 0) xx1 = 0;
+        if (xx2 >= IMG_W) xx2 = IMG_W - 1;
+        hline(plane, y, xx1, xx2);
+      }
+    }
+    edge[0].x += edge[0].dx;
+    edge[1].x += edge[1].dx;
+  } while (++y <= (int)ymax);
+}
+
+/* Circle() with fill: Bresenham circle, horizontal spans */
+RP_FN void circle_filled(uint32_t* plane, int cx, int cy, int radius) {
+  int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+  while (dx >= dy) {
+    const int y11 = cy - dy, y12 = cy + dy, y21 = cy - dx, y22 = cy + dx;
+    int x11 = cx - dx, x12 = cx + dx, x21 = cx - dy, x22 = cx + dy;
+    if (x11 < IMG_W && x12 >= 0 && y21 < IMG_H && y22 >= 0) {
+      x11 = x11 > 0 ? x11 : 0;
+      x12 = x12 < IMG_W - 1 ? x12 : IMG_W - 1;
+      if ((unsigned)y11 < (unsigned)IMG_H) hline(plane, y11, x11, x12);
+      if ((unsigned)y12 < (unsigned)IMG_H) hline(plane, y12, x11, x12);
+      if (x21 < IMG_W && x22 >= 0) {
+        x21 = x21 > 0 ? x21 : 0;
+        x22 = x22 < IMG_W - 1 ? x22 : IMG_W - 1;
+        if ((unsigned)y21 < (unsigned)IMG_H) hline(plane, y21, x21, x22);
+        if ((unsigned)y22 < (unsigned)IMG_H) hline(plane, y22, x21, x22);
+      }
+    }
+    dy++;
+    err += plus;
+    plus += 2;
+    const int mask = (err <= 0) - 1;
+    err -= minus & mask;
+    dx += mask;
+    minus -= mask & 2;
+  }
+}
+
+RP_FN int64_t cv_round(double v) { /* cvRound: round half to even (lrint in the default rounding mode) */
+#ifdef __CUDA_ARCH__
+  return (int64_t)__double2ll_rn(v);
+#else
+  return (int64_t)__builtin_llrint(v);
+#endif
+}
+
+/* ThickLine() with integer end points; flags bit 0 / 1: round cap at p0 / p1 */
+RP_FN void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags) {
+  const double INV_XY_ONE = 1. / XY_ONE;
+  if (thickness <= 1) { /* shift == 0: the end points are integers */
+    line_thin(plane, p0, p1);
+    return;
+  }
+  { /* OpenCV 4.13 first clips the centre line to the image grown by `thickness` on every side */
+    const int64_t m = thickness;
+    p0.x += m; p0.y += m; p1.x += m; p1.y += m;
+    if (!clip_line(IMG_W + 2 * m, IMG_H + 2 * m, p0, p1)) return;
+    p0.x -= m; p0.y -= m; p1.x -= m; p1.y -= m;
+  }
+  p0.x <<= XY_SHIFT; p0.y <<= XY_SHIFT; p1.x <<= XY_SHIFT; p1.y <<= XY_SHIFT;
+  P2 pt[4], dp;
+  dp.x = dp.y = 0;
+  double dx = (p0.x - p1.x) * INV_XY_ONE, dy = (p1.y - p0.y) * INV_XY_ONE;
+  double r = dx * dx + dy * dy;
+  const int oddThickness = thickness & 1;
+  thickness <<= XY_SHIFT - 1;
+  if ((r < 0 ? -r : r) > 2.220446049250313e-16) {
+#ifdef __CUDA_ARCH__
+    r = (thickness + oddThickness * XY_ONE * 0.5) / sqrt(r);
+#else
+    r = (thickness + oddThickness * XY_ONE * 0.5) / __builtin_sqrt(r);
+#endif
+    dp.x = cv_round(dy * r);
+    dp.y = cv_round(dx * r);
+    pt[0].x = p0.x + dp.x; pt[0].y = p0.y + dp.y;
+    pt[1].x = p0.x - dp.x; pt[1].y = p0.y - dp.y;
+    pt[2].x = p1.x - dp.x; pt[2].y = p1.y - dp.y;
+    pt[3].x = p1.x + dp.x; pt[3].y = p1.y + dp.y;
+    fill_convex4(plane, pt, XY_SHIFT);
+  }
+  for (int i = 0; i < 2; i++) {
+    if (flags & (i + 1)) {
+      const int cx = (int)((p0.x + (XY_ONE >> 1)) >> XY_SHIFT), cy = (int)((p0.y + (XY_ONE >> 1)) >> XY_SHIFT);
+      circle_filled(plane, cx, cy, (int)((thickness + (XY_ONE >> 1)) >> XY_SHIFT));
+    }
+    p0 = p1;
+  }
+}
+
+/* cv2.line(img, p0, p1, 1, thickness) */
+RP_FN void cv_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thickness) {
+  P2 a, b;
+  a.x = x0; a.y = y0; b.x = x1; b.y = y1;
+  thick_line(plane, a, b, thickness, 3);
+}
+/* cv2.rectangle(img, p0, p1, 1, -1) */
+RP_FN void cv_rectangle_filled(uint32_t* plane, int x0, int y0, int x1, int y1) {
+  P2 pt[4];
+  pt[0].x = x0; pt[0].y = y0; pt[1].x = x1; pt[1].y = y0; pt[2].x = x1; pt[2].y = y1; pt[3].x = x0; pt[3].y = y1;
+  fill_convex4(plane, pt, 0);
+}
+/* segment i (1 <= i < count) of cv2.polylines(img, [pts], False, 1, thickness): PolyLine() caps the first segment at
+   both ends and every later one at its far end */
+RP_FN void cv_polyline_segment(uint32_t* plane, int xa, int ya, int xb, int yb, int thickness, int i) {
+  P2 a, b;
+  a.x = xa; a.y = ya; b.x = xb; b.y = yb;
+  thick_line(plane, a, b, thickness, i == 1 ? 3 : 2);
+}
+
+}  // namespace raster

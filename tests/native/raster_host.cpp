@@ -1,0 +1,10 @@
+// CPU build of dynenv_b200/csrc/raster_prims.cuh for tests/test_raster_prims.py (compared with the installed cv2)
+#include "../../dynenv_b200/csrc/raster_prims.cuh"
+extern "C" {
+void rp_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thickness) { raster::cv_line(plane, x0, y0, x1, y1, thickness); }
+void rp_rect(uint32_t* plane, int x0, int y0, int x1, int y1) { raster::cv_rectangle_filled(plane, x0, y0, x1, y1); }
+void rp_circle(uint32_t* plane, int cx, int cy, int r) { raster::circle_filled(plane, cx, cy, r); }
+void rp_polyline(uint32_t* plane, const int* pts, int n, int thickness) {
+  for (int i = 1; i < n; i++) raster::cv_polyline_segment(plane, pts[2 * i - 2], pts[2 * i - 1], pts[2 * i], pts[2 * i + 1], thickness, i);
+}
+}

@@ -1,0 +1,75 @@
+"""CPU: the rasterisation primitives of the IMAGE observation (dynenv_b200/csrc/raster_prims.cuh, the code the CUDA
+raster kernel runs) compiled for the host with g++ and compared with the installed cv2 -- the library the reference
+draws with (RoboCupEnvironment.py:1318-1467) -- on random lines, poly-lines, filled rectangles and filled circles,
+including primitives far outside the image.  Bit-exact planes are required."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    out = os.path.join(ROOT, "tests", "native", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libraster_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "native", "raster_host.cpp")])
+    return C.CDLL(so)
+
+
+def _unpack(w):
+    return ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(480, 640).astype(np.uint8)
+
+
+def _coord(rng, far):
+    if far:
+        return int(rng.integers(-3000, 4000)), int(rng.integers(-3000, 4000))
+    return int(rng.integers(-60, 700)), int(rng.integers(-60, 540))
+
+
+def test_primitives_match_cv2(lib):
+    rng = np.random.default_rng(7)
+    for it in range(1500):
+        far = rng.random() < 0.3
+        x0, y0 = _coord(rng, far)
+        x1, y1 = _coord(rng, far)
+        if rng.random() < 0.15:
+            x1 = x0
+        if rng.random() < 0.15:
+            y1 = y0
+        t = int(rng.integers(1, 40))
+        ref = np.zeros((480, 640))
+        cv2.line(ref, (x0, y0), (x1, y1), 1, t)
+        p = np.zeros((480, 20), np.uint32)
+        lib.rp_line(p.ctypes.data, x0, y0, x1, y1, t)
+        assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("line", x0, y0, x1, y1, t)
+        ref = np.zeros((480, 640))
+        cv2.rectangle(ref, (x0, y0), (x1, y1), 1, -1)
+        p = np.zeros((480, 20), np.uint32)
+        lib.rp_rect(p.ctypes.data, x0, y0, x1, y1)
+        assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("rectangle", x0, y0, x1, y1)
+        r = int(rng.integers(0, 300)) if rng.random() < 0.8 else int(rng.integers(0, 5))
+        ref = np.zeros((480, 640))
+        cv2.circle(ref, (x0, y0), r, 1, -1)
+        p = np.zeros((480, 20), np.uint32)
+        lib.rp_circle(p.ctypes.data, x0, y0, r)
+        assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("circle", x0, y0, r)
+
+
+def test_polylines_match_cv2(lib):
+    rng = np.random.default_rng(8)
+    for it in range(150):
+        n = int(rng.integers(1, 60))
+        t = int(rng.integers(1, 31))
+        pts = (np.cumsum(rng.integers(-15, 16, (n, 2)), 0) + np.array(_coord(rng, False))).astype(np.int32)
+        ref = np.zeros((480, 640))
+        cv2.polylines(ref, [pts], False, 1, t)
+        p = np.zeros((480, 20), np.uint32)
+        pc = np.ascontiguousarray(pts)
+        lib.rp_polyline(p.ctypes.data, pc.ctypes.data, n, t)
+        assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("polyline", pts.tolist(), t)
