@@ -12,7 +12,7 @@ _LIB = None
 EXPORTS = ["dynenv_abi_version", "dynenv_last_error", "dynenv_create", "dynenv_destroy", "dynenv_state_words",
            "dynenv_reset", "dynenv_step", "dynenv_set_seed", "dynenv_get_state", "dynenv_set_state",
            "dynenv_last_launch_count", "dynenv_debug_substep_range", "dynenv_debug_timing",
-           "dynenv_last_kernel_ms"]
+           "dynenv_last_kernel_ms", "dynenv_render_images"]
 
 
 class DynEnvConfig(C.Structure):
@@ -23,7 +23,7 @@ class DynEnvConfig(C.Structure):
 
 
 class DynEnvRoboCupOut(C.Structure):
-    _fields_ = [("obs", C.c_void_p), ("full", C.c_void_p), ("info", C.c_void_p)]
+    _fields_ = [("obs", C.c_void_p), ("full", C.c_void_p), ("info", C.c_void_p), ("raw", C.c_void_p)]
 
 
 class DynEnvDrivingOut(C.Structure):
@@ -57,6 +57,7 @@ def lib():
         lb.dynenv_debug_substep_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lb.dynenv_debug_timing.argtypes = [C.c_void_p, C.c_int]
         lb.dynenv_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        lb.dynenv_render_images.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         if lb.dynenv_abi_version() != L.DYNENV_ABI_VERSION:
             raise RuntimeError("dynenv_b200: library ABI %d != header ABI %d" % (lb.dynenv_abi_version(),
                                                                                  L.DYNENV_ABI_VERSION))

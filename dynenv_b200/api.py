@@ -91,9 +91,6 @@ class RoboCupEnvironment(object):
             raise ValueError("Error: The noise magnitude must be between 0 and 5!")
         if render:
             raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
-        if ObservationType(observationType) == ObservationType.IMAGE:
-            raise NotImplementedError("IMAGE observations are not built yet (the reference's own step() raises "
-                                      "TypeError in IMAGE mode, RoboCupEnvironment.py:1571)")
         from .batched import BatchedRoboCup
         self.observationType = ObservationType(observationType)
         self.noiseType = NoiseType(noiseType)
@@ -114,8 +111,15 @@ class RoboCupEnvironment(object):
                                    randomInit=type(self).randomInit, deterministicTurn=type(self).deterministicTurn,
                                    canFall=type(self).canFall, useObsRewards=type(self).useObsRewards, seed=seed, device=device)
         self._full = self.observationType == ObservationType.FULL
+        self._image = self.observationType == ObservationType.IMAGE
         self._last = None
         self.reset()
+
+    def _observations(self, out):
+        """the reference's nested observation lists; IMAGE: one (8, 480, 640) float64 array per agent and tick"""
+        if self._image:
+            return RF.image_observations(self._sim.render_images().cpu().numpy(), 0, 2 * self.nPlayers)
+        return RF.observations(self._last, 0, 2 * self.nPlayers, self._full)
 
     # ---- the reference's calls
     def set_random_seed(self, seed):
@@ -125,9 +129,10 @@ class RoboCupEnvironment(object):
     setRandomSeed = set_random_seed  # README.md:139 spelling
 
     def reset(self):
-        self._last = RF.host_views(self._sim.reset(), self._full)
+        out = self._sim.reset()
+        self._last = RF.host_views(out, self._full)
         self.elapsed = 0
-        return RF.observations(self._last, 0, 2 * self.nPlayers, self._full)
+        return self._observations(out)
 
     def step(self, actions):
         import torch
@@ -136,8 +141,9 @@ class RoboCupEnvironment(object):
         v = self._last = RF.host_views(out, self._full)
         P = 2 * self.nPlayers
         self.elapsed += self.stepIterCnt
-        return RF.observations(v, 0, P, self._full), v["rewards"][0, :P].astype(np.float64), bool(v["done"][0]), \
-            RF.info_dict(v, 0, P)
+        # (the reference's own step() raises TypeError in IMAGE mode, RoboCupEnvironment.py:1571; here it works and
+        # the observation reward is the PARTIAL one)
+        return self._observations(out), v["rewards"][0, :P].astype(np.float64), bool(v["done"][0]), RF.info_dict(v, 0, P)
 
     def getFullState(self, robot=None):
         v, P = self._last, 2 * self.nPlayers
@@ -311,10 +317,20 @@ class BatchedVecEnv(object):
 
     # ---- format adapters (RoboCup / Driving)
     def _views(self, out, env_ids=None):
-        return RF.drv_host_views(out, env_ids) if self.driving else RF.host_views(out, self._full, env_ids)
+        if self.driving:
+            return RF.drv_host_views(out, env_ids)
+        v = RF.host_views(out, self._full, env_ids)
+        if self.observationType == ObservationType.IMAGE:  # host format: every image is materialised (small batches)
+            imgs = self.sim.render_images(outputs=out).cpu().numpy()
+            v["images"] = imgs if env_ids is None else imgs[env_ids]
+        return v
 
     def _obs(self, v, e):
-        return RF.drv_observations(v, e, self.nAgents, self._full) if self.driving else RF.observations(v, e, self.nAgents, self._full)
+        if self.driving:
+            return RF.drv_observations(v, e, self.nAgents, self._full)
+        if "images" in v:  # IMAGE mode: v["images"] holds the rendered planes of the environments in v
+            return RF.image_observations(v["images"], e, self.nAgents)
+        return RF.observations(v, e, self.nAgents, self._full)
 
     def _info(self, v, e):
         return RF.drv_info_dict(v, e, self.nAgents) if self.driving else RF.info_dict(v, e, self.nAgents)

@@ -30,15 +30,17 @@ class RoboCupOutputs(object):
     def __init__(self, nEnvs, P, obs_type, device):
         T = L.RC_NTICK
         self.P = P
-        self.obs = self.full = None
-        if obs_type == int(ObservationType.PARTIAL):
-            self.obs = torch.zeros((nEnvs, T, P, L.RC_OBS_WORDS), dtype=torch.float32, device=device)
-        else:
+        self.obs = self.full = self.raw = None
+        if obs_type == int(ObservationType.FULL):
             self.full = torch.zeros((nEnvs, T, P, L.RC_FULL_WORDS), dtype=torch.float32, device=device)
+        else:
+            self.obs = torch.zeros((nEnvs, T, P, L.RC_OBS_WORDS), dtype=torch.float32, device=device)
+        if obs_type == int(ObservationType.IMAGE):  # raw detection records, drawn by render_images()
+            self.raw = torch.zeros((nEnvs, T, P, L.RC_RAW_WORDS), dtype=torch.float32, device=device)
         self.info = torch.zeros((nEnvs, L.RC_INFO_WORDS), dtype=torch.float32, device=device)
         self.c_struct = _lib.DynEnvRoboCupOut(self.obs.data_ptr() if self.obs is not None else None,
                                               self.full.data_ptr() if self.full is not None else None,
-                                              self.info.data_ptr())
+                                              self.info.data_ptr(), self.raw.data_ptr() if self.raw is not None else None)
         self._build_views()
 
     def _build_views(self):
@@ -58,7 +60,7 @@ class RoboCupOutputs(object):
         self.recon_ball = recon[..., L.RC_U_BALL:L.RC_U_BALL + 4]
         self.recon_self = recon[..., L.RC_U_SELF:L.RC_U_SELF + 8]
         self.recon_others = recon[..., L.RC_U_OTHERS:L.RC_U_OTHERS + (L.RC_MAXP - 1) * 6].unflatten(-1, (L.RC_MAXP - 1, 6))
-        if self.obs is not None:
+        if self.obs is not None:  # PARTIAL, and IMAGE (the same detections, also emitted as raw records)
             obs_i = self.obs.view(torch.int32)
             for name, off, cap, feat in _TYPES:
                 setattr(self, name, self.obs[..., off:off + cap * feat].unflatten(-1, (cap, feat)))
@@ -137,6 +139,24 @@ class BatchedRoboCup(object):
         term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
         _lib.check(self._lib.dynenv_step(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
         return self.out
+
+    def render_images(self, env_begin=0, env_end=None, out=None, outputs=None):
+        """IMAGE observations of environments [env_begin, env_end): uint32 [n, T, P, 8, 480, 20] bit planes (bit x % 32
+        of word x // 32 = pixel x; planes 0..3 top camera, 4..7 bottom camera) drawn from the raw detection records
+        of the last reset() / step().  15.4 MB per environment: render the range you need into `out`."""
+        o = outputs if outputs is not None else self.out
+        if o.raw is None:
+            raise RuntimeError("render_images needs observationType IMAGE")
+        env_end = self.nEnvs if env_end is None else env_end
+        n = env_end - env_begin
+        raw = o.raw[env_begin:env_end]
+        shape = (n, L.RC_NTICK, self.P, L.RC_IMG_PLANES, L.RC_IMG_H, L.RC_IMG_WORDS_PER_ROW)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.int32, device=self.device)
+        assert out.is_cuda and out.is_contiguous() and out.numel() == n * L.RC_NTICK * self.P * L.RC_IMG_WORDS and out.element_size() == 4
+        _lib.check(self._lib.dynenv_render_images(self.device.index or 0, raw.data_ptr(), n * L.RC_NTICK * self.P, out.data_ptr(),
+                                                  self._stream()))
+        return out.view(shape)
 
     def debug_timing(self, enable=True):
         _lib.check(self._lib.dynenv_debug_timing(self._h, int(bool(enable))))

@@ -10,7 +10,7 @@ import sys
 _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libdynenv_b200.so")
 SOURCES = ["csrc/dynenv_api.cu"]
-HEADERS = ["csrc/dynenv_common.cuh", "csrc/rc_sim.cuh", "csrc/drv_sim.cuh", "../include/dynenv_b200.h", "../include/dynenv_rng.h"]
+HEADERS = ["csrc/dynenv_common.cuh", "csrc/rc_sim.cuh", "csrc/drv_sim.cuh", "csrc/rc_raster.cuh", "csrc/raster_compose.cuh", "csrc/raster_prims.cuh", "../include/dynenv_b200.h", "../include/dynenv_rng.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

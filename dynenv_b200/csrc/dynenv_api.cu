@@ -11,6 +11,7 @@
 
 #include "drv_sim.cuh"
 #include "rc_sim.cuh"
+#include "rc_raster.cuh"
 
 using namespace dynenv;
 
@@ -89,14 +90,16 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
 }
 
 /* observation tick t of the step in flight (after substep 10 t + 9) */
+template <bool RAW>
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, int t, int subs_left,
-              float* __restrict__ obs, float* __restrict__ full, float* __restrict__ term_obs, float* __restrict__ term_full) {
+              float* __restrict__ obs, float* __restrict__ full, float* __restrict__ term_obs, float* __restrict__ term_full,
+              float* __restrict__ raw, float* __restrict__ term_raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
-  const int base = CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  const int base = CFG_WORDS + warp * (RAW ? rc::ENV_SMEM_WORDS_RAW : rc::ENV_SMEM_WORDS);
   uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
@@ -107,7 +110,9 @@ rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, 
   const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + subs_left >= rc::MAXTIME;
   float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
   float* f = finishing ? (term_full ? term_full + e * full_stride : nullptr) : (full ? full + e * full_stride : nullptr);
-  rc::observe_tick(E, t, (uint32_t)E.i[RC_S_ELAPSED], o, f);
+  const size_t raw_stride = (size_t)RC_NTICK * P * RC_RAW_WORDS;
+  float* r = finishing ? (term_raw ? term_raw + e * raw_stride : nullptr) : (raw ? raw + e * raw_stride : nullptr);
+  rc::observe_tick<RAW>(E, t, (uint32_t)E.i[RC_S_ELAPSED], o, f, r);
   /* only the processSeens sums changed */
   __syncwarp();
   uint32_t* g = state + (size_t)e * RC_STATE_WORDS;
@@ -115,14 +120,15 @@ rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, 
 }
 
 /* rewards, info, done, episode statistics; finished environments are re-initialised (auto-reset) */
+template <bool RAW>
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_finish_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, float* __restrict__ obs,
-                 float* __restrict__ full, float* __restrict__ info) {
+                 float* __restrict__ full, float* __restrict__ info, float* __restrict__ raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
-  const int base = CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  const int base = CFG_WORDS + warp * (RAW ? rc::ENV_SMEM_WORDS_RAW : rc::ENV_SMEM_WORDS);
   uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
@@ -131,26 +137,28 @@ rc_finish_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ stat
   float* inf = info ? info + (size_t)e * RC_INFO_WORDS : nullptr;
   rc::finish_step(E, inf);
   if (cfg.auto_reset && E.i[RC_S_ELAPSED] >= rc::MAXTIME)
-    rc::reset_env(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr, inf, false);
+    rc::reset_env<RAW>(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr, inf, false,
+                       raw ? raw + (size_t)e * RC_NTICK * P * RC_RAW_WORDS : nullptr);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
 }
 
+template <bool RAW>
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const uint8_t* __restrict__ mask,
-                float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info) {
+                float* __restrict__ obs, float* __restrict__ full, float* __restrict__ info, float* __restrict__ raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
   if (e >= cfg.n_envs) return;
   if (mask && !mask[e]) return;
-  const int base = CFG_WORDS + warp * rc::ENV_SMEM_WORDS;
+  const int base = CFG_WORDS + warp * (RAW ? rc::ENV_SMEM_WORDS_RAW : rc::ENV_SMEM_WORDS);
   uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
   const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
-  rc::reset_env(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr,
-                info ? info + (size_t)e * RC_INFO_WORDS : nullptr, true);
+  rc::reset_env<RAW>(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr,
+                     info ? info + (size_t)e * RC_INFO_WORDS : nullptr, true, raw ? raw + (size_t)e * RC_NTICK * P * RC_RAW_WORDS : nullptr);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
 }
 
@@ -260,8 +268,8 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   if (cfg->kind != DYNENV_KIND_ROBOCUP && cfg->kind != DYNENV_KIND_DRIVING) return fail(DYNENV_E_INVALID, "unknown environment kind");
   if (cfg->kind == DYNENV_KIND_DRIVING && cfg->obs_type == DYNENV_OBS_IMAGE)
     return fail(DYNENV_E_INVALID, "Image observation type is not supported for this environment"); /* DrivingEnvironment.py:33-35 */
-  if (cfg->obs_type != DYNENV_OBS_FULL && cfg->obs_type != DYNENV_OBS_PARTIAL)
-    return fail(DYNENV_E_UNSUPPORTED, "observation type not built (FULL and PARTIAL are)");
+  if (cfg->obs_type != DYNENV_OBS_FULL && cfg->obs_type != DYNENV_OBS_PARTIAL && cfg->obs_type != DYNENV_OBS_IMAGE)
+    return fail(DYNENV_E_INVALID, "unknown observation type");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) {
@@ -339,8 +347,13 @@ int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* s
   const DynEnvRoboCupOut* o = static_cast<const DynEnvRoboCupOut*>(out);
   int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
   size_t smem = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
-  rc_reset_kernel<<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(h->sim, h->state, env_mask_dev, o->obs,
-                                                                                   o->full, o->info);
+  if (h->cfg.obs_type == DYNENV_OBS_IMAGE) {
+    smem = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS_RAW) * sizeof(uint32_t);
+    rc_reset_kernel<true><<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(h->sim, h->state, env_mask_dev, o->obs,
+                                                                                           o->full, o->info, o->raw);
+  } else
+    rc_reset_kernel<false><<<grid, RC_WPC * 32, smem, static_cast<cudaStream_t>(stream)>>>(h->sim, h->state, env_mask_dev, o->obs,
+                                                                                            o->full, o->info, nullptr);
   h->last_launches = 1;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "rc_reset_kernel launch");
@@ -372,6 +385,8 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
   const DynEnvRoboCupOut* t = static_cast<const DynEnvRoboCupOut*>(terminal_out);
   const int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
   const size_t smem = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
+  const size_t smem_raw = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS_RAW) * sizeof(uint32_t);
+  const bool image = h->cfg.obs_type == DYNENV_OBS_IMAGE;
   int launches = 0;
   h->n_timed = 0;
   auto mark = [&](int cls) { /* event after launch number `launches` (and one before the first) */
@@ -389,14 +404,19 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
     launches++;
     mark(0);
     if (e % 10 == 0) {
-      rc_obs_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
-                                                      t ? t->obs : nullptr, t ? t->full : nullptr);
+      if (image)
+        rc_obs_kernel<true><<<grid, RC_WPC * 32, smem_raw, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
+                                                                  t ? t->obs : nullptr, t ? t->full : nullptr, o->raw, t ? t->raw : nullptr);
+      else
+        rc_obs_kernel<false><<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
+                                                               t ? t->obs : nullptr, t ? t->full : nullptr, nullptr, nullptr);
       launches++;
       mark(1);
     }
     b = e;
   }
-  rc_finish_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, o->obs, o->full, o->info);
+  if (image) rc_finish_kernel<true><<<grid, RC_WPC * 32, smem_raw, st>>>(h->sim, h->state, o->obs, o->full, o->info, o->raw);
+  else rc_finish_kernel<false><<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, o->obs, o->full, o->info, nullptr);
   launches++;
   mark(2);
   h->last_launches = launches;
@@ -410,6 +430,26 @@ int dynenv_set_seed(DynEnvHandle h, uint64_t seed) {
   h->cfg.seed = seed;
   h->sim.seed_lo = (uint32_t)seed;
   h->sim.seed_hi = (uint32_t)(seed >> 32);
+  return DYNENV_OK;
+}
+
+int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, uint32_t* image_dev, void* stream) {
+  if (!raw_dev || !image_dev || n_records < 0) return fail(DYNENV_E_INVALID, "bad argument");
+  if (n_records == 0) return DYNENV_OK;
+  if (n_records > (int64_t)1 << 29) return fail(DYNENV_E_INVALID, "too many records for one call");
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+  const size_t smem = (size_t)rcimg::SMEM_WORDS * sizeof(uint32_t);
+  static thread_local int configured = -1;
+  if (configured != device) {
+    ce = cudaFuncSetAttribute(rcimg::rc_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(rc_raster_kernel)");
+    configured = device;
+  }
+  rcimg::rc_raster_kernel<<<(unsigned)(2 * n_records), rcimg::THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      raw_dev, (long long)n_records, image_dev);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "rc_raster_kernel launch");
   return DYNENV_OK;
 }
 

@@ -94,7 +94,11 @@ enum {
   V_CNT = V_RAW + 3 * RC_CAP_ROBOT, /* I[6] list lengths */
   V_STAGE = (V_CNT + 6 + 3) / 4 * 4, /* [RC_OBS_WORDS] the observation record being built */
   V_END = V_STAGE + RC_OBS_WORDS,
-  ENV_SMEM_WORDS = ((X_BP_END > V_END ? X_BP_END : V_END) + 31) / 32 * 32
+  ENV_SMEM_WORDS = ((X_BP_END > V_END ? X_BP_END : V_END) + 31) / 32 * 32,
+  /* IMAGE observations: the raw detection record (RC_R_*) is staged behind the slice; only the kernels instantiated
+     for IMAGE mode allocate these words (per-warp stride ENV_SMEM_WORDS_RAW) */
+  V_RAWREC = ENV_SMEM_WORDS,
+  ENV_SMEM_WORDS_RAW = ENV_SMEM_WORDS + RC_RAW_WORDS
 };
 
 /* ---- static scene tables (RoboCupEnvironment.py:153-227,296-302) */
@@ -1574,6 +1578,7 @@ __device__ __forceinline__ float fast_len(V2 a) {
 /* getAgentVision of one observer (PARTIAL): builds the record in shared memory (V_STAGE).
    Point objects: lane = object (ball, 9 robot slots, 4 posts, 3 penalty crosses, 16 line crosses = 33,
    so a second, usually empty, pass handles the last line cross); lines: lane = line. */
+template <bool RAW>
 __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   const int lane = E.lane;
   const int P = E.c->P;
@@ -1841,6 +1846,65 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
       dst[1] = ld > 0 ? ldir.x * ild : 1.f;
       dst[2] = ld > 0 ? ldir.y * ild : 0.f;
       dst[3] = tx; dst[4] = ty;
+      if (RAW) { /* the end points the image branch draws (RoboCupEnvironment.py:1324-1341) */
+        float* r = E.f + (V_RAWREC + RC_R_LINE + __popc(mLine & lt) * 4);
+        r[0] = lp1.x; r[1] = lp1.y; r[2] = lp1.x + ldir.x; r[3] = lp1.y + ldir.y;
+      }
+    }
+  }
+  if (RAW) {
+    /* the centre circle: isSeenInArea without partial sightings (cutils.py:699-747) and addNoise (:417-468); the
+       PARTIAL observation does not contain it, the image does (RoboCupEnvironment.py:1224,1251,1343-1393) */
+    if (lane == 31) {
+      const float radius0 = CC_RADIUS * 2;
+      V2 pt = v2(520.f, 370.f) - pos;
+      const float dist1 = cross(vec1, pt), dist2 = cross(vec2, pt);
+      int seen = S_NO;
+      float radius = radius0;
+      V2 p = v2(0, 0);
+      if (dist1 < radius0 && dist2 > -radius0) {
+        if (dist1 < -radius0 && dist2 > radius0) seen = lensq(pt) < maxVis1 ? S_NORMAL : S_DISTANT;
+        else {
+          float b1 = -2.f * (vec1.x * pt.x - vec1.y * pt.y), b2 = -2.f * (vec2.x * pt.x - vec2.y * pt.y);
+          float c = dot(pt, pt) - radius0 * radius0;
+          float sqr1 = b1 * b1 - 4.f * c, sqr2 = b2 * b2 - 4.f * c;
+          bool found = false;
+          if (sqr1 >= 0) {
+            float sq = sqrtf(sqr1);
+            if ((-b1 + sq) > 0 || (-b1 - sq) > 0) { seen = S_PARTIAL; found = true; }
+          }
+          if (!found && sqr2 >= 0) {
+            float sq = sqrtf(sqr2);
+            if ((-b2 + sq) > 0 || (-b2 - sq) > 0) seen = S_PARTIAL;
+          }
+        }
+        p = rot_cs(pt, hc, -hs);
+      }
+      if (seen != S_NO) {
+        Rand6 ru = rng_block(E, tick, RC_SITE_OBS_CIRCLE, ag, 0, 0);
+        V2 noiseVec = v2((ru.u(0) - 0.5f) * magn, (ru.u(1) - 0.5f) * magn);
+        if (!realistic) {
+          if (ru.u(2) < randB) seen = S_NO;
+          p = p + noiseVec;
+          radius *= (1.f - (ru.u(4) - 0.5f) * 0.2f);
+        } else {
+          float range = 0.25f + 3.75f * lensq(p) * (1.f / maxVis1);
+          float mult = range;
+          if (seen == S_DISTANT) mult = range * 3;
+          else if (seen == S_PARTIAL) mult = range * 4;
+          V2 dsp = v2(noiseVec.x * mult / 4, noiseVec.y * mult / 4);
+          V2 newPos = p + dsp;
+          float lsum = len(newPos) + len(p);
+          float diff = lsum > 0 ? (2.f * dot(p, dsp) + dot(dsp, dsp)) / lsum : 0.f;
+          if (ru.u(2) < randB * mult) seen = S_NO;
+          p = newPos;
+          radius *= 1.f + (ru.u(4) * 0.1f * diff);
+        }
+      }
+      E.i[V_RAWREC + RC_R_CIRCLE_SEEN] = seen != S_NO ? 1 : 0;
+      E.f[V_RAWREC + RC_R_CIRCLE] = seen != S_NO ? p.x : 0.f;
+      E.f[V_RAWREC + RC_R_CIRCLE + 1] = seen != S_NO ? p.y : 0.f;
+      E.f[V_RAWREC + RC_R_CIRCLE + 2] = seen != S_NO ? radius : 0.f;
     }
   }
   if (lane == 0) {
@@ -1895,10 +1959,48 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   }
   if (lane >= 1 && lane < 10) E.i[X_RSEEN + 9 * ag + lane - 1] += E.i[V_STAGE + RC_O_ROBSEEN + lane - 1];
   __syncwarp();
+  if (RAW) {
+    /* positions and sizes of the point detections back from the encoded rows (the encoders are affine / polar maps,
+       RoboCupEnvironment.py:1537-1548, cutils.py:295-315): row k of every list, false positives included */
+    for (int slot = lane; slot < RC_CAP_BALL + RC_CAP_ROBOT + RC_CAP_POST + RC_CAP_CROSS + RC_CAP_FCROSS; slot += 32) {
+      int type, k = slot;
+      if (k < RC_CAP_BALL) type = 0;
+      else if ((k -= RC_CAP_BALL) < RC_CAP_ROBOT) type = 1;
+      else if ((k -= RC_CAP_ROBOT) < RC_CAP_POST) type = 2;
+      else if ((k -= RC_CAP_POST) < RC_CAP_CROSS) type = 3;
+      else { k -= RC_CAP_CROSS; type = 4; }
+      const int off = type == 0 ? RC_O_BALL : (type == 1 ? RC_O_ROBOT : (type == 2 ? RC_O_POST : (type == 3 ? RC_O_CROSS : RC_O_FCROSS)));
+      const int feat = type == 0 ? RC_F_BALL : (type == 1 ? RC_F_ROBOT : (type == 4 ? RC_F_FCROSS : 6));
+      const int roff = type == 0 ? RC_R_BALL : (type == 1 ? RC_R_ROBOT : (type == 2 ? RC_R_POST : (type == 3 ? RC_R_CROSS : RC_R_FCROSS)));
+      const float* row = E.f + (V_STAGE + off + k * feat);
+      float x = 0.f, y = 0.f, r = 0.f;
+      if (k < E.i[V_CNT + type]) {
+        if (type <= 1) {
+          x = row[0] * (1.f / STDNORM2); y = row[1] * (1.f / STDNORM2);
+          r = row[2] * 0.5f + (type == 0 ? BALL_RADIUS * 2 : ROB_TOTAL);
+        } else {
+          float dist = (row[0] * 0.5f + 0.5f) * (1.f / STDNORM);
+          x = row[1] * team * dist; y = row[2] * team * dist;
+          r = row[3] * 0.5f + (type == 2 ? POST_RADIUS : PEN_RADIUS);
+        }
+      }
+      float* dst = E.f + (V_RAWREC + roff + 3 * k);
+      dst[0] = x; dst[1] = y; dst[2] = r;
+    }
+    if (lane < RC_NTYPES) E.i[V_RAWREC + RC_R_COUNTS + lane] = E.i[V_CNT + lane];
+    {
+      const int nl = E.i[V_CNT + 5]; /* unused line rows stay zero */
+      for (int w = lane; w < RC_CAP_LINE * 4; w += 32)
+        if (w >= nl * 4) E.f[V_RAWREC + RC_R_LINE + w] = 0.f;
+      for (int w = RC_RAW_WORDS_RAW + lane; w < RC_RAW_WORDS; w += 32) E.f[V_RAWREC + w] = 0.f;
+    }
+    __syncwarp();
+  }
 }
 
 /* one observation tick of every agent; records go straight to HBM with coalesced stores */
-__device__ __noinline__ void observe_tick(const Env E, int t, uint32_t tick, float* obs_env, float* full_env) {
+template <bool RAW>
+__device__ __noinline__ void observe_tick(const Env E, int t, uint32_t tick, float* obs_env, float* full_env, float* raw_env = nullptr) {
   const int P = E.c->P;
   const int lane = E.lane;
   if (E.c->obs_type == DYNENV_OBS_FULL) {
@@ -1908,7 +2010,12 @@ __device__ __noinline__ void observe_tick(const Env E, int t, uint32_t tick, flo
     return;
   }
   for (int ag = 0; ag < P; ag++) {
-    agent_vision(E, ag, tick);
+    agent_vision<RAW>(E, ag, tick);
+    if (RAW && raw_env) {
+      float4* dst = reinterpret_cast<float4*>(raw_env + ((size_t)t * P + ag) * RC_RAW_WORDS);
+      const float4* src = reinterpret_cast<const float4*>(E.f + V_RAWREC);
+      for (int w = lane; w < RC_RAW_WORDS / 4; w += 32) dst[w] = src[w];
+    }
     if (obs_env) {
       float4* dst = reinterpret_cast<float4*>(obs_env + ((size_t)t * P + ag) * RC_OBS_WORDS);
       const float4* src = reinterpret_cast<const float4*>(E.f + V_STAGE);
@@ -2097,10 +2204,11 @@ __device__ __forceinline__ void finish_step(const Env E, float* info_env) {
 }
 
 /* environment_base.reset: new scene + nTimeSteps copies of the initial observation (:205-224) */
-__device__ __noinline__ void reset_env(const Env E, float* obs_env, float* full_env, float* info_env, bool write_info) {
+template <bool RAW>
+__device__ __noinline__ void reset_env(const Env E, float* obs_env, float* full_env, float* info_env, bool write_info, float* raw_env = nullptr) {
   init_scene(E);
   clear_step_scratch(E);
-  for (int t = 0; t < RC_NTICK; t++) observe_tick(E, t, DYNENV_TICK_RESETOBS | (uint32_t)t, obs_env, full_env);
+  for (int t = 0; t < RC_NTICK; t++) observe_tick<RAW>(E, t, DYNENV_TICK_RESETOBS | (uint32_t)t, obs_env, full_env, raw_env);
   if (info_env && write_info) {
     const int lane = E.lane;
     fill_info(E, info_env);

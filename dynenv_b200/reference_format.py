@@ -35,6 +35,19 @@ def full_observation(views, e, t, a, P):
             [np.array(views["full_self"][e, t, a][None], dtype=np.float32)], (1, 1, 1))
 
 
+def unpack_image(words):
+    """uint32 / int32 bit planes [..., 480, 20] -> float64 [..., 480, 640] of 0.0 / 1.0, the dtype the reference returns
+    (np.zeros((4, 480, 640)) planes drawn with colour 1, RoboCupEnvironment.py:1321-1322,1533-1534)"""
+    w = np.ascontiguousarray(words).view(np.uint32)
+    bits = (w[..., None] >> np.arange(32, dtype=np.uint32)) & 1
+    return bits.reshape(w.shape[:-1] + (w.shape[-1] * 32,)).astype(np.float64)
+
+
+def image_observations(images, e, P):
+    """IMAGE mode: [[img(8, 480, 640) float64 for every agent] for every tick] (RoboCupEnvironment.py:488-492,1533-1534)"""
+    return [[unpack_image(images[e, t, a]) for a in range(P)] for t in range(L.RC_NTICK)]
+
+
 def observations(views, e, P, full):
     T = L.RC_NTICK
     fn = full_observation if full else partial_observation

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DYNENV_ABI_VERSION 1
+#define DYNENV_ABI_VERSION 2
 
 /* ---- error codes */
 #define DYNENV_OK 0
@@ -258,10 +258,39 @@ enum {
 #define RC_IF_ACTIVE_OVERFLOW 2 /* more than RC_MAXACTIVE touching pairs in one substep           */
 #define RC_MAXACTIVE 16
 
+/*
+ * IMAGE observations (obs_type IMAGE; the image branch of getAgentVision, RoboCupEnvironment.py:1318-1467,1533-1534).
+ * The observation kernel emits, per (env, tick, observer), the detection lists the reference draws -- positions and
+ * sizes in the observer's head frame -- as one raw record raw[E][T][P][RC_RAW_WORDS]; dynenv_render_images turns raw
+ * records into the reference's 8 x 480 x 640 planes (top camera 0..3, bottom camera 4..7; channel 0 balls, 1 robots,
+ * 2 goal posts, 3 lines / centre circle / crosses), one bit per pixel: image[record][8][480][RC_IMG_WORDS_PER_ROW],
+ * bit x % 32 of word x / 32 = pixel x.  An environment-step of 5 ticks x 10 observers is 15.4 MB of planes, so the
+ * caller renders the records it needs (any sub-range) into a buffer of its own size.
+ */
+enum {
+  RC_R_COUNTS = 0,                                   /* I [RC_NTYPES] rows per list (as RC_O_COUNTS)       */
+  RC_R_CIRCLE_SEEN = RC_R_COUNTS + RC_NTYPES,        /* I centre circle sighted                             */
+  RC_R_CIRCLE = RC_R_CIRCLE_SEEN + 1,                /* F [3] x, y, radius                                  */
+  RC_R_BALL = RC_R_CIRCLE + 3,                       /* F [RC_CAP_BALL][3] x, y, size                       */
+  RC_R_ROBOT = RC_R_BALL + RC_CAP_BALL * 3,          /* F [RC_CAP_ROBOT][3]                                 */
+  RC_R_POST = RC_R_ROBOT + RC_CAP_ROBOT * 3,         /* F [RC_CAP_POST][3]                                  */
+  RC_R_CROSS = RC_R_POST + RC_CAP_POST * 3,          /* F [RC_CAP_CROSS][3]                                 */
+  RC_R_FCROSS = RC_R_CROSS + RC_CAP_CROSS * 3,       /* F [RC_CAP_FCROSS][3]                                */
+  RC_R_LINE = RC_R_FCROSS + RC_CAP_FCROSS * 3,       /* F [RC_CAP_LINE][4] x1, y1, x2, y2                   */
+  RC_RAW_WORDS_RAW = RC_R_LINE + RC_CAP_LINE * 4,
+  RC_RAW_WORDS = (RC_RAW_WORDS_RAW + 31) / 32 * 32
+};
+#define RC_IMG_PLANES 8
+#define RC_IMG_H 480
+#define RC_IMG_W 640
+#define RC_IMG_WORDS_PER_ROW 20
+#define RC_IMG_WORDS (RC_IMG_PLANES * RC_IMG_H * RC_IMG_WORDS_PER_ROW) /* per (env, tick, observer): 307 200 bytes */
+
 typedef struct DynEnvRoboCupOut {
-  float* obs;   /* [E][T][P][RC_OBS_WORDS]  PARTIAL observations (obs_type PARTIAL), else NULL */
+  float* obs;   /* [E][T][P][RC_OBS_WORDS]  PARTIAL / IMAGE observations (obs_type PARTIAL or IMAGE), else NULL */
   float* full;  /* [E][T][P][RC_FULL_WORDS] FULL observations (obs_type FULL), else NULL       */
   float* info;  /* [E][RC_INFO_WORDS]       rewards, done, episode stats, full/recon state     */
+  float* raw;   /* [E][T][P][RC_RAW_WORDS]  raw detection records (obs_type IMAGE), else NULL  */
 } DynEnvRoboCupOut;
 
 /* ======================================================================= Driving
@@ -428,6 +457,12 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
                 void* stream);
 
 int dynenv_set_seed(DynEnvHandle h, uint64_t seed);
+
+/* IMAGE observations: draw n_records raw records (raw_dev: [n_records][RC_RAW_WORDS], e.g. any slice of
+   DynEnvRoboCupOut.raw) into image_dev: [n_records][RC_IMG_WORDS] uint32 (layout above).  Replaces the drawing half
+   of getAgentVision (RoboCupEnvironment.py:1318-1467) and cutils.projectPoints / estimateConic / getConicPoints
+   (cutils.py:206-284).  `device`: CUDA device ordinal of the buffers. */
+int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, uint32_t* image_dev, void* stream);
 
 /* copy the whole state ([nEnvs][state_words] 32-bit words) to / from a device buffer */
 int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream);

@@ -108,6 +108,33 @@ class RcRawOut(C.Structure):
     _fields_ = [("v", (RcRawVision * _P) * _T)]
 
 
+def raw_to_record(raw):
+    """RcRawVision dict -> the float32 raw record of the C ABI (include/dynenv_b200.h, RC_R_*)"""
+    rec = np.zeros(L.RC_RAW_WORDS, dtype=np.float32)
+    ri = rec.view(np.int32)
+    ri[L.RC_R_COUNTS:L.RC_R_COUNTS + L.RC_NTYPES] = raw["counts"]
+    ri[L.RC_R_CIRCLE_SEEN] = int(raw["circle"][0] != 0)
+    rec[L.RC_R_CIRCLE:L.RC_R_CIRCLE + 3] = raw["circle"][1:4]
+    for name, off, cap in (("ball", L.RC_R_BALL, L.RC_CAP_BALL), ("robot", L.RC_R_ROBOT, L.RC_CAP_ROBOT), ("post", L.RC_R_POST, L.RC_CAP_POST),
+                           ("cross", L.RC_R_CROSS, L.RC_CAP_CROSS), ("fcross", L.RC_R_FCROSS, L.RC_CAP_FCROSS)):
+        rec[off:off + cap * 3] = raw[name].reshape(-1)
+    rec[L.RC_R_LINE:L.RC_R_LINE + L.RC_CAP_LINE * 4] = raw["line"].reshape(-1)
+    return rec
+
+
+def record_to_raw(rec):
+    """inverse of raw_to_record (values as float64 of the float32 words): what the raster oracle draws for a record"""
+    rec = np.asarray(rec, dtype=np.float32)
+    ri = rec.view(np.int32)
+    raw = {"counts": ri[L.RC_R_COUNTS:L.RC_R_COUNTS + L.RC_NTYPES].copy(),
+           "circle": np.concatenate([[float(ri[L.RC_R_CIRCLE_SEEN])], rec[L.RC_R_CIRCLE:L.RC_R_CIRCLE + 3].astype(np.float64)])}
+    for name, off, cap in (("ball", L.RC_R_BALL, L.RC_CAP_BALL), ("robot", L.RC_R_ROBOT, L.RC_CAP_ROBOT), ("post", L.RC_R_POST, L.RC_CAP_POST),
+                           ("cross", L.RC_R_CROSS, L.RC_CAP_CROSS), ("fcross", L.RC_R_FCROSS, L.RC_CAP_FCROSS)):
+        raw[name] = rec[off:off + cap * 3].astype(np.float64).reshape(cap, 3)
+    raw["line"] = rec[L.RC_R_LINE:L.RC_R_LINE + L.RC_CAP_LINE * 4].astype(np.float64).reshape(L.RC_CAP_LINE, 4)
+    return raw
+
+
 class RcOracle(object):
     """One RoboCup environment of the CPU oracle."""
 

@@ -1,6 +1,11 @@
 // CPU build of dynenv_b200/csrc/raster_prims.cuh for tests/test_raster_prims.py (compared with the installed cv2)
-#include "../../dynenv_b200/csrc/raster_prims.cuh"
+#include "../../dynenv_b200/csrc/raster_compose.cuh"
 extern "C" {
+// one raw record (float32 [RC_RAW_WORDS]) -> the 8 planes of the IMAGE observation (zeroed by the caller)
+void rp_render(const float* raw, uint32_t* planes) {
+  raster::render_camera_host(raw, 0, planes);
+  raster::render_camera_host(raw, 1, planes + 4 * raster::PLANE_WORDS);
+}
 void rp_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thickness) { raster::cv_line(plane, x0, y0, x1, y1, thickness); }
 void rp_rect(uint32_t* plane, int x0, int y0, int x1, int y1) { raster::cv_rectangle_filled(plane, x0, y0, x1, y1); }
 void rp_circle(uint32_t* plane, int cx, int cy, int r) { raster::circle_filled(plane, cx, cy, r); }

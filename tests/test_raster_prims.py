@@ -73,3 +73,32 @@ def test_polylines_match_cv2(lib):
         pc = np.ascontiguousarray(pts)
         lib.rp_polyline(p.ctypes.data, pc.ctypes.data, n, t)
         assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("polyline", pts.tolist(), t)
+
+
+def test_compose_matches_raster_oracle(lib):
+    """the whole image of a raw detection record (projection, conic fit, primitives) by the host build of
+    raster_compose.cuh against the cv2-based raster oracle, for every agent and tick of the golden IMAGE scenes"""
+    import glob
+    from helpers import GOLDEN, golden_cfg
+    from oracle import raster_oracle
+    from oracle.oracle import RcOracle, raw_to_record, record_to_raw
+    from oracle.ref_loader import UniformTape
+    n = 0
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "image_*.npz"))):
+        g = dict(np.load(path))
+        cfg = golden_cfg(g)
+        orc = RcOracle(cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"], cfg["allowHeadTurn"], cfg["flags"])
+        r0, r1 = g["tape_reset_off"]
+        orc.set_tape(UniformTape.regenerate(int(g["tape_seed"]), 0, r1)[r0:r1])
+        orc.capture_raw()
+        orc.reset()
+        orc.reset_obs()
+        for t in (0, 3):
+            for a in range(2 * cfg["nPlayers"]):
+                rec = raw_to_record(orc.raw_vision(t, a))
+                ref = raster_oracle.pack(raster_oracle.render(record_to_raw(rec)))
+                planes = np.zeros((8, 480, 20), np.uint32)
+                lib.rp_render(rec.ctypes.data, planes.ctypes.data)
+                assert np.array_equal(planes, ref), (os.path.basename(path), t, a)
+                n += 1
+    assert n >= 40
