@@ -40,6 +40,7 @@ class RoboCupWorkload(object):
     P, act = 10, 4
     launches_per_step = {"phys": 5, "obs": 5, "finish": 1}
     prefix = "rc"
+    cpu_steps, ref_steps, cpu_warm = 20000, 1000, 50  # env-steps per host thread: cpu_baseline sample, reference-arm step, warm-up
 
     def make_sim(self, E, local, rank, full=False):
         import dynenv_b200
@@ -72,8 +73,10 @@ class RoboCupWorkload(object):
 
     def cpu_env(self, i):
         from oracle import oracle as O
+        import ctypes as C
         env = O.RcOracle(5, 1, 1, 2.0, False, seed=42, env_id=i)
-        return env, env._lib.rc_step
+        ref = C.byref(env._out)
+        return env, lambda a: env._lib.rc_step(env._h, a.ctypes.data, ref)
 
     def cpu_actions(self, rng, n_steps):
         return np.stack([rng.integers(0, 5, (n_steps, self.P)), rng.integers(0, 3, (n_steps, self.P)),
@@ -88,6 +91,7 @@ class DrivingWorkload(object):
     P, act = 10, 2
     launches_per_step = {"phys": 1, "obs": 1, "finish": 0}
     prefix = "drv"
+    cpu_steps, ref_steps, cpu_warm = 10000, 1000, 50
 
     def make_sim(self, E, local, rank, full=False):
         import dynenv_b200
@@ -116,14 +120,125 @@ class DrivingWorkload(object):
 
     def cpu_env(self, i):
         from oracle import oracle as O
+        import ctypes as C
         env = O.DrvOracle(10, 1, 1, 2.0, True, seed=42, env_id=i)
-        return env, env._lib.drv_step
+        ref = C.byref(env._out)
+        return env, lambda a: env._lib.drv_step(env._h, a.ctypes.data, ref)
 
     def cpu_actions(self, rng, n_steps):
         return rng.uniform(-3, 3, (n_steps, self.P, 2))
 
 
-WORKLOADS = {"robocup": RoboCupWorkload, "driving": DrivingWorkload}
+class _ImageSim(object):
+    """RoboCup simulator in IMAGE mode + the raster kernel over every record of the step, in environment chunks that
+    fit one reusable plane buffer (15.36 MB of bit-planes per environment-step)"""
+
+    def __init__(self, sim, chunk):
+        import torch
+        from dynenv_b200 import layout as L
+        self.sim, self.chunk = sim, chunk
+        self.out = sim.out
+        self.buf = torch.empty((chunk, L.RC_NTICK, sim.P, L.RC_IMG_PLANES, L.RC_IMG_H, L.RC_IMG_WORDS_PER_ROW), dtype=torch.int32,
+                               device=sim.device)
+        self.timing = False
+        self.ev = None
+
+    def reset(self):
+        return self.sim.reset()
+
+    def step(self, actions):
+        import torch
+        out = self.sim.step(actions)
+        if self.timing:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        for b in range(0, self.sim.nEnvs, self.chunk):
+            e = min(b + self.chunk, self.sim.nEnvs)
+            self.sim.render_images(b, e, out=self.buf[:e - b])
+        if self.timing:
+            self.ev[1].record()
+        return out
+
+    def debug_timing(self, enable=True):
+        self.timing = bool(enable)
+        self.sim.debug_timing(enable)
+
+    def last_kernel_ms(self):
+        k = self.sim.last_kernel_ms()
+        n = (self.sim.nEnvs + self.chunk - 1) // self.chunk
+        self.ev[1].synchronize()
+        k["raster"] = (self.ev[0].elapsed_time(self.ev[1]), n)
+        return k
+
+    def last_launch_count(self):
+        return self.sim.last_launch_count() + (self.sim.nEnvs + self.chunk - 1) // self.chunk
+
+
+class ImageWorkload(RoboCupWorkload):
+    """BASELINE.json configs[3]"""
+    name = "image"
+    metric = "env-steps/sec (RoboCup 5v5 IMAGE, 50 substeps + 100 camera images)"
+    workload = "RoboCup 5v5 IMAGE (top / bottom camera raster, 8 x 480 x 640 bit-planes per robot and tick) allowHeadTurn REALISTIC noise 2, auto-reset"
+    launches_per_step = {"phys": 5, "obs": 5, "finish": 1, "raster": 1}
+    chunk = 1024
+    default_envs = 16384
+    cpu_steps, ref_steps, cpu_warm = 16, 4, 1  # an env-step draws 100 images with cv2 (~0.3 s)
+
+    def make_sim(self, E, local, rank, full=False):
+        import dynenv_b200
+        sim = dynenv_b200.BatchedRoboCup(E, 5, dynenv_b200.ObservationType.IMAGE, dynenv_b200.NoiseType.REALISTIC, 2.0, allowHeadTurn=True,
+                                         canFall=True, useObsRewards=True, auto_reset=True, seed=42, device=local, env_id_offset=rank * E)
+        self.launches_per_step = dict(self.launches_per_step, raster=(E + self.chunk - 1) // self.chunk)
+        self.E = E
+        return _ImageSim(sim, min(self.chunk, E))
+
+    def make_actions(self, E, g, dev):
+        """three categorical columns as floats + head turn uniform [-3, 3)"""
+        import torch
+        a = torch.rand((E, self.P, 4), generator=g, device=dev)
+        a[..., :3] = (a[..., :3] * torch.tensor([5, 3, 3], device=dev)).floor()
+        a[..., 3] = a[..., 3] * 6.0 - 3.0
+        return a.contiguous()
+
+    def config(self, L):
+        return dict(RoboCupWorkload.config(self, L), images_per_env_step=2 * L.RC_NTICK * self.P, render_chunk_envs=self.chunk)
+
+    def algorithmic_bytes_per_env_step(self):
+        from dynenv_b200 import layout as L
+        return RoboCupWorkload.algorithmic_bytes_per_env_step(self) + 4 * L.RC_NTICK * self.P * (2 * L.RC_RAW_WORDS + L.RC_IMG_WORDS)
+
+    def kernel_bytes_per_env(self):
+        from dynenv_b200 import layout as L
+        kb = RoboCupWorkload.kernel_bytes_per_env(self)
+        kb["obs"] += 4 * self.P * L.RC_RAW_WORDS
+        # one raster launch covers `chunk` environments: raw records in, bit-planes out (bytes per environment of the chunk
+        # x chunk / E so that kb * E is the launch's traffic)
+        kb["raster"] = 4 * L.RC_NTICK * self.P * (L.RC_RAW_WORDS + L.RC_IMG_WORDS) * min(self.chunk, self.E) / self.E
+        return kb
+
+    def cpu_env(self, i):
+        """the C oracle's step with the raw detection lists captured, then the reference's drawing calls (real cv2) for
+        every robot and tick"""
+        import ctypes as C
+        from oracle import oracle as O, raster_oracle
+        env = O.RcOracle(5, 2, 1, 2.0, True, seed=42, env_id=i)
+        env.capture_raw()
+        ref = C.byref(env._out)
+
+        def step(a):
+            env._lib.rc_step(env._h, a.ctypes.data, ref)
+            for t in range(5):
+                for ag in range(self.P):
+                    raster_oracle.render(env.raw_vision(t, ag))
+        return env, step
+
+    def cpu_actions(self, rng, n_steps):
+        a = RoboCupWorkload.cpu_actions(self, rng, n_steps)
+        a[..., 3] = rng.uniform(-3, 3, a.shape[:-1])
+        return a
+
+
+WORKLOADS = {"robocup": RoboCupWorkload, "driving": DrivingWorkload, "image": ImageWorkload}
 
 
 def measured_peaks():
@@ -196,11 +311,10 @@ def cpu_env_steps_per_s(wl, n_steps, threads=None):
         env.reset()
         rng = np.random.default_rng(1234 + i)
         acts = np.ascontiguousarray(wl.cpu_actions(rng, n_steps), dtype=np.float64)
-        ref = C.byref(env._out)
         barrier.wait()
         t0 = time.perf_counter()
         for s in range(n_steps):
-            step_fn(env._h, acts[s].ctypes.data, ref)
+            step_fn(acts[s])
             if env._out.done:  # the vec-env's auto-reset (utils/subproc_vec_env.py:17-23)
                 env.reset()
         out[i] = time.perf_counter() - t0
@@ -220,9 +334,9 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]()
     METRIC, WORKLOAD = wl.metric, wl.workload
     # each "step" = every host thread advancing a bounded sample of env-steps of the same workload
-    per_step = 1000
+    per_step = wl.ref_steps
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_env_steps_per_s(wl, 50)
+        cpu_env_steps_per_s(wl, wl.cpu_warm)
     t_total, n_total, threads = 0.0, 0, 0
     for _ in range(args.steps):
         rate, threads, dt = cpu_env_steps_per_s(wl, per_step)
@@ -257,8 +371,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    E = args.envs
     wl = WORKLOADS[args.workload]()
+    E = args.envs or getattr(wl, "default_envs", 65536)
     METRIC, WORKLOAD, P = wl.metric, wl.workload, wl.P
     sim = wl.make_sim(E, local, rank, full=args.debug_full_obs)
     sim.reset()
@@ -280,7 +394,7 @@ def run_gpu(args):
     pool = pool[args.warmup % n_pool:] + pool[:args.warmup % n_pool]
     barrier()
     sim.debug_timing(True)
-    kms = {"phys": [0.0, 0], "obs": [0.0, 0], "finish": [0.0, 0]}
+    kms = {k: [0.0, 0] for k in wl.launches_per_step}
     sampler = ClockSampler(local)
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -370,10 +484,11 @@ def run_gpu(args):
                                       "frac": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12 / FP32_NOMINAL_TFLOPS}},
                 "diag_flags": diag}
         if not args.no_cpu and world == 1:
-            rate, threads, dt = cpu_env_steps_per_s(wl, args.cpu_steps)
+            cpu_steps = args.cpu_steps or wl.cpu_steps
+            rate, threads, dt = cpu_env_steps_per_s(wl, cpu_steps)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d host threads x %d env-steps of the same workload (%.1f s), C restatement "
-                                              "of the reference" % (threads, args.cpu_steps, dt)}
+                                              "of the reference" % (threads, cpu_steps, dt)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -384,12 +499,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 65536; image workload 16384)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="robocup", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--debug-full-obs", action="store_true", help="(profiling aid) FULL observations: physics and rules only")
-    ap.add_argument("--cpu-steps", type=int, default=20000, help="env-steps per host thread of the cpu_baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=None, help="env-steps per host thread of the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -436,7 +436,7 @@ int dynenv_set_seed(DynEnvHandle h, uint64_t seed) {
 int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, uint32_t* image_dev, void* stream) {
   if (!raw_dev || !image_dev || n_records < 0) return fail(DYNENV_E_INVALID, "bad argument");
   if (n_records == 0) return DYNENV_OK;
-  if (n_records > (int64_t)1 << 29) return fail(DYNENV_E_INVALID, "too many records for one call");
+  if (n_records > (int64_t)1 << 27) return fail(DYNENV_E_INVALID, "too many records for one call");
   cudaError_t ce = cudaSetDevice(device);
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
   const size_t smem = (size_t)rcimg::SMEM_WORDS * sizeof(uint32_t);
@@ -446,7 +446,7 @@ int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, ui
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(rc_raster_kernel)");
     configured = device;
   }
-  rcimg::rc_raster_kernel<<<(unsigned)(2 * n_records), rcimg::THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  rcimg::rc_raster_kernel<<<(unsigned)(8 * n_records), rcimg::THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       raw_dev, (long long)n_records, image_dev);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "rc_raster_kernel launch");

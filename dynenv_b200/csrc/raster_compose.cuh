@@ -3,8 +3,8 @@
  * RC_R_*): which primitives to draw where.  Restates, for a record,
  *   RoboCupEnvironment.py:1318-1467   the drawing calls of getAgentVision's image branch
  *   cutils.py:166-200                 pin-hole camera matrices (top / bottom camera of the robot's head)
- *   cutils.py:206-222 projectPoints, :226-257 getConicPoints, :261-284 estimateConic (null vector of the 8 x 6
- *                                     design matrix; the reference uses numpy's SVD, here a one-sided Jacobi SVD)
+ *   cutils.py:206-222 projectPoints, :226-257 getConicPoints, :261-284 estimateConic (the conic through eight
+ *                                     projected circle points; evaluated in closed form, see conic_setup)
  * in float64 like the reference (the projected coordinates are truncated to integer pixels; float32 would move
  * one coordinate in ~1e3 across a pixel boundary).  The pixel work is raster_prims.cuh.
  *
@@ -66,48 +66,24 @@ struct Conic {
   short y[CONIC_ROWS];
 };
 
-RP_FN void draw_prim(uint32_t* planes, const Prim& p) {
-  uint32_t* plane = planes + p.plane * PLANE_WORDS;
-  if (p.type == PRIM_LINE) cv_line(plane, p.x0, p.y0, p.x1, p.y1, p.t);
-  else if (p.type == PRIM_RECT) cv_rectangle_filled(plane, p.x0, p.y0, p.x1, p.y1);
-  else circle_filled(plane, p.x0, p.y0, p.t);
+/* a primitive that can cover a large part of the image: drawn by the whole block instead of one warp */
+RP_FN bool prim_is_big(const Prim& p) {
+  if (p.type == PRIM_LINE) return p.t >= 24;
+  if (p.type == PRIM_CIRCLE) return p.t >= 40;
+  const long long w = (long long)p.x1 - p.x0, h = (long long)p.y1 - p.y0;
+  return (w < 0 ? -w : w) * (h < 0 ? -h : h) >= 64 * 64;
+}
+/* `plane`: the bit-plane the primitive belongs to (p.plane) */
+RP_FN void draw_prim(uint32_t* plane, const Prim& p, Lanes L) {
+  if (p.type == PRIM_LINE) cv_line(plane, p.x0, p.y0, p.x1, p.y1, p.t, L);
+  else if (p.type == PRIM_RECT) cv_rectangle_filled(plane, p.x0, p.y0, p.x1, p.y1, L);
+  else circle_filled(plane, p.x0, p.y0, p.t, L);
 }
 /* segment s (0-based) of the two poly-lines of the conic: branch s / (n - 1), points i - 1 -> i with i = s % (n - 1) + 1 */
-RP_FN void draw_conic_segment(uint32_t* planes, const Conic& c, int s) {
+RP_FN void draw_conic_segment(uint32_t* plane3, const Conic& c, int s, Lanes L) {
   const int b = s / (c.n - 1), i = s % (c.n - 1) + 1;
   const int* x = b ? c.x2 : c.x1;
-  cv_polyline_segment(planes + 3 * PLANE_WORDS, x[i - 1], c.y[i - 1], x[i], c.y[i], c.thickness, i);
-}
-
-/* estimateConic: null vector of X (8 x 6) by one-sided Jacobi rotations on the columns */
-RP_FN void conic_null_vector(double X[8][6], double out[6]) {
-  double V[6][6];
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < 6; j++) V[i][j] = i == j ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 40; sweep++) {
-    bool rotated = false;
-    for (int p = 0; p < 5; p++)
-      for (int q = p + 1; q < 6; q++) {
-        double alpha = 0, beta = 0, gamma = 0;
-        for (int i = 0; i < 8; i++) { alpha += X[i][p] * X[i][p]; beta += X[i][q] * X[i][q]; gamma += X[i][p] * X[i][q]; }
-        if (gamma == 0.0 || rp_fabs(gamma) <= 1e-15 * rp_sqrt(alpha * beta)) continue;
-        rotated = true;
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = (zeta >= 0 ? 1.0 : -1.0) / (rp_fabs(zeta) + rp_sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / rp_sqrt(1.0 + t * t), s = c * t;
-        for (int i = 0; i < 8; i++) { const double a = X[i][p], b = X[i][q]; X[i][p] = c * a - s * b; X[i][q] = s * a + c * b; }
-        for (int i = 0; i < 6; i++) { const double a = V[i][p], b = V[i][q]; V[i][p] = c * a - s * b; V[i][q] = s * a + c * b; }
-      }
-    if (!rotated) break;
-  }
-  int best = 0;
-  double bn = 1e300;
-  for (int j = 0; j < 6; j++) {
-    double nrm = 0;
-    for (int i = 0; i < 8; i++) nrm += X[i][j] * X[i][j];
-    if (nrm < bn) { bn = nrm; best = j; }
-  }
-  for (int i = 0; i < 6; i++) out[i] = -V[i][best];
+  cv_polyline_segment(plane3, x[i - 1], c.y[i - 1], x[i], c.y[i], c.thickness, i, L);
 }
 
 RP_FN double round_half_even(double v) {
@@ -134,23 +110,52 @@ RP_FN bool conic_row(const double* params, double cx, double cy, int y, int* x1,
   return true;
 }
 
+/* the 3 x 3 homography of the ground plane (Y = 0) into the image of camera `cam`: columns X, Z, 1 of the projection */
+RP_FN void ground_homography(int cam, double H[3][3]) {
+  /* H = [m0 m2 m3; m4 m6 m7; m8 m10 m11] of the matrices in project() */
+  const double top[12] = {543.60000000000002, -85.497791791539967, 307.84797806510034, 3182.6176409012332,
+                          0, -587.86504541553177, 85.298876772176541, 33809.365805102643,
+                          0, -0.26759872235223775, 0.96353044777809183, 9.9612445724608243};
+  const double bot[12] = {543.60000000000002, -258.56019545653214, 187.68823971011045, 12952.04888690959,
+                          0, -513.15334559704377, -299.22375223661794, 29111.671653727328,
+                          0, -0.80926508750088311, 0.58744362976560394, 40.538494168731113};
+  const double* m = cam ? bot : top;
+  for (int r = 0; r < 3; r++) { H[r][0] = m[4 * r]; H[r][1] = m[4 * r + 2]; H[r][2] = m[4 * r + 3]; }
+}
+
 /* the centre circle (RoboCupEnvironment.py:1343-1393): conic parameters of camera `cam`; returns false when nothing
-   can be drawn.  cx, cy: projected centre. */
+   can be drawn.  cx, cy: projected centre.  The reference fits the conic through the projections of eight points
+   of the circle (estimateConic: null vector of the 8 x 6 design matrix by SVD, cutils.py:261-284).  Those points
+   lie exactly on the image of the circle under the ground-plane homography H, so the fitted conic IS
+   H^-T C H^-1 (C: the circle's matrix) up to scale and rounding; it is evaluated in closed form here (the scale and
+   sign of the parameter vector do not matter: they swap the two branches, which are drawn alike). */
 RP_FN bool conic_setup(const float* raw, int cam, double* params, double* cx, double* cy, int* thickness) {
   if (reinterpret_cast<const int*>(raw)[RC_R_CIRCLE_SEEN] == 0) return false;
   const double X = raw[RC_R_CIRCLE], Y = raw[RC_R_CIRCLE + 1], R = raw[RC_R_CIRCLE + 2];
-  const double ex = R * 0.70710678118654757, ey = R * 0.70710678118654746; /* Vec2d(R, 0).rotated(pi / 4) */
-  const double px[9] = {-Y, -Y, -Y, -Y - R, -Y + R, -Y - ey, -Y + ex, -Y + ey, -Y - ex};
-  const double pz[9] = {X, X - R, X + R, X, X, X + ex, X - ey, X + ex, X - ey};
-  double u[9], v[9];
-  for (int k = 0; k < 9; k++) project(cam, px[k], 0.0, pz[k], &u[k], &v[k]);
-  double M[8][6];
-  for (int k = 0; k < 8; k++) {
-    const double x = u[k + 1] - u[0], y = v[k + 1] - v[0];
-    M[k][0] = x * x; M[k][1] = y * y; M[k][2] = x * y; M[k][3] = x; M[k][4] = y; M[k][5] = 1.0;
-  }
-  conic_null_vector(M, params);
-  *cx = u[0]; *cy = v[0];
+  project(cam, -Y, 0.0, X, cx, cy);
+  double H[3][3];
+  ground_homography(cam, H);
+  /* G = adj(H) (= det H * H^-1): image point (u, v, 1) -> ground point up to scale */
+  double G[3][3];
+  G[0][0] = H[1][1] * H[2][2] - H[1][2] * H[2][1]; G[0][1] = H[0][2] * H[2][1] - H[0][1] * H[2][2]; G[0][2] = H[0][1] * H[1][2] - H[0][2] * H[1][1];
+  G[1][0] = H[1][2] * H[2][0] - H[1][0] * H[2][2]; G[1][1] = H[0][0] * H[2][2] - H[0][2] * H[2][0]; G[1][2] = H[0][2] * H[1][0] - H[0][0] * H[1][2];
+  G[2][0] = H[1][0] * H[2][1] - H[1][1] * H[2][0]; G[2][1] = H[0][1] * H[2][0] - H[0][0] * H[2][1]; G[2][2] = H[0][0] * H[1][1] - H[0][1] * H[1][0];
+  /* centred image coordinates: (u, v, 1) = T (x, y, 1); ground point g = G T (x, y, 1) */
+  double GT[3][3];
+  for (int r = 0; r < 3; r++) { GT[r][0] = G[r][0]; GT[r][1] = G[r][1]; GT[r][2] = G[r][0] * *cx + G[r][1] * *cy + G[r][2]; }
+  /* circle (a, b, R) in ground coordinates g = (gx, gz, gw): (gx - a gw)^2 + (gz - b gw)^2 - R^2 gw^2 = 0 */
+  const double a = -Y, b = X;
+  double P[3], Q[3]; /* gx - a gw and gz - b gw as linear forms in (x, y, 1) */
+  for (int c = 0; c < 3; c++) { P[c] = GT[0][c] - a * GT[2][c]; Q[c] = GT[1][c] - b * GT[2][c]; }
+  const double* Wf = GT[2];
+  const double R2 = R * R;
+  /* A x^2 + B y^2 + C xy + D x + E y + F */
+  params[0] = P[0] * P[0] + Q[0] * Q[0] - R2 * Wf[0] * Wf[0];
+  params[1] = P[1] * P[1] + Q[1] * Q[1] - R2 * Wf[1] * Wf[1];
+  params[2] = 2 * (P[0] * P[1] + Q[0] * Q[1] - R2 * Wf[0] * Wf[1]);
+  params[3] = 2 * (P[0] * P[2] + Q[0] * Q[2] - R2 * Wf[0] * Wf[2]);
+  params[4] = 2 * (P[1] * P[2] + Q[1] * Q[2] - R2 * Wf[1] * Wf[2]);
+  params[5] = P[2] * P[2] + Q[2] * Q[2] - R2 * Wf[2] * Wf[2];
   const double len = rp_sqrt(X * X + Y * Y);
   if (!(len < 1.0e9)) return false;
   int q = (int)(len / (cam ? 20.0 : 40.0));
@@ -166,6 +171,9 @@ RP_FN bool conic_setup(const float* raw, int cam, double* params, double* cx, do
 constexpr int SLOT_ROBOT = RC_CAP_LINE, SLOT_POST = SLOT_ROBOT + RC_CAP_ROBOT, SLOT_CROSS = SLOT_POST + RC_CAP_POST,
               SLOT_FCROSS = SLOT_CROSS + RC_CAP_CROSS, SLOT_BALL = SLOT_FCROSS + RC_CAP_FCROSS, N_SLOTS = SLOT_BALL + RC_CAP_BALL;
 static_assert(N_SLOTS + 4 <= MAX_PRIMS, "primitive slots");
+RP_FN int slot_plane(int slot) { /* channel 0 balls, 1 robots, 2 goal posts, 3 lines / crosses (and the centre circle) */
+  return slot < SLOT_ROBOT ? 3 : (slot < SLOT_POST ? 1 : (slot < SLOT_CROSS ? 2 : (slot < SLOT_BALL ? 3 : 0)));
+}
 RP_FN bool build_prim_slot(const float* raw, int cam, int slot, Prim* out) {
   const int* cnt = reinterpret_cast<const int*>(raw) + RC_R_COUNTS;
   double u[4], v[4];
@@ -244,10 +252,11 @@ inline void render_camera_host(const float* raw, int cam, uint32_t* planes /* [4
     }
     n = conic_closures(conic, prims, n);
   }
+  const Lanes one = {0, 1};
   for (int k = 0; k < n; k++)
-    if (prims[k].type >= 0) draw_prim(planes, prims[k]);
+    if (prims[k].type >= 0) draw_prim(planes + prims[k].plane * PLANE_WORDS, prims[k], one);
   if (conic.n > 1)
-    for (int s = 0; s < 2 * (conic.n - 1); s++) draw_conic_segment(planes, conic, s);
+    for (int s = 0; s < 2 * (conic.n - 1); s++) draw_conic_segment(planes + 3 * PLANE_WORDS, conic, s, one);
 }
 #endif
 

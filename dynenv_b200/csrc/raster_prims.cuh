@@ -90,8 +90,17 @@ RP_FN bool clip_line(int64_t width, int64_t height, P2& pt1, P2& pt2) {
   return (c1 | c2) == 0;
 }
 
-/* Line(): cv::LineIterator, 8-connected, left to right, after clipping to the image */
-RP_FN void line_thin(uint32_t* plane, P2 pt1, P2 pt2) {
+/* Every drawing routine takes the calling lane and the number of cooperating lanes: its set-up (clipping, slopes,
+   edge tables -- a few dozen integer operations) is computed redundantly by every lane, its pixels / rows are spread
+   over the lanes in closed form.  The host build passes {0, 1}; the CUDA raster kernel a warp's {lane, 32}. */
+struct Lanes {
+  int lane, n;
+};
+
+/* Line(): cv::LineIterator, 8-connected, left to right, after clipping to the image.  Pixel i lies i steps along the
+   major axis and m_i steps along the minor one, where m_i counts the earlier iterations whose error term was negative:
+   m_i = max(0, ceil((2 dy i - dx) / (2 dx))) for the iterator's err_0 = dx - 2 dy, err += -2 dy (+ 2 dx when negative). */
+RP_FN void line_thin(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
   if ((uint64_t)pt1.x >= (uint64_t)IMG_W || (uint64_t)pt2.x >= (uint64_t)IMG_W || (uint64_t)pt1.y >= (uint64_t)IMG_H ||
       (uint64_t)pt2.y >= (uint64_t)IMG_H) {
     if (!clip_line(IMG_W, IMG_H, pt1, pt2)) return;
@@ -102,23 +111,20 @@ RP_FN void line_thin(uint32_t* plane, P2 pt1, P2 pt2) {
   if (dy < 0) { dy = -dy; delta_y = -1; }
   const bool vert = dy > dx;
   if (vert) { int t = dx; dx = dy; dy = t; t = delta_x; delta_x = delta_y; delta_y = t; }
-  int err = dx - (dy + dy);
-  const int plusDelta = dx + dx, minusDelta = -(dy + dy);
-  int minusShift = delta_x, plusShift = 0, minusStep = 0, plusStep = delta_y;
+  /* major step (delta_x along the major axis), minor step delta_y; `vert` swaps which image axis is which */
   const int count = dx + 1;
-  if (vert) { int t = plusStep; plusStep = plusShift; plusShift = t; t = minusStep; minusStep = minusShift; minusShift = t; }
-  int x = (int)pt1.x, y = (int)pt1.y;
-  for (int i = 0; i < count; i++) {
+  const int x0 = (int)pt1.x, y0 = (int)pt1.y;
+  for (int i = L.lane; i < count; i += L.n) {
+    const int num = 2 * dy * i - dx;
+    const int m = num > 0 ? (num + 2 * dx - 1) / (2 * dx) : 0;
+    const int x = vert ? x0 + m * delta_y : x0 + i * delta_x;
+    const int y = vert ? y0 + i * delta_x : y0 + m * delta_y;
     put_point(plane, x, y);
-    const int mask = err < 0 ? -1 : 0;
-    err += minusDelta + (plusDelta & mask);
-    x += minusShift + (plusShift & mask);
-    y += minusStep + (plusStep & mask);
   }
 }
 
 /* Line2(): line between fixed-point (XY_SHIFT) end points */
-RP_FN void line2(uint32_t* plane, P2 pt1, P2 pt2) {
+RP_FN void line2(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
   if (!clip_line((int64_t)IMG_W << XY_SHIFT, (int64_t)IMG_H << XY_SHIFT, pt1, pt2)) return;
   int64_t dx = pt2.x - pt1.x, dy = pt2.y - pt1.y;
   int64_t j = dx < 0 ? -1 : 0;
@@ -144,35 +150,31 @@ RP_FN void line2(uint32_t* plane, P2 pt1, P2 pt2) {
   }
   pt1.x += (XY_ONE >> 1);
   pt1.y += (XY_ONE >> 1);
-  put_point(plane, (pt2.x + (XY_ONE >> 1)) >> XY_SHIFT, (pt2.y + (XY_ONE >> 1)) >> XY_SHIFT);
+  if (L.lane == 0) put_point(plane, (pt2.x + (XY_ONE >> 1)) >> XY_SHIFT, (pt2.y + (XY_ONE >> 1)) >> XY_SHIFT);
   if (ax > ay) {
-    pt1.x >>= XY_SHIFT;
-    while (ecount >= 0) {
-      put_point(plane, pt1.x, pt1.y >> XY_SHIFT);
-      pt1.x++;
-      pt1.y += y_step;
-      ecount--;
-    }
+    const int64_t xs = pt1.x >> XY_SHIFT;
+    for (int k = L.lane; k <= ecount; k += L.n) put_point(plane, xs + k, (pt1.y + k * y_step) >> XY_SHIFT);
   } else {
-    pt1.y >>= XY_SHIFT;
-    while (ecount >= 0) {
-      put_point(plane, pt1.x >> XY_SHIFT, pt1.y);
-      pt1.x += x_step;
-      pt1.y++;
-      ecount--;
-    }
+    const int64_t ys = pt1.y >> XY_SHIFT;
+    for (int k = L.lane; k <= ecount; k += L.n) put_point(plane, (pt1.x + k * x_step) >> XY_SHIFT, ys + k);
   }
 }
 
-/* FillConvexPoly() for 4 vertices, line_type LINE_8; `shift` = 0 (integer vertices) or XY_SHIFT */
-RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift) {
+/* FillConvexPoly() for 4 vertices, line_type LINE_8; `shift` = 0 (integer vertices) or XY_SHIFT.  OpenCV walks the
+   rows with two edge cursors (x += dx per row) that it re-seeds at vertex rows; here the re-seeding events are found
+   first (row, x, dx per cursor: the same control flow, jumping from vertex row to vertex row), then every row's span
+   follows in closed form and the rows are spread over the lanes. */
+RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift, Lanes L) {
   const int npts = 4;
-  struct Edge { int idx, di; int64_t x, dx; int ye; } edge[2];
+  struct Edge { int idx, di; int ye; } edge[2];
+  int ev_n[2] = {0, 0};
+  int ev_y[2][5];
+  int64_t ev_x[2][5], ev_dx[2][5];
   const int delta = 1 << shift >> 1;
   int i, y, imin = 0;
   int edges = npts;
   int64_t xmin, xmax, ymin, ymax;
-  const int delta1 = (int)(XY_ONE >> 1), delta2 = (int)(XY_ONE >> 1);
+  const int delta1 = (int)(XY_ONE >> 1);
   P2 p0 = v[npts - 1];
   p0.x <<= XY_SHIFT - shift;
   p0.y <<= XY_SHIFT - shift;
@@ -189,8 +191,8 @@ RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift) {
     if (shift == 0) {
       P2 a, b;
       a.x = p0.x >> XY_SHIFT; a.y = p0.y >> XY_SHIFT; b.x = p.x >> XY_SHIFT; b.y = p.y >> XY_SHIFT;
-      line_thin(plane, a, b);
-    } else line2(plane, p0, p);
+      line_thin(plane, a, b, L);
+    } else line2(plane, p0, p, L);
     p0 = p;
   }
   xmin = (xmin + delta) >> shift;
@@ -203,9 +205,8 @@ RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift) {
   edge[0].ye = edge[1].ye = y = (int)ymin;
   edge[0].di = 1;
   edge[1].di = npts - 1;
-  edge[0].x = edge[1].x = -XY_ONE;
-  edge[0].dx = edge[1].dx = 0;
-  do {
+  int yend;
+  for (;;) { /* row y: a cursor whose edge ends here takes the next edge that reaches below y */
     for (i = 0; i < 2; i++) {
       if (y >= edge[i].ye) {
         int idx0 = edge[i].idx, di = edge[i].di;
@@ -218,9 +219,11 @@ RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift) {
             int64_t xs = v[idx0].x, xe = v[idx].x;
             if (shift != XY_SHIFT) { xs <<= XY_SHIFT - shift; xe <<= XY_SHIFT - shift; }
             edge[i].ye = ty;
-            edge[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
-            edge[i].x = xs;
             edge[i].idx = idx;
+            const int k = ev_n[i]++;
+            ev_y[i][k] = y;
+            ev_x[i][k] = xs;
+            ev_dx[i][k] = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
             break;
           }
           idx0 = idx;
@@ -229,41 +232,54 @@ RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift) {
         }
       }
     }
-    if (edges < 0) break;
-    if (y >= 0) {
-      int left = 0, right = 1;
-      if (edge[0].x > edge[1].x) { left = 1; right = 0; }
-      int xx1 = (int)((edge[left].x + delta1) >> XY_SHIFT);
-      int xx2 = (int)((edge[right].x + delta2) >> XY_SHIFT);
-      if (xx2 >= 0 && xx1 < IMG_W) {
-        if (xx1 < 0) xx1 = 0;
-        if (xx2 >= IMG_W) xx2 = IMG_W - 1;
-        hline(plane, y, xx1, xx2);
-      }
+    if (edges < 0) { yend = y - 1; break; }
+    const int ynext = edge[0].ye < edge[1].ye ? edge[0].ye : edge[1].ye;
+    if (ynext > (int)ymax) { yend = (int)ymax; break; }
+    y = ynext;
+  }
+  if (ev_n[0] == 0 || ev_n[1] == 0) return;
+  const int ystart = (int)ymin > 0 ? (int)ymin : 0;
+  for (int yy = ystart + L.lane; yy <= yend; yy += L.n) {
+    int64_t x[2];
+    for (i = 0; i < 2; i++) {
+      int k = ev_n[i] - 1;
+      while (k > 0 && ev_y[i][k] > yy) k--;
+      x[i] = ev_x[i][k] + ev_dx[i][k] * (yy - ev_y[i][k]);
     }
-    edge[0].x += edge[0].dx;
-    edge[1].x += edge[1].dx;
-  } while (++y <= (int)ymax);
+    const int64_t xl = x[0] > x[1] ? x[1] : x[0], xr = x[0] > x[1] ? x[0] : x[1];
+    int xx1 = (int)((xl + delta1) >> XY_SHIFT);
+    int xx2 = (int)((xr + delta1) >> XY_SHIFT);
+    if (xx2 >= 0 && xx1 < IMG_W) {
+      if (xx1 < 0) xx1 = 0;
+      if (xx2 >= IMG_W) xx2 = IMG_W - 1;
+      hline(plane, yy, xx1, xx2);
+    }
+  }
 }
 
-/* Circle() with fill: Bresenham circle, horizontal spans */
-RP_FN void circle_filled(uint32_t* plane, int cx, int cy, int radius) {
+/* Circle() with fill: Bresenham circle, horizontal spans.  The (dx, dy) sequence is walked by every lane; iteration k
+   draws its four spans on lane k % n. */
+RP_FN void circle_filled(uint32_t* plane, int cx, int cy, int radius, Lanes L) {
   int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+  int it = 0;
   while (dx >= dy) {
-    const int y11 = cy - dy, y12 = cy + dy, y21 = cy - dx, y22 = cy + dx;
-    int x11 = cx - dx, x12 = cx + dx, x21 = cx - dy, x22 = cx + dy;
-    if (x11 < IMG_W && x12 >= 0 && y21 < IMG_H && y22 >= 0) {
-      x11 = x11 > 0 ? x11 : 0;
-      x12 = x12 < IMG_W - 1 ? x12 : IMG_W - 1;
-      if ((unsigned)y11 < (unsigned)IMG_H) hline(plane, y11, x11, x12);
-      if ((unsigned)y12 < (unsigned)IMG_H) hline(plane, y12, x11, x12);
-      if (x21 < IMG_W && x22 >= 0) {
-        x21 = x21 > 0 ? x21 : 0;
-        x22 = x22 < IMG_W - 1 ? x22 : IMG_W - 1;
-        if ((unsigned)y21 < (unsigned)IMG_H) hline(plane, y21, x21, x22);
-        if ((unsigned)y22 < (unsigned)IMG_H) hline(plane, y22, x21, x22);
+    if (it % L.n == L.lane) {
+      const int y11 = cy - dy, y12 = cy + dy, y21 = cy - dx, y22 = cy + dx;
+      int x11 = cx - dx, x12 = cx + dx, x21 = cx - dy, x22 = cx + dy;
+      if (x11 < IMG_W && x12 >= 0 && y21 < IMG_H && y22 >= 0) {
+        x11 = x11 > 0 ? x11 : 0;
+        x12 = x12 < IMG_W - 1 ? x12 : IMG_W - 1;
+        if ((unsigned)y11 < (unsigned)IMG_H) hline(plane, y11, x11, x12);
+        if ((unsigned)y12 < (unsigned)IMG_H) hline(plane, y12, x11, x12);
+        if (x21 < IMG_W && x22 >= 0) {
+          x21 = x21 > 0 ? x21 : 0;
+          x22 = x22 < IMG_W - 1 ? x22 : IMG_W - 1;
+          if ((unsigned)y21 < (unsigned)IMG_H) hline(plane, y21, x21, x22);
+          if ((unsigned)y22 < (unsigned)IMG_H) hline(plane, y22, x21, x22);
+        }
       }
     }
+    it++;
     dy++;
     err += plus;
     plus += 2;
@@ -283,10 +299,10 @@ RP_FN int64_t cv_round(double v) { /* cvRound: round half to even (lrint in the 
 }
 
 /* ThickLine() with integer end points; flags bit 0 / 1: round cap at p0 / p1 */
-RP_FN void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags) {
+RP_FN void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, Lanes L) {
   const double INV_XY_ONE = 1. / XY_ONE;
   if (thickness <= 1) { /* shift == 0: the end points are integers */
-    line_thin(plane, p0, p1);
+    line_thin(plane, p0, p1, L);
     return;
   }
   { /* OpenCV 4.13 first clips the centre line to the image grown by `thickness` on every side */
@@ -314,35 +330,35 @@ RP_FN void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags) {
     pt[1].x = p0.x - dp.x; pt[1].y = p0.y - dp.y;
     pt[2].x = p1.x - dp.x; pt[2].y = p1.y - dp.y;
     pt[3].x = p1.x + dp.x; pt[3].y = p1.y + dp.y;
-    fill_convex4(plane, pt, XY_SHIFT);
+    fill_convex4(plane, pt, XY_SHIFT, L);
   }
   for (int i = 0; i < 2; i++) {
     if (flags & (i + 1)) {
       const int cx = (int)((p0.x + (XY_ONE >> 1)) >> XY_SHIFT), cy = (int)((p0.y + (XY_ONE >> 1)) >> XY_SHIFT);
-      circle_filled(plane, cx, cy, (int)((thickness + (XY_ONE >> 1)) >> XY_SHIFT));
+      circle_filled(plane, cx, cy, (int)((thickness + (XY_ONE >> 1)) >> XY_SHIFT), L);
     }
     p0 = p1;
   }
 }
 
 /* cv2.line(img, p0, p1, 1, thickness) */
-RP_FN void cv_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thickness) {
+RP_FN void cv_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thickness, Lanes L) {
   P2 a, b;
   a.x = x0; a.y = y0; b.x = x1; b.y = y1;
-  thick_line(plane, a, b, thickness, 3);
+  thick_line(plane, a, b, thickness, 3, L);
 }
 /* cv2.rectangle(img, p0, p1, 1, -1) */
-RP_FN void cv_rectangle_filled(uint32_t* plane, int x0, int y0, int x1, int y1) {
+RP_FN void cv_rectangle_filled(uint32_t* plane, int x0, int y0, int x1, int y1, Lanes L) {
   P2 pt[4];
   pt[0].x = x0; pt[0].y = y0; pt[1].x = x1; pt[1].y = y0; pt[2].x = x1; pt[2].y = y1; pt[3].x = x0; pt[3].y = y1;
-  fill_convex4(plane, pt, 0);
+  fill_convex4(plane, pt, 0, L);
 }
 /* segment i (1 <= i < count) of cv2.polylines(img, [pts], False, 1, thickness): PolyLine() caps the first segment at
    both ends and every later one at its far end */
-RP_FN void cv_polyline_segment(uint32_t* plane, int xa, int ya, int xb, int yb, int thickness, int i) {
+RP_FN void cv_polyline_segment(uint32_t* plane, int xa, int ya, int xb, int yb, int thickness, int i, Lanes L) {
   P2 a, b;
   a.x = xa; a.y = ya; b.x = xb; b.y = yb;
-  thick_line(plane, a, b, thickness, i == 1 ? 3 : 2);
+  thick_line(plane, a, b, thickness, i == 1 ? 3 : 2, L);
 }
 
 }  // namespace raster

@@ -1,11 +1,13 @@
 /*
- * IMAGE observation raster kernel: one thread block draws the four bit-planes of one camera of one raw detection
- * record (include/dynenv_b200.h RC_R_*, raster_compose.cuh) in shared memory and streams them to HBM.
+ * IMAGE observation raster kernel: one thread block draws ONE bit-plane (480 x 640 bits, 38 400 bytes) of one raw
+ * detection record (include/dynenv_b200.h RC_R_*, raster_compose.cuh) in shared memory and hands it to the TMA engine
+ * (cp.async.bulk shared -> global), so that the next block on the SM draws while the previous plane drains to HBM.
  *
  * Replaces the drawing half of getAgentVision (RoboCupEnvironment.py:1318-1467) -- cv2.line / polylines / rectangle /
  * circle on 2 x 4 planes of 480 x 640 float64 per robot and tick, 19.7 MB in the reference -- by 307 KB of bit-planes.
- * The kernel is HBM-write bound by construction: 153 600 bytes per block leave through coalesced 128-bit stores,
- * the drawing is atomicOr on shared-memory words (primitives and poly-line segments spread over the threads).
+ * HBM-write bound by construction: every plane is written exactly once.  Drawing: one warp per primitive (or
+ * poly-line segment of the centre-circle conic), its rows / pixels in closed form on the 32 lanes (raster_prims.cuh),
+ * atomicOr on shared-memory words.  Four to five blocks fit an SM.
  */
 #pragma once
 #include "dynenv_common.cuh"
@@ -14,10 +16,10 @@
 namespace dynenv {
 namespace rcimg {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 256, WARPS = THREADS / 32;
 /* shared-memory layout in 32-bit words */
-constexpr int S_PLANES = 0;                                   /* [4][PLANE_WORDS] */
-constexpr int S_RAW = S_PLANES + 4 * raster::PLANE_WORDS;     /* [RC_RAW_WORDS]   */
+constexpr int S_PLANE = 0;                                    /* [PLANE_WORDS]    */
+constexpr int S_RAW = S_PLANE + raster::PLANE_WORDS;          /* [RC_RAW_WORDS]   */
 constexpr int S_PRIMS = S_RAW + RC_RAW_WORDS;                 /* Prim[MAX_PRIMS]  */
 constexpr int PRIM_WORDS = sizeof(raster::Prim) / 4;
 constexpr int S_CONIC = S_PRIMS + raster::MAX_PRIMS * PRIM_WORDS; /* Conic */
@@ -27,13 +29,24 @@ constexpr int S_PARAMS = (S_TMP + 3 * raster::CONIC_ROWS + 1) / 2 * 2; /* double
 constexpr int S_MISC = S_PARAMS + 16;                         /* [0] number of primitives, [1] conic present */
 constexpr int SMEM_WORDS = S_MISC + 4;
 
-__global__ void __launch_bounds__(THREADS, 1)
+__device__ __forceinline__ void bulk_store_plane(uint32_t* gdst, const uint32_t* ssrc) {
+  /* generic-proxy writes (atomicOr) -> async proxy read; one elected thread issues the copy and keeps the block
+     alive until the engine has read the shared memory */
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(raster::PLANE_WORDS * 4)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 4)
 rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* __restrict__ images) {
-  const int tid = threadIdx.x;
-  const long long rec = blockIdx.x >> 1;
-  const int cam = blockIdx.x & 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long rec = blockIdx.x >> 3;
+  const int plane_id = blockIdx.x & 7, cam = plane_id >> 2, ch = plane_id & 3;
   if (rec >= n_records) return;
-  uint32_t* planes = g_smem + S_PLANES;
+  uint32_t* plane = g_smem + S_PLANE;
   float* sraw = reinterpret_cast<float*>(g_smem + S_RAW);
   raster::Prim* prims = reinterpret_cast<raster::Prim*>(g_smem + S_PRIMS);
   raster::Conic* conic = reinterpret_cast<raster::Conic*>(g_smem + S_CONIC);
@@ -41,57 +54,75 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   double* params = reinterpret_cast<double*>(g_smem + S_PARAMS);
   int* misc = reinterpret_cast<int*>(g_smem + S_MISC);
   {
-    uint4* p4 = reinterpret_cast<uint4*>(planes);
-    for (int w = tid; w < raster::PLANE_WORDS; w += THREADS) p4[w] = make_uint4(0, 0, 0, 0); /* 4 planes = PLANE_WORDS uint4 */
+    uint4* p4 = reinterpret_cast<uint4*>(plane);
+    for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) p4[w] = make_uint4(0, 0, 0, 0);
     if (tid < RC_RAW_WORDS) sraw[tid] = raw[rec * RC_RAW_WORDS + tid];
+    if (tid == 0) { misc[0] = raster::N_SLOTS; misc[1] = 0; conic->n = 0; }
   }
   __syncthreads();
-  /* primitives: one slot per thread (float64 projections); the conic fit on another warp */
+  /* primitives of this plane: one slot per thread (float64 projections); the conic fit on another warp */
   if (tid < raster::N_SLOTS) {
     raster::Prim p;
-    if (!raster::build_prim_slot(sraw, cam, tid, &p)) p.type = -1;
+    p.type = -1;
+    if (raster::slot_plane(tid) == ch && !raster::build_prim_slot(sraw, cam, tid, &p)) p.type = -1;
     prims[tid] = p;
   }
-  if (tid == 64) {
+  if (ch == 3 && tid == 64) {
     int thickness = 0;
     double cx, cy;
     const bool ok = raster::conic_setup(sraw, cam, params, &cx, &cy, &thickness);
     params[6] = cx; params[7] = cy;
     misc[1] = ok ? 1 : 0;
     conic->thickness = thickness;
-    conic->n = 0;
   }
   __syncthreads();
-  int nprims = raster::N_SLOTS;
-  if (misc[1]) {
+  if (misc[1]) { /* block-uniform */
     for (int y = tid; y < raster::CONIC_ROWS; y += THREADS) {
       int x1 = 0, x2 = 0;
       const bool v = raster::conic_row(params, params[6], params[7], y, &x1, &x2);
       tmp[y] = x1; tmp[raster::CONIC_ROWS + y] = x2; tmp[2 * raster::CONIC_ROWS + y] = v ? 1 : 0;
     }
     __syncthreads();
-    if (tid == 0) { /* compaction in row order (rare path, 480 steps) */
+    if (warp == 0) { /* compaction in row order: ballot prefix over 15 groups of 32 rows */
       int n = 0;
-      for (int y = 0; y < raster::CONIC_ROWS; y++)
-        if (tmp[2 * raster::CONIC_ROWS + y]) { conic->x1[n] = tmp[y]; conic->x2[n] = tmp[raster::CONIC_ROWS + y]; conic->y[n] = (short)y; n++; }
-      conic->n = n;
-      misc[0] = raster::conic_closures(*conic, prims, raster::N_SLOTS);
+      for (int y0 = 0; y0 < raster::CONIC_ROWS; y0 += 32) {
+        const int y = y0 + lane;
+        const bool v = tmp[2 * raster::CONIC_ROWS + y] != 0;
+        const unsigned bal = __ballot_sync(FULLMASK, v);
+        if (v) {
+          const int k = n + __popc(bal & ((1u << lane) - 1));
+          conic->x1[k] = tmp[y]; conic->x2[k] = tmp[raster::CONIC_ROWS + y]; conic->y[k] = (short)y;
+        }
+        n += __popc(bal);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        conic->n = n;
+        misc[0] = raster::conic_closures(*conic, prims, raster::N_SLOTS);
+      }
     }
     __syncthreads();
-    nprims = misc[0];
   }
+  const int nprims = misc[0];
   const int nseg = conic->n > 1 ? 2 * (conic->n - 1) : 0;
-  for (int w = tid; w < nprims + nseg; w += THREADS) {
-    if (w < nprims) {
-      if (prims[w].type >= 0) raster::draw_prim(planes, prims[w]);
-    } else raster::draw_conic_segment(planes, *conic, w - nprims);
-  }
-  __syncthreads();
+  const raster::Lanes L = {lane, 32};
   {
-    uint4* dst = reinterpret_cast<uint4*>(images + (size_t)rec * RC_IMG_WORDS + (size_t)cam * 4 * raster::PLANE_WORDS);
-    const uint4* src = reinterpret_cast<const uint4*>(planes);
-    for (int w = tid; w < raster::PLANE_WORDS; w += THREADS) dst[w] = src[w];
+    /* large primitives (a field line next to the robot is hundreds of pixels thick): rows over the whole block;
+       the others: one warp per primitive, rows / pixels on its lanes */
+    const raster::Lanes B = {tid, THREADS};
+    int k = 0; /* small primitives seen so far (block-uniform) */
+    for (int w = 0; w < nprims; w++) {
+      const raster::Prim p = prims[w];
+      if (p.type < 0) continue;
+      if (raster::prim_is_big(p)) raster::draw_prim(plane, p, B);
+      else if ((k++ % WARPS) == warp) raster::draw_prim(plane, p, L);
+    }
   }
+  /* the conic's ~2 x 479 poly-line segments are one pixel high and `thickness` wide: one thread per segment */
+  const raster::Lanes one = {0, 1};
+  for (int sgm = tid; sgm < nseg; sgm += THREADS) raster::draw_conic_segment(plane, *conic, sgm, one);
+  __syncthreads();
+  if (tid == 0) bulk_store_plane(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS, plane);
 }
 
 }  // namespace rcimg

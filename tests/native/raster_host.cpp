@@ -6,10 +6,14 @@ void rp_render(const float* raw, uint32_t* planes) {
   raster::render_camera_host(raw, 0, planes);
   raster::render_camera_host(raw, 1, planes + 4 * raster::PLANE_WORDS);
 }
-void rp_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thickness) { raster::cv_line(plane, x0, y0, x1, y1, thickness); }
-void rp_rect(uint32_t* plane, int x0, int y0, int x1, int y1) { raster::cv_rectangle_filled(plane, x0, y0, x1, y1); }
-void rp_circle(uint32_t* plane, int cx, int cy, int r) { raster::circle_filled(plane, cx, cy, r); }
+// `lanes` > 1 emulates the cooperating lanes of a warp one after the other (same pixels, any order)
+static int g_lanes = 1;
+void rp_set_lanes(int n) { g_lanes = n; }
+#define FOR_LANES for (raster::Lanes L = {0, g_lanes}; L.lane < g_lanes; L.lane++)
+void rp_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thickness) { FOR_LANES raster::cv_line(plane, x0, y0, x1, y1, thickness, L); }
+void rp_rect(uint32_t* plane, int x0, int y0, int x1, int y1) { FOR_LANES raster::cv_rectangle_filled(plane, x0, y0, x1, y1, L); }
+void rp_circle(uint32_t* plane, int cx, int cy, int r) { FOR_LANES raster::circle_filled(plane, cx, cy, r, L); }
 void rp_polyline(uint32_t* plane, const int* pts, int n, int thickness) {
-  for (int i = 1; i < n; i++) raster::cv_polyline_segment(plane, pts[2 * i - 2], pts[2 * i - 1], pts[2 * i], pts[2 * i + 1], thickness, i);
+  for (int i = 1; i < n; i++) FOR_LANES raster::cv_polyline_segment(plane, pts[2 * i - 2], pts[2 * i - 1], pts[2 * i], pts[2 * i + 1], thickness, i, L);
 }
 }

@@ -61,6 +61,35 @@ def test_primitives_match_cv2(lib):
         assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("circle", x0, y0, r)
 
 
+def test_cooperative_lanes_draw_the_same_pixels(lib):
+    """the CUDA kernel spreads rows / pixels of a primitive over 32 lanes (or 256 threads) in closed form: emulate the
+    lanes one after the other on the host"""
+    rng = np.random.default_rng(9)
+    for lanes in (32, 256):
+        lib.rp_set_lanes(lanes)
+        try:
+            for it in range(250):
+                far = rng.random() < 0.3
+                x0, y0 = _coord(rng, far)
+                x1, y1 = _coord(rng, far)
+                t = int(rng.integers(1, 60))
+                ref = np.zeros((480, 640))
+                cv2.line(ref, (x0, y0), (x1, y1), 1, t)
+                p = np.zeros((480, 20), np.uint32)
+                lib.rp_line(p.ctypes.data, x0, y0, x1, y1, t)
+                assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("line", lanes, x0, y0, x1, y1, t)
+                r = int(rng.integers(0, 200))
+                ref = np.zeros((480, 640))
+                cv2.circle(ref, (x0, y0), r, 1, -1)
+                cv2.rectangle(ref, (x0, y0), (x1, y1), 1, -1)
+                p = np.zeros((480, 20), np.uint32)
+                lib.rp_circle(p.ctypes.data, x0, y0, r)
+                lib.rp_rect(p.ctypes.data, x0, y0, x1, y1)
+                assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("circle+rect", lanes, x0, y0, x1, y1, r)
+        finally:
+            lib.rp_set_lanes(1)
+
+
 def test_polylines_match_cv2(lib):
     rng = np.random.default_rng(8)
     for it in range(150):
