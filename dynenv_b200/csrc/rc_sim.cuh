@@ -2153,9 +2153,17 @@ __device__ __forceinline__ void clear_step_scratch(const Env E) {
 __device__ __forceinline__ void phys_substeps(const Env E, const float* actions_env, int sub_b, int sub_e, bool first) {
   if (first) clear_step_scratch(E);
   const uint32_t pairs4 = broadphase_pairs(E);
+#ifndef RC_PHASE_SYNC
+#define RC_PHASE_SYNC 0
+#endif
   for (int sub = sub_b; sub < sub_e; sub++) {
+    /* (RC_PHASE_SYNC: the warps of a block enter every phase together, so that they share its instructions in the
+       instruction cache -- the kernel is bound by instruction fetch) */
+    if (RC_PHASE_SYNC >= 1) __syncthreads();
     robots_phase(E, sub, actions_env);
+    if (RC_PHASE_SYNC >= 2) __syncthreads();
     ball_out_of_field(E);
+    if (RC_PHASE_SYNC >= 2) __syncthreads();
     space_step(E, pairs4);
     if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
     __syncwarp();
