@@ -41,6 +41,7 @@ class RoboCupWorkload(object):
     launches_per_step = {"phys": 5, "obs": 5, "finish": 1}
     prefix = "rc"
     cpu_steps, ref_steps, cpu_warm = 20000, 1000, 50  # env-steps per host thread: cpu_baseline sample, reference-arm step, warm-up
+    default_steps = 240  # one whole episode (12000 / 50): contacts, falls and penalties build up over an episode
 
     def make_sim(self, E, local, rank, full=False):
         import dynenv_b200
@@ -92,6 +93,7 @@ class DrivingWorkload(object):
     launches_per_step = {"phys": 1, "obs": 1, "finish": 0}
     prefix = "drv"
     cpu_steps, ref_steps, cpu_warm = 10000, 1000, 50
+    default_steps = 600  # one whole episode (6000 / 10)
 
     def make_sim(self, E, local, rank, full=False):
         import dynenv_b200
@@ -183,6 +185,7 @@ class ImageWorkload(RoboCupWorkload):
     chunk = 1024
     default_envs = 16384
     cpu_steps, ref_steps, cpu_warm = 16, 4, 1  # an env-step draws 100 images with cv2 (~0.3 s)
+    default_steps = 10
 
     def make_sim(self, E, local, rank, full=False):
         import dynenv_b200
@@ -464,6 +467,7 @@ def run_gpu(args):
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict({"workload": WORKLOAD, "envs_per_gpu": E, "envs_total": total_envs,
+                                "episode_steps": [args.warmup, args.warmup + args.steps],  # window of the timed steps in the episode(s)
                                 "l2": "state + outputs per step (%.1f GB) exceed the 126 MB L2" % (bytes_launch / 1e9)},
                                **wl.config(L)),
                 "clocks": clocks, "gpu_launches": launches,
@@ -497,7 +501,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: one episode of the workload; reference arm 3)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 65536; image workload 16384)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -506,6 +510,8 @@ def main():
     ap.add_argument("--debug-full-obs", action="store_true", help="(profiling aid) FULL observations: physics and rules only")
     ap.add_argument("--cpu-steps", type=int, default=None, help="env-steps per host thread of the cpu_baseline sample")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 3 if args.impl == "reference" else WORKLOADS[args.workload].default_steps
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -159,3 +159,27 @@ def test_driving_results_do_not_depend_on_sharding():
         assert torch.equal(ow.record, torch.cat([o.record for o in op]))
         assert torch.equal(ow.info, torch.cat([o.info for o in op]))
     assert torch.equal(whole.get_state(), torch.cat([p.get_state() for p in parts]))
+
+
+def test_device_arranger_on_simulator_outputs():
+    """the InOutArranger equivalent on the device tensors of a step == the same arrays built from the reference-format
+    nested lists (what the reference's model would do in Python)"""
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import reference_format as RF
+    from dynenv_b200.arranger import DeviceArranger, robocup_rows
+    sim = dynenv_b200.BatchedRoboCup(5, 3, noiseMagnitude=2.0, seed=3)
+    sim.reset()
+    out = sim.step((torch.rand((5, 6, 4)) * torch.tensor([5, 3, 3, 7])).floor().cuda())
+    arr = DeviceArranger(*robocup_rows(out))
+    inputs, (counts, maxCount, objCounts) = arr.rearrange_inputs()
+    v = RF.host_views(out, False)
+    obs = [RF.observations(v, e, 6, False) for e in range(5)]
+    for i in range(6):  # flat per-type arrays in (time, env x player, row) order
+        ref = [obs[e][t][a][i // 2 if i < 2 else 1][i if i < 2 else i - 2] for t in range(5) for e in range(5) for a in range(6)]
+        ref = [r for r in ref if r.ndim == 2]
+        ref = np.concatenate(ref) if ref else np.zeros((0, inputs[i].shape[1]), np.float32)
+        assert np.array_equal(inputs[i].cpu().numpy(), ref), i
+    padded, masks = arr.rearrange_outputs([x[:, :2] for x in inputs])
+    assert padded.shape == (5, maxCount, 30, 2) and len(masks) == 5 and masks[0].shape == (30, maxCount)
+    assert int((~masks[2]).sum()) == int(objCounts[2].sum())
