@@ -459,8 +459,8 @@ def run_gpu(args):
         traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s_%s_kernel" % (wl.prefix, dom))
-            if tr:
-                traffic = tr["dram_bytes_per_launch"] * E / tr["envs"]
+            if tr:  # scaled to the environments one launch of this run covers
+                traffic = tr["dram_bytes_per_launch"] * (min(getattr(wl, "chunk", E), E) if dom == "raster" else E) / tr["envs"]
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

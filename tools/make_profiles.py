@@ -51,7 +51,8 @@ for short, (kern, what, units) in KERNELS.items():
             lines.append("  %-92s %-16s %s" % (m, u[i], v[i]))
             if m.startswith("dram__bytes"):
                 dram += float(v[i]) * BYTE_UNITS.get(u[i], 1)
-    traffic[kern] = {"dram_bytes_per_launch": dram, "units_per_launch": units, "source": "profiles/%s_ncu_%s.txt" % (tag, short)}
+    traffic[kern] = {"dram_bytes_per_launch": dram, "envs": 1024 if short == "rc_raster" else 65536,
+                     "source": "profiles/%s_ncu_%s.txt" % (tag, short)}
     env = dict(os.environ, KERNEL=kern, NENV=str(units))
     tab = subprocess.run([sys.executable, "tools/prof_by_func.py", rep], capture_output=True, text=True, env=env).stdout
     lines += ["", "per device function (instructions per unit = per environment-substep / observer-tick / plane; stall samples):", tab]
