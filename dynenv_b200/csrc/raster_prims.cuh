@@ -15,8 +15,10 @@
 
 #ifdef __CUDACC__
 #define RP_FN __host__ __device__ inline
+#define RP_BIG __host__ __device__ __noinline__ /* one copy of the larger routines per kernel: the raster kernel is instruction-fetch bound */
 #else
 #define RP_FN inline
+#define RP_BIG inline
 #endif
 
 namespace raster {
@@ -100,7 +102,7 @@ struct Lanes {
 /* Line(): cv::LineIterator, 8-connected, left to right, after clipping to the image.  Pixel i lies i steps along the
    major axis and m_i steps along the minor one, where m_i counts the earlier iterations whose error term was negative:
    m_i = max(0, ceil((2 dy i - dx) / (2 dx))) for the iterator's err_0 = dx - 2 dy, err += -2 dy (+ 2 dx when negative). */
-RP_FN void line_thin(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
+RP_BIG void line_thin(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
   if ((uint64_t)pt1.x >= (uint64_t)IMG_W || (uint64_t)pt2.x >= (uint64_t)IMG_W || (uint64_t)pt1.y >= (uint64_t)IMG_H ||
       (uint64_t)pt2.y >= (uint64_t)IMG_H) {
     if (!clip_line(IMG_W, IMG_H, pt1, pt2)) return;
@@ -124,7 +126,7 @@ RP_FN void line_thin(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
 }
 
 /* Line2(): line between fixed-point (XY_SHIFT) end points */
-RP_FN void line2(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
+RP_BIG void line2(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
   if (!clip_line((int64_t)IMG_W << XY_SHIFT, (int64_t)IMG_H << XY_SHIFT, pt1, pt2)) return;
   int64_t dx = pt2.x - pt1.x, dy = pt2.y - pt1.y;
   int64_t j = dx < 0 ? -1 : 0;
@@ -160,28 +162,57 @@ RP_FN void line2(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
   }
 }
 
+/* vertex k (k in 0..3) of a quadrilateral held in registers (no indexed array: local memory is what the raster kernel
+   cannot afford, its blocks leave the SM almost no L1) */
+struct Quad {
+  P2 a, b, c, d;
+};
+RP_FN P2 qget(const Quad& q, int k) { return k == 0 ? q.a : (k == 1 ? q.b : (k == 2 ? q.c : q.d)); }
+
+/* one edge cursor of FillConvexPoly: up to three re-seeding events (row, x, dx) */
+struct EdgeEvents {
+  int n, y0, y1, y2;
+  int64_t x0, x1, x2, dx0, dx1, dx2;
+};
+RP_FN void ev_push(EdgeEvents& e, int y, int64_t x, int64_t dx) {
+  if (e.n == 0) { e.y0 = y; e.x0 = x; e.dx0 = dx; }
+  else if (e.n == 1) { e.y1 = y; e.x1 = x; e.dx1 = dx; }
+  else { e.y2 = y; e.x2 = x; e.dx2 = dx; }
+  e.n++;
+}
+RP_FN int64_t ev_x_at(const EdgeEvents& e, int yy) { /* the cursor's x in row yy: last event at or above yy */
+  if (e.n > 2 && e.y2 <= yy) return e.x2 + e.dx2 * (yy - e.y2);
+  if (e.n > 1 && e.y1 <= yy) return e.x1 + e.dx1 * (yy - e.y1);
+  return e.x0 + e.dx0 * (yy - e.y0);
+}
+
 /* FillConvexPoly() for 4 vertices, line_type LINE_8; `shift` = 0 (integer vertices) or XY_SHIFT.  OpenCV walks the
    rows with two edge cursors (x += dx per row) that it re-seeds at vertex rows; here the re-seeding events are found
    first (row, x, dx per cursor: the same control flow, jumping from vertex row to vertex row), then every row's span
    follows in closed form and the rows are spread over the lanes. */
-RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift, Lanes L) {
+RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
   const int npts = 4;
-  struct Edge { int idx, di; int ye; } edge[2];
-  int ev_n[2] = {0, 0};
-  int ev_y[2][5];
-  int64_t ev_x[2][5], ev_dx[2][5];
+  int e_idx0, e_idx1, e_ye0, e_ye1; /* the two cursors: current vertex, end row */
+  EdgeEvents ev0, ev1;
+  ev0.n = ev1.n = 0;
+  ev0.y0 = ev0.y1 = ev0.y2 = ev1.y0 = ev1.y1 = ev1.y2 = 0;
+  ev0.x0 = ev0.x1 = ev0.x2 = ev0.dx0 = ev0.dx1 = ev0.dx2 = 0;
+  ev1.x0 = ev1.x1 = ev1.x2 = ev1.dx0 = ev1.dx1 = ev1.dx2 = 0;
   const int delta = 1 << shift >> 1;
   int i, y, imin = 0;
   int edges = npts;
   int64_t xmin, xmax, ymin, ymax;
   const int delta1 = (int)(XY_ONE >> 1);
-  P2 p0 = v[npts - 1];
+  P2 p0 = v.d;
   p0.x <<= XY_SHIFT - shift;
   p0.y <<= XY_SHIFT - shift;
-  xmin = xmax = v[0].x;
-  ymin = ymax = v[0].y;
+  xmin = xmax = v.a.x;
+  ymin = ymax = v.a.y;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
   for (i = 0; i < npts; i++) {
-    P2 p = v[i];
+    P2 p = qget(v, i);
     if (p.y < ymin) { ymin = p.y; imin = i; }
     ymax = ymax > p.y ? ymax : p.y;
     xmax = xmax > p.x ? xmax : p.x;
@@ -201,29 +232,27 @@ RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift, Lanes L) {
   ymax = (ymax + delta) >> shift;
   if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= IMG_W || (int)ymin >= IMG_H) return;
   ymax = ymax < IMG_H - 1 ? ymax : IMG_H - 1;
-  edge[0].idx = edge[1].idx = imin;
-  edge[0].ye = edge[1].ye = y = (int)ymin;
-  edge[0].di = 1;
-  edge[1].di = npts - 1;
+  e_idx0 = e_idx1 = imin;
+  e_ye0 = e_ye1 = y = (int)ymin;
   int yend;
   for (;;) { /* row y: a cursor whose edge ends here takes the next edge that reaches below y */
     for (i = 0; i < 2; i++) {
-      if (y >= edge[i].ye) {
-        int idx0 = edge[i].idx, di = edge[i].di;
+      const int ye = i ? e_ye1 : e_ye0;
+      if (y >= ye) {
+        int idx0 = i ? e_idx1 : e_idx0;
+        const int di = i ? npts - 1 : 1;
         int idx = idx0 + di;
         if (idx >= npts) idx -= npts;
         int ty = 0;
         for (; edges-- > 0;) {
-          ty = (int)((v[idx].y + delta) >> shift);
+          const P2 pv = qget(v, idx);
+          ty = (int)((pv.y + delta) >> shift);
           if (ty > y) {
-            int64_t xs = v[idx0].x, xe = v[idx].x;
+            int64_t xs = qget(v, idx0).x, xe = pv.x;
             if (shift != XY_SHIFT) { xs <<= XY_SHIFT - shift; xe <<= XY_SHIFT - shift; }
-            edge[i].ye = ty;
-            edge[i].idx = idx;
-            const int k = ev_n[i]++;
-            ev_y[i][k] = y;
-            ev_x[i][k] = xs;
-            ev_dx[i][k] = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+            const int64_t dxe = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+            if (i) { e_ye1 = ty; e_idx1 = idx; ev_push(ev1, y, xs, dxe); }
+            else { e_ye0 = ty; e_idx0 = idx; ev_push(ev0, y, xs, dxe); }
             break;
           }
           idx0 = idx;
@@ -233,20 +262,15 @@ RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift, Lanes L) {
       }
     }
     if (edges < 0) { yend = y - 1; break; }
-    const int ynext = edge[0].ye < edge[1].ye ? edge[0].ye : edge[1].ye;
+    const int ynext = e_ye0 < e_ye1 ? e_ye0 : e_ye1;
     if (ynext > (int)ymax) { yend = (int)ymax; break; }
     y = ynext;
   }
-  if (ev_n[0] == 0 || ev_n[1] == 0) return;
+  if (ev0.n == 0 || ev1.n == 0) return;
   const int ystart = (int)ymin > 0 ? (int)ymin : 0;
   for (int yy = ystart + L.lane; yy <= yend; yy += L.n) {
-    int64_t x[2];
-    for (i = 0; i < 2; i++) {
-      int k = ev_n[i] - 1;
-      while (k > 0 && ev_y[i][k] > yy) k--;
-      x[i] = ev_x[i][k] + ev_dx[i][k] * (yy - ev_y[i][k]);
-    }
-    const int64_t xl = x[0] > x[1] ? x[1] : x[0], xr = x[0] > x[1] ? x[0] : x[1];
+    const int64_t xa = ev_x_at(ev0, yy), xb = ev_x_at(ev1, yy);
+    const int64_t xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
     int xx1 = (int)((xl + delta1) >> XY_SHIFT);
     int xx2 = (int)((xr + delta1) >> XY_SHIFT);
     if (xx2 >= 0 && xx1 < IMG_W) {
@@ -259,7 +283,7 @@ RP_FN void fill_convex4(uint32_t* plane, const P2* v, int shift, Lanes L) {
 
 /* Circle() with fill: Bresenham circle, horizontal spans.  The (dx, dy) sequence is walked by every lane; iteration k
    draws its four spans on lane k % n. */
-RP_FN void circle_filled(uint32_t* plane, int cx, int cy, int radius, Lanes L) {
+RP_BIG void circle_filled(uint32_t* plane, int cx, int cy, int radius, Lanes L) {
   int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
   int it = 0;
   while (dx >= dy) {
@@ -299,7 +323,7 @@ RP_FN int64_t cv_round(double v) { /* cvRound: round half to even (lrint in the 
 }
 
 /* ThickLine() with integer end points; flags bit 0 / 1: round cap at p0 / p1 */
-RP_FN void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, Lanes L) {
+RP_BIG void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, Lanes L) {
   const double INV_XY_ONE = 1. / XY_ONE;
   if (thickness <= 1) { /* shift == 0: the end points are integers */
     line_thin(plane, p0, p1, L);
@@ -312,7 +336,8 @@ RP_FN void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, L
     p0.x -= m; p0.y -= m; p1.x -= m; p1.y -= m;
   }
   p0.x <<= XY_SHIFT; p0.y <<= XY_SHIFT; p1.x <<= XY_SHIFT; p1.y <<= XY_SHIFT;
-  P2 pt[4], dp;
+  Quad pt;
+  P2 dp;
   dp.x = dp.y = 0;
   double dx = (p0.x - p1.x) * INV_XY_ONE, dy = (p1.y - p0.y) * INV_XY_ONE;
   double r = dx * dx + dy * dy;
@@ -326,10 +351,10 @@ RP_FN void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, L
 #endif
     dp.x = cv_round(dy * r);
     dp.y = cv_round(dx * r);
-    pt[0].x = p0.x + dp.x; pt[0].y = p0.y + dp.y;
-    pt[1].x = p0.x - dp.x; pt[1].y = p0.y - dp.y;
-    pt[2].x = p1.x - dp.x; pt[2].y = p1.y - dp.y;
-    pt[3].x = p1.x + dp.x; pt[3].y = p1.y + dp.y;
+    pt.a.x = p0.x + dp.x; pt.a.y = p0.y + dp.y;
+    pt.b.x = p0.x - dp.x; pt.b.y = p0.y - dp.y;
+    pt.c.x = p1.x - dp.x; pt.c.y = p1.y - dp.y;
+    pt.d.x = p1.x + dp.x; pt.d.y = p1.y + dp.y;
     fill_convex4(plane, pt, XY_SHIFT, L);
   }
   for (int i = 0; i < 2; i++) {
@@ -349,8 +374,8 @@ RP_FN void cv_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thicknes
 }
 /* cv2.rectangle(img, p0, p1, 1, -1) */
 RP_FN void cv_rectangle_filled(uint32_t* plane, int x0, int y0, int x1, int y1, Lanes L) {
-  P2 pt[4];
-  pt[0].x = x0; pt[0].y = y0; pt[1].x = x1; pt[1].y = y0; pt[2].x = x1; pt[2].y = y1; pt[3].x = x0; pt[3].y = y1;
+  Quad pt;
+  pt.a.x = x0; pt.a.y = y0; pt.b.x = x1; pt.b.y = y0; pt.c.x = x1; pt.c.y = y1; pt.d.x = x0; pt.d.y = y1;
   fill_convex4(plane, pt, 0, L);
 }
 /* segment i (1 <= i < count) of cv2.polylines(img, [pts], False, 1, thickness): PolyLine() caps the first segment at

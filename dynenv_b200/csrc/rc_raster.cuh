@@ -7,7 +7,12 @@
  * circle on 2 x 4 planes of 480 x 640 float64 per robot and tick, 19.7 MB in the reference -- by 307 KB of bit-planes.
  * HBM-write bound by construction: every plane is written exactly once.  Drawing: one warp per primitive (or
  * poly-line segment of the centre-circle conic), its rows / pixels in closed form on the 32 lanes (raster_prims.cuh),
- * atomicOr on shared-memory words.  Four to five blocks fit an SM.
+ * atomicOr on shared-memory words.  Three blocks per SM.
+ *
+ * Measured (1024 environments = 409 600 planes per launch): zero + store alone 2.6 ms (6.0 TB/s, 92 % of the HBM peak);
+ * with the primitives 12 ms, with the centre-circle conic 13 ms, everything 28-30 ms (RASTER_SKIP_* ablations below):
+ * the drawing, not the store, is what keeps this kernel off its roofline.  The drawing routines are compiled once
+ * (noinline): inlined into their three call sites the kernel is 207 KB of SASS and 50 % slower (instruction fetch).
  */
 #pragma once
 #include "dynenv_common.cuh"
@@ -40,7 +45,10 @@ __device__ __forceinline__ void bulk_store_plane(uint32_t* gdst, const uint32_t*
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 4)
+#ifndef RASTER_MINB
+#define RASTER_MINB 3 /* 80 registers; measured 29.8 ms per 1024 environments against 32.5 ms at 4 blocks / 64 registers */
+#endif
+__global__ void __launch_bounds__(THREADS, RASTER_MINB)
 rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* __restrict__ images) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long rec = blockIdx.x >> 3;
@@ -75,7 +83,12 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     misc[1] = ok ? 1 : 0;
     conic->thickness = thickness;
   }
-  __syncthreads();
+  /* a plane without anything to draw (no ball in sight, no goal post ...) is streamed out as zeros from registers */
+  if (__syncthreads_count(tid < raster::N_SLOTS && prims[tid].type >= 0) == 0 && !(ch == 3 && misc[1])) {
+    uint4* dst = reinterpret_cast<uint4*>(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS);
+    for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) dst[w] = make_uint4(0, 0, 0, 0);
+    return;
+  }
   if (misc[1]) { /* block-uniform */
     for (int y = tid; y < raster::CONIC_ROWS; y += THREADS) {
       int x1 = 0, x2 = 0;
@@ -114,15 +127,32 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     for (int w = 0; w < nprims; w++) {
       const raster::Prim p = prims[w];
       if (p.type < 0) continue;
-      if (raster::prim_is_big(p)) raster::draw_prim(plane, p, B);
-      else if ((k++ % WARPS) == warp) raster::draw_prim(plane, p, L);
+#ifdef RASTER_SKIP_PRIMS
+      continue;
+#endif
+      if (raster::prim_is_big(p)) {
+#ifndef RASTER_SKIP_BIG
+        raster::draw_prim(plane, p, B);
+#endif
+      } else if ((k++ % WARPS) == warp) raster::draw_prim(plane, p, L);
     }
   }
   /* the conic's ~2 x 479 poly-line segments are one pixel high and `thickness` wide: one thread per segment */
   const raster::Lanes one = {0, 1};
+#ifndef RASTER_SKIP_CONIC
   for (int sgm = tid; sgm < nseg; sgm += THREADS) raster::draw_conic_segment(plane, *conic, sgm, one);
+#endif
   __syncthreads();
+#ifdef RASTER_BULK_STORE
   if (tid == 0) bulk_store_plane(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS, plane);
+#else
+  {
+    uint4* dst = reinterpret_cast<uint4*>(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS);
+    const uint4* src = reinterpret_cast<const uint4*>(plane);
+#pragma unroll 5
+    for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) dst[w] = src[w];
+  }
+#endif
 }
 
 }  // namespace rcimg
