@@ -53,6 +53,21 @@ RP_FN void put_point(uint32_t* plane, int64_t x, int64_t y) {
   if (x >= 0 && x < IMG_W && y >= 0 && y < IMG_H) or_word(plane + (int)y * WORDS_PER_ROW + ((int)x >> 5), 1u << ((int)x & 31));
 }
 
+/* a / b of C (truncation towards zero) for b > 0 and |a| < 2^53: on the device a float64 division and one correction
+   instead of the ~100-instruction 64-bit integer division routine (the quotient of the correctly rounded division can
+   only exceed the exact one by 1) */
+RP_FN int64_t div_trunc(int64_t a, int64_t b) {
+#ifdef __CUDA_ARCH__
+  const bool neg = a < 0;
+  const int64_t ua = neg ? -a : a;
+  int64_t q = (int64_t)((double)ua / (double)b);
+  if (q * b > ua) q--;
+  return neg ? -q : q;
+#else
+  return a / b;
+#endif
+}
+
 /* cv::clipLine(Size2l, Point2l&, Point2l&) */
 RP_FN bool clip_line(int64_t width, int64_t height, P2& pt1, P2& pt2) {
   const int64_t right = width - 1, bottom = height - 1;
@@ -140,13 +155,13 @@ RP_BIG void line2(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
     pt1.x ^= pt2.x & j; pt2.x ^= pt1.x & j; pt1.x ^= pt2.x & j;
     pt1.y ^= pt2.y & j; pt2.y ^= pt1.y & j; pt1.y ^= pt2.y & j;
     x_step = XY_ONE;
-    y_step = (dy << XY_SHIFT) / (ax | 1);
+    y_step = div_trunc(dy << XY_SHIFT, ax | 1);
     ecount = (int)((pt2.x - pt1.x) >> XY_SHIFT);
   } else {
     dx = (dx ^ i) - i;
     pt1.x ^= pt2.x & i; pt2.x ^= pt1.x & i; pt1.x ^= pt2.x & i;
     pt1.y ^= pt2.y & i; pt2.y ^= pt1.y & i; pt1.y ^= pt2.y & i;
-    x_step = (dx << XY_SHIFT) / (ay | 1);
+    x_step = div_trunc(dx << XY_SHIFT, ay | 1);
     y_step = XY_ONE;
     ecount = (int)((pt2.y - pt1.y) >> XY_SHIFT);
   }
@@ -250,7 +265,7 @@ RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
           if (ty > y) {
             int64_t xs = qget(v, idx0).x, xe = pv.x;
             if (shift != XY_SHIFT) { xs <<= XY_SHIFT - shift; xe <<= XY_SHIFT - shift; }
-            const int64_t dxe = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+            const int64_t dxe = div_trunc((xe - xs) * 2 + (ty - y), 2 * (int64_t)(ty - y));
             if (i) { e_ye1 = ty; e_idx1 = idx; ev_push(ev1, y, xs, dxe); }
             else { e_ye0 = ty; e_idx0 = idx; ev_push(ev0, y, xs, dxe); }
             break;
