@@ -116,3 +116,45 @@ def test_rollout_states(nPlayers, obs, noise, mag, canFall, rinit):
     assert len(envs_bad) <= (6 * n) // 10, total_bad[:10]
     hard = [b for b in total_bad if b[2] in ("diag", "done", "state.elapsed", "state.episode")]
     assert not hard, hard[:10]
+
+
+def test_noise_statistics_match_in_distribution():
+    """north_star: noise statistics match the reference in distribution (KS test, p > 0.01).  The kernels draw from
+    Philox streams, the reference from a sequential generator: the noisy first observation of the same scene over
+    many environments (GPU, Philox) against the oracle fed with an independent sequential stream of uniforms (tape
+    mode, the mode in which it is pinned against the reference's own Python)."""
+    import torch
+    from scipy import stats
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    from oracle.oracle import RcOracle
+    n_gpu, n_cpu = 4096, 600
+    sim = dynenv_b200.BatchedRoboCup(n_gpu, 2, 1, 1, 3.0, canFall=True, seed=5)
+    out = sim.reset()
+    torch.cuda.synchronize()
+    g_ball = out.ball.cpu().numpy()[:, 0, 0, 0, :3]        # first ball row of observer 0, tick 0: x, y, size
+    g_nb = out.counts.cpu().numpy()[:, 0, 0, 0]
+    g_line = out.line.cpu().numpy()[:, 0, 0, 0, 0]          # first line row: distance
+    g_nl = out.counts.cpu().numpy()[:, 0, 0, 5]
+    rng = np.random.default_rng(77)
+    c_ball, c_nb, c_line, c_nl = [], [], [], []
+    flags = L.DYNENV_FLAG_CAN_FALL | L.DYNENV_FLAG_USE_OBS_REWARDS
+    for i in range(n_cpu):
+        orc = RcOracle(2, 1, 1, 3.0, False, flags)
+        orc.set_tape(rng.random(4000))
+        orc.reset()
+        o = orc.reset_obs()
+        assert not orc.tape_underflow()
+        c_ball.append(o["ball"][0, 0, 0, :3]); c_nb.append(o["counts"][0, 0, 0])
+        c_line.append(o["line"][0, 0, 0, 0]); c_nl.append(o["counts"][0, 0, 5])
+    c_ball, c_nb, c_line, c_nl = np.array(c_ball), np.array(c_nb), np.array(c_line), np.array(c_nl)
+    for k in range(3):  # position noise and size noise of the ball sighting (where it was sighted)
+        p = stats.ks_2samp(g_ball[g_nb > 0, k], c_ball[c_nb > 0, k]).pvalue
+        assert p > 0.01, ("ball", k, p)
+    p = stats.ks_2samp(g_line[g_nl > 0], c_line[c_nl > 0]).pvalue
+    assert p > 0.01, ("line", p)
+    # false negatives: the sighting rates agree within 4 sigma of the binomial error
+    for g, c in ((g_nb > 0, c_nb > 0), (g_nl == g_nl.max(), c_nl == g_nl.max())):
+        pg, pc = g.mean(), c.mean()
+        sigma = np.sqrt(pc * (1 - pc) / n_cpu + pg * (1 - pg) / n_gpu) + 1e-9
+        assert abs(pg - pc) < 4 * sigma + 1e-3, (pg, pc, sigma)
