@@ -1127,7 +1127,7 @@ __device__ __forceinline__ float fast_atan2(float y, float x) {
 
 /* cutils.doesInteractPoly (cutils.py:643-696, canOcclude = True) of a point-like sighting at p1 (angle ang1 in the
    observer frame) against occluder o, whose view-block data the observer's pass has put into shared memory */
-__device__ __noinline__ int interact_poly(const Env E, float p1x, float p1y, float ang1, int o, float radius) {
+__device__ __forceinline__ int interact_poly(const Env E, float p1x, float p1y, float ang1, int o, float radius) {
   int ret = I_NO;
   if (radius > 0.f) {
     float dx = E.f[V_PX + o] - p1x, dy = E.f[V_PY + o] - p1y;
@@ -1151,7 +1151,7 @@ __device__ __noinline__ int interact_poly(const Env E, float p1x, float p1y, flo
 
 /* getViewBlockAngle part of doesInteractPoly for an occluder with centre p (observer frame) and axis-aligned
    corners tr + (+-hx, +-hy) (NOT rotated: the reference discards its rotated() results) */
-__device__ __noinline__ void occluder_store(const Env E, int o, V2 p, V2 tr, float hx, float hy, float ang2, bool ok) {
+__device__ __forceinline__ void occluder_store(const Env E, int o, V2 p, V2 tr, float hx, float hy, float ang2, bool ok) {
   const float sx[4] = {1.f, -1.f, -1.f, 1.f}, sy[4] = {1.f, 1.f, -1.f, -1.f};
   float ang[4], dist[4];
   V2 cr[4];
@@ -1189,13 +1189,13 @@ struct Det { /* one sighting (cutils.isSeenInRadius result) held by a lane */
 };
 
 /* cutils.addNoiseRect (cutils.py:479-542); the corner updates are not restated: nothing reads them afterwards */
-__device__ __noinline__ Det noise_rect(const Env E, Rand6 r, Det d, int interaction, float maxDist, bool misClass) {
-  if (!d.seen) return d;
+__device__ __forceinline__ void noise_rect(const Env E, const Rand6& r, Det& d, int interaction, float maxDist, bool misClass) {
+  if (!d.seen) return;
   const float magn = E.c->noise_mag, rand_ = E.c->rand_base;
   float nx = (r.u(0) - 0.5f) * magn, ny = (r.u(1) - 0.5f) * magn;
   float angleDiff;
   if (E.c->noise_type == DYNENV_NOISE_RANDOM) {
-    if (r.u(2) < rand_) { d.seen = S_NO; return d; }
+    if (r.u(2) < rand_) { d.seen = S_NO; return; }
     angleDiff = (r.u(4) - 0.5f) * magn * ANGLE_NOISE;
   } else {
     float range = 0.25f + 3.75f * sqrtf(d.px * d.px + d.py * d.py) / maxDist;
@@ -1204,7 +1204,7 @@ __device__ __noinline__ Det noise_rect(const Env E, Rand6 r, Det d, int interact
     if (d.seen == S_DISTANT) mult = range * 3.f;
     else if (d.seen == S_PARTIAL) mult = range * 4.f;
     nx *= mult; ny *= mult;
-    if (r.u(2) < rand_ * mult) { d.seen = S_NO; return d; }
+    if (r.u(2) < rand_ * mult) { d.seen = S_NO; return; }
     if (misClass && r.u(3) < rand_ * mult / 2.f) d.seen = S_MISCLASS;
     angleDiff = (r.u(4) - 0.5f) * magn * ANGLE_NOISE * 0.25f;
   }
@@ -1213,25 +1213,16 @@ __device__ __noinline__ Det noise_rect(const Env E, Rand6 r, Det d, int interact
   float c = d.c * cd - d.s * sd, s = d.s * cd + d.c * sd; /* cos / sin of (atan2(s, c) + angleDiff) */
   d.c = c; d.s = s;
   d.px += nx; d.py += ny;
-  return d;
 }
 
 /* rows of one list group into the staged record: lanes with `valid` append their row after `count` rows
    (list order = lane order), rows beyond the capacity are dropped; returns the new row count */
-struct Row7 {
-  float v[7];
-};
-__device__ __noinline__ int emit_rows(const Env E, bool valid, int off, int stride, int cap, int count, Row7 row, int nf) {
-  const int lane = E.lane;
+__device__ __forceinline__ int emit_rows(const Env E, int lane, bool valid, int off, int stride, int cap, int count,
+                                         const float* row, int nf) {
   unsigned bal = __ballot_sync(FULLMASK, valid);
   int idx = count + __popc(bal & ((1u << lane) - 1));
-  if (valid && idx < cap) {
-    float* dst = E.f + (V_STAGE + off + idx * stride);
-    dst[0] = row.v[0]; dst[1] = row.v[1];
-    if (nf > 2) { dst[2] = row.v[2]; dst[3] = row.v[3]; }
-    if (nf > 4) { dst[4] = row.v[4]; dst[5] = row.v[5]; }
-    if (nf > 6) dst[6] = row.v[6];
-  }
+  if (valid && idx < cap)
+    for (int k = 0; k < nf; k++) E.f[V_STAGE + off + idx * stride + k] = row[k];
   return count + __popc(bal);
 }
 
@@ -1318,13 +1309,11 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   /* ---- occlusion by buildings (:785-792): occluded sightings leave their lists */
   if (listA) {
     int m = 0;
-#pragma unroll 1
     for (int b = 0; b < 4; b++) m = max(m, interact_poly(E, A.px, A.py, angA, 30 + b, 0.f));
     if (m == I_OCCLUDE) { listA = false; A.seen = S_NO; }
   }
   if (listB) {
     int m = 0;
-#pragma unroll 1
     for (int b = 0; b < 4; b++) m = max(m, interact_poly(E, B.px, B.py, angB, 30 + b, 0.f));
     if (m == I_OCCLUDE) { listB = false; B.seen = S_NO; }
   }
@@ -1370,7 +1359,7 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
     if (__any_sync(FULLMASK, listA)) {
       Rand6 r;
       if (listA) r = rng_block(E, tick, lane < 10 ? DRV_SITE_OBS_CAR : DRV_SITE_OBS_OBST, ag, lane < 10 ? lane : lane - 10, 0);
-      if (listA) A = noise_rect(E, r, A, I_NO, MAXVIS1, true);
+      if (listA) noise_rect(E, r, A, I_NO, MAXVIS1, true);
     }
     {
       const bool isLaneRow = lane >= 25 && lane < 31 && B.seen;
@@ -1381,7 +1370,8 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
         int b = lane < 20 ? lane : (lane == 24 ? 0 : lane - 25);
         r = rng_block(E, tick, site, ag, b, 0);
       }
-      if (listB || lane == 24) B = noise_rect(E, r, B, lane == 24 ? (int)I_NO : pedInter, lane == 24 ? MAXVIS1 : MAXVIS0, false);
+      if (listB) noise_rect(E, r, B, pedInter, MAXVIS0, false);
+      else if (lane == 24) noise_rect(E, r, B, I_NO, MAXVIS1, false);
       else if (isLaneRow) { /* cutils.addNoiseLane (cutils.py:380-413) */
         const float magn = E.c->noise_mag, rand_ = E.c->rand_base;
         float distNoise = (r.u(0) - 0.5f) * magn, angleDiff = (r.u(1) - 0.5f) * magn, da;
@@ -1429,32 +1419,32 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
     }
   }
   /* ---- lists in the reference's order, final filters and encoding (:821-826, :877-977) */
-  Row7 row;
+  float row[7];
   /* cars: real sightings, obstacles misclassified as cars, false positives */
   const unsigned balListCars = __ballot_sync(FULLMASK, lane < 10 && listA);
   const unsigned balMisObst = __ballot_sync(FULLMASK, lane >= 10 && lane < 30 && listA && A.seen == S_MISCLASS);
   const unsigned balFpCar = __ballot_sync(FULLMASK, fpClass == 0);
-  row.v[0] = normalize_(A.px, NORMX, 0.f); row.v[1] = normalize_(A.py, NORMY, 0.f); row.v[2] = A.c; row.v[3] = A.s;
-  row.v[4] = normalize_(A.w, NORMW, 0.5f); row.v[5] = normalize_(A.h, NORMH, 0.5f); row.v[6] = lane < 10 ? A.fin : 0.f;
+  row[0] = normalize_(A.px, NORMX, 0.f); row[1] = normalize_(A.py, NORMY, 0.f); row[2] = A.c; row[3] = A.s;
+  row[4] = normalize_(A.w, NORMW, 0.5f); row[5] = normalize_(A.h, NORMH, 0.5f); row[6] = lane < 10 ? A.fin : 0.f;
   int cnt = 0;
-  cnt = emit_rows(E, lane < 10 && listA && A.seen != S_NO && A.seen != S_MISCLASS, DRV_O_CAR, DRV_F_CAR, DRV_CAP_CAR, cnt, row, 7);
-  cnt = emit_rows(E, lane >= 10 && lane < 30 && listA && A.seen == S_MISCLASS, DRV_O_CAR, DRV_F_CAR, DRV_CAP_CAR, cnt, row, 7);
-  Row7 frow;
-  frow.v[0] = normalize_(F.px, NORMX, 0.f); frow.v[1] = normalize_(F.py, NORMY, 0.f); frow.v[2] = F.c; frow.v[3] = F.s;
-  frow.v[4] = normalize_(F.w, NORMW, 0.5f); frow.v[5] = normalize_(F.h, NORMH, 0.5f); frow.v[6] = 0.f;
-  cnt = emit_rows(E, fpClass == 0, DRV_O_CAR, DRV_F_CAR, DRV_CAP_CAR, cnt, frow, 7);
+  cnt = emit_rows(E, lane, lane < 10 && listA && A.seen != S_NO && A.seen != S_MISCLASS, DRV_O_CAR, DRV_F_CAR, DRV_CAP_CAR, cnt, row, 7);
+  cnt = emit_rows(E, lane, lane >= 10 && lane < 30 && listA && A.seen == S_MISCLASS, DRV_O_CAR, DRV_F_CAR, DRV_CAP_CAR, cnt, row, 7);
+  float frow[7];
+  frow[0] = normalize_(F.px, NORMX, 0.f); frow[1] = normalize_(F.py, NORMY, 0.f); frow[2] = F.c; frow[3] = F.s;
+  frow[4] = normalize_(F.w, NORMW, 0.5f); frow[5] = normalize_(F.h, NORMH, 0.5f); frow[6] = 0.f;
+  cnt = emit_rows(E, lane, fpClass == 0, DRV_O_CAR, DRV_F_CAR, DRV_CAP_CAR, cnt, frow, 7);
   const int nCarRows = min(cnt, DRV_CAP_CAR);
   /* obstacles: real sightings, cars misclassified as obstacles, false positives */
   cnt = 0;
-  cnt = emit_rows(E, lane >= 10 && lane < 30 && listA && A.seen != S_NO && A.seen != S_MISCLASS, DRV_O_OBS, DRV_F_OBS, DRV_CAP_OBS, cnt, row, 6);
-  cnt = emit_rows(E, lane < 10 && listA && A.seen == S_MISCLASS, DRV_O_OBS, DRV_F_OBS, DRV_CAP_OBS, cnt, row, 6);
-  cnt = emit_rows(E, fpClass == 1, DRV_O_OBS, DRV_F_OBS, DRV_CAP_OBS, cnt, frow, 6);
+  cnt = emit_rows(E, lane, lane >= 10 && lane < 30 && listA && A.seen != S_NO && A.seen != S_MISCLASS, DRV_O_OBS, DRV_F_OBS, DRV_CAP_OBS, cnt, row, 6);
+  cnt = emit_rows(E, lane, lane < 10 && listA && A.seen == S_MISCLASS, DRV_O_OBS, DRV_F_OBS, DRV_CAP_OBS, cnt, row, 6);
+  cnt = emit_rows(E, lane, fpClass == 1, DRV_O_OBS, DRV_F_OBS, DRV_CAP_OBS, cnt, frow, 6);
   const int nObsRows = min(cnt, DRV_CAP_OBS);
   /* pedestrians: real sightings, false positives, false positives near cars (REALISTIC, :877-882) */
   cnt = 0;
-  row.v[0] = normalize_(B.px, NORMX, 0.f); row.v[1] = normalize_(B.py, NORMY, 0.f);
-  cnt = emit_rows(E, lane < 20 && listB && B.seen != S_NO, DRV_O_PED, DRV_F_PED, DRV_CAP_PED, cnt, row, 2);
-  cnt = emit_rows(E, fpClass == 2, DRV_O_PED, DRV_F_PED, DRV_CAP_PED, cnt, frow, 2);
+  row[0] = normalize_(B.px, NORMX, 0.f); row[1] = normalize_(B.py, NORMY, 0.f);
+  cnt = emit_rows(E, lane, lane < 20 && listB && B.seen != S_NO, DRV_O_PED, DRV_F_PED, DRV_CAP_PED, cnt, row, 2);
+  cnt = emit_rows(E, lane, fpClass == 2, DRV_O_PED, DRV_F_PED, DRV_CAP_PED, cnt, frow, 2);
   if (noisy && E.c->noise_type == DYNENV_NOISE_REALISTIC) {
     /* rows of the car list in list order: group 1 = lanes 0..9, group 2 = lanes 10..29, group 3 = false positives */
     const int n1 = __popc(balListCars), n2 = __popc(balMisObst);
@@ -1473,21 +1463,21 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
           Rand6 r = rng_block(E, tick, DRV_SITE_OBS_FPPED, ag, idx, 0);
           if (r.u(0) < E.c->rand_base * 10.f && sqrtf(cx * cx + cy * cy) < 250.f) {
             hit = true;
-            row.v[0] = normalize_(cx + (2.f * r.u(1) - 1.f) * 10.f, NORMX, 0.f);
-            row.v[1] = normalize_(cy + (2.f * r.u(2) - 1.f) * 10.f, NORMY, 0.f);
+            row[0] = normalize_(cx + (2.f * r.u(1) - 1.f) * 10.f, NORMX, 0.f);
+            row[1] = normalize_(cy + (2.f * r.u(2) - 1.f) * 10.f, NORMY, 0.f);
           }
         }
       }
-      cnt = emit_rows(E, hit, DRV_O_PED, DRV_F_PED, DRV_CAP_PED, cnt, row, 2);
+      cnt = emit_rows(E, lane, hit, DRV_O_PED, DRV_F_PED, DRV_CAP_PED, cnt, row, 2);
     }
   }
   const int nPedRows = min(cnt, DRV_CAP_PED);
   /* lanes */
   cnt = 0;
-  row.v[0] = laneDist; row.v[1] = B.c; row.v[2] = B.s; row.v[3] = laneType;
-  cnt = emit_rows(E, lane >= 25 && lane < 31 && B.seen != S_NO, DRV_O_LANE, DRV_F_LANE_FULL, DRV_CAP_LANE, cnt, row, 4);
-  frow.v[0] = fpLaneDist; frow.v[1] = F.c; frow.v[2] = F.s; frow.v[3] = fpLaneType;
-  cnt = emit_rows(E, fpClass == 3, DRV_O_LANE, DRV_F_LANE_FULL, DRV_CAP_LANE, cnt, frow, 4);
+  row[0] = laneDist; row[1] = B.c; row[2] = B.s; row[3] = laneType;
+  cnt = emit_rows(E, lane, lane >= 25 && lane < 31 && B.seen != S_NO, DRV_O_LANE, DRV_F_LANE_FULL, DRV_CAP_LANE, cnt, row, 4);
+  frow[0] = fpLaneDist; frow[1] = F.c; frow[2] = F.s; frow[3] = fpLaneType;
+  cnt = emit_rows(E, lane, fpClass == 3, DRV_O_LANE, DRV_F_LANE_FULL, DRV_CAP_LANE, cnt, frow, 4);
   const int nLaneRows = min(cnt, DRV_CAP_LANE);
   if (lane == 24) {
     const int t = E.i[DRV_S_CTYPE + ag];
