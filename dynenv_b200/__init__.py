@@ -14,4 +14,7 @@ def __getattr__(name):
     if name in ("RoboCupEnvironment", "DrivingEnvironment", "make_dyn_env", "BatchedVecEnv"):
         from . import api
         return getattr(api, name)
+    if name == "DeviceRolloutStorage":
+        from . import rollout
+        return rollout.DeviceRolloutStorage
     raise AttributeError(name)

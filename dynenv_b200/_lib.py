@@ -12,7 +12,7 @@ _LIB = None
 EXPORTS = ["dynenv_abi_version", "dynenv_last_error", "dynenv_create", "dynenv_destroy", "dynenv_state_words",
            "dynenv_reset", "dynenv_step", "dynenv_set_seed", "dynenv_get_state", "dynenv_set_state",
            "dynenv_last_launch_count", "dynenv_debug_substep_range", "dynenv_debug_timing",
-           "dynenv_last_kernel_ms", "dynenv_render_images"]
+           "dynenv_last_kernel_ms", "dynenv_render_images", "dynenv_rollout_insert", "dynenv_discount_rewards"]
 
 
 class DynEnvConfig(C.Structure):
@@ -58,6 +58,10 @@ def lib():
         lb.dynenv_debug_timing.argtypes = [C.c_void_p, C.c_int]
         lb.dynenv_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         lb.dynenv_render_images.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        lb.dynenv_rollout_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
+        lb.dynenv_discount_rewards.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                               C.c_int64, C.c_float, C.c_void_p]
         if lb.dynenv_abi_version() != L.DYNENV_ABI_VERSION:
             raise RuntimeError("dynenv_b200: library ABI %d != header ABI %d" % (lb.dynenv_abi_version(),
                                                                                  L.DYNENV_ABI_VERSION))

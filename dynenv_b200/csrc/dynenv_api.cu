@@ -12,6 +12,7 @@
 #include "drv_sim.cuh"
 #include "rc_sim.cuh"
 #include "rc_raster.cuh"
+#include "rollout.cuh"
 
 using namespace dynenv;
 
@@ -455,6 +456,49 @@ int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, ui
       raw_dev, (long long)n_records, image_dev);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "rc_raster_kernel launch");
+  return DYNENV_OK;
+}
+
+int dynenv_rollout_insert(DynEnvHandle h, const void* out, int step, int rollout_size, float* rewards_dev,
+                          uint8_t* agent_finished_dev, uint8_t* dones_dev, float* episode_acc_dev, void* stream) {
+  if (!h || !out || !rewards_dev || !agent_finished_dev || !dones_dev) return fail(DYNENV_E_INVALID, "null argument");
+  if (step < 0 || step >= rollout_size) return fail(DYNENV_E_INVALID, "step outside the rollout");
+  cudaSetDevice(h->cfg.device);
+  rollout::InfoLayout L;
+  const float* info;
+  int A;
+  if (h->cfg.kind == DYNENV_KIND_DRIVING) {
+    info = static_cast<const DynEnvDrivingOut*>(out)->info;
+    A = h->cfg.n_players < DRV_MAXCARS ? h->cfg.n_players : DRV_MAXCARS;
+    L = {DRV_INFO_WORDS, DRV_I_REWARDS, DRV_I_DONE, DRV_I_EPR, DRV_I_EPPR, -1, DRV_I_EPG, DRV_I_STATE_CARS, 7};
+  } else {
+    info = static_cast<const DynEnvRoboCupOut*>(out)->info;
+    A = 2 * (h->cfg.n_players < 5 ? h->cfg.n_players : 5);
+    L = {RC_INFO_WORDS, RC_I_REWARDS, RC_I_DONE, RC_I_EPR, RC_I_EPPR, RC_I_EPOR, RC_I_EPG, RC_I_STATE_ROBOTS, 6};
+  }
+  if (!info) return fail(DYNENV_E_INVALID, "out->info is null");
+  const long long E = h->cfg.n_envs, n = E * A;
+  rollout::insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      info, L, E, A, rewards_dev + (size_t)step * n, agent_finished_dev + (size_t)step * n, dones_dev + (size_t)step * E,
+      episode_acc_dev);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "rollout insert_kernel launch");
+  return DYNENV_OK;
+}
+
+int dynenv_discount_rewards(int device, const float* rewards_dev, const float* final_value_dev, const uint8_t* dones_dev,
+                            int agents_per_env, float* out_dev, int rollout_size, int64_t n_columns, float discount,
+                            void* stream) {
+  if (!rewards_dev || !final_value_dev || !out_dev) return fail(DYNENV_E_INVALID, "null argument");
+  if (rollout_size < 0 || n_columns < 0 || agents_per_env <= 0 || n_columns % agents_per_env)
+    return fail(DYNENV_E_INVALID, "bad rollout shape");
+  if (rollout_size == 0 || n_columns == 0) return DYNENV_OK;
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+  rollout::discount_kernel<<<(unsigned)((n_columns + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rewards_dev, final_value_dev, dones_dev, agents_per_env, out_dev, rollout_size, (long long)n_columns, discount);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "rollout discount_kernel launch");
   return DYNENV_OK;
 }
 

@@ -464,6 +464,24 @@ int dynenv_set_seed(DynEnvHandle h, uint64_t seed);
    (cutils.py:206-284).  `device`: CUDA device ordinal of the buffers. */
 int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, uint32_t* image_dev, void* stream);
 
+/* Rollout buffers on the device (models/storage.py): what the learner keeps of every env.step() result, without the host
+   round trip of models/train.py:269-284.  All buffers are the caller's.
+   dynenv_rollout_insert -- storage.insert (models/storage.py:133-168) for the environment-side fields, from the result record
+   `out` that dynenv_step just filled: rewards_dev[step][nEnvs * nAgents], agent_finished_dev[step][nEnvs * nAgents] (the last
+   column of every agent's row of info['Full State'][0], models/train.py:276), dones_dev[step][nEnvs]; and
+   storage.log_episode_rewards (:292-308) as running sums per environment in episode_acc_dev[nEnvs][DYNENV_EPISODE_ACC_WORDS]
+   (may be NULL): episodes finished, sums of the agent-mean episode_r / episode_p_r / episode_o_r, sums of episode_g[0..1],
+   min and max of the agent-mean episode_r.  The three step-indexed pointers are the buffers' bases.
+   dynenv_discount_rewards -- storage._discount_rewards (models/storage.py:170-205): out[i] = rewards[i] + discount * out[i+1],
+   out[T] = final_value, over n_columns = nEnvs * nAgents columns.  dones_dev NULL reproduces the reference (its mask is built
+   from zeros, :194); with dones_dev ([T][n_columns / agents_per_env]) the chain restarts at a step that ended an episode. */
+#define DYNENV_EPISODE_ACC_WORDS 8
+int dynenv_rollout_insert(DynEnvHandle h, const void* out, int step, int rollout_size, float* rewards_dev,
+                          uint8_t* agent_finished_dev, uint8_t* dones_dev, float* episode_acc_dev, void* stream);
+int dynenv_discount_rewards(int device, const float* rewards_dev, const float* final_value_dev, const uint8_t* dones_dev,
+                            int agents_per_env, float* out_dev, int rollout_size, int64_t n_columns, float discount,
+                            void* stream);
+
 /* copy the whole state ([nEnvs][state_words] 32-bit words) to / from a device buffer */
 int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream);
 int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);
