@@ -79,3 +79,45 @@ def test_rollout_states(nPlayers, obs, noise, mag, cont):
     assert len(envs_bad) <= (8 * n) // 50, total_bad[:12]
     hard = [b for b in total_bad if b[2] in ("diag", "done", "state.elapsed", "state.episode")]
     assert not hard, hard[:10]
+
+
+def test_noise_statistics_match_in_distribution():
+    """north_star: noise statistics match the reference in distribution (KS test, p > 0.01).  The first noisy observation
+    of freshly drawn scenes over many environments (GPU, Philox streams) against the oracle fed with an independent
+    sequential stream of uniforms (tape mode, the mode in which it is pinned against the reference's own Python)."""
+    import torch
+    from scipy import stats
+    import dynenv_b200
+    from oracle.oracle import DrvOracle
+    n_gpu, n_cpu, N = 4096, 500, 10
+    sim = dynenv_b200.BatchedDriving(n_gpu, N, 1, 1, 3.0, continuousActions=True, seed=5)
+    out = sim.reset()
+    torch.cuda.synchronize()
+    cnt = out.counts.cpu().numpy()[:, 0]           # observer 0: rows per list (cars, obstacles, pedestrians, lanes)
+    g_car = out.car.cpu().numpy()[:, 0, 0, :4]     # first car row: position, orientation
+    g_obs = out.obs.cpu().numpy()[:, 0, 0, :2]
+    g_ped = out.ped.cpu().numpy()[:, 0, 0, :2]
+    g_lane = out.lane.cpu().numpy()[:, 0, 0, 0]
+    rng = np.random.default_rng(78)
+    c_cnt, c_car, c_obs, c_ped, c_lane = [], [], [], [], []
+    for i in range(n_cpu):
+        orc = DrvOracle(N, 1, 1, 3.0, True)
+        orc.set_tape(rng.random(20000))
+        orc.reset()
+        o = orc.reset_obs()
+        assert not orc.tape_underflow()
+        c_cnt.append(o["counts"][0]); c_car.append(o["car"][0, 0, :4]); c_obs.append(o["obs"][0, 0, :2])
+        c_ped.append(o["ped"][0, 0, :2]); c_lane.append(o["lane"][0, 0, 0])
+    c_cnt, c_car, c_obs, c_ped, c_lane = [np.array(x) for x in (c_cnt, c_car, c_obs, c_ped, c_lane)]
+    for name, k, g, c in (("car", 0, g_car, c_car), ("obs", 1, g_obs, c_obs), ("ped", 2, g_ped, c_ped)):
+        for f in range(g.shape[1]):
+            p = stats.ks_2samp(g[cnt[:, k] > 0, f], c[c_cnt[:, k] > 0, f]).pvalue
+            assert p > 0.01, (name, f, p)
+    p = stats.ks_2samp(g_lane[cnt[:, 3] > 0], c_lane[c_cnt[:, 3] > 0]).pvalue
+    assert p > 0.01, ("lane", p)
+    # sighting counts (false negatives, false positives, misclassification between cars and obstacles): the means agree
+    # within 4 sigma of the sampling error
+    for k in range(3):
+        mg, mc = cnt[:, k].mean(), c_cnt[:, k].mean()
+        sigma = np.sqrt(cnt[:, k].var() / n_gpu + c_cnt[:, k].var() / n_cpu) + 1e-9
+        assert abs(mg - mc) < 4 * sigma + 1e-3, (k, mg, mc, sigma)

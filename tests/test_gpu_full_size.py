@@ -1,0 +1,210 @@
+"""BASELINE.json's full sizes on the GPU (65 536 RoboCup / Driving environments, 16 384 IMAGE environments), checked
+through properties that do not need the oracle on every environment:
+  * the whole batch equals the same environments stepped as two shards with global env ids (what two GPUs run), bit for bit,
+    across an episode end with auto-reset;
+  * structural invariants of every output record (counts within capacities, finite rows, no capacity-overflow flag, rewards
+    finite, done exactly where the episode clock says);
+  * a random sample of the batch against the oracle from the very same states (1e-4, integer fields exact);
+  * IMAGE: rendering is idempotent, independent of the chunking, and a sample of records is bit-equal to the cv2 oracle.
+"""
+import numpy as np
+import pytest
+
+from helpers import compare_step, drv_compare_step, drv_oracle_step_batch, oracle_step_batch
+
+pytestmark = pytest.mark.gpu
+N_FULL = 65536
+N_SAMPLE = 40
+
+
+class _Rows(object):
+    """the rows `idx` of a batched outputs object, for compare_step"""
+
+    def __init__(self, out, idx):
+        self._o, self._i = out, idx
+
+    def __getattr__(self, k):
+        return getattr(self._o, k)[self._i]
+
+
+def _rc_actions(g, n, P, dev):
+    import torch
+    return (torch.rand((n, P, 4), generator=g, device=dev) * torch.tensor([5, 3, 3, 7], device=dev)).floor()
+
+
+def test_robocup_full_size():
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    from oracle.oracle import f32_record_to_words
+    cfg = dict(nPlayers=5, obsType=1, noiseType=1, noiseMag=2.0, canFall=True, allowHeadTurn=False, randomInit=False)
+    cfg["flags"] = L.DYNENV_FLAG_CAN_FALL | L.DYNENV_FLAG_USE_OBS_REWARDS
+    n, P, seed, half = N_FULL, 10, 42, N_FULL // 2
+    kw = dict(nPlayers=5, observationType=1, noiseType=1, noiseMagnitude=2.0, canFall=True, auto_reset=True, seed=seed)
+    whole = dynenv_b200.BatchedRoboCup(n, **kw)
+    parts = [dynenv_b200.BatchedRoboCup(half, env_id_offset=o, **kw) for o in (0, half)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    assert torch.equal(whole.out.obs[:half], parts[0].out.obs) and torch.equal(whole.out.obs[half:], parts[1].out.obs)
+    # every 16th environment two steps before its episode end
+    st = whole.get_state()
+    st[::16, L.RC_S_ELAPSED] = 12000 - 100
+    whole.set_state(st)
+    for k, p in enumerate(parts):
+        p.set_state(st[k * half:(k + 1) * half].contiguous())
+    dev = whole.device
+    g = torch.Generator(device=dev).manual_seed(1234)
+    n_done = 0
+    for step in range(4):
+        a = _rc_actions(g, n, P, dev)
+        before = whole.get_state()
+        ow = whole.step(a)
+        op = [p.step(a[k * half:(k + 1) * half].contiguous()) for k, p in enumerate(parts)]
+        for k in range(2):
+            assert torch.equal(ow.obs[k * half:(k + 1) * half], op[k].obs), step
+            assert torch.equal(ow.info[k * half:(k + 1) * half], op[k].info), step
+        # invariants over all 65 536 records
+        assert int(ow.diag.max()) == 0
+        counts = ow.counts
+        caps = torch.tensor([L.RC_CAP_BALL, L.RC_CAP_ROBOT, L.RC_CAP_POST, L.RC_CAP_CROSS, L.RC_CAP_FCROSS, L.RC_CAP_LINE], device=dev)
+        assert bool((counts >= 0).all()) and bool((counts <= caps).all())
+        assert bool(torch.isfinite(ow.obs[..., :L.RC_O_COUNTS]).all()) and bool(torch.isfinite(ow.rewards).all())
+        done = ow.done != 0
+        expect = before[:, L.RC_S_ELAPSED] + 50 >= 12000
+        assert torch.equal(done, expect)
+        n_done += int(done.sum())
+        after = whole.get_state()
+        assert bool((after[done][:, L.RC_S_ELAPSED] == 0).all())  # auto-reset
+        assert bool((after[~done][:, L.RC_S_ELAPSED] == before[~done][:, L.RC_S_ELAPSED] + 50).all())
+    assert n_done == n // 16
+    assert torch.equal(whole.get_state()[:half], parts[0].get_state()) and torch.equal(whole.get_state()[half:], parts[1].get_state())
+    for p in parts:
+        p.close()
+    # a sample of the batch against the oracle, from the batch's own states (no auto-reset in the sampled step)
+    idx = np.sort(np.random.default_rng(9).choice(n, N_SAMPLE, replace=False))
+    idx = idx[idx % 16 != 0]
+    recs = whole.get_state().cpu().numpy().view(np.uint32)[idx]
+    a = _rc_actions(g, n, P, dev)
+    out = whole.step(a)
+    torch.cuda.synchronize()
+    gw = f32_record_to_words(whole.get_state().cpu().numpy().view(np.uint32)[idx])
+    an = a.cpu().numpy()
+    bad = []
+    for j, e in enumerate(idx):
+        outs, ow_ = oracle_step_batch(cfg, recs[j:j + 1], an[e:e + 1], seed, env_id0=int(e))
+        bad += [(int(e),) + b[1:] for b in compare_step(cfg, _Rows(out, torch.tensor([int(e)], device=dev)), gw[j:j + 1], outs, ow_, 1e-4)]
+    assert len(set(b[0] for b in bad)) <= 3, bad[:10]  # float32 ties at the reference's thresholds (test_gpu_robocup.py)
+    assert not [b for b in bad if b[1] in ("diag", "done", "state.elapsed", "state.episode")], bad[:10]
+
+
+def test_driving_full_size():
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    from oracle.oracle import drv_f32_record_to_words
+    cfg = dict(nPlayers=10, obsType=1, noiseType=1, noiseMag=2.0, continuous=True)
+    n, N, seed, half = N_FULL, 10, 42, N_FULL // 2
+    kw = dict(nPlayers=10, observationType=1, noiseType=1, noiseMagnitude=2.0, continuousActions=True, auto_reset=True, seed=seed)
+    whole = dynenv_b200.BatchedDriving(n, **kw)
+    parts = [dynenv_b200.BatchedDriving(half, env_id_offset=o, **kw) for o in (0, half)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    assert torch.equal(whole.out.record[:half], parts[0].out.record) and torch.equal(whole.out.record[half:], parts[1].out.record)
+    # scenes: 10..20 pedestrians and at most 20 obstacles everywhere, both extremes present in 65 536 draws
+    n_ped, n_obs = whole.out.n_ped, whole.out.n_obs
+    assert int(n_ped.min()) == 10 and int(n_ped.max()) == 20 and int(n_obs.min()) >= 0 and int(n_obs.max()) <= L.DRV_MAXOBS
+    st = whole.get_state()
+    st[::16, L.DRV_S_ELAPSED] = 6000 - 20
+    whole.set_state(st)
+    for k, p in enumerate(parts):
+        p.set_state(st[k * half:(k + 1) * half].contiguous())
+    dev = whole.device
+    g = torch.Generator(device=dev).manual_seed(1234)
+    caps = torch.tensor([L.DRV_CAP_CAR, L.DRV_CAP_OBS, L.DRV_CAP_PED, L.DRV_CAP_LANE], device=dev)
+    n_done = 0
+    for step in range(4):
+        a = torch.rand((n, N, 2), generator=g, device=dev) * 6 - 3
+        before = whole.get_state()
+        ow = whole.step(a)
+        op = [p.step(a[k * half:(k + 1) * half].contiguous()) for k, p in enumerate(parts)]
+        for k in range(2):
+            assert torch.equal(ow.record[k * half:(k + 1) * half], op[k].record), step
+            assert torch.equal(ow.info[k * half:(k + 1) * half], op[k].info), step
+        assert int(ow.diag.max()) == 0
+        assert bool((ow.counts >= 0).all()) and bool((ow.counts <= caps).all())
+        assert bool(torch.isfinite(ow.record[..., :L.DRV_O_COUNTS]).all()) and bool(torch.isfinite(ow.rewards).all())
+        done = ow.done != 0
+        timed_out = before[:, L.DRV_S_ELAPSED] + 10 >= 6000
+        assert bool((done | ~timed_out).all())  # the clock always ends an episode (all cars finished may end it earlier)
+        n_done += int(done.sum())
+        after = whole.get_state()
+        assert bool((after[done][:, L.DRV_S_ELAPSED] == 0).all())
+    assert n_done >= n // 16
+    assert torch.equal(whole.get_state()[:half], parts[0].get_state()) and torch.equal(whole.get_state()[half:], parts[1].get_state())
+    for p in parts:
+        p.close()
+    idx = np.sort(np.random.default_rng(10).choice(n, N_SAMPLE, replace=False))
+    recs = whole.get_state().cpu().numpy().view(np.uint32)[idx]
+    a = torch.rand((n, N, 2), generator=g, device=dev) * 6 - 3
+    out = whole.step(a)
+    torch.cuda.synchronize()
+    keep = (out.done[torch.from_numpy(idx).to(dev)] == 0).cpu().numpy()  # an auto-reset replaces the state the oracle would return
+    gw = drv_f32_record_to_words(whole.get_state().cpu().numpy().view(np.uint32)[idx])
+    an = a.cpu().numpy()
+    bad = []
+    for j, e in enumerate(idx):
+        if not keep[j]:
+            continue
+        outs, ow_ = drv_oracle_step_batch(cfg, recs[j:j + 1], an[e:e + 1], seed, env_id0=int(e))
+        bad += [(int(e),) + b[1:] for b in drv_compare_step(cfg, _Rows(out, torch.tensor([int(e)], device=dev)), gw[j:j + 1], outs, ow_, 1e-4)]
+    assert len(set(b[0] for b in bad)) <= 1, bad[:10]
+
+
+def test_image_full_size():
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    from oracle import raster_oracle
+    from oracle.oracle import record_to_raw
+    n, P = 16384, 10
+    sim = dynenv_b200.BatchedRoboCup(n, 5, dynenv_b200.ObservationType.IMAGE, 1, 2.0, allowHeadTurn=True, auto_reset=True, seed=42)
+    sim.reset()
+    dev = sim.device
+    g = torch.Generator(device=dev).manual_seed(1234)
+    for _ in range(3):
+        a = _rc_actions(g, n, P, dev)
+        a[..., 3] = torch.rand((n, P), generator=g, device=dev) * 6 - 3  # continuous head turn
+        out = sim.step(a)
+    assert int(out.diag.max()) == 0
+    ri = out.raw.view(torch.int32)
+    caps = torch.tensor([L.RC_CAP_BALL, L.RC_CAP_ROBOT, L.RC_CAP_POST, L.RC_CAP_CROSS, L.RC_CAP_FCROSS, L.RC_CAP_LINE], device=dev)
+    rc = ri[..., L.RC_R_COUNTS:L.RC_R_COUNTS + 6]
+    assert bool((rc >= 0).all()) and bool((rc <= caps).all())
+    assert torch.equal(rc, out.counts)  # the raw record lists what the encoded record lists
+    # a chunk from the far end of the batch: rendering is idempotent and does not depend on the chunking
+    lo, hi = n - 40, n - 8
+    img = sim.render_images(lo, hi)
+    again = sim.render_images(lo, hi)
+    assert torch.equal(img, again)
+    split = torch.cat([sim.render_images(lo, lo + 5), sim.render_images(lo + 5, hi)])
+    assert torch.equal(img, split)
+    # plane checksum: the bottom camera never sees more field-line pixels than a full image, empty lists give empty planes
+    flat = img.view(-1, 8, L.RC_IMG_H * L.RC_IMG_WORDS_PER_ROW)
+    rcc = rc[lo:hi].reshape(-1, 6)
+    no_ball = rcc[:, 0] == 0
+    assert int(flat[no_ball][:, 0].abs().sum()) == 0 and int(flat[no_ball][:, 4].abs().sum()) == 0
+    no_robot = rcc[:, 1] == 0
+    assert int(flat[no_robot][:, 1].abs().sum()) == 0 and int(flat[no_robot][:, 5].abs().sum()) == 0
+    # a sample of the chunk against the cv2 oracle
+    raw = out.raw[lo:hi].cpu().numpy().reshape(-1, L.RC_RAW_WORDS)
+    got = img.cpu().numpy().view(np.uint32).reshape(-1, 8, L.RC_IMG_H, L.RC_IMG_WORDS_PER_ROW)
+    pick = np.random.default_rng(2).choice(len(raw), 24, replace=False)
+    bad = []
+    for k in pick:
+        ref = raster_oracle.pack(raster_oracle.render(record_to_raw(raw[k])))
+        diff = int(np.unpackbits((got[k] ^ ref).view(np.uint8)).sum())
+        if diff:
+            bad.append((int(k), diff))
+    assert len(bad) <= 1 and all(d < 200 for _, d in bad), bad  # see test_gpu_image.py (one conic vertex may round differently)
