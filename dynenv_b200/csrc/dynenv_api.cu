@@ -502,6 +502,15 @@ int dynenv_discount_rewards(int device, const float* rewards_dev, const float* f
   return DYNENV_OK;
 }
 
+#ifdef RASTER_PROFILE
+int dynenv_debug_raster_prof(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, rcimg::g_raster_prof, 16 * sizeof(unsigned long long));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rcimg::g_raster_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream) {
   if (!h || !state_dev) return fail(DYNENV_E_INVALID, "null argument");
   cudaSetDevice(h->cfg.device);

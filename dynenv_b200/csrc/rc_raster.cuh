@@ -7,12 +7,17 @@
  * circle on 2 x 4 planes of 480 x 640 float64 per robot and tick, 19.7 MB in the reference -- by 307 KB of bit-planes.
  * HBM-write bound by construction: every plane is written exactly once.  Drawing: one warp per primitive (or
  * poly-line segment of the centre-circle conic), its rows / pixels in closed form on the 32 lanes (raster_prims.cuh),
- * atomicOr on shared-memory words.  Three blocks per SM.
+ * atomicOr on shared-memory words.  Three blocks of 256 threads per SM.
  *
  * Measured (1024 environments = 409 600 planes per launch): zero + store alone 2.6 ms (6.0 TB/s, 92 % of the HBM peak);
- * with the primitives 12 ms, with the centre-circle conic 13 ms, everything 28-30 ms (RASTER_SKIP_* ablations below):
- * the drawing, not the store, is what keeps this kernel off its roofline.  The drawing routines are compiled once
- * (noinline): inlined into their three call sites the kernel is 207 KB of SASS and 50 % slower (instruction fetch).
+ * with the primitives 12 ms, with the centre-circle conic 13 ms, everything 24-27 ms (RASTER_SKIP_* ablations below):
+ * the drawing, not the store, is what keeps this kernel off its roofline.  Per non-empty plane (clock64 per phase,
+ * -DRASTER_PROFILE, tools/gpu_raster_prof.py): 48 k cycles = set-up 5 k + primitives 27 k (slowest warp; mean 17 k) +
+ * conic segments 13 k (mean 4 k) + store 8 k; the lines channel costs 33 k of them.  The launch shape does not matter
+ * (256 x 3 blocks per SM 41.0 k env-steps/s, 320 x 3 41.0, 384 x 2 40.5, 512 x 2 39.4, 256 x 4 38.3, 192 x 4 37.9,
+ * 128 x 5 35.9): the warps are bound by the latency of their own 64-bit integer chains, i.e. by the work per plane.
+ * The drawing routines are compiled once (noinline): inlined into their three call sites the kernel is 207 KB of SASS
+ * and 50 % slower (instruction fetch).
  */
 #pragma once
 #include "dynenv_common.cuh"
@@ -21,18 +26,26 @@
 namespace dynenv {
 namespace rcimg {
 
-constexpr int THREADS = 256, WARPS = THREADS / 32;
-/* shared-memory layout in 32-bit words */
+#ifndef RASTER_THREADS
+#define RASTER_THREADS 256
+#endif
+constexpr int THREADS = RASTER_THREADS, WARPS = THREADS / 32;
+static_assert(THREADS >= 64 && THREADS % 32 == 0, "one warp builds primitives while another fits the conic");
+/* shared-memory layout in 32-bit words: 45.3 KB (up to five blocks per SM).  The plane doubles as the scratch of the conic's
+   uncompacted rows (x1[480], x2[480], valid[480]) before it is zeroed. */
+constexpr int PLANE_PRIMS = 40;                               /* most primitives of one channel: 11 lines + 24 crosses + 4 closures */
+static_assert(RC_CAP_LINE + RC_CAP_CROSS + RC_CAP_FCROSS + 4 <= PLANE_PRIMS && RC_CAP_ROBOT <= PLANE_PRIMS, "primitive list");
 constexpr int S_PLANE = 0;                                    /* [PLANE_WORDS]    */
 constexpr int S_RAW = S_PLANE + raster::PLANE_WORDS;          /* [RC_RAW_WORDS]   */
-constexpr int S_PRIMS = S_RAW + RC_RAW_WORDS;                 /* Prim[MAX_PRIMS]  */
+constexpr int S_PRIMS = S_RAW + RC_RAW_WORDS;                 /* Prim[PLANE_PRIMS] */
 constexpr int PRIM_WORDS = sizeof(raster::Prim) / 4;
-constexpr int S_CONIC = S_PRIMS + raster::MAX_PRIMS * PRIM_WORDS; /* Conic */
+constexpr int S_CONIC = S_PRIMS + PLANE_PRIMS * PRIM_WORDS;   /* Conic */
 constexpr int CONIC_WORDS = (sizeof(raster::Conic) + 3) / 4;
-constexpr int S_TMP = S_CONIC + CONIC_WORDS;                  /* x1[480], x2[480], valid[480] of the uncompacted rows */
-constexpr int S_PARAMS = (S_TMP + 3 * raster::CONIC_ROWS + 1) / 2 * 2; /* double[8]: conic parameters, centre */
+constexpr int S_PARAMS = (S_CONIC + CONIC_WORDS + 1) / 2 * 2; /* double[8]: conic parameters, centre */
 constexpr int S_MISC = S_PARAMS + 16;                         /* [0] number of primitives, [1] conic present */
 constexpr int SMEM_WORDS = S_MISC + 4;
+static_assert(5 * (SMEM_WORDS * 4 + 1024) <= 228 * 1024, "five blocks per SM");
+static_assert(3 * raster::CONIC_ROWS <= raster::PLANE_WORDS, "conic scratch inside the plane");
 
 __device__ __forceinline__ void bulk_store_plane(uint32_t* gdst, const uint32_t* ssrc) {
   /* generic-proxy writes (atomicOr) -> async proxy read; one elected thread issues the copy and keeps the block
@@ -45,8 +58,17 @@ __device__ __forceinline__ void bulk_store_plane(uint32_t* gdst, const uint32_t*
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+#ifdef RASTER_PROFILE
+/* dev experiment: cycles per phase, summed over the non-empty planes of a launch.  [0] blocks, [1] setup, [2] conic rows,
+   [3] sum over warps of the primitive loop, [4] its max over warps x 8, [5] sum of the conic segments, [6] max x 8,
+   [7] store, [8] total */
+__device__ unsigned long long g_raster_prof[16];
+#define RPROF(x) x
+#else
+#define RPROF(x)
+#endif
 #ifndef RASTER_MINB
-#define RASTER_MINB 3 /* 80 registers; measured 29.8 ms per 1024 environments against 32.5 ms at 4 blocks / 64 registers */
+#define RASTER_MINB 3
 #endif
 __global__ void __launch_bounds__(THREADS, RASTER_MINB)
 rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* __restrict__ images) {
@@ -58,24 +80,20 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   float* sraw = reinterpret_cast<float*>(g_smem + S_RAW);
   raster::Prim* prims = reinterpret_cast<raster::Prim*>(g_smem + S_PRIMS);
   raster::Conic* conic = reinterpret_cast<raster::Conic*>(g_smem + S_CONIC);
-  int* tmp = reinterpret_cast<int*>(g_smem + S_TMP);
+  int* tmp = reinterpret_cast<int*>(plane);
   double* params = reinterpret_cast<double*>(g_smem + S_PARAMS);
   int* misc = reinterpret_cast<int*>(g_smem + S_MISC);
-  {
-    uint4* p4 = reinterpret_cast<uint4*>(plane);
-    for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) p4[w] = make_uint4(0, 0, 0, 0);
-    if (tid < RC_RAW_WORDS) sraw[tid] = raw[rec * RC_RAW_WORDS + tid];
-    if (tid == 0) { misc[0] = raster::N_SLOTS; misc[1] = 0; conic->n = 0; }
-  }
+  RPROF(__shared__ unsigned long long pmax[2]; const long long t0 = clock64(); if (tid == 0) { pmax[0] = pmax[1] = 0; })
+  for (int w = tid; w < RC_RAW_WORDS; w += THREADS) sraw[w] = raw[rec * RC_RAW_WORDS + w];
+  if (tid == 0) { misc[0] = 0; misc[1] = 0; conic->n = 0; }
   __syncthreads();
-  /* primitives of this plane: one slot per thread (float64 projections); the conic fit on another warp */
-  if (tid < raster::N_SLOTS) {
+  /* primitives of this plane's channel, compacted (the order does not matter: drawing is a bitwise OR); float64
+     projections, one slot per thread; the conic fit on the last warp */
+  for (int slot = tid; slot < raster::N_SLOTS; slot += THREADS) {
     raster::Prim p;
-    p.type = -1;
-    if (raster::slot_plane(tid) == ch && !raster::build_prim_slot(sraw, cam, tid, &p)) p.type = -1;
-    prims[tid] = p;
+    if (raster::slot_plane(slot) == ch && raster::build_prim_slot(sraw, cam, slot, &p)) prims[atomicAdd(&misc[0], 1)] = p;
   }
-  if (ch == 3 && tid == 64) {
+  if (ch == 3 && tid == THREADS - 32) {
     int thickness = 0;
     double cx, cy;
     const bool ok = raster::conic_setup(sraw, cam, params, &cx, &cy, &thickness);
@@ -83,12 +101,14 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     misc[1] = ok ? 1 : 0;
     conic->thickness = thickness;
   }
+  __syncthreads();
   /* a plane without anything to draw (no ball in sight, no goal post ...) is streamed out as zeros from registers */
-  if (__syncthreads_count(tid < raster::N_SLOTS && prims[tid].type >= 0) == 0 && !(ch == 3 && misc[1])) {
+  if (misc[0] == 0 && !misc[1]) {
     uint4* dst = reinterpret_cast<uint4*>(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS);
     for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) dst[w] = make_uint4(0, 0, 0, 0);
     return;
   }
+  RPROF(const long long t1 = clock64();)
   if (misc[1]) { /* block-uniform */
     for (int y = tid; y < raster::CONIC_ROWS; y += THREADS) {
       int x1 = 0, x2 = 0;
@@ -111,11 +131,17 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
       __syncwarp();
       if (lane == 0) {
         conic->n = n;
-        misc[0] = raster::conic_closures(*conic, prims, raster::N_SLOTS);
+        misc[0] = raster::conic_closures(*conic, prims, misc[0]);
       }
     }
     __syncthreads();
   }
+  {
+    uint4* p4 = reinterpret_cast<uint4*>(plane);
+    for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) p4[w] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  RPROF(const long long t2 = clock64();)
   const int nprims = misc[0];
   const int nseg = conic->n > 1 ? 2 * (conic->n - 1) : 0;
   const raster::Lanes L = {lane, 32};
@@ -126,7 +152,6 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     int k = 0; /* small primitives seen so far (block-uniform) */
     for (int w = 0; w < nprims; w++) {
       const raster::Prim p = prims[w];
-      if (p.type < 0) continue;
 #ifdef RASTER_SKIP_PRIMS
       continue;
 #endif
@@ -137,12 +162,15 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
       } else if ((k++ % WARPS) == warp) raster::draw_prim(plane, p, L);
     }
   }
+  RPROF(const long long t3 = clock64(); if (lane == 0) { atomicAdd(&g_raster_prof[3], (unsigned long long)(t3 - t2)); atomicMax(&pmax[0], (unsigned long long)(t3 - t2)); })
   /* the conic's ~2 x 479 poly-line segments are one pixel high and `thickness` wide: one thread per segment */
   const raster::Lanes one = {0, 1};
 #ifndef RASTER_SKIP_CONIC
   for (int sgm = tid; sgm < nseg; sgm += THREADS) raster::draw_conic_segment(plane, *conic, sgm, one);
 #endif
+  RPROF(const long long t4 = clock64(); if (lane == 0) { atomicAdd(&g_raster_prof[5], (unsigned long long)(t4 - t3)); atomicMax(&pmax[1], (unsigned long long)(t4 - t3)); })
   __syncthreads();
+  RPROF(const long long t5 = clock64();)
 #ifdef RASTER_BULK_STORE
   if (tid == 0) bulk_store_plane(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS, plane);
 #else
@@ -153,6 +181,10 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) dst[w] = src[w];
   }
 #endif
+  RPROF(if (tid == 0) { const long long t6 = clock64(); atomicAdd(&g_raster_prof[0], 1ull); atomicAdd(&g_raster_prof[1], (unsigned long long)(t1 - t0));
+    atomicAdd(&g_raster_prof[2], (unsigned long long)(t2 - t1)); atomicAdd(&g_raster_prof[4], 8 * pmax[0]); atomicAdd(&g_raster_prof[6], 8 * pmax[1]);
+    atomicAdd(&g_raster_prof[7], (unsigned long long)(t6 - t5)); atomicAdd(&g_raster_prof[8], (unsigned long long)(t6 - t0));
+    atomicAdd(&g_raster_prof[9 + (plane_id & 3)], (unsigned long long)(t6 - t0)); })
 }
 
 }  // namespace rcimg

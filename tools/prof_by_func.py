@@ -48,7 +48,8 @@ nenv = float(os.environ.get("NENV", "65536"))
 print("%-52s %8s %8s %12s %8s %8s %8s %6s" % ("function", "samples%", "inst%", "inst/envstep", "no_inst%", "wait+br%", "sb%", "lanes"))
 for nm, a in sorted(agg.items(), key=lambda x: -x[1][0])[:26]:
     dn = subprocess.run(['c++filt', nm], capture_output=True, text=True).stdout.strip()
-    dn = re.sub(r'dynenv::(rc::)?', '', dn)[:52]
+    dn = re.sub(r'dynenv::(rc::)?', '', dn)
+    dn = (dn.split('$_ZN6raster')[-1] if '$_ZN6raster' in dn else dn)[:52]
     print("%-52s %8.1f %8.1f %12.0f %8.0f %8.0f %8.0f %6.1f" % (dn, 100 * a[0] / tot, 100 * a[1] / toti, a[1] / nenv, 100 * a[2] / max(a[0], 1),
                                                       100 * a[4] / max(a[0], 1), 100 * a[5] / max(a[0], 1), a[3] / max(a[1], 1)))
 print('total warp-instructions per env-step: %.0f' % (toti / nenv))
