@@ -425,16 +425,17 @@ def run_gpu(args):
     h_act = [p.cpu().pin_memory() for p in pool[:min(n_pool, 32)]]
     n_pool = len(h_act)
     d_act = torch.empty((E, P, wl.act), device=dev)
-    h_rew = torch.empty((E, P), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((E,), dtype=torch.int32).pin_memory()
+    # rewards [maxAgents] and done are the first words of every environment's result record: one strided copy
+    # (two copies of the `rewards` / `done` views cost 0.45-1.0 ms per step, tools/gpu_e2e_parts.py)
+    n_res = (L.DRV_I_DONE if args.workload == "driving" else L.RC_I_DONE) + 1
+    h_res = torch.empty((E, n_res), dtype=torch.float32).pin_memory()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for s in range(args.steps):
         d_act.copy_(h_act[s % n_pool], non_blocking=True)
         out = sim.step(d_act)
-        h_rew.copy_(out.rewards, non_blocking=True)
-        h_done.copy_(out.done, non_blocking=True)
+        h_res.copy_(out.info[:, :n_res], non_blocking=True)
         stream.synchronize()
     e1.record(stream)
     barrier()
@@ -446,6 +447,10 @@ def run_gpu(args):
         ms_total, ms_e2e, kernel_ms = [float(x) for x in t.tolist()]
     if rank == 0:
         peaks, which = measured_peaks()
+        import ctypes
+        from dynenv_b200 import _lib as _l
+        tf = ctypes.c_float(0)
+        fp32_peak = float(tf.value) if _l.lib().dynenv_debug_fp32_peak(local, ctypes.byref(tf)) == 0 else None
         total_envs = E * world
         value = total_envs * args.steps / (ms_total * 1e-3)
         e2e = total_envs * args.steps / (ms_e2e * 1e-3)
@@ -472,7 +477,7 @@ def run_gpu(args):
                                **wl.config(L)),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * P * wl.act * 4,
-                        "d2h_bytes_per_step": E * P * 4 + E * 4,
+                        "d2h_bytes_per_step": E * n_res * 4,
                         "note": "observations stay device-resident for the learner; rewards + done return to the host"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
@@ -485,7 +490,8 @@ def run_gpu(args):
                              "fp32": {"flop_per_env_step": FLOP_PER_ENV_STEP,
                                       "achieved_tflops": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12,
                                       "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
-                                      "frac": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12 / FP32_NOMINAL_TFLOPS}},
+                                      "measured_peak_tflops": fp32_peak,  # FMA probe of the library, this run
+                                      "frac": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12 / (fp32_peak or FP32_NOMINAL_TFLOPS)}},
                 "diag_flags": diag}
         if not args.no_cpu and world == 1:
             cpu_steps = args.cpu_steps or wl.cpu_steps

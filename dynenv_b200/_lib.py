@@ -12,7 +12,7 @@ _LIB = None
 EXPORTS = ["dynenv_abi_version", "dynenv_last_error", "dynenv_create", "dynenv_destroy", "dynenv_state_words",
            "dynenv_reset", "dynenv_step", "dynenv_set_seed", "dynenv_get_state", "dynenv_set_state",
            "dynenv_last_launch_count", "dynenv_debug_substep_range", "dynenv_debug_timing",
-           "dynenv_last_kernel_ms", "dynenv_render_images", "dynenv_rollout_insert", "dynenv_discount_rewards"]
+           "dynenv_last_kernel_ms", "dynenv_render_images", "dynenv_rollout_insert", "dynenv_discount_rewards", "dynenv_debug_fp32_peak"]
 
 
 class DynEnvConfig(C.Structure):
@@ -62,6 +62,7 @@ def lib():
                                              C.c_void_p, C.c_void_p]
         lb.dynenv_discount_rewards.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                                C.c_int64, C.c_float, C.c_void_p]
+        lb.dynenv_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_float)]
         if lb.dynenv_abi_version() != L.DYNENV_ABI_VERSION:
             raise RuntimeError("dynenv_b200: library ABI %d != header ABI %d" % (lb.dynenv_abi_version(),
                                                                                  L.DYNENV_ABI_VERSION))

@@ -1538,7 +1538,8 @@ __device__ __noinline__ void full_obs_agent(const Env E, int ag) {
        geometry of lane offset (i - nLanes) mod (2*nLanes+1) - nLanes under the type tag of i (:690-696) */
     const int road = lane < 5 ? 0 : 1, nL = road_lanes(road), i = (lane < 5 ? lane : lane - 5) - nL;
     const int cntL = 2 * nL + 1;
-    const int off = (((i - nL) % cntL) + cntL) % cntL - nL;
+    const int t = i - nL; /* in [-2 nL, 0]: Python's modulo is one wrap */
+    const int off = (t < 0 ? t + cntL : t) - nL;
     V2 nrm = road_normal(road), p0 = road_p0(road), p1 = road_p1(road);
     V2 l0 = p0 + nrm * ((float)off * ROAD_W), l1 = p1 + nrm * ((float)off * ROAD_W);
     float* o = E.f + (V_STAGE + DRV_O_LANE + lane * DRV_F_LANE_FULL);

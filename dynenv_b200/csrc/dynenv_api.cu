@@ -246,6 +246,24 @@ drv_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ stat
 }  // namespace
 
 constexpr int MAX_TIMED = 16; /* launches of one step */
+/* FP32 FMA throughput probe (dynenv_debug_fp32_peak) */
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters, float a, float b) {
+  float x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = (float)(threadIdx.x + k);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) x[k] = fmaf(x[k], a, b);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += x[k];
+  if (s == 123.456f) out[0] = s; /* never true: keeps the chains alive */
+}
+
 struct DynEnvHandle_s {
   DynEnvConfig cfg;
   SimCfg sim;
@@ -502,6 +520,25 @@ int dynenv_discount_rewards(int device, const float* rewards_dev, const float* f
   return DYNENV_OK;
 }
 
+#ifdef DYNENV_BOUNDS_CHECK
+__global__ void bounds_selftest_kernel(float* out) { /* one deliberate access behind the block's 64 bytes */
+  SharedF f{0};
+  out[0] = f[threadIdx.x == 0 ? 1000 : 1];
+}
+int dynenv_debug_bounds_selftest(void) {
+  float* d = nullptr;
+  cudaMalloc(&d, 4);
+  bounds_selftest_kernel<<<1, 32, 64>>>(d);
+  cudaDeviceSynchronize();
+  cudaFree(d);
+  cudaGetLastError();
+  return 0;
+}
+int dynenv_debug_bounds_violations(unsigned long long* out4) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out4, g_bounds_violations, 4 * sizeof(unsigned long long)) == cudaSuccess ? 0 : DYNENV_E_CUDA;
+}
+#endif
 #ifdef RASTER_PROFILE
 int dynenv_debug_raster_prof(unsigned long long* out16, int reset) {
   cudaDeviceSynchronize();
@@ -526,6 +563,41 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream) {
   cudaError_t ce = cudaMemcpyAsync(h->state, state_dev, (size_t)h->sim.n_envs * h->state_words * sizeof(uint32_t),
                                    cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(set_state)");
+  return DYNENV_OK;
+}
+
+int dynenv_debug_fp32_peak(int device, float* tflops_out) {
+  if (!tflops_out) return fail(DYNENV_E_INVALID, "null argument");
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  float* d = nullptr;
+  ce = cudaMalloc(&d, 4);
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaMalloc");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sms * 8, iters = 4096;
+  fma_probe_kernel<<<blocks, 256>>>(d, iters, 0.999f, 0.001f); /* warm-up */
+  float best = 0.f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    fma_probe_kernel<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 64.0 * iters * 256.0 * blocks;
+    const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "fma_probe_kernel");
+  *tflops_out = best;
   return DYNENV_OK;
 }
 

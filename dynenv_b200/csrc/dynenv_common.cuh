@@ -114,14 +114,34 @@ extern __shared__ __align__(16) uint32_t g_smem[];
 constexpr int CFG_WORDS = 32;
 static_assert(sizeof(SimCfg) <= CFG_WORDS * 4, "SimCfg must fit its shared-memory slot");
 
+#ifdef DYNENV_BOUNDS_CHECK
+/* Debug build (tools/gpu_bounds.sh): every access through SharedF / SharedI and every bit-plane word of the raster is
+   checked against the block's dynamic shared memory; violations are counted and read by dynenv_debug_bounds_violations.
+   (One environment per block, so the block's allocation is exactly one slice.) */
+__device__ unsigned long long g_bounds_violations[4]; /* count, first word index, first block, first thread */
+__device__ __forceinline__ void bounds_check(int word) {
+  unsigned bytes;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(bytes));
+  if (word < 0 || (unsigned)word * 4u >= bytes) {
+    if (atomicAdd(&g_bounds_violations[0], 1ull) == 0) {
+      g_bounds_violations[1] = (unsigned long long)(long long)word;
+      g_bounds_violations[2] = blockIdx.x;
+      g_bounds_violations[3] = threadIdx.x;
+    }
+  }
+}
+#define DYNENV_BC(word) bounds_check(word)
+#else
+#define DYNENV_BC(word)
+#endif
 struct SharedF { /* this warp's slice viewed as float */
   int base;
-  __device__ __forceinline__ float& operator[](int k) const { return reinterpret_cast<float*>(g_smem)[base + k]; }
+  __device__ __forceinline__ float& operator[](int k) const { DYNENV_BC(base + k); return reinterpret_cast<float*>(g_smem)[base + k]; }
   __device__ __forceinline__ float* operator+(int k) const { return reinterpret_cast<float*>(g_smem) + base + k; }
 };
 struct SharedI { /* ... and as int */
   int base;
-  __device__ __forceinline__ int& operator[](int k) const { return reinterpret_cast<int*>(g_smem)[base + k]; }
+  __device__ __forceinline__ int& operator[](int k) const { DYNENV_BC(base + k); return reinterpret_cast<int*>(g_smem)[base + k]; }
 };
 struct SharedCfg {
   __device__ __forceinline__ const SimCfg* operator->() const { return reinterpret_cast<const SimCfg*>(g_smem); }

@@ -33,6 +33,12 @@ struct P2 { /* cv::Point2l */
 
 RP_FN void or_word(uint32_t* p, uint32_t m) {
 #ifdef __CUDA_ARCH__
+#ifdef DYNENV_BOUNDS_CHECK
+  { /* the plane is the first PLANE_WORDS words of the block's shared memory (rc_raster.cuh) */
+    const long long w = (long long)(p - reinterpret_cast<uint32_t*>(dynenv::g_smem));
+    dynenv::bounds_check(w < 0 || w >= PLANE_WORDS ? -1 : (int)w);
+  }
+#endif
   atomicOr(p, m);
 #else
   *p |= m;

@@ -493,6 +493,11 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);
 int dynenv_debug_timing(DynEnvHandle h, int enable);
 int dynenv_last_kernel_ms(DynEnvHandle h, float* ms3, int* launches3);
 
+/* Measurement aid: FP32 (CUDA-core, non-tensor) FMA throughput of `device` in TFLOP/s, from a register-resident FMA
+   kernel timed with CUDA events (8 independent chains per thread, 148 x 8 blocks of 256 threads, warmed up): the
+   denominator SURVEY 8d asks for next to the step kernels' flop rate.  Synchronises the device. */
+int dynenv_debug_fp32_peak(int device, float* tflops_out);
+
 /* number of kernels launched by the last dynenv_step / dynenv_reset call on this handle */
 int dynenv_last_launch_count(DynEnvHandle h);
 
