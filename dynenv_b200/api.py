@@ -89,8 +89,6 @@ class RoboCupEnvironment(object):
                  noiseMagnitude=2, obs_space_cast=False, allowHeadTurn=False, seed=0, device=0):
         if noiseMagnitude < 0 or noiseMagnitude > 5:  # environment_base.py:162-164 (which prints and exits)
             raise ValueError("Error: The noise magnitude must be between 0 and 5!")
-        if render:
-            raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
         from .batched import BatchedRoboCup
         self.observationType = ObservationType(observationType)
         self.noiseType = NoiseType(noiseType)
@@ -103,7 +101,9 @@ class RoboCupEnvironment(object):
         self.stepNum = self.maxTime / self.stepIterCnt
         self.W, self.H = 1040, 740
         self.mean = 2.0  # `2.0 if ObservationType.PARTIAL else 1.0` is always 2.0 (RoboCupEnvironment.py:67)
-        self.renderMode, self.agentVisID = False, None
+        # render=True: renderMode 'memory' -- one top-down frame per step() / reset() in self.screenShots (the reference
+        # draws every substep into a pygame window, environment_base.py:152-159; here frames come from dynenv_b200.render)
+        self.renderMode, self.agentVisID, self.screenShots = ('memory' if render else False), None, []
         self.elapsed = 0
         self.agents = [_Agent(i, self.nPlayers) for i in range(2 * self.nPlayers)]
         self.action_space, self.observation_space = robocup_spaces(self.observationType, allowHeadTurn, self.mean)
@@ -132,6 +132,8 @@ class RoboCupEnvironment(object):
         out = self._sim.reset()
         self._last = RF.host_views(out, self._full)
         self.elapsed = 0
+        if self.renderMode:
+            self.render()
         return self._observations(out)
 
     def step(self, actions):
@@ -141,6 +143,8 @@ class RoboCupEnvironment(object):
         v = self._last = RF.host_views(out, self._full)
         P = 2 * self.nPlayers
         self.elapsed += self.stepIterCnt
+        if self.renderMode:
+            self.render()
         # (the reference's own step() raises TypeError in IMAGE mode, RoboCupEnvironment.py:1571; here it works and
         # the observation reward is the PARTIAL one)
         return self._observations(out), v["rewards"][0, :P].astype(np.float64), bool(v["done"][0]), RF.info_dict(v, 0, P)
@@ -162,7 +166,12 @@ class RoboCupEnvironment(object):
         return [self.allowHeadTurn]
 
     def render(self):
-        raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+        """top-down RGB frame of the current state (uint8 [H, W, 3]); appended to screenShots in renderMode 'memory'"""
+        from . import render as R
+        frame = R.render_env(self._sim, 0)
+        if self.renderMode == 'memory':
+            self.screenShots.append(frame)
+        return frame
 
     def close(self):
         self._sim.close()
@@ -212,8 +221,6 @@ class DrivingEnvironment(object):
                  noiseMagnitude=2, obs_space_cast=False, continuousActions=False, seed=0, device=0):
         if noiseMagnitude < 0 or noiseMagnitude > 5:  # environment_base.py:162-164 (which prints and exits)
             raise ValueError("Error: The noise magnitude must be between 0 and 5!")
-        if render:
-            raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
         if ObservationType(observationType) == ObservationType.IMAGE:  # DrivingEnvironment.py:33-35 (prints and exits)
             raise ValueError("Image observation type is not supported for this environment")
         from .batched import BatchedDriving
@@ -228,7 +235,9 @@ class DrivingEnvironment(object):
         self.stepNum = self.maxTime / self.stepIterCnt
         self.W, self.H = 1750, 1000
         self.mean = 5.0
-        self.renderMode, self.agentVisID = False, None
+        # render=True: renderMode 'memory' -- one top-down frame per step() / reset() in self.screenShots (the reference
+        # draws every substep into a pygame window, environment_base.py:152-159; here frames come from dynenv_b200.render)
+        self.renderMode, self.agentVisID, self.screenShots = ('memory' if render else False), None, []
         self.elapsed = 0
         self.agents = [_Agent(i, self.nPlayers) for i in range(self.nPlayers)]
         self.action_space, self.observation_space = driving_spaces(self.observationType, continuousActions, self.mean)
@@ -247,6 +256,8 @@ class DrivingEnvironment(object):
     def reset(self):
         self._last = RF.drv_host_views(self._sim.reset())
         self.elapsed = 0
+        if self.renderMode:
+            self.render()
         return RF.drv_observations(self._last, 0, self.nPlayers, self._full)
 
     def step(self, actions):
@@ -256,6 +267,8 @@ class DrivingEnvironment(object):
         v = self._last = RF.drv_host_views(out)
         N = self.nPlayers
         self.elapsed += self.stepIterCnt
+        if self.renderMode:
+            self.render()
         return RF.drv_observations(v, 0, N, self._full), v["rewards"][0, :N].astype(np.float64), bool(v["done"][0]), \
             RF.drv_info_dict(v, 0, N)
 
@@ -273,7 +286,12 @@ class DrivingEnvironment(object):
         return [self.continuousActions]
 
     def render(self):
-        raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+        """top-down RGB frame of the current state (uint8 [H, W, 3]); appended to screenShots in renderMode 'memory'"""
+        from . import render as R
+        frame = R.render_env(self._sim, 0)
+        if self.renderMode == 'memory':
+            self.screenShots.append(frame)
+        return frame
 
     def close(self):
         self._sim.close()
