@@ -382,7 +382,9 @@ def run_gpu(args):
     # synthetic actions, generator seed 1234
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
-    n_pool = min(args.steps + args.warmup, 128)  # fresh uniform actions every step (a short cycle would bias the play)
+    # fresh uniform actions every step: a cycle biases the play (every robot repeats its walk, they drift together and
+    # collide: a 32-step cycle costs 12 % env-steps/s, tools/gpu_e2e_parts.py), so the pool covers the whole run
+    n_pool = min(args.steps + args.warmup, 640)
     pool = [wl.make_actions(E, g, dev) for _ in range(n_pool)]
     stream = torch.cuda.current_stream()
 
@@ -422,7 +424,7 @@ def run_gpu(args):
     diag = int(sim.out.diag.max().item())
 
     # end to end through the host-facing call: pinned host actions in, rewards + done out, every step
-    h_act = [p.cpu().pin_memory() for p in pool[:min(n_pool, 32)]]
+    h_act = [p.cpu().pin_memory() for p in pool[:min(n_pool, args.steps)]]  # the timed steps' own actions, from pinned host memory
     n_pool = len(h_act)
     d_act = torch.empty((E, P, wl.act), device=dev)
     # rewards [maxAgents] and done are the first words of every environment's result record: one strided copy

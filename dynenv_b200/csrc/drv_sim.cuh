@@ -1324,11 +1324,13 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   int pedInter = I_NO;
   {
     int carPed = 0, obsPed = 0;
+    /* the cars / obstacles still in their lists: a warp-uniform set, visited bit by bit */
+    const unsigned inList = __ballot_sync(FULLMASK, lane < 30 && (lane < 10 ? lane < N : lane < 10 + nObs) && (E.i[V_OK + lane] & 1));
     if (listB) {
-      for (int o = 0; o < N; o++)
-        if (E.i[V_OK + o] & 1) carPed = max(carPed, interact_poly(E, B.px, B.py, angB, o, 400.f));
-      for (int o = 10; o < 10 + nObs; o++)
-        if (E.i[V_OK + o] & 1) obsPed = max(obsPed, interact_poly(E, B.px, B.py, angB, o, 400.f));
+      for (unsigned m = inList & 0x3FFu; m; m &= m - 1)
+        carPed = max(carPed, interact_poly(E, B.px, B.py, angB, __ffs(m) - 1, 400.f));
+      for (unsigned m = inList >> 10; m; m &= m - 1)
+        obsPed = max(obsPed, interact_poly(E, B.px, B.py, angB, 10 + __ffs(m) - 1, 400.f));
     }
     unsigned differ = __ballot_sync(FULLMASK, listB && carPed != obsPed);
     unsigned obsWins = __ballot_sync(FULLMASK, listB && obsPed > carPed);
