@@ -88,7 +88,7 @@ enum {
   R_BLOCKS = X_UNION,          /* U[NRESET_BLOCKS][4] */
   R_END = R_BLOCKS + 4 * NRESET_BLOCKS,
   ENV_SMEM_WORDS_A = X_PHYS_END > V_END ? X_PHYS_END : V_END,
-  ENV_SMEM_WORDS = ((ENV_SMEM_WORDS_A > R_END ? ENV_SMEM_WORDS_A : R_END) + 31) / 32 * 32
+  ENV_SMEM_WORDS = ((ENV_SMEM_WORDS_A > R_END ? ENV_SMEM_WORDS_A : R_END) + 3) / 4 * 4
 };
 
 struct Env {

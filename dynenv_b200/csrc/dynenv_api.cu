@@ -30,6 +30,8 @@ namespace {
 #define RC_MINB_ 32
 #endif
 constexpr int RC_WPC = RC_WPC_; /* environments (warps) per CTA */
+/* 32 one-warp blocks per SM: 228 KB of shared memory / 32 - 1 KB reserved per block = 6272 bytes */
+static_assert((CFG_WORDS + rc::ENV_SMEM_WORDS) * 4 <= 6272 && (CFG_WORDS + drv::ENV_SMEM_WORDS) * 4 <= 6272, "one more block per SM");
 
 thread_local std::string g_err;
 
@@ -521,9 +523,9 @@ int dynenv_discount_rewards(int device, const float* rewards_dev, const float* f
 }
 
 #ifdef DYNENV_BOUNDS_CHECK
-__global__ void bounds_selftest_kernel(float* out) { /* one deliberate access behind the block's 64 bytes */
-  SharedF f{0};
-  out[0] = f[threadIdx.x == 0 ? 1000 : 1];
+__global__ void bounds_selftest_kernel(float* out) { /* one index behind the block's 64 bytes (checked, not accessed) */
+  bounds_check(threadIdx.x == 0 ? 1000 : 1);
+  out[0] = 1.f;
 }
 int dynenv_debug_bounds_selftest(void) {
   float* d = nullptr;

@@ -111,7 +111,7 @@ struct Rand6 {
    per warp.  Everything is addressed through this symbol so that the compiler emits LDS/STS (a pointer
    handed to a non-inlined function would degrade to generic loads). */
 extern __shared__ __align__(16) uint32_t g_smem[];
-constexpr int CFG_WORDS = 32;
+constexpr int CFG_WORDS = 20; /* a multiple of 4: the slices behind it are copied with 128-bit accesses */
 static_assert(sizeof(SimCfg) <= CFG_WORDS * 4, "SimCfg must fit its shared-memory slot");
 
 #ifdef DYNENV_BOUNDS_CHECK

@@ -84,8 +84,8 @@ enum {
   X_GY = X_GX + 16,
   X_GR = X_GY + 16,
   X_NCAND = X_GR + 16,         /* I */
-  X_CAND = X_NCAND + 1,        /* I[RC_MAXCAND] i * 32 + j */
-  X_BP_END = X_CAND + RC_MAXCAND,
+  X_CAND = X_NCAND + 1,        /* U16[RC_MAXCAND] i * 32 + j, two per word */
+  X_BP_END = X_CAND + RC_MAXCAND / 2,
   /* vision view of the union */
   V_ROB = X_UNION,             /* F[9][3] other robots' sightings: x, y, has */
   V_BALL = V_ROB + 27,         /* F[3] */
@@ -94,7 +94,8 @@ enum {
   V_CNT = V_RAW + 3 * RC_CAP_ROBOT, /* I[6] list lengths */
   V_STAGE = (V_CNT + 6 + 3) / 4 * 4, /* [RC_OBS_WORDS] the observation record being built */
   V_END = V_STAGE + RC_OBS_WORDS,
-  ENV_SMEM_WORDS = ((X_BP_END > V_END ? X_BP_END : V_END) + 31) / 32 * 32,
+  /* CFG_WORDS + ENV_SMEM_WORDS <= 1568 words: 32 one-warp blocks per SM (228 KB / 32 - 1 KB reserved per block) */
+  ENV_SMEM_WORDS = ((X_BP_END > V_END ? X_BP_END : V_END) + 3) / 4 * 4,
   /* IMAGE observations: the raw detection record (RC_R_*) is staged behind the slice; only the kernels instantiated
      for IMAGE mode allocate these words (per-warp stride ENV_SMEM_WORDS_RAW) */
   V_RAWREC = ENV_SMEM_WORDS,
@@ -1175,12 +1176,13 @@ __device__ bool shapes_touch(const Env E, int i, int j) {
    collided in Chipmunk's ascending (i, j) insertion order (lane 0) */
 __device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsigned g0, unsigned g1, unsigned g2, unsigned g3) {
   const int lane = E.lane;
+  unsigned short* cand = reinterpret_cast<unsigned short*>(g_smem + E.i.base + X_CAND);
   if (lane == 0) {
     int n = 0;
     while (own) {
       int j = __ffs(own) - 1;
       own &= own - 1;
-      E.i[X_CAND + n++] = (j - 1) * 32 + j;
+      cand[n++] = (j - 1) * 32 + j;
     }
     unsigned g[4] = {g0, g1, g2, g3};
     for (int w = 0; w < 4; w++) {
@@ -1197,7 +1199,7 @@ __device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsig
             float dx = E.f[X_BCX + i] - E.f[X_BCX + j], dy = E.f[X_BCY + i] - E.f[X_BCY + j];
             float rr = (i < 20 ? ROB_LEN + ROB_RAD : 10.f) + (j < 20 ? ROB_LEN + ROB_RAD : 10.f) + 0.05f;
             if (dx * dx + dy * dy < rr * rr) { /* bounding circles of the two shapes */
-              if (n < RC_MAXCAND) E.i[X_CAND + n++] = i * 32 + j;
+              if (n < RC_MAXCAND) cand[n++] = i * 32 + j;
               else E.i[X_DIAG] |= RC_IF_ACTIVE_OVERFLOW;
             }
           }
@@ -1210,21 +1212,21 @@ __device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsig
   int kept = 0;
   for (int base = 0; base < n; base += 32) {
     int c = base + lane;
-    int key = c < n ? E.i[X_CAND + c] : 0;
+    int key = c < n ? cand[c] : 0;
     bool touch = c < n && shapes_touch(E, key >> 5, key & 31);
     unsigned km = __ballot_sync(FULLMASK, touch);
     __syncwarp();
-    if (touch) E.i[X_CAND + kept + __popc(km & ((1u << lane) - 1))] = key; /* kept + rank <= c: no overwrite of unread keys */
+    if (touch) cand[kept + __popc(km & ((1u << lane) - 1))] = key; /* kept + rank <= c: no overwrite of unread keys */
     kept += __popc(km);
     __syncwarp();
   }
   if (lane == 0 && kept) {
     for (int x = 1; x < kept; x++) { /* insertion sort: tiny */
-      int key = E.i[X_CAND + x], y = x - 1;
-      while (y >= 0 && E.i[X_CAND + y] > key) { E.i[X_CAND + y + 1] = E.i[X_CAND + y]; y--; }
-      E.i[X_CAND + y + 1] = key;
+      int key = cand[x], y = x - 1;
+      while (y >= 0 && cand[y] > key) { cand[y + 1] = cand[y]; y--; }
+      cand[y + 1] = key;
     }
-    for (int x = 0; x < kept; x++) collide_pair(E, E.i[X_CAND + x] >> 5, E.i[X_CAND + x] & 31);
+    for (int x = 0; x < kept; x++) collide_pair(E, cand[x] >> 5, cand[x] & 31);
   }
   __syncwarp();
 }

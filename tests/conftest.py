@@ -31,6 +31,6 @@ def pytest_sessionfinish(session, exitstatus):
     print("\n[bounds check] rc=%d violations=%d first word=%d block=%d thread=%d" % (rc, v[0], C.c_longlong(v[1]).value, v[2], v[3]))
     if rc != 0 or v[0] != 0:
         session.exitstatus = 1
-    lb.dynenv_debug_bounds_selftest()  # the checker itself: one deliberate access behind a 64-byte allocation
-    lb.dynenv_debug_bounds_violations(v)
-    print("[bounds check] self-test: %d new violation(s), word %d (expected 1, word 1000)" % (v[0], C.c_longlong(v[1]).value))
+    lb.dynenv_debug_bounds_selftest()  # the checker itself: one index behind a 64-byte allocation
+    rc = lb.dynenv_debug_bounds_violations(v)
+    print("[bounds check] self-test: rc=%d, %d new violation(s), word %d (expected 1, word 1000)" % (rc, v[0], C.c_longlong(v[1]).value))
