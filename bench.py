@@ -431,6 +431,11 @@ def run_gpu(args):
     # (two copies of the `rewards` / `done` views cost 0.45-1.0 ms per step, tools/gpu_e2e_parts.py)
     n_res = (L.DRV_I_DONE if args.workload == "driving" else L.RC_I_DONE) + 1
     h_res = torch.empty((E, n_res), dtype=torch.float32).pin_memory()
+    # the same window of the episode as the device-resident measurement: reset, the same warm-up steps, then the timed
+    # steps on their own actions (step times grow over an episode; a later window would not be comparable)
+    sim.reset()
+    for w in range(args.warmup):
+        sim.step(pool[(len(pool) - (args.warmup % len(pool)) + w) % len(pool)])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
