@@ -68,7 +68,8 @@ enum {
   X_BPMASK = X_CEY + DRV_MAXCARS,    /* I[64] per shape: cars whose bounding box overlaps it */
   X_NCAND = X_BPMASK + 64,
   X_CAND = X_NCAND + 1,              /* I[NCAND] lo * 64 + hi */
-  X_PHYS_END = X_CAND + NCAND,
+  X_CBOX = (X_CAND + NCAND + 3) / 4 * 4, /* F[10][4] per car: centre and bounding-box half extents, one 128-bit load */
+  X_PHYS_END = X_CBOX + 4 * DRV_MAXCARS,
   /* vision view */
   V_ANG2 = X_UNION,            /* F[NOCC] per occluder: angle of its centre, min / max corner angle ... */
   V_AMN = V_ANG2 + NOCC,
@@ -997,8 +998,10 @@ __device__ __noinline__ void space_step(const Env E) {
     const int t = E.i[DRV_S_CTYPE + i];
     const float h = car_length(t), w = car_width(t);
     E.f[X_CC + i] = cs; E.f[X_CS + i] = sn;
-    E.f[X_CEX + i] = fabsf(h * cs) + fabsf(w * sn);
-    E.f[X_CEY + i] = fabsf(h * sn) + fabsf(w * cs);
+    const float bex = fabsf(h * cs) + fabsf(w * sn), bey = fabsf(h * sn) + fabsf(w * cs);
+    E.f[X_CEX + i] = bex;
+    E.f[X_CEY + i] = bey;
+    *reinterpret_cast<float4*>(&E.f[X_CBOX + 4 * i]) = make_float4(px, py, bex, bey);
   } else if (isPed) {
     const int i = lane - 10;
     float px = E.f[DRV_S_PPX + i], pxl = E.f[DRV_S_PPXL + i], py = E.f[DRV_S_PPY + i], pyl = E.f[DRV_S_PPYL + i];
@@ -1035,10 +1038,13 @@ __device__ __noinline__ void space_step(const Env E) {
         if (j < nObs) { cx = E.f[DRV_S_OPX + j]; cy = E.f[DRV_S_OPY + j]; ex = OBST_HALF; ey = OBST_HALF; }
       }
       int m = 0;
-      for (int i = 0; i < N; i++) {
-        float dx = fabsf(E.f[DRV_S_CPX + i] - cx), dy = fabsf(E.f[DRV_S_CPY + i] - cy);
-        bool ov = dx <= E.f[X_CEX + i] + ex + 0.01f && dy <= E.f[X_CEY + i] + ey + 0.01f;
-        if (ov && (selfCar == 99 || i < selfCar)) m |= 1 << i;
+#pragma unroll
+      for (int i = 0; i < DRV_MAXCARS; i++) {
+        if (i < N) { /* warp-uniform */
+          const float4 b = *reinterpret_cast<const float4*>(&E.f[X_CBOX + 4 * i]);
+          const bool ov = fabsf(b.x - cx) <= b.z + ex + 0.01f && fabsf(b.y - cy) <= b.w + ey + 0.01f;
+          if (ov && i < selfCar) m |= 1 << i; /* selfCar = 99 for everything that is not a car */
+        }
       }
       mask[r] = m;
       if (m) {
