@@ -743,7 +743,8 @@ __device__ __forceinline__ void friction_phase(const Env E, bool isCar, bool isP
    cached pairs, pre-step, the friction velocity update, warm start and the 10 solver iterations.  Pairs that share
    no dynamic body are independent systems and iterate in the registers of their lane; otherwise the contacts are
    solved in pair order on lane 0 (Gauss-Seidel like the reference). */
-__device__ __noinline__ void contacts_substep(const Env E, int prevStepped, bool haveCand, bool isCar, bool isPed) {
+/* keepMask: cached pairs of bodies that nothing can reach in this substep -- neither collided nor aged */
+__device__ __noinline__ void contacts_substep(const Env E, int prevStepped, bool haveCand, bool isCar, bool isPed, unsigned keepMask) {
   const int lane = E.lane;
   const unsigned lt = (1u << lane) - 1;
   int ncand = 0;
@@ -822,7 +823,7 @@ __device__ __noinline__ void contacts_substep(const Env E, int prevStepped, bool
   if (act && q >= DRV_MAXACTIVE) { act = false; E.i[X_DIAG] |= RC_IF_ACTIVE_OVERFLOW; }
   actMask = __ballot_sync(FULLMASK, act);
   const int nact = __popc(actMask);
-  const unsigned touched = __reduce_or_sync(FULLMASK, hit ? (1u << k) : 0u);
+  const unsigned touched = __reduce_or_sync(FULLMASK, hit ? (1u << k) : 0u) | keepMask;
   float jn0 = 0.f, jn1 = 0.f;
   if (hit) {
     E.i[DRV_S_ARBKEY + k] = key16 | (state << 16); /* age = 0 */
@@ -1015,12 +1016,29 @@ __device__ __noinline__ void space_step(const Env E) {
   /* broad phase: every shape against the N cars (Chipmunk's bounding-box test; the margin covers the float32
      rounding of the absolute coordinates, the narrow phase decides exactly) */
   {
-    /* bit per dynamic body (cars 0..9, pedestrians 10..29): at rest.  Pairs of resting bodies are exactly where they
-       were in the previous substep and their contacts carry no impulse: if that holds for every overlapping pair and
-       every cached pair, the collision half of this substep changes nothing and is skipped. */
-    const unsigned restMask = __ballot_sync(FULLMASK, atRest);
-    bool pairsRest = true;
+    /* Bit per dynamic body (cars 0..9, pedestrians 10..29).  A pair of bodies at rest is exactly where it was in the
+       previous substep and its contacts carry no impulse; unless an impulse can reach it through a chain of overlapping
+       pairs from a body that moves (or from a cached pair that still stores an impulse, is ageing or has just begun),
+       colliding and solving it again changes nothing.  `dirty` is the closure of the moving bodies under "overlaps or
+       is cached with"; only pairs with a dirty body go through the collision half of the substep, the cached pairs of
+       clean bodies are kept as they are. */
+    unsigned dirty = __ballot_sync(FULLMASK, (isCar || isPed) && !atRest);
+    unsigned pairBodies = 0; /* lane < nArb: the dynamic bodies of cached pair `lane` */
+    {
+      unsigned seed = 0;
+      if (lane < nArb) {
+        const int key = E.i[DRV_S_ARBKEY + lane];
+        const int a = key & 255, b = (key >> 8) & 255;
+        if (a >= DRV_SHAPE_CAR0 && a < DRV_SHAPE_OBS0) pairBodies |= 1u << (a - DRV_SHAPE_CAR0);
+        if (b >= DRV_SHAPE_CAR0 && b < DRV_SHAPE_OBS0) pairBodies |= 1u << (b - DRV_SHAPE_CAR0);
+        const int st = (key >> 16) & 0xffff; /* state | age << 8 */
+        const bool quiet = (st == RC_ARB_NORMAL || st == RC_ARB_IGNORE) && E.f[DRV_S_ARBJN0 + lane] == 0.f && E.f[DRV_S_ARBJN1 + lane] == 0.f;
+        if (!quiet) seed = pairBodies;
+      }
+      if (nArb) dirty |= __reduce_or_sync(FULLMASK, seed);
+    }
     int mask[2];
+    unsigned own[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const int s = lane + 32 * r;
@@ -1047,33 +1065,34 @@ __device__ __noinline__ void space_step(const Env E) {
         }
       }
       mask[r] = m;
-      if (m) {
-        const int ownBit = s - DRV_SHAPE_CAR0; /* cars 4..13 -> 0..9, pedestrians 14..33 -> 10..29 */
-        const bool ownDyn = s >= DRV_SHAPE_CAR0 && s < DRV_SHAPE_OBS0;
-        if ((ownDyn && !((restMask >> ownBit) & 1)) || (m & ~restMask & 0x3ff)) pairsRest = false;
+      own[r] = (s >= DRV_SHAPE_CAR0 && s < DRV_SHAPE_OBS0) ? 1u << (s - DRV_SHAPE_CAR0) : 0u; /* cars 4..13 -> 0..9, pedestrians 14..33 -> 10..29 */
+    }
+    const bool anyPair = __any_sync(FULLMASK, (mask[0] | mask[1]) != 0) || nArb;
+    if (anyPair && dirty) {
+      for (;;) { /* closure: a few rounds at most (chains of touching bodies are short) */
+        unsigned add = 0;
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          if (mask[r] && ((own[r] & dirty) || ((unsigned)mask[r] & dirty))) add |= own[r] | (unsigned)mask[r];
+        if (pairBodies & dirty) add |= pairBodies;
+        const unsigned nd = dirty | __reduce_or_sync(FULLMASK, add);
+        if (nd == dirty) break;
+        dirty = nd;
       }
     }
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+      if (!(own[r] & dirty)) mask[r] &= (int)(dirty & 0x3ffu); /* pairs without a dirty body drop out */
     const bool haveCand = __any_sync(FULLMASK, (mask[0] | mask[1]) != 0);
-    bool skip = false;
-    if (haveCand || nArb) {
-      if (lane < nArb) { /* cached pairs: touched in the previous substep, no stored impulse, both bodies at rest */
-        const int key = E.i[DRV_S_ARBKEY + lane];
-        const int a = key & 255, b = (key >> 8) & 255;
-        const bool aOk = !(a >= DRV_SHAPE_CAR0 && a < DRV_SHAPE_OBS0) || ((restMask >> (a - DRV_SHAPE_CAR0)) & 1);
-        const bool bOk = !(b >= DRV_SHAPE_CAR0 && b < DRV_SHAPE_OBS0) || ((restMask >> (b - DRV_SHAPE_CAR0)) & 1);
-        const int st = (key >> 16) & 0xffff; /* state | age << 8 */
-        if (!(aOk && bOk && (st == RC_ARB_NORMAL || st == RC_ARB_IGNORE) && E.f[DRV_S_ARBJN0 + lane] == 0.f && E.f[DRV_S_ARBJN1 + lane] == 0.f))
-          pairsRest = false;
-      }
-      skip = __all_sync(FULLMASK, pairsRest);
-    }
-    if ((haveCand || nArb) && !skip) {
+    const unsigned keepMask = __ballot_sync(FULLMASK, lane < nArb && !(pairBodies & dirty)); /* cached pairs left alone */
+    const bool dirtyCached = __any_sync(FULLMASK, lane < nArb && (pairBodies & dirty) != 0);
+    if (haveCand || dirtyCached) {
       if (haveCand) {
         E.i[X_BPMASK + lane] = mask[0];
         E.i[X_BPMASK + 32 + lane] = mask[1];
         __syncwarp();
       }
-      contacts_substep(E, prevStepped, haveCand, isCar, isPed);
+      contacts_substep(E, prevStepped, haveCand, isCar, isPed, keepMask);
     } else friction_phase(E, isCar, isPed);
   }
 }
