@@ -69,7 +69,10 @@ enum {
   X_NCAND = X_BPMASK + 64,
   X_CAND = X_NCAND + 1,              /* I[NCAND] lo * 64 + hi */
   X_CBOX = (X_CAND + NCAND + 3) / 4 * 4, /* F[10][4] per car: centre and bounding-box half extents, one 128-bit load */
-  X_PHYS_END = X_CBOX + 4 * DRV_MAXCARS,
+  X_CMASS = X_CBOX + 4 * DRV_MAXCARS, /* F[10] mass, 1 / mass, 1 / moment of every car: once per launch (phys_substeps) */
+  X_CMINV = X_CMASS + DRV_MAXCARS,
+  X_CIINV = X_CMINV + DRV_MAXCARS,
+  X_PHYS_END = X_CIINV + DRV_MAXCARS,
   /* vision view */
   V_ANG2 = X_UNION,            /* F[NOCC] per occluder: angle of its centre, min / max corner angle ... */
   V_AMN = V_ANG2 + NOCC,
@@ -170,11 +173,11 @@ __device__ __forceinline__ V2 pos_diff(const Env E, int b, int a) { /* position 
   return v2(__fadd_rn(__fsub_rn(bx, ax), __fsub_rn(bxl, axl)), __fadd_rn(__fsub_rn(by, ay), __fsub_rn(byl, ayl)));
 }
 __device__ __forceinline__ float body_minv(const Env E, int s) {
-  if (is_car(s)) return 1.f / car_mass(E.i[DRV_S_CTYPE + s - DRV_SHAPE_CAR0]);
+  if (is_car(s)) return E.f[X_CMINV + s - DRV_SHAPE_CAR0];
   return is_ped(s) ? PED_MINV : 0.f;
 }
 __device__ __forceinline__ float body_iinv(const Env E, int s) {
-  if (is_car(s)) return car_iinv(E.i[DRV_S_CTYPE + s - DRV_SHAPE_CAR0]);
+  if (is_car(s)) return E.f[X_CIINV + s - DRV_SHAPE_CAR0];
   return 0.f; /* pedestrians: contact anchors are parallel to the normal, their spin never changes */
 }
 
@@ -727,7 +730,7 @@ __device__ __forceinline__ void friction_phase(const Env E, bool isCar, bool isP
     const int i = lane;
     float x = E.f[DRV_S_CVX + i], y = E.f[DRV_S_CVY + i], th = E.f[DRV_S_CW + i];
     const bool fin = E.i[DRV_S_CFLAGS + i] & DRV_CF_FINISHED;
-    friction(car_mass(E.i[DRV_S_CTYPE + i]), fin ? 5e-4f : 5e-5f, fin ? 2e-5f : 1e-5f, x, y, th);
+    friction(E.f[X_CMASS + i], fin ? 5e-4f : 5e-5f, fin ? 2e-5f : 1e-5f, x, y, th);
     E.f[DRV_S_CVX + i] = x; E.f[DRV_S_CVY + i] = y; E.f[DRV_S_CW + i] = th;
   } else if (isPed && (E.i[DRV_S_PFLAGS + lane - 10] & DRV_PF_DEAD)) {
     const int i = lane - 10;
@@ -1102,6 +1105,12 @@ __device__ __forceinline__ void phys_substeps(const Env E, const float* actions_
   if (first) { /* DrivingEnvironment.py:251-256 */
     if (lane < DRV_MAXCARS) { E.f[X_REW + lane] = 0.f; E.f[X_POSREW + lane] = 0.f; }
     if (lane == 0) { E.f[X_TEAMREW] = 0.f; E.i[X_DIAG] = 0; }
+  }
+  if (lane < DRV_MAXCARS) { /* Car.py:9-13: mass by type; moment_for_poly of the box */
+    const int t = E.i[DRV_S_CTYPE + lane];
+    E.f[X_CMASS + lane] = car_mass(t);
+    E.f[X_CMINV + lane] = 1.f / car_mass(t);
+    E.f[X_CIINV + lane] = car_iinv(t);
   }
   __syncwarp();
   const int N = E.c->P;
