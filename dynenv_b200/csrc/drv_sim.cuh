@@ -72,7 +72,8 @@ enum {
   X_CMASS = X_CBOX + 4 * DRV_MAXCARS, /* F[10] mass, 1 / mass, 1 / moment of every car: once per launch (phys_substeps) */
   X_CMINV = X_CMASS + DRV_MAXCARS,
   X_CIINV = X_CMINV + DRV_MAXCARS,
-  X_PHYS_END = X_CIINV + DRV_MAXCARS,
+  X_CC0 = X_CIINV + DRV_MAXCARS,      /* F[10] cos(road 0 angle - car angle); with X_CC / X_CS refreshed when the angle changes */
+  X_PHYS_END = X_CC0 + DRV_MAXCARS,
   /* vision view */
   V_ANG2 = X_UNION,            /* F[NOCC] per occluder: angle of its centre, min / max corner angle ... */
   V_AMN = V_ANG2 + NOCC,
@@ -209,6 +210,15 @@ __device__ __forceinline__ V2 road_p0(int r) { return r == 0 ? v2(875.f, 0.f) : 
 __device__ __forceinline__ V2 road_p1(int r) { return r == 0 ? v2(875.f, 1000.f) : v2(1750.f, 500.f); }
 __device__ __forceinline__ int road_lanes(int r) { return r == 0 ? 2 : 1; }
 
+/* cos / sin of car i's angle and cos(road 0's angle - angle), cached in the launch's scratch: the angle changes only
+   when the car steers or spins, the double-double reductions are needed only then */
+__device__ __forceinline__ void refresh_trig(const Env E, int i, double an) {
+  float sn, cs, s0, c0;
+  sincos_d(an, &sn, &cs);
+  sincos_d(__dsub_rn(PIO2_D, an), &s0, &c0); /* road 0: cos(road.angle - angle) with the reference's rounding */
+  E.f[X_CC + i] = cs; E.f[X_CS + i] = sn; E.f[X_CC0 + i] = c0;
+}
+
 /* ================================================================= per-substep game logic */
 /* processAction (substep 0) + tick for car `lane` (DrivingEnvironment.py:357-426, Car.py:55-117) */
 __device__ __noinline__ void cars_phase(const Env E, int sub, const float* actions_env) {
@@ -220,8 +230,7 @@ __device__ __noinline__ void cars_phase(const Env E, int sub, const float* actio
   int fl = E.i[DRV_S_CFLAGS + i];
   const int type = E.i[DRV_S_CTYPE + i];
   float rew = E.f[X_REW + i], posrew = E.f[X_POSREW + i];
-  float sn, cs;
-  sincos_d(an, &sn, &cs);
+  float sn = E.f[X_CS + i], cs = E.f[X_CC + i];
   if (sub % 10 == 0) {
     float a0 = actions_env[2 * i], a1 = actions_env[2 * i + 1];
     const bool cont = E.c->continuous != 0;
@@ -254,14 +263,14 @@ __device__ __noinline__ void cars_phase(const Env E, int sub, const float* actio
         V2 v = rot_cs(v2(vx, vy), rc_, rs);
         E.f[DRV_S_CDIRX + i] = d.x; E.f[DRV_S_CDIRY + i] = d.y;
         vx = v.x; vy = v.y;
-        sincos_d(an, &sn, &cs);
+        refresh_trig(E, i, an);
+        sn = E.f[X_CS + i]; cs = E.f[X_CC + i];
         store_ang(E, i, an);
       }
     }
   }
   /* tick */
-  float s0, c0;
-  sincos_d(__dsub_rn(PIO2_D, an), &s0, &c0); /* road 0: cos(road.angle - angle) with the reference's rounding */
+  const float c0 = E.f[X_CC0 + i];
   int l0 = point_on_road(0, px, pxl, py, pyl, c0), l1 = point_on_road(1, px, pxl, py, pyl, cs);
   int lane = l0 < l1 ? l0 : l1;
   float gx = E.f[DRV_S_CGOALX + i], gy = E.f[DRV_S_CGOALY + i];
@@ -992,16 +1001,14 @@ __device__ __noinline__ void space_step(const Env E) {
     two_add(px, pxl, __fmul_rn(E.f[DRV_S_CVX + i] + E.f[DRV_S_CVBX + i], DT));
     two_add(py, pyl, __fmul_rn(E.f[DRV_S_CVY + i] + E.f[DRV_S_CVBY + i], DT));
     const float wsum = E.f[DRV_S_CW + i] + E.f[DRV_S_CWB + i];
-    if (wsum != 0.f) { an += (double)wsum * 0.01; store_ang(E, i, an); }
+    if (wsum != 0.f) { an += (double)wsum * 0.01; store_ang(E, i, an); refresh_trig(E, i, an); }
     atRest = E.f[DRV_S_CVX + i] == 0.f && E.f[DRV_S_CVY + i] == 0.f && E.f[DRV_S_CW + i] == 0.f && E.f[DRV_S_CVBX + i] == 0.f &&
              E.f[DRV_S_CVBY + i] == 0.f && E.f[DRV_S_CWB + i] == 0.f;
     E.f[DRV_S_CPX + i] = px; E.f[DRV_S_CPXL + i] = pxl; E.f[DRV_S_CPY + i] = py; E.f[DRV_S_CPYL + i] = pyl;
     E.f[DRV_S_CVBX + i] = 0.f; E.f[DRV_S_CVBY + i] = 0.f; E.f[DRV_S_CWB + i] = 0.f;
-    float sn, cs;
-    sincos_d(an, &sn, &cs);
+    const float sn = E.f[X_CS + i], cs = E.f[X_CC + i];
     const int t = E.i[DRV_S_CTYPE + i];
     const float h = car_length(t), w = car_width(t);
-    E.f[X_CC + i] = cs; E.f[X_CS + i] = sn;
     const float bex = fabsf(h * cs) + fabsf(w * sn), bey = fabsf(h * sn) + fabsf(w * cs);
     E.f[X_CEX + i] = bex;
     E.f[X_CEY + i] = bey;
@@ -1111,6 +1118,7 @@ __device__ __forceinline__ void phys_substeps(const Env E, const float* actions_
     E.f[X_CMASS + lane] = car_mass(t);
     E.f[X_CMINV + lane] = 1.f / car_mass(t);
     E.f[X_CIINV + lane] = car_iinv(t);
+    refresh_trig(E, lane, load_ang(E, lane));
   }
   __syncwarp();
   const int N = E.c->P;
