@@ -1032,7 +1032,11 @@ __device__ __noinline__ void space_step(const Env E) {
        colliding and solving it again changes nothing.  `dirty` is the closure of the moving bodies under "overlaps or
        is cached with"; only pairs with a dirty body go through the collision half of the substep, the cached pairs of
        clean bodies are kept as they are. */
+#ifdef DRV_NO_QUIET_SKIP /* dev check (tools/gpu_drv_quiet_check.py): collide and solve every pair, every substep */
+    unsigned dirty = __ballot_sync(FULLMASK, isCar || isPed);
+#else
     unsigned dirty = __ballot_sync(FULLMASK, (isCar || isPed) && !atRest);
+#endif
     unsigned pairBodies = 0; /* lane < nArb: the dynamic bodies of cached pair `lane` */
     {
       unsigned seed = 0;
