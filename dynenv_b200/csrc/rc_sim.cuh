@@ -1600,7 +1600,7 @@ __device__ __noinline__ void agent_vision(const Env E, int ag, uint32_t tick) {
   const float agFlag = (E.i[RC_S_RFLAGS + ag] & (RC_RF_FALLEN | RC_RF_PENALIZED)) ? 1.f : 0.f;
   const float closest = (ag == E.i[RC_S_CLOSEST] || ag == E.i[RC_S_CLOSEST + 1]) ? 1.f : 0.f;
   const unsigned lt = (1u << lane) - 1;
-  for (int w = lane; w < RC_OBS_WORDS; w += 32) E.f[V_STAGE + w] = 0.f;
+  for (int w = lane; w < RC_OBS_WORDS / 4; w += 32) reinterpret_cast<float4*>(E.f + V_STAGE)[w] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
 
   int nb = 0, nr = 0, np = 0, ncr = 0, nf = 0;
