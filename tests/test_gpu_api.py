@@ -183,3 +183,13 @@ def test_device_arranger_on_simulator_outputs():
     padded, masks = arr.rearrange_outputs([x[:, :2] for x in inputs])
     assert padded.shape == (5, maxCount, 30, 2) and len(masks) == 5 and masks[0].shape == (30, maxCount)
     assert int((~masks[2]).sum()) == int(objCounts[2].sum())
+
+
+def test_fp32_peak_probe():
+    """the FMA probe behind roofline.fp32.measured_peak_tflops: a plausible FP32 rate for a B200 (nominal 74.4 TFLOP/s)"""
+    import ctypes as C
+    from dynenv_b200 import _lib
+    tf = C.c_float(0)
+    assert _lib.lib().dynenv_debug_fp32_peak(0, C.byref(tf)) == 0
+    assert 20.0 < tf.value < 90.0, tf.value
+    assert _lib.lib().dynenv_debug_fp32_peak(0, None) != 0
