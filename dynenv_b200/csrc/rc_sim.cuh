@@ -1268,7 +1268,7 @@ __device__ __noinline__ void space_step(const Env E, const uint32_t pairs4) {
     if (((key >> 16) & 255) == RC_ARB_FIRST) E.i[RC_S_ARBKEY + lane] = (key & ~0xff0000) | (RC_ARB_NORMAL << 16);
   }
   /* integrate positions (cpBodyUpdatePosition), refresh shape geometry, bounding circles in registers */
-  float bcx = 0, bcy = 0, bcr = 0;
+  float bcx = 0, bcy = 0; /* bounding-circle centre of this lane's shape (radius: 17.5 for a foot, 10 otherwise) */
   const bool active = lane < NSHAPE && shape_active(E, lane);
   if (lane <= BALL && active) {
     float px = E.f[RC_S_PX + lane], pxl = E.f[RC_S_PXL + lane];
@@ -1285,10 +1285,9 @@ __device__ __noinline__ void space_step(const Env E, const uint32_t pairs4) {
     E.f[RC_S_CAX + lane] = ta.x; E.f[RC_S_CAY + lane] = ta.y;
     E.f[RC_S_CBX + lane] = tb.x; E.f[RC_S_CBY + lane] = tb.y;
     bcx = (ta.x + tb.x) * 0.5f; bcy = (ta.y + tb.y) * 0.5f;
-    bcr = lane < 20 ? ROB_LEN + ROB_RAD : 10.f;
   } else if (lane >= POST0 && lane < NSHAPE) {
     V2 p = post_pos(lane - POST0);
-    bcx = p.x; bcy = p.y; bcr = 10.f;
+    bcx = p.x; bcy = p.y;
   }
   __syncwarp();
   /* collide.  Broad phase on groups first (robot = bounding circle of its two feet, ball, posts): 99 group
