@@ -5,7 +5,7 @@ import os
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["DYNENV_B200_LIB"] = os.path.join(ROOT, "tools", "tmp", "libprof.so")
+os.environ.setdefault("DYNENV_B200_LIB", os.path.join(ROOT, "tools", "tmp", "libprof.so"))
 import torch
 import dynenv_b200
 from dynenv_b200 import _lib
