@@ -1035,7 +1035,9 @@ __device__ __noinline__ void space_step(const Env E) {
 #ifdef DRV_NO_QUIET_SKIP /* dev check (tools/gpu_drv_quiet_check.py): collide and solve every pair, every substep */
     unsigned dirty = __ballot_sync(FULLMASK, isCar || isPed);
 #else
-    unsigned dirty = __ballot_sync(FULLMASK, (isCar || isPed) && !atRest);
+    /* (the first substep after a reset or a state injection collides everything: overlapping bodies at rest have no
+       cached pair yet) */
+    unsigned dirty = __ballot_sync(FULLMASK, (isCar || isPed) && (!atRest || !prevStepped));
 #endif
     unsigned pairBodies = 0; /* lane < nArb: the dynamic bodies of cached pair `lane` */
     {
