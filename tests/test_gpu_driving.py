@@ -121,3 +121,39 @@ def test_noise_statistics_match_in_distribution():
         mg, mc = cnt[:, k].mean(), c_cnt[:, k].mean()
         sigma = np.sqrt(cnt[:, k].var() / n_gpu + c_cnt[:, k].var() / n_cpu) + 1e-9
         assert abs(mg - mc) < 4 * sigma + 1e-3, (k, mg, mc, sigma)
+
+
+def test_overlapping_bodies_at_rest_collide_after_injection():
+    """two cars put on top of each other with zero velocity and no cached pair (a hand-made state, first substep after the
+    injection): the quiet-pair logic must not skip them -- the crash is detected like in the oracle"""
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    from oracle.oracle import drv_f32_record_to_words
+    cfg = dict(nPlayers=4, obsType=1, noiseType=0, noiseMag=0.0, continuous=False)
+    n, seed = 4, 17
+    sim = _sim(cfg, n, seed)
+    sim.reset()
+    st = sim.get_state()
+    F = L.DRV_FIELDS
+    for name in ("cpx", "cpy", "cpxLo", "cpyLo", "cang", "cangLo"):
+        st[:, F[name][0] + 1] = st[:, F[name][0] + 0]          # car 1 onto car 0
+    stf = st.view(torch.float32)                               # the same storage, float view
+    stf[:, F["cpx"][0] + 1] = stf[:, F["cpx"][0]] + 3.0
+    for name in ("cvx", "cvy", "cw", "cvbx", "cvby", "cwb"):
+        st[:, F[name][0]:F[name][0] + 10] = 0                  # everything at rest
+    st[:, F["stepped"][0]] = 0
+    st[:, F["nArb"][0]] = 0
+    sim.set_state(st)
+    recs = sim.get_state().cpu().numpy().view(np.uint32)
+    a = np.ones((n, 4, 2), np.float32)                           # categorical (1, 1): no acceleration, no steering
+    out = sim.step(torch.from_numpy(a).cuda())
+    torch.cuda.synchronize()
+    gw = drv_f32_record_to_words(sim.get_state().cpu().numpy().view(np.uint32))
+    outs, ow = drv_oracle_step_batch(cfg, recs, a, seed)
+    fl_g = gw[:, F["cflags"][0]:F["cflags"][0] + 2].astype(int)
+    fl_o = ow[:, F["cflags"][0]:F["cflags"][0] + 2].astype(int)
+    assert (fl_o & L.DRV_CF_CRASHED).all(), fl_o             # the oracle crashes both cars ...
+    assert np.array_equal(fl_g, fl_o), (fl_g, fl_o)           # ... and so does the kernel
+    bad = drv_compare_step(cfg, out, gw, outs, ow, TOL)
+    assert not [b for b in bad if b[1] in ("diag", "done", "state.cflags", "rewards")], bad[:10]
