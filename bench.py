@@ -424,7 +424,9 @@ def run_gpu(args):
     diag = int(sim.out.diag.max().item())
 
     # end to end through the host-facing call: pinned host actions in, rewards + done out, every step
-    h_act = [p.cpu().pin_memory() for p in pool[:min(n_pool, args.steps)]]  # the timed steps' own actions, from pinned host memory
+    # the timed steps' own actions, from pinned host memory (at most ~3.5 GB of it per rank; cycled beyond that)
+    n_host = min(n_pool, args.steps, max(32, int(3.5e9 // (E * P * wl.act * 4))))
+    h_act = [p.cpu().pin_memory() for p in pool[:n_host]]
     n_pool = len(h_act)
     d_act = torch.empty((E, P, wl.act), device=dev)
     # rewards [maxAgents] and done are the first words of every environment's result record: one strided copy
