@@ -11,6 +11,7 @@
 
 #include "drv_sim.cuh"
 #include "rc_sim.cuh"
+#include "rc_obs.cuh"
 #include "rc_raster.cuh"
 #include "rollout.cuh"
 
@@ -127,6 +128,61 @@ rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, 
   for (int w = RC_S_STEP_LSUM + lane; w < RC_S_STEP_END; w += 32) g[w] = S[w];
 }
 
+/* PARTIAL observations: the flattened tick of rc_obs.cuh.  No copy of the state in shared memory: the robot table is
+   built from the HBM record, only the processSeens sums go back. */
+struct GlobalRec {
+  const uint32_t* g;
+  __device__ __forceinline__ uint32_t operator()(int k) const { return g[k]; }
+};
+struct SharedRec {
+  int base;
+  __device__ __forceinline__ uint32_t operator()(int k) const { return g_smem[base + k]; }
+};
+
+__global__ void __launch_bounds__(32, 32)
+rc_obsp_kernel(const __grid_constant__ SimCfg cfg, uint32_t* state, int t, int subs_left, float* __restrict__ obs,
+               float* __restrict__ term_obs) {
+  const int lane = threadIdx.x;
+  const int e = blockIdx.x;
+  stage_cfg(cfg);
+  rc::Env E;
+  E.f.base = CFG_WORDS; E.i.base = CFG_WORDS; E.lane = lane;
+  uint32_t* rec = state + (size_t)e * RC_STATE_WORDS;
+  const int elapsed = (int)rec[RC_S_ELAPSED];
+  rc::o_prologue(E, GlobalRec{rec}, cfg.env_id_offset + (uint32_t)e, true);
+  const size_t obs_stride = (size_t)RC_NTICK * cfg.P * RC_OBS_WORDS;
+  const bool finishing = cfg.auto_reset && elapsed + subs_left >= rc::MAXTIME;
+  float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
+  rc::observe_partial(E, (uint32_t)elapsed, o ? o + (size_t)t * cfg.P * RC_OBS_WORDS : nullptr);
+  for (int w = lane; w < rc::O_ACC_WORDS; w += 32) rec[RC_S_STEP_LSUM + w] = (uint32_t)E.i[rc::O_ACC + w];
+}
+
+/* environment_base.reset for PARTIAL observations: new scene, record to HBM, then the flattened observation ticks over
+   the slice the record occupied (they need only the robot table, gathered before the overlay) */
+__device__ __forceinline__ void reset_env_partial(const rc::Env E, uint32_t* S, uint32_t* rec, uint32_t env_id, float* obs_env,
+                                                  float* info_env, bool write_info) {
+  const int lane = E.lane;
+  rc::init_scene(E);
+  rc::clear_step_scratch(E);
+  if (info_env && write_info) {
+    rc::fill_info(E, info_env);
+    if (lane < RC_MAXP) {
+      info_env[RC_I_REWARDS + lane] = 0.f;
+      info_env[RC_I_EPR + lane] = 0.f; info_env[RC_I_EPPR + lane] = 0.f; info_env[RC_I_EPOR + lane] = 0.f;
+    }
+    if (lane == 0) {
+      int* ii = reinterpret_cast<int*>(info_env);
+      ii[RC_I_DONE] = 0; ii[RC_I_FLAGS] = 0; ii[RC_I_EPG] = 0; ii[RC_I_EPG + 1] = 0;
+    }
+  }
+  store_record(rec, S, lane);
+  __syncwarp();
+  rc::o_prologue(E, SharedRec{E.i.base}, env_id, false);
+  const int P = E.c->P;
+  for (int t = 0; t < RC_NTICK; t++)
+    rc::observe_partial(E, DYNENV_TICK_RESETOBS | (uint32_t)t, obs_env ? obs_env + (size_t)t * P * RC_OBS_WORDS : nullptr);
+}
+
 /* rewards, info, done, episode statistics; finished environments are re-initialised (auto-reset) */
 template <bool RAW>
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
@@ -144,9 +200,15 @@ rc_finish_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ stat
   const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
   float* inf = info ? info + (size_t)e * RC_INFO_WORDS : nullptr;
   rc::finish_step(E, inf);
-  if (cfg.auto_reset && E.i[RC_S_ELAPSED] >= rc::MAXTIME)
+  if (cfg.auto_reset && E.i[RC_S_ELAPSED] >= rc::MAXTIME) {
+    if (!RAW && cfg.obs_type == DYNENV_OBS_PARTIAL) {
+      reset_env_partial(E, S, state + (size_t)e * RC_STATE_WORDS, cfg.env_id_offset + (uint32_t)e, obs ? obs + e * obs_stride : nullptr,
+                        inf, false);
+      return;
+    }
     rc::reset_env<RAW>(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr, inf, false,
                        raw ? raw + (size_t)e * RC_NTICK * P * RC_RAW_WORDS : nullptr);
+  }
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
 }
 
@@ -165,6 +227,11 @@ rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state
   rc::Env E = make_env(base, cfg, e, lane);
   const int P = cfg.P;
   const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
+  if (!RAW && cfg.obs_type == DYNENV_OBS_PARTIAL) {
+    reset_env_partial(E, S, state + (size_t)e * RC_STATE_WORDS, cfg.env_id_offset + (uint32_t)e, obs ? obs + e * obs_stride : nullptr,
+                      info ? info + (size_t)e * RC_INFO_WORDS : nullptr, true);
+    return;
+  }
   rc::reset_env<RAW>(E, obs ? obs + e * obs_stride : nullptr, full ? full + e * full_stride : nullptr,
                      info ? info + (size_t)e * RC_INFO_WORDS : nullptr, true, raw ? raw + (size_t)e * RC_NTICK * P * RC_RAW_WORDS : nullptr);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
@@ -412,6 +479,7 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
   const int grid = (h->sim.n_envs + RC_WPC - 1) / RC_WPC;
   const size_t smem = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS) * sizeof(uint32_t);
   const size_t smem_raw = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS_RAW) * sizeof(uint32_t);
+  const size_t smem_obsp = ((size_t)CFG_WORDS + rc::OBS_SMEM_WORDS) * sizeof(uint32_t);
   const bool image = h->cfg.obs_type == DYNENV_OBS_IMAGE;
   int launches = 0;
   h->n_timed = 0;
@@ -433,6 +501,9 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
       if (image)
         rc_obs_kernel<true><<<grid, RC_WPC * 32, smem_raw, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
                                                                   t ? t->obs : nullptr, t ? t->full : nullptr, o->raw, t ? t->raw : nullptr);
+      else if (h->cfg.obs_type == DYNENV_OBS_PARTIAL)
+        rc_obsp_kernel<<<h->sim.n_envs, 32, smem_obsp, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs,
+                                                              t ? t->obs : nullptr);
       else
         rc_obs_kernel<false><<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
                                                                t ? t->obs : nullptr, t ? t->full : nullptr, nullptr, nullptr);
