@@ -162,10 +162,11 @@ class BatchedRoboCup(object):
         _lib.check(self._lib.dynenv_debug_timing(self._h, int(bool(enable))))
 
     def last_kernel_ms(self):
-        """{'phys': (ms, launches), 'obs': ..., 'finish': ...} of the last step (needs debug_timing(True))"""
-        ms, n = (C.c_float * 3)(), (C.c_int * 3)()
+        """{'phys': (ms, launches), 'obs': ..., 'finish': ..., 'phys_slow': ...} of the last step (needs debug_timing(True));
+        'phys_slow' = the substeps of the environments handed over to the record-based code (RoboCup)"""
+        ms, n = (C.c_float * 4)(), (C.c_int * 4)()
         _lib.check(self._lib.dynenv_last_kernel_ms(self._h, ms, n))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("phys", "obs", "finish"))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("phys", "obs", "finish", "phys_slow"))}
 
     def debug_substep_range(self, begin, end):
         _lib.check(self._lib.dynenv_debug_substep_range(self._h, int(begin), int(end)))

@@ -12,6 +12,7 @@
 #include "drv_sim.cuh"
 #include "rc_sim.cuh"
 #include "rc_obs.cuh"
+#include "rc_phys2.cuh"
 #include "rc_raster.cuh"
 #include "rollout.cuh"
 
@@ -69,8 +70,8 @@ __device__ __forceinline__ void stage_cfg(const SimCfg& cfg) {
 
 __device__ __forceinline__ rc::Env make_env(int base, const SimCfg& cfg, int e, int lane) {
   rc::Env E;
-  E.f.base = base;
-  E.i.base = base;
+  static_assert(RC_WPC_ == 1, "the slice base is a compile-time constant: one warp per block");
+  (void)base;
   E.lane = lane;
   if (lane == 0) E.i[rc::X_ENVID] = (int)(cfg.env_id_offset + (uint32_t)e);
   __syncwarp();
@@ -85,7 +86,8 @@ __device__ __forceinline__ rc::Env make_env(int base, const SimCfg& cfg, int e, 
  */
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
-               int sub_b, int sub_e, int first) {
+               int sub_b, int sub_e, int first, uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count,
+               uint8_t* __restrict__ slow_mark) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
@@ -94,8 +96,52 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
   uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
+#ifdef RC_PHYS_RECORD /* the first version: every phase on the record in shared memory */
   rc::phys_substeps(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
+#else
+  const int handover = rc::phys_substeps2(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
+  store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
+  if (lane == 0) {
+    slow_mark[e] = handover >= 0;
+    if (handover >= 0) slow_list[atomicAdd(slow_count, 1u)] = ((uint32_t)handover << 24) | (uint32_t)e;
+  }
+#endif
+}
+
+/* the environments rc_phys_kernel handed over (falls, penalties, touching or cached pairs: a few percent of them): the
+   rest of their substeps on the record-based code of rc_sim.cuh.  A fixed grid walks the list. */
+__global__ void __launch_bounds__(32, 32)
+rc_phys_slow_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions, int sub_e,
+                    const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
+  const int lane = threadIdx.x;
+  stage_cfg(cfg);
+  const uint32_t n = *slow_count;
+  uint32_t* S = g_smem + CFG_WORDS;
+  for (uint32_t k = blockIdx.x; k < n; k += gridDim.x) {
+    const uint32_t item = slow_list[k];
+    const int e = (int)(item & 0xFFFFFFu), code = (int)(item >> 24);
+    load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
+    rc::Env E = make_env(CFG_WORDS, cfg, e, lane);
+    rc::phys_resume(E, actions + (size_t)e * cfg.P * 4, code >> 1, code & 1, sub_e);
+    store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
+    __syncwarp();
+  }
+}
+
+/* The observation kernels run twice per tick: on the caller's stream for every environment that rc_phys_kernel finished
+   itself (slow_mark[e] == 0; slow_list == nullptr), and on the side stream, behind rc_phys_slow_kernel, for the
+   handed-over ones (a fixed grid walks slow_list).  next_env returns the block's next environment or -1. */
+__device__ __forceinline__ int next_env(int& cursor, int n_envs, const uint8_t* slow_mark, const uint32_t* slow_list, const uint32_t* slow_count) {
+  if (slow_list) {
+    const uint32_t n = *slow_count;
+    if (cursor < 0) cursor = blockIdx.x; else cursor += gridDim.x;
+    return (uint32_t)cursor < n ? (int)(slow_list[cursor] & 0xFFFFFFu) : -1;
+  }
+  if (cursor >= 0) return -1;
+  cursor = blockIdx.x;
+  if (cursor >= n_envs || (slow_mark && slow_mark[cursor])) return -1;
+  return cursor;
 }
 
 /* observation tick t of the step in flight (after substep 10 t + 9) */
@@ -103,29 +149,33 @@ template <bool RAW>
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_obs_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, int t, int subs_left,
               float* __restrict__ obs, float* __restrict__ full, float* __restrict__ term_obs, float* __restrict__ term_full,
-              float* __restrict__ raw, float* __restrict__ term_raw) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * RC_WPC + warp;
+              float* __restrict__ raw, float* __restrict__ term_raw, const uint8_t* __restrict__ slow_mark,
+              const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
+  const int lane = threadIdx.x & 31;
   stage_cfg(cfg);
-  if (e >= cfg.n_envs) return;
-  const int base = CFG_WORDS + warp * (RAW ? rc::ENV_SMEM_WORDS_RAW : rc::ENV_SMEM_WORDS);
+  const int base = CFG_WORDS;
   uint32_t* S = g_smem + base;
-  load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
-  rc::Env E = make_env(base, cfg, e, lane);
-  const int P = cfg.P;
-  const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
-  /* a finishing episode's last observations go to the terminal buffers, its first ones (written by the
-     finish kernel after the reset) to `out` */
-  const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + subs_left >= rc::MAXTIME;
-  float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
-  float* f = finishing ? (term_full ? term_full + e * full_stride : nullptr) : (full ? full + e * full_stride : nullptr);
-  const size_t raw_stride = (size_t)RC_NTICK * P * RC_RAW_WORDS;
-  float* r = finishing ? (term_raw ? term_raw + e * raw_stride : nullptr) : (raw ? raw + e * raw_stride : nullptr);
-  rc::observe_tick<RAW>(E, t, (uint32_t)E.i[RC_S_ELAPSED], o, f, r);
-  /* only the processSeens sums changed */
-  __syncwarp();
-  uint32_t* g = state + (size_t)e * RC_STATE_WORDS;
-  for (int w = RC_S_STEP_LSUM + lane; w < RC_S_STEP_END; w += 32) g[w] = S[w];
+  int cursor = -1;
+  for (int e = next_env(cursor, cfg.n_envs, slow_mark, slow_list, slow_count); e >= 0;
+       e = next_env(cursor, cfg.n_envs, slow_mark, slow_list, slow_count)) {
+    load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
+    rc::Env E = make_env(base, cfg, e, lane);
+    const int P = cfg.P;
+    const size_t obs_stride = (size_t)RC_NTICK * P * RC_OBS_WORDS, full_stride = (size_t)RC_NTICK * P * RC_FULL_WORDS;
+    /* a finishing episode's last observations go to the terminal buffers, its first ones (written by the
+       finish kernel after the reset) to `out` */
+    const bool finishing = cfg.auto_reset && E.i[RC_S_ELAPSED] + subs_left >= rc::MAXTIME;
+    float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
+    float* f = finishing ? (term_full ? term_full + e * full_stride : nullptr) : (full ? full + e * full_stride : nullptr);
+    const size_t raw_stride = (size_t)RC_NTICK * P * RC_RAW_WORDS;
+    float* r = finishing ? (term_raw ? term_raw + e * raw_stride : nullptr) : (raw ? raw + e * raw_stride : nullptr);
+    rc::observe_tick<RAW>(E, t, (uint32_t)E.i[RC_S_ELAPSED], o, f, r);
+    /* only the processSeens sums changed */
+    __syncwarp();
+    uint32_t* g = state + (size_t)e * RC_STATE_WORDS;
+    for (int w = RC_S_STEP_LSUM + lane; w < RC_S_STEP_END; w += 32) g[w] = S[w];
+    __syncwarp();
+  }
 }
 
 /* PARTIAL observations: the flattened tick of rc_obs.cuh.  No copy of the state in shared memory: the robot table is
@@ -141,20 +191,25 @@ struct SharedRec {
 
 __global__ void __launch_bounds__(32, 32)
 rc_obsp_kernel(const __grid_constant__ SimCfg cfg, uint32_t* state, int t, int subs_left, float* __restrict__ obs,
-               float* __restrict__ term_obs) {
+               float* __restrict__ term_obs, const uint8_t* __restrict__ slow_mark, const uint32_t* __restrict__ slow_list,
+               const uint32_t* __restrict__ slow_count) {
   const int lane = threadIdx.x;
-  const int e = blockIdx.x;
   stage_cfg(cfg);
   rc::Env E;
-  E.f.base = CFG_WORDS; E.i.base = CFG_WORDS; E.lane = lane;
-  uint32_t* rec = state + (size_t)e * RC_STATE_WORDS;
-  const int elapsed = (int)rec[RC_S_ELAPSED];
-  rc::o_prologue(E, GlobalRec{rec}, cfg.env_id_offset + (uint32_t)e, true);
-  const size_t obs_stride = (size_t)RC_NTICK * cfg.P * RC_OBS_WORDS;
-  const bool finishing = cfg.auto_reset && elapsed + subs_left >= rc::MAXTIME;
-  float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
-  rc::observe_partial(E, (uint32_t)elapsed, o ? o + (size_t)t * cfg.P * RC_OBS_WORDS : nullptr);
-  for (int w = lane; w < rc::O_ACC_WORDS; w += 32) rec[RC_S_STEP_LSUM + w] = (uint32_t)E.i[rc::O_ACC + w];
+  E.lane = lane;
+  int cursor = -1;
+  for (int e = next_env(cursor, cfg.n_envs, slow_mark, slow_list, slow_count); e >= 0;
+       e = next_env(cursor, cfg.n_envs, slow_mark, slow_list, slow_count)) {
+    uint32_t* rec = state + (size_t)e * RC_STATE_WORDS;
+    const int elapsed = (int)rec[RC_S_ELAPSED];
+    rc::o_prologue(E, GlobalRec{rec}, cfg.env_id_offset + (uint32_t)e, true);
+    const size_t obs_stride = (size_t)RC_NTICK * cfg.P * RC_OBS_WORDS;
+    const bool finishing = cfg.auto_reset && elapsed + subs_left >= rc::MAXTIME;
+    float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
+    rc::observe_partial(E, (uint32_t)elapsed, o ? o + (size_t)t * cfg.P * RC_OBS_WORDS : nullptr);
+    for (int w = lane; w < rc::O_ACC_WORDS; w += 32) rec[RC_S_STEP_LSUM + w] = (uint32_t)E.i[rc::O_ACC + w];
+    __syncwarp();
+  }
 }
 
 /* environment_base.reset for PARTIAL observations: new scene, record to HBM, then the flattened observation ticks over
@@ -177,7 +232,7 @@ __device__ __forceinline__ void reset_env_partial(const rc::Env E, uint32_t* S, 
   }
   store_record(rec, S, lane);
   __syncwarp();
-  rc::o_prologue(E, SharedRec{E.i.base}, env_id, false);
+  rc::o_prologue(E, SharedRec{SharedI::base}, env_id, false);
   const int P = E.c->P;
   for (int t = 0; t < RC_NTICK; t++)
     rc::observe_partial(E, DYNENV_TICK_RESETOBS | (uint32_t)t, obs_env ? obs_env + (size_t)t * P * RC_OBS_WORDS : nullptr);
@@ -247,11 +302,11 @@ rc_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state
 #define DRV_MINB_ 32
 #endif
 constexpr int DRV_WPC = DRV_WPC_;
+static_assert(DRV_WPC_ == 1, "the slice base is a compile-time constant: one warp per block");
 
 __device__ __forceinline__ drv::Env make_drv_env(int base, const SimCfg& cfg, int e, int lane) {
   drv::Env E;
-  E.f.base = base;
-  E.i.base = base;
+  (void)base;
   E.lane = lane;
   if (lane == 0) E.i[drv::X_ENVID] = (int)(cfg.env_id_offset + (uint32_t)e);
   __syncwarp();
@@ -314,7 +369,7 @@ drv_reset_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ stat
 
 }  // namespace
 
-constexpr int MAX_TIMED = 16; /* launches of one step */
+constexpr int MAX_TIMED = 24; /* launches of one step */
 /* FP32 FMA throughput probe (dynenv_debug_fp32_peak) */
 __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters, float a, float b) {
   float x[8];
@@ -337,12 +392,18 @@ struct DynEnvHandle_s {
   DynEnvConfig cfg;
   SimCfg sim;
   uint32_t* state;
+  uint32_t* slow_list;   /* RoboCup: environments handed over to rc_phys_slow_kernel, (2 sub + phase) << 24 | env */
+  uint32_t* slow_count;  /* [8] one counter per substep block of the step */
+  uint8_t* slow_mark;    /* [n_envs] 1 = handed over in the substep block in flight */
+  cudaStream_t side;     /* the handed-over environments' substeps and observations run here, beside the others' observations */
+  cudaEvent_t ev_fork[8], ev_join[8];
+  int sms;
   int state_words;
   int last_launches;
   /* optional per-launch timing (dynenv_debug_timing): events bracketing every launch of the last step */
   int timing;
   cudaEvent_t ev[MAX_TIMED + 1];
-  int ev_class[MAX_TIMED]; /* 0 substep block, 1 observation tick, 2 finish */
+  int ev_class[MAX_TIMED]; /* 0 substep block, 1 observation tick, 2 finish, 3 substep block of the handed-over environments */
   int n_timed;
 };
 
@@ -408,6 +469,39 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
     delete h;
     return cuda_fail(ce, "cudaMemset(state)");
   }
+  h->slow_list = nullptr;
+  h->slow_count = nullptr;
+  h->slow_mark = nullptr;
+  h->side = nullptr;
+  h->sms = 148;
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  if (!driving) {
+    /* the side stream outranks the caller's: its few long blocks must get SM slots while the caller's stream still has
+       tens of thousands of short blocks to dispatch, or nothing would overlap */
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cfg->n_envs >= (1 << 24)) {
+      cudaFree(h->state);
+      delete h;
+      return fail(DYNENV_E_INVALID, "at most 2^24 - 1 RoboCup environments per handle");
+    }
+    if ((ce = cudaMalloc(&h->slow_list, (size_t)cfg->n_envs * sizeof(uint32_t))) != cudaSuccess ||
+        (ce = cudaMalloc(&h->slow_count, 8 * sizeof(uint32_t))) != cudaSuccess ||
+        (ce = cudaMalloc(&h->slow_mark, (size_t)cfg->n_envs)) != cudaSuccess ||
+        (ce = cudaMemset(h->slow_mark, 0, (size_t)cfg->n_envs)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
+      cudaFree(h->slow_list);
+      cudaFree(h->slow_count);
+      cudaFree(h->slow_mark);
+      cudaFree(h->state);
+      delete h;
+      return cuda_fail(ce, "cudaMalloc(slow list)");
+    }
+    for (int k = 0; k < 8; k++) {
+      cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
+    }
+  }
   *out = h;
   return DYNENV_OK;
 }
@@ -416,6 +510,13 @@ int dynenv_destroy(DynEnvHandle h) {
   if (!h) return DYNENV_OK;
   cudaSetDevice(h->cfg.device);
   cudaFree(h->state);
+  cudaFree(h->slow_list);
+  cudaFree(h->slow_count);
+  cudaFree(h->slow_mark);
+  if (h->side) {
+    cudaStreamDestroy(h->side);
+    for (int k = 0; k < 8; k++) { cudaEventDestroy(h->ev_fork[k]); cudaEventDestroy(h->ev_join[k]); }
+  }
   if (h->timing)
     for (int k = 0; k <= MAX_TIMED; k++) cudaEventDestroy(h->ev[k]);
   delete h;
@@ -481,35 +582,56 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
   const size_t smem_raw = ((size_t)CFG_WORDS + (size_t)RC_WPC * rc::ENV_SMEM_WORDS_RAW) * sizeof(uint32_t);
   const size_t smem_obsp = ((size_t)CFG_WORDS + rc::OBS_SMEM_WORDS) * sizeof(uint32_t);
   const bool image = h->cfg.obs_type == DYNENV_OBS_IMAGE;
-  int launches = 0;
+  int launches = 0, nmark = 0;
   h->n_timed = 0;
-  auto mark = [&](int cls) { /* event after launch number `launches` (and one before the first) */
-    if (!h->timing || launches > MAX_TIMED) return;
-    if (cls >= 0) h->ev_class[launches - 1] = cls;
-    cudaEventRecord(h->ev[launches], st);
-    h->n_timed = launches;
+  auto mark = [&](int cls) { /* an event in front of the first launch (cls < 0), then one behind every timed group of launches */
+    if (!h->timing || nmark > MAX_TIMED) return;
+    if (cls >= 0) { h->ev_class[nmark - 1] = cls; h->n_timed = nmark; }
+    cudaEventRecord(h->ev[nmark++], st);
   };
+  int blk = 0;
+  cudaMemsetAsync(h->slow_count, 0, 8 * sizeof(uint32_t), st);
   mark(-1);
-  /* blocks of substeps up to the next observation tick (every 10th substep) */
+  /* blocks of substeps up to the next observation tick (every 10th substep); each is followed by the few environments
+     it handed over to the record-based code */
   for (int b = h->sim.sub_begin; b < h->sim.sub_end;) {
     int e = (b / 10 + 1) * 10;
     if (e > h->sim.sub_end) e = h->sim.sub_end;
-    rc_phys_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, actions_dev, b, e, b == h->sim.sub_begin);
+    const int bi = blk++ & 7;
+    uint32_t* cnt = h->slow_count + bi;
+    rc_phys_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, actions_dev, b, e, b == h->sim.sub_begin, h->slow_list, cnt,
+                                                     h->slow_mark);
     launches++;
     mark(0);
+    /* fork: the handed-over environments finish their substeps (and are observed) on the side stream ... */
+    cudaEventRecord(h->ev_fork[bi], st);
+    cudaStreamWaitEvent(h->side, h->ev_fork[bi], 0);
+    rc_phys_slow_kernel<<<h->sms * 32, 32, smem, h->side>>>(h->sim, h->state, actions_dev, e, h->slow_list, cnt);
+    launches++;
     if (e % 10 == 0) {
-      if (image)
-        rc_obs_kernel<true><<<grid, RC_WPC * 32, smem_raw, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
-                                                                  t ? t->obs : nullptr, t ? t->full : nullptr, o->raw, t ? t->raw : nullptr);
-      else if (h->cfg.obs_type == DYNENV_OBS_PARTIAL)
-        rc_obsp_kernel<<<h->sim.n_envs, 32, smem_obsp, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs,
-                                                              t ? t->obs : nullptr);
-      else
-        rc_obs_kernel<false><<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, e / 10 - 1, h->sim.sub_end - e, o->obs, o->full,
-                                                               t ? t->obs : nullptr, t ? t->full : nullptr, nullptr, nullptr);
-      launches++;
+      /* ... while the caller's stream observes all the others */
+      const int tick = e / 10 - 1, left = h->sim.sub_end - e;
+      for (int pass = 0; pass < 2; pass++) {
+        cudaStream_t s2 = pass ? h->side : st;
+        const uint8_t* mk = pass ? nullptr : h->slow_mark;
+        const uint32_t* ls = pass ? h->slow_list : nullptr;
+        const int g2 = pass ? h->sms * 32 : grid;
+        if (image)
+          rc_obs_kernel<true><<<g2, 32, smem_raw, s2>>>(h->sim, h->state, tick, left, o->obs, o->full, t ? t->obs : nullptr,
+                                                         t ? t->full : nullptr, o->raw, t ? t->raw : nullptr, mk, ls, cnt);
+        else if (h->cfg.obs_type == DYNENV_OBS_PARTIAL)
+          rc_obsp_kernel<<<g2, 32, smem_obsp, s2>>>(h->sim, h->state, tick, left, o->obs, t ? t->obs : nullptr, mk, ls, cnt);
+        else
+          rc_obs_kernel<false><<<g2, 32, smem, s2>>>(h->sim, h->state, tick, left, o->obs, o->full, t ? t->obs : nullptr,
+                                                      t ? t->full : nullptr, nullptr, nullptr, mk, ls, cnt);
+        launches++;
+      }
       mark(1);
     }
+    /* join */
+    cudaEventRecord(h->ev_join[bi], h->side);
+    cudaStreamWaitEvent(st, h->ev_join[bi], 0);
+    mark(3); /* what the side stream's work took beyond the observations it ran beside */
     b = e;
   }
   if (image) rc_finish_kernel<true><<<grid, RC_WPC * 32, smem_raw, st>>>(h->sim, h->state, o->obs, o->full, o->info, o->raw);
@@ -612,6 +734,14 @@ int dynenv_debug_bounds_violations(unsigned long long* out4) {
   return cudaMemcpyFromSymbol(out4, g_bounds_violations, 4 * sizeof(unsigned long long)) == cudaSuccess ? 0 : DYNENV_E_CUDA;
 }
 #endif
+#ifdef RC_DBG_COUNTERS
+int dynenv_debug_counters(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, rc::g_dbg, 16 * sizeof(unsigned long long));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rc::g_dbg, z, sizeof(z)); }
+  return 0;
+}
+#endif
 #ifdef RASTER_PROFILE
 int dynenv_debug_raster_prof(unsigned long long* out16, int reset) {
   cudaDeviceSynchronize();
@@ -690,7 +820,7 @@ int dynenv_debug_timing(DynEnvHandle h, int enable) {
 
 int dynenv_last_kernel_ms(DynEnvHandle h, float* ms3, int* launches3) {
   if (!h || !ms3 || !launches3) return fail(DYNENV_E_INVALID, "null argument");
-  for (int k = 0; k < 3; k++) { ms3[k] = 0.f; launches3[k] = 0; }
+  for (int k = 0; k < 4; k++) { ms3[k] = 0.f; launches3[k] = 0; }
   if (!h->timing || h->n_timed == 0) return DYNENV_OK;
   cudaSetDevice(h->cfg.device);
   cudaError_t ce = cudaEventSynchronize(h->ev[h->n_timed]);

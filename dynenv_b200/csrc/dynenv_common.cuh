@@ -72,6 +72,9 @@ __device__ __forceinline__ V2 rot(V2 a, float ang) {
   return rot_cs(a, c, s);
 }
 
+/* the same, out of line: for rare call sites inside hot loops (instruction-cache footprint) */
+__device__ __noinline__ V2 rot_ni(V2 a, float ang) { return rot(a, ang); }
+
 /* Philox4x32-10 (Salmon et al., SC'11) */
 __device__ __noinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
@@ -134,13 +137,15 @@ __device__ __forceinline__ void bounds_check(int word) {
 #else
 #define DYNENV_BC(word)
 #endif
+/* One warp per thread block everywhere: the slice starts right behind the SimCfg copy, so
+   every shared-memory address is an immediate or lane * stride + immediate. */
 struct SharedF { /* this warp's slice viewed as float */
-  int base;
+  static constexpr int base = CFG_WORDS;
   __device__ __forceinline__ float& operator[](int k) const { DYNENV_BC(base + k); return reinterpret_cast<float*>(g_smem)[base + k]; }
   __device__ __forceinline__ float* operator+(int k) const { return reinterpret_cast<float*>(g_smem) + base + k; }
 };
 struct SharedI { /* ... and as int */
-  int base;
+  static constexpr int base = CFG_WORDS;
   __device__ __forceinline__ int& operator[](int k) const { DYNENV_BC(base + k); return reinterpret_cast<int*>(g_smem)[base + k]; }
 };
 struct SharedCfg {

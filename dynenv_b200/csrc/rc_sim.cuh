@@ -1172,9 +1172,10 @@ __device__ bool shapes_touch(const Env E, int i, int j) {
 }
 
 /* group pairs that came close (bit k of g[k / 32] = pair g_pairs[k]) and own-feet pairs (bit = odd foot):
-   expanded to shape pairs (lane 0), tested exactly in parallel (lane = candidate), and the touching ones
-   collided in Chipmunk's ascending (i, j) insertion order (lane 0) */
-__device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsigned g0, unsigned g1, unsigned g2, unsigned g3) {
+   expanded to shape pairs (lane 0) and tested exactly in parallel (lane = candidate) on the cached shape geometry and
+   the bounding-circle centres X_BCX / X_BCY; returns how many touch (their keys stay in X_CAND).  Reads nothing else
+   of the record: the register-resident substep calls it without flushing. */
+__device__ __noinline__ int filter_candidates(const Env E, unsigned own, unsigned g0, unsigned g1, unsigned g2, unsigned g3) {
   const int lane = E.lane;
   unsigned short* cand = reinterpret_cast<unsigned short*>(g_smem + E.i.base + X_CAND);
   if (lane == 0) {
@@ -1220,7 +1221,13 @@ __device__ __noinline__ void collide_candidates(const Env E, unsigned own, unsig
     kept += __popc(km);
     __syncwarp();
   }
-  if (lane == 0 && kept) {
+  return kept;
+}
+
+/* the touching candidates (filter_candidates left them in X_CAND) collided in ascending (i, j) order: lane 0 */
+__device__ __noinline__ void collide_kept(const Env E, int kept) {
+  unsigned short* cand = reinterpret_cast<unsigned short*>(g_smem + E.i.base + X_CAND);
+  if (E.lane == 0) {
     for (int x = 1; x < kept; x++) { /* insertion sort: tiny */
       int key = cand[x], y = x - 1;
       while (y >= 0 && cand[y] > key) { cand[y + 1] = cand[y]; y--; }
@@ -1250,8 +1257,11 @@ __device__ __forceinline__ uint32_t broadphase_pairs(const Env E) {
   return packed;
 }
 
-__device__ __noinline__ void space_step(const Env E, const uint32_t pairs4) {
-  /* cpSpaceStep (Chipmunk2D 7.0.x), dt = 0.01 */
+__device__ __noinline__ void space_step_rest(const Env E, int kept, int prevStepped);
+
+__device__ __noinline__ void space_step(const Env E, const uint32_t pairs4, const bool integrate = true) {
+  /* cpSpaceStep (Chipmunk2D 7.0.x), dt = 0.01.  integrate = false: the positions were integrated and the shape geometry
+     cached already (an environment handed over by the register-resident substep of rc_phys2.cuh in mid-substep) */
   const int lane = E.lane;
   const int P = E.c->P;
   const float dt = DT;
@@ -1270,7 +1280,9 @@ __device__ __noinline__ void space_step(const Env E, const uint32_t pairs4) {
   /* integrate positions (cpBodyUpdatePosition), refresh shape geometry, bounding circles in registers */
   float bcx = 0, bcy = 0; /* bounding-circle centre of this lane's shape (radius: 17.5 for a foot, 10 otherwise) */
   const bool active = lane < NSHAPE && shape_active(E, lane);
-  if (lane <= BALL && active) {
+  if (lane <= BALL && active && !integrate) {
+    bcx = (E.f[RC_S_CAX + lane] + E.f[RC_S_CBX + lane]) * 0.5f; bcy = (E.f[RC_S_CAY + lane] + E.f[RC_S_CBY + lane]) * 0.5f;
+  } else if (lane <= BALL && active) {
     float px = E.f[RC_S_PX + lane], pxl = E.f[RC_S_PXL + lane];
     float py = E.f[RC_S_PY + lane], pyl = E.f[RC_S_PYL + lane];
     float an = E.f[RC_S_ANG + lane], anl = E.f[RC_S_ANGL + lane];
@@ -1326,8 +1338,20 @@ __device__ __noinline__ void space_step(const Env E, const uint32_t pairs4) {
       }
       g0 = gh[0]; g1 = gh[1]; g2 = gh[2]; g3 = gh[3];
     }
-    if (own | g0 | g1 | g2 | g3) collide_candidates(E, own, g0, g1, g2, g3);
+    const int kept = (own | g0 | g1 | g2 | g3) ? filter_candidates(E, own, g0, g1, g2, g3) : 0;
+    space_step_rest(E, kept, prevStepped);
   }
+}
+
+/* cpSpaceStep after the positions are integrated and the broad phase has run: narrow phase of the candidate pairs,
+   cached-pair ageing, friction callbacks, warm start, solver sweeps, post-solve.  Reads and writes the record in shared
+   memory (the register-resident substep of rc_phys2.cuh enters here whenever a pair comes close or is cached). */
+__device__ __noinline__ void space_step_rest(const Env E, int kept, int prevStepped) {
+  const int lane = E.lane;
+  const int P = E.c->P;
+  const float dt = DT;
+  const bool active = lane < NSHAPE && shape_active(E, lane);
+  if (kept) collide_kept(E, kept);
   if (E.i[RC_S_NARB]) age_cached_pairs(E);
   const int nact = E.i[X_NACTIVE];
   const float biasCoef = 6.1259606640e-02f; /* 1 - collisionBias^dt, collisionBias = 0.9^60 */
@@ -2165,6 +2189,26 @@ __device__ __forceinline__ void phys_substeps(const Env E, const float* actions_
     if (RC_PHASE_SYNC >= 2) __syncthreads();
     ball_out_of_field(E);
     if (RC_PHASE_SYNC >= 2) __syncthreads();
+    space_step(E, pairs4);
+    if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
+    __syncwarp();
+  }
+}
+
+/* an environment the register-resident substeps (rc_phys2.cuh) handed over: at the start of substep `sub` (phase 0) or
+   inside its Space.step, positions integrated (phase 1); the rest of the launch's substeps runs on the record */
+__device__ __forceinline__ void phys_resume(const Env E, const float* actions_env, int sub, int phase, int sub_e) {
+  const uint32_t pairs4 = broadphase_pairs(E);
+  __syncwarp();
+  if (phase == 1) {
+    space_step(E, pairs4, false);
+    if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
+    __syncwarp();
+    sub++;
+  }
+  for (; sub < sub_e; sub++) {
+    robots_phase(E, sub, actions_env);
+    ball_out_of_field(E);
     space_step(E, pairs4);
     if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
     __syncwarp();

@@ -488,10 +488,12 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);
 
 /* Measurement aid: with timing enabled, every launch of the following dynenv_step calls is bracketed by
    CUDA events on the caller's stream; dynenv_last_kernel_ms waits for the last step's launches and returns
-   the summed duration (ms) and the launch count per kernel class: [0] substep blocks (rc_phys_kernel),
-   [1] observation ticks (rc_obs_kernel), [2] finish (rc_finish_kernel). */
+   the summed duration (ms) and the launch count per kernel class (arrays of FOUR entries): [0] substep blocks
+   (rc_phys_kernel / drv_phys_kernel), [1] observation ticks (rc_obsp_kernel / rc_obs_kernel / drv_obs_kernel),
+   [2] finish (rc_finish_kernel), [3] substep blocks of the environments handed over to the record-based code
+   (rc_phys_slow_kernel). */
 int dynenv_debug_timing(DynEnvHandle h, int enable);
-int dynenv_last_kernel_ms(DynEnvHandle h, float* ms3, int* launches3);
+int dynenv_last_kernel_ms(DynEnvHandle h, float* ms4, int* launches4);
 
 /* Measurement aid: FP32 (CUDA-core, non-tensor) FMA throughput of `device` in TFLOP/s, from a register-resident FMA
    kernel timed with CUDA events (8 independent chains per thread, 148 x 8 blocks of 256 threads, warmed up): the

@@ -48,7 +48,7 @@ def test_one_step_from_golden_states(name):
     sim.set_state(torch.from_numpy(recs.view(np.int32)))
     out = sim.step(torch.from_numpy(np.ascontiguousarray(g["actions"], dtype=np.float32)).cuda())
     torch.cuda.synchronize()
-    assert sim.last_launch_count() == 11  # 5 x (substep block + observation tick) + finish
+    assert sim.last_launch_count() == 21  # 5 x (substep block, its handed-over environments, observation tick of both groups) + finish
     gw = f32_record_to_words(sim.get_state().cpu().numpy().view(np.uint32))
     outs, ow = oracle_step_batch(cfg, recs, g["actions"], seed)
     n = len(recs)

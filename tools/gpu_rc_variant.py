@@ -16,10 +16,11 @@ for s in range(n):
     sim.step(a)
     k = sim.last_kernel_ms()
     b = "early" if s < 30 else ("late" if s >= n - 30 else "mid")
-    for kk in ("phys", "obs"):
+    for kk in ("phys", "obs", "phys_slow"):
         acc.setdefault((b, kk), []).append(k[kk][0])
-    acc.setdefault(("all", "step"), []).append(k["phys"][0] + k["obs"][0] + k["finish"][0])
+    acc.setdefault(("all", "step"), []).append(k["phys"][0] + k["obs"][0] + k["finish"][0] + k["phys_slow"][0])
 m = lambda v: sum(v) / len(v)
-print("%-28s phys early %.2f late %.2f | obs early %.2f late %.2f | mean step %.2f ms -> %.2f M env-steps/s" % (
+print("%-28s phys early %.2f late %.2f + handed over %.2f / %.2f | obs early %.2f late %.2f | mean step %.2f ms -> %.2f M env-steps/s" % (
     os.path.basename(os.environ.get("DYNENV_B200_LIB", "default")), m(acc[("early", "phys")]), m(acc[("late", "phys")]),
+    m(acc[("early", "phys_slow")]), m(acc[("late", "phys_slow")]),
     m(acc[("early", "obs")]), m(acc[("late", "obs")]), m(acc[("all", "step")]), E / m(acc[("all", "step")]) / 1e3))
