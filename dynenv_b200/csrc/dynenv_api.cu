@@ -189,6 +189,7 @@ struct SharedRec {
   __device__ __forceinline__ uint32_t operator()(int k) const { return g_smem[base + k]; }
 };
 
+template <bool LINES>
 __global__ void __launch_bounds__(32, 32)
 rc_obsp_kernel(const __grid_constant__ SimCfg cfg, uint32_t* state, int t, int subs_left, float* __restrict__ obs,
                float* __restrict__ term_obs, const uint8_t* __restrict__ slow_mark, const uint32_t* __restrict__ slow_list,
@@ -202,12 +203,18 @@ rc_obsp_kernel(const __grid_constant__ SimCfg cfg, uint32_t* state, int t, int s
        e = next_env(cursor, cfg.n_envs, slow_mark, slow_list, slow_count)) {
     uint32_t* rec = state + (size_t)e * RC_STATE_WORDS;
     const int elapsed = (int)rec[RC_S_ELAPSED];
-    rc::o_prologue(E, GlobalRec{rec}, cfg.env_id_offset + (uint32_t)e, true);
+    rc::o_prologue(E, GlobalRec{rec}, cfg.env_id_offset + (uint32_t)e, !LINES);
     const size_t obs_stride = (size_t)RC_NTICK * cfg.P * RC_OBS_WORDS;
     const bool finishing = cfg.auto_reset && elapsed + subs_left >= rc::MAXTIME;
     float* o = finishing ? (term_obs ? term_obs + e * obs_stride : nullptr) : (obs ? obs + e * obs_stride : nullptr);
-    rc::observe_partial(E, (uint32_t)elapsed, o ? o + (size_t)t * cfg.P * RC_OBS_WORDS : nullptr);
-    for (int w = lane; w < rc::O_ACC_WORDS; w += 32) rec[RC_S_STEP_LSUM + w] = (uint32_t)E.i[rc::O_ACC + w];
+    float* ot = o ? o + (size_t)t * cfg.P * RC_OBS_WORDS : nullptr;
+    if (LINES) { /* first launch of the tick: the lines; their counts join the processSeens sum of the landmarks */
+      rc::observe_lines(E, (uint32_t)elapsed, ot);
+      if (lane < cfg.P) rec[RC_S_STEP_LSUM + lane] += (uint32_t)E.i[rc::O_CNT + 8 * lane + 5];
+    } else {     /* second launch: the point objects, false positives, counts */
+      rc::observe_partial(E, (uint32_t)elapsed, ot);
+      for (int w = lane; w < rc::O_ACC_WORDS; w += 32) rec[RC_S_STEP_LSUM + w] = (uint32_t)E.i[rc::O_ACC + w];
+    }
     __syncwarp();
   }
 }
@@ -234,8 +241,11 @@ __device__ __forceinline__ void reset_env_partial(const rc::Env E, uint32_t* S, 
   __syncwarp();
   rc::o_prologue(E, SharedRec{SharedI::base}, env_id, false);
   const int P = E.c->P;
-  for (int t = 0; t < RC_NTICK; t++)
-    rc::observe_partial(E, DYNENV_TICK_RESETOBS | (uint32_t)t, obs_env ? obs_env + (size_t)t * P * RC_OBS_WORDS : nullptr);
+  for (int t = 0; t < RC_NTICK; t++) {
+    float* ot = obs_env ? obs_env + (size_t)t * P * RC_OBS_WORDS : nullptr;
+    rc::observe_lines(E, DYNENV_TICK_RESETOBS | (uint32_t)t, ot);
+    rc::observe_partial(E, DYNENV_TICK_RESETOBS | (uint32_t)t, ot);
+  }
 }
 
 /* rewards, info, done, episode statistics; finished environments are re-initialised (auto-reset) */
@@ -619,8 +629,11 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
         if (image)
           rc_obs_kernel<true><<<g2, 32, smem_raw, s2>>>(h->sim, h->state, tick, left, o->obs, o->full, t ? t->obs : nullptr,
                                                          t ? t->full : nullptr, o->raw, t ? t->raw : nullptr, mk, ls, cnt);
-        else if (h->cfg.obs_type == DYNENV_OBS_PARTIAL)
-          rc_obsp_kernel<<<g2, 32, smem_obsp, s2>>>(h->sim, h->state, tick, left, o->obs, t ? t->obs : nullptr, mk, ls, cnt);
+        else if (h->cfg.obs_type == DYNENV_OBS_PARTIAL) {
+          rc_obsp_kernel<true><<<g2, 32, smem_obsp, s2>>>(h->sim, h->state, tick, left, o->obs, t ? t->obs : nullptr, mk, ls, cnt);
+          rc_obsp_kernel<false><<<g2, 32, smem_obsp, s2>>>(h->sim, h->state, tick, left, o->obs, t ? t->obs : nullptr, mk, ls, cnt);
+          launches++;
+        }
         else
           rc_obs_kernel<false><<<g2, 32, smem, s2>>>(h->sim, h->state, tick, left, o->obs, o->full, t ? t->obs : nullptr,
                                                       t ? t->full : nullptr, nullptr, nullptr, mk, ls, cnt);

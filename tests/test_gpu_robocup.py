@@ -48,7 +48,8 @@ def test_one_step_from_golden_states(name):
     sim.set_state(torch.from_numpy(recs.view(np.int32)))
     out = sim.step(torch.from_numpy(np.ascontiguousarray(g["actions"], dtype=np.float32)).cuda())
     torch.cuda.synchronize()
-    assert sim.last_launch_count() == 21  # 5 x (substep block, its handed-over environments, observation tick of both groups) + finish
+    # 5 x (substep block, its handed-over environments, observation tick of both groups [PARTIAL: lines + points]) + finish
+    assert sim.last_launch_count() == (31 if cfg["obsType"] == 1 else 21)  # 1 = DYNENV_OBS_PARTIAL
     gw = f32_record_to_words(sim.get_state().cpu().numpy().view(np.uint32))
     outs, ow = oracle_step_batch(cfg, recs, g["actions"], seed)
     n = len(recs)
