@@ -2,7 +2,12 @@
 """Benchmark of the rollout hot path: env-steps/s of RoboCup 5v5 (50 substeps + 5 observation ticks x 10
 observers per env-step), PARTIAL observation, REALISTIC noise magnitude 2 (BASELINE.json configs[1]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference] [--workload robocup|driving]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference] [--workload robocup|driving|image]
+
+The timed window starts mid-episode (an untimed fast-forward of 110 RoboCup / 290 Driving steps in front of the W warm-up
+steps): contacts, falls and penalties build up over an episode, and the first steps of an episode are its cheapest.
+The default RoboCup line also carries short legs of the other BASELINE.json configs (`other_workloads`: Driving, IMAGE,
+single-environment latency) and the drop-in API's end-to-end rate (`e2e_dropin`).
 
 `--workload driving` measures BASELINE.json configs[2] instead (DrivingEnvironment, 10 cars, PARTIAL, continuous
 actions, REALISTIC noise 2: 10 substeps + 1 observation x 10 observers per env-step); the default is configs[1].
@@ -38,7 +43,9 @@ class RoboCupWorkload(object):
     metric = "env-steps/sec (RoboCup 5v5, 50 substeps)"
     workload = "RoboCup 5v5 PARTIAL REALISTIC noise 2, canFall, auto-reset"
     P, act = 10, 4
-    launches_per_step = {"phys": 5, "obs": 5, "finish": 1}
+    launches_per_step = {"phys": 5, "phys_slow": 5, "obs": 5, "finish": 1}  # obs: one tick = lines + point objects, both groups
+    kernel_names = {"phys": "rc_phys_kernel", "phys_slow": "rc_phys_slow_kernel", "obs": "rc_obsp_kernel<lines> + rc_obsp_kernel<points>",
+                    "finish": "rc_finish_kernel", "raster": "rc_raster_kernel"}
     prefix = "rc"
     cpu_steps, ref_steps, cpu_warm = 20000, 1000, 50  # env-steps per host thread: cpu_baseline sample, reference-arm step, warm-up
     default_steps = 240  # one whole episode (12000 / 50): contacts, falls and penalties build up over an episode
@@ -69,7 +76,9 @@ class RoboCupWorkload(object):
         from dynenv_b200 import layout as L
         rec = 4 * L.RC_STATE_WORDS
         return {"phys": 2 * rec + 4 * self.P * 4,                                   # record in + out, actions
-                "obs": rec + 4 * self.P * L.RC_OBS_WORDS + 4 * (L.RC_S_STEP_END - L.RC_S_STEP_LSUM),  # record in, 10 records out
+                # one tick: the robot table of the record (21 positions, 20 angles, 10 heads, 10 flags, 7 scalars) twice,
+                # 10 records out, the processSeens sums in + out
+                "obs": 2 * 4 * 89 + 4 * self.P * L.RC_OBS_WORDS + 2 * 4 * (L.RC_S_STEP_END - L.RC_S_STEP_LSUM),
                 "finish": 2 * rec + 4 * L.RC_INFO_WORDS}
 
     def cpu_env(self, i):
@@ -91,6 +100,7 @@ class DrivingWorkload(object):
     workload = "Driving 10 cars PARTIAL continuous actions REALISTIC noise 2, auto-reset"
     P, act = 10, 2
     launches_per_step = {"phys": 1, "obs": 1, "finish": 0}
+    kernel_names = {"phys": "drv_phys_kernel", "obs": "drv_obs_kernel"}
     prefix = "drv"
     cpu_steps, ref_steps, cpu_warm = 10000, 1000, 50
     default_steps = 600  # one whole episode (6000 / 10)
@@ -181,7 +191,7 @@ class ImageWorkload(RoboCupWorkload):
     name = "image"
     metric = "env-steps/sec (RoboCup 5v5 IMAGE, 50 substeps + 100 camera images)"
     workload = "RoboCup 5v5 IMAGE (top / bottom camera raster, 8 x 480 x 640 bit-planes per robot and tick) allowHeadTurn REALISTIC noise 2, auto-reset"
-    launches_per_step = {"phys": 5, "obs": 5, "finish": 1, "raster": 1}
+    launches_per_step = {"phys": 5, "phys_slow": 5, "obs": 5, "finish": 1, "raster": 1}
     chunk = 1024
     default_envs = 16384
     cpu_steps, ref_steps, cpu_warm = 16, 4, 1  # an env-step draws 100 images with cv2 (~0.3 s)
@@ -359,10 +369,150 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+FAST_FORWARD = {"robocup": 110, "driving": 290, "image": 20}  # untimed steps in front of the warm-up: mid-episode
+
+
+def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=True, full=False, sampler=None):
+    """One workload on this rank's GPU.  Three passes over the SAME window of the episode (reset, `ff` untimed
+    fast-forward steps, `warmup` steps, `steps` timed steps on the same actions):
+      1. device-resident: actions already in HBM, CUDA events around the K steps          -> value
+      2. end to end: pinned host actions -> H2D -> step -> rewards + done D2H, every step  -> e2e
+      3. per kernel class: events bracketing every launch inside the library (untimed)     -> launch_ms
+    Returns a dict of raw numbers (this rank's)."""
+    import torch
+    import torch.distributed as dist
+    from dynenv_b200 import layout as L
+    dev = torch.device("cuda", local)
+    P = wl.P
+    sim = wl.make_sim(E, local, rank, full=full)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    # fresh uniform actions for every step of the window (a short cycle biases the play: robots repeat their walk, drift
+    # together and collide); the fast-forward steps draw theirs on the fly
+    pool = [wl.make_actions(E, g, dev) for _ in range(min(steps, 640))]
+    n_pool = len(pool)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def rewind():
+        """reset + fast-forward + warm-up: the same episode window for every pass (same seeds, same actions)"""
+        sim.reset()
+        gf = torch.Generator(device=dev)
+        gf.manual_seed(99 + rank)
+        for _ in range(ff + warmup):
+            sim.step(wl.make_actions(E, gf, dev))
+        barrier()
+
+    res = {"E": E, "launches": 0}
+    # ---- pass 1: device-resident
+    rewind()
+    if sampler is not None:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for s in range(steps):
+        sim.step(pool[s % n_pool])
+        res["launches"] += sim.last_launch_count()
+    t1.record(stream)
+    barrier()
+    if sampler is not None:
+        res["clocks"] = sampler.stop()
+    res["ms_total"] = t0.elapsed_time(t1)
+    res["diag"] = int(sim.out.diag.max().item())
+    # ---- pass 2: end to end through the host-facing call
+    n_res = (L.DRV_I_DONE if wl.name == "driving" else L.RC_I_DONE) + 1
+    res["h2d"], res["d2h"] = E * P * wl.act * 4, E * n_res * 4
+    if e2e:
+        n_host = min(n_pool, max(8, int(3.5e9 // (E * P * wl.act * 4))))  # at most ~3.5 GB of pinned actions per rank
+        h_act = [p.cpu().pin_memory() for p in pool[:n_host]]
+        d_act = torch.empty((E, P, wl.act), device=dev)
+        # rewards [maxAgents] and done are the first words of every environment's result record: one strided copy
+        h_res = torch.empty((E, n_res), dtype=torch.float32).pin_memory()
+        rewind()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(steps):
+            d_act.copy_(h_act[s % n_host], non_blocking=True)
+            out = sim.step(d_act)
+            h_res.copy_(out.info[:, :n_res], non_blocking=True)
+            stream.synchronize()
+        e1.record(stream)
+        barrier()
+        res["ms_e2e"] = e0.elapsed_time(e1)
+        del h_act, h_res
+    # ---- pass 3: per kernel class (the events serialise nothing, but the blocking read does: its own pass)
+    if per_kernel:
+        rewind()
+        sim.debug_timing(True)
+        kms = {}
+        n3 = min(steps, 40)
+        for s in range(n3):
+            sim.step(pool[s % n_pool])
+            for k, (ms, n) in sim.last_kernel_ms().items():
+                a = kms.setdefault(k, [0.0, 0])
+                a[0] += ms
+                a[1] += n
+        sim.debug_timing(False)
+        res["kernel_ms_per_step"] = {k: v[0] / n3 for k, v in kms.items() if v[1]}
+        res["kernel_launches_per_step"] = {k: v[1] / n3 for k, v in kms.items() if v[1]}
+    del sim, pool
+    torch.cuda.empty_cache()
+    return res
+
+
+def single_env_latency(local):
+    """BASELINE.json configs[0]: RoboCupEnvironment nPlayers=1, FULL observation, noise off, ONE environment -- the
+    latency of a step through the batched simulator (launch-bound), over one episode"""
+    import torch
+    import dynenv_b200
+    sim = dynenv_b200.BatchedRoboCup(1, 1, dynenv_b200.ObservationType.FULL, dynenv_b200.NoiseType.REALISTIC, 0.0, canFall=False,
+                                     auto_reset=True, seed=42, device=local)
+    sim.reset()
+    rng = np.random.default_rng(1234)
+    acts = torch.from_numpy(np.stack([rng.integers(0, 5, (240, 1, 2)), rng.integers(0, 3, (240, 1, 2)), rng.integers(0, 3, (240, 1, 2)),
+                                      rng.integers(0, 7, (240, 1, 2))], -1).astype(np.float32)).cuda(local)
+    for s in range(10):
+        sim.step(acts[s])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(240):
+        out = sim.step(acts[s])
+        out.rewards.cpu()  # the caller reads the rewards back: synchronises every step
+    dt = time.perf_counter() - t0
+    return {"workload": "RoboCup 1v1 FULL noise off, 1 environment (configs[0])", "ms_per_step": 1e3 * dt / 240,
+            "value": 240 / dt, "unit": UNIT, "steps": 240, "note": "host-synchronous step latency, 21 launches per step"}
+
+
+def dropin_e2e(local):
+    """the path a DynEnv user calls: make_dyn_env(...) -> vec_env.step(actions) with host numpy actions in, the reference's
+    nested observation lists, rewards, dones and infos out (dynenv_b200/api.py) -- env-steps/s at three widths"""
+    import dynenv_b200
+    out = {}
+    for n_envs, n_steps in ((8, 20), (256, 5), (4096, 2)):
+        env, name = dynenv_b200.make_dyn_env(dynenv_b200.DynEnvType.ROBO_CUP, n_envs, 5, False, dynenv_b200.ObservationType.PARTIAL,
+                                             dynenv_b200.NoiseType.REALISTIC, 2.0, False)
+        env.reset()
+        rng = np.random.default_rng(5)
+        acts = [np.stack([rng.integers(0, 5, (n_envs, 10)), rng.integers(0, 3, (n_envs, 10)), rng.integers(0, 3, (n_envs, 10)),
+                          rng.integers(0, 7, (n_envs, 10))], -1) for _ in range(n_steps + 1)]
+        env.step(acts[0])
+        t0 = time.perf_counter()
+        for s in range(n_steps):
+            env.step(acts[s + 1])
+        dt = time.perf_counter() - t0
+        out[str(n_envs)] = {"value": n_envs * n_steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n_steps}
+        env.close()
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    import dynenv_b200
     from dynenv_b200 import layout as L
 
     rank = int(os.environ.get("RANK", "0"))
@@ -376,84 +526,13 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]()
     E = args.envs or getattr(wl, "default_envs", 65536)
-    METRIC, WORKLOAD, P = wl.metric, wl.workload, wl.P
-    sim = wl.make_sim(E, local, rank, full=args.debug_full_obs)
-    sim.reset()
-    # synthetic actions, generator seed 1234
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    # fresh uniform actions every step: a cycle biases the play (every robot repeats its walk, they drift together and
-    # collide: a 32-step cycle costs 12 % env-steps/s, tools/gpu_e2e_parts.py), so the pool covers the whole run
-    n_pool = min(args.steps + args.warmup, 640)
-    pool = [wl.make_actions(E, g, dev) for _ in range(n_pool)]
-    stream = torch.cuda.current_stream()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for w in range(args.warmup):
-        sim.step(pool[w % n_pool])
-    pool = pool[args.warmup % n_pool:] + pool[:args.warmup % n_pool]
-    barrier()
-    sim.debug_timing(True)
-    kms = {k: [0.0, 0] for k in wl.launches_per_step}
-    sampler = ClockSampler(local)
-    sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    t_start.record(stream)
-    for s in range(args.steps):
-        evs[s][0].record(stream)
-        sim.step(pool[s % n_pool])
-        evs[s][1].record(stream)
-        launches += sim.last_launch_count()
-        if s % 4 == 3 or s == args.steps - 1:  # per-kernel durations (waits for that step; every 4th only)
-            for k, (ms, n) in sim.last_kernel_ms().items():
-                kms[k][0] += ms
-                kms[k][1] += n
-    t_end.record(stream)
-    barrier()
-    sim.debug_timing(False)
-    clocks = sampler.stop()
-    ms_total = t_start.elapsed_time(t_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    diag = int(sim.out.diag.max().item())
-
-    # end to end through the host-facing call: pinned host actions in, rewards + done out, every step
-    # the timed steps' own actions, from pinned host memory (at most ~3.5 GB of it per rank; cycled beyond that)
-    n_host = min(n_pool, args.steps, max(32, int(3.5e9 // (E * P * wl.act * 4))))
-    h_act = [p.cpu().pin_memory() for p in pool[:n_host]]
-    n_pool = len(h_act)
-    d_act = torch.empty((E, P, wl.act), device=dev)
-    # rewards [maxAgents] and done are the first words of every environment's result record: one strided copy
-    # (two copies of the `rewards` / `done` views cost 0.45-1.0 ms per step, tools/gpu_e2e_parts.py)
-    n_res = (L.DRV_I_DONE if args.workload == "driving" else L.RC_I_DONE) + 1
-    h_res = torch.empty((E, n_res), dtype=torch.float32).pin_memory()
-    # the same window of the episode as the device-resident measurement: reset, the same warm-up steps, then the timed
-    # steps on their own actions (step times grow over an episode; a later window would not be comparable)
-    sim.reset()
-    for w in range(args.warmup):
-        sim.step(pool[(len(pool) - (args.warmup % len(pool)) + w) % len(pool)])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for s in range(args.steps):
-        d_act.copy_(h_act[s % n_pool], non_blocking=True)
-        out = sim.step(d_act)
-        h_res.copy_(out.info[:, :n_res], non_blocking=True)
-        stream.synchronize()
-    e1.record(stream)
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-
+    ff = FAST_FORWARD[wl.name] if args.fast_forward is None else args.fast_forward
+    r = measure(wl, E, local, rank, world, args.steps, args.warmup, ff, full=args.debug_full_obs, sampler=ClockSampler(local))
+    ms_total, ms_e2e = r["ms_total"], r["ms_e2e"]
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, kernel_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, kernel_ms = [float(x) for x in t.tolist()]
+        ms_total, ms_e2e = [float(x) for x in t.tolist()]
     if rank == 0:
         peaks, which = measured_peaks()
         import ctypes
@@ -461,53 +540,78 @@ def run_gpu(args):
         tf = ctypes.c_float(0)
         fp32_peak = float(tf.value) if _l.lib().dynenv_debug_fp32_peak(local, ctypes.byref(tf)) == 0 else None
         total_envs = E * world
+        step_ms = ms_total / args.steps
         value = total_envs * args.steps / (ms_total * 1e-3)
         e2e = total_envs * args.steps / (ms_e2e * 1e-3)
-        bytes_launch = wl.algorithmic_bytes_per_env_step() * E
+        P = wl.P
+        # the dominant kernel class of the step and its HBM figure: algorithmic bytes per launch / launch duration
         kb = wl.kernel_bytes_per_env()
-        per_launch = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kms.items()}  # ms per launch
-        per_step = {k: per_launch[k] * wl.launches_per_step[k] for k in per_launch}
-        dom = max(per_step, key=per_step.get)  # dominant kernel class of the step
-        achieved = kb[dom] * E / (per_launch[dom] * 1e-3) / 1e9 if per_launch[dom] else 0.0
-        step_gbs = bytes_launch / (kernel_ms * 1e-3) / 1e9
-        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s_%s_kernel" % (wl.prefix, dom))
-            if tr:  # scaled to the environments one launch of this run covers
-                traffic = tr["dram_bytes_per_launch"] * (min(getattr(wl, "chunk", E), E) if dom == "raster" else E) / tr["envs"]
-        except Exception:
-            pass
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        k_ms, k_n = r["kernel_ms_per_step"], r["kernel_launches_per_step"]
+        dom = max((k for k in k_ms if k in kb), key=lambda k: k_ms[k])
+        dom_launch_ms = k_ms[dom] / wl.launches_per_step[dom]
+        hbm_dom = kb[dom] * E / (dom_launch_ms * 1e-3) / 1e9
+        step_bytes = wl.algorithmic_bytes_per_env_step()
+        step_gbs = step_bytes * E / (step_ms * 1e-3) / 1e9
+        tflops = FLOP_PER_ENV_STEP * E / (step_ms * 1e-3) / 1e12
+        hbm_block = {"bound": "hbm", "achieved": hbm_dom, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_dom / peaks["hbm_gbs"],
+                     "peak_source": which, "kernel": wl.kernel_names[dom], "kernel_ms_per_launch": dom_launch_ms,
+                     "algorithmic_bytes_per_launch": kb[dom] * E,
+                     "step": {"algorithmic_bytes_per_env_step": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peaks["hbm_gbs"]}}
+        if wl.name == "image":  # the raster is HBM-write bound: its HBM figure is the primary roofline
+            roofline = dict(hbm_block, traffic=None)
+        else:  # the step kernels are bound by instruction issue on the FP32 / INT pipes: FP32 fraction first
+            roofline = {"bound": "fp32-issue", "achieved": tflops, "peak": fp32_peak or FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+                        "frac": tflops / (fp32_peak or FP32_NOMINAL_TFLOPS), "traffic": None,
+                        "flop_per_env_step": FLOP_PER_ENV_STEP, "peak_source": "FMA probe of the library, this run" if fp32_peak else "nominal",
+                        "nominal_peak_tflops": FP32_NOMINAL_TFLOPS, "hbm": hbm_block}
+        roofline["kernel_ms_per_step"] = k_ms
+        roofline["kernel_launches_per_step"] = k_n
+        roofline["share_of_step"] = {k: v / max(sum(k_ms.values()), 1e-9) for k, v in k_ms.items()}
+        roofline["note"] = ("traffic: not measurable inside the run (ncu captures of the same command: profiles/); kernel_ms_per_step from "
+                            "a separate, untimed pass over the same episode window; phys_slow = what the handed-over environments' "
+                            "side stream adds beyond the observations it runs beside")
+        line = {"metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict({"workload": WORKLOAD, "envs_per_gpu": E, "envs_total": total_envs,
-                                "episode_steps": [args.warmup, args.warmup + args.steps],  # window of the timed steps in the episode(s)
-                                "l2": "state + outputs per step (%.1f GB) exceed the 126 MB L2" % (bytes_launch / 1e9)},
+                "config": dict({"workload": wl.workload, "envs_per_gpu": E, "envs_total": total_envs,
+                                # window of the timed steps inside the episode (240 / 600 steps long): contacts, falls and
+                                # penalties build up over an episode, so the window starts mid-episode whatever --warmup says
+                                "episode_steps": [ff + args.warmup, ff + args.warmup + args.steps], "fast_forward_steps": ff,
+                                "l2": "state + outputs per step (%.1f GB) exceed the 126 MB L2" % (step_bytes * E / 1e9)},
                                **wl.config(L)),
-                "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * P * wl.act * 4,
-                        "d2h_bytes_per_step": E * n_res * 4,
+                "clocks": r["clocks"], "gpu_launches": r["launches"],
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                         "note": "observations stay device-resident for the learner; rewards + done return to the host"},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
-                             "kernel": "%s_%s_kernel" % (wl.prefix, dom), "kernel_ms_per_launch": per_launch[dom],
-                             "algorithmic_bytes_per_launch": kb[dom] * E,
-                             "launch_ms": per_launch, "share_of_step": {k: v / max(sum(per_step.values()), 1e-9) for k, v in per_step.items()},
-                             "step": {"ms": kernel_ms, "algorithmic_bytes_per_env_step": wl.algorithmic_bytes_per_env_step(),
-                                      "achieved_gbs": step_gbs, "frac": step_gbs / peaks["hbm_gbs"]},
-                             "note": "the step is instruction-issue bound (FP32/INT pipes), not HBM bound; see DESIGN.md section 4",
-                             "fp32": {"flop_per_env_step": FLOP_PER_ENV_STEP,
-                                      "achieved_tflops": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12,
-                                      "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
-                                      "measured_peak_tflops": fp32_peak,  # FMA probe of the library, this run
-                                      "frac": FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12 / (fp32_peak or FP32_NOMINAL_TFLOPS)}},
-                "diag_flags": diag}
+                "roofline": roofline, "diag_flags": r["diag"]}
         if not args.no_cpu and world == 1:
             cpu_steps = args.cpu_steps or wl.cpu_steps
             rate, threads, dt = cpu_env_steps_per_s(wl, cpu_steps)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d host threads x %d env-steps of the same workload (%.1f s), C restatement "
                                               "of the reference" % (threads, cpu_steps, dt)}
+        if not args.no_other and world == 1 and wl.name == "robocup" and not args.debug_full_obs:
+            # short legs of the other BASELINE.json configs, so that the driver's record carries them
+            other = {}
+            for name, (e_o, k_o) in (("driving", (65536, 20)), ("image", (4096, 2))):
+                try:
+                    w2 = WORKLOADS[name]()
+                    r2 = measure(w2, e_o, local, rank, 1, k_o, 3, FAST_FORWARD[name], per_kernel=False)
+                    other[name] = {"metric": w2.metric, "workload": w2.workload, "envs": e_o, "steps": k_o,
+                                   "episode_steps": [FAST_FORWARD[name] + 3, FAST_FORWARD[name] + 3 + k_o],
+                                   "value": e_o * k_o / (r2["ms_total"] * 1e-3), "unit": UNIT, "ms_per_step": r2["ms_total"] / k_o,
+                                   "e2e": e_o * k_o / (r2["ms_e2e"] * 1e-3), "gpu_launches": r2["launches"]}
+                except Exception as ex:  # a leg must not cost the headline
+                    other[name] = {"error": repr(ex)}
+            try:
+                other["single_env"] = single_env_latency(local)
+            except Exception as ex:
+                other["single_env"] = {"error": repr(ex)}
+            line["other_workloads"] = other
+            try:
+                line["e2e_dropin"] = dict(dropin_e2e(local), note="make_dyn_env('RoboCup', n, 5, ...).step(numpy actions): the reference's "
+                                          "nested observation lists built on the host (dynenv_b200/api.py)")
+            except Exception as ex:
+                line["e2e_dropin"] = {"error": repr(ex)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -522,6 +626,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="robocup", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the short legs of the other workloads / the drop-in API")
+    ap.add_argument("--fast-forward", type=int, default=None, help="untimed steps in front of the warm-up (default: to mid-episode)")
     ap.add_argument("--debug-full-obs", action="store_true", help="(profiling aid) FULL observations: physics and rules only")
     ap.add_argument("--cpu-steps", type=int, default=None, help="env-steps per host thread of the cpu_baseline sample")
     args = ap.parse_args()
