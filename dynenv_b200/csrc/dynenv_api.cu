@@ -100,7 +100,7 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
   rc::phys_substeps(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
 #else
-  const int handover = rc::phys_substeps2(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
+  const int handover = rc::phys_substeps2<false>(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
   if (lane == 0) {
     slow_mark[e] = handover >= 0;
@@ -110,7 +110,8 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
 }
 
 /* the environments rc_phys_kernel handed over (falls, penalties, touching or cached pairs: a few percent of them): the
-   rest of their substeps on the record-based code of rc_sim.cuh.  A fixed grid walks the list. */
+   rest of their substeps, still register-resident between the ordered robot phases (rc_sim.cuh) and the contact halves
+   (rc_contact.cuh) they need.  A fixed grid walks the list. */
 __global__ void __launch_bounds__(32, 32)
 rc_phys_slow_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions, int sub_e,
                     const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
@@ -123,7 +124,11 @@ rc_phys_slow_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ s
     const int e = (int)(item & 0xFFFFFFu), code = (int)(item >> 24);
     load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
     rc::Env E = make_env(CFG_WORDS, cfg, e, lane);
+#ifdef RC_SLOW_RECORD /* the first version: the handed-over environments entirely on the record-based code */
     rc::phys_resume(E, actions + (size_t)e * cfg.P * 4, code >> 1, code & 1, sub_e);
+#else
+    rc::phys_substeps2<true>(E, actions + (size_t)e * cfg.P * 4, code >> 1, sub_e, false, code & 1);
+#endif
     store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
     __syncwarp();
   }

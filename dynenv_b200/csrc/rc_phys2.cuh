@@ -23,6 +23,7 @@
  */
 #pragma once
 #include "rc_sim.cuh"
+#include "rc_contact.cuh"
 
 namespace dynenv {
 namespace rc {
@@ -97,9 +98,24 @@ __device__ __forceinline__ void regs_store(const Env E, const Body& B, const Rob
    phase 1 = from the narrow phase of its Space.step (a pair touches or is cached; positions are integrated).  The caller
    queues the environment for rc_phys_slow_kernel, which runs the rest of the launch's substeps (phys_resume): keeping
    the rare code out of this kernel keeps its instruction footprint at the size of the common substep. */
-__device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_env, int sub_b, int sub_e, bool first) {
+/* SLOW = false: rc_phys_kernel, as above.  SLOW = true: rc_phys_slow_kernel -- the same register-resident substeps for
+   the handed-over environments, which run the rare code in place: the ordered robot phase of rc_sim.cuh and the contact
+   half of rc_contact.cuh, each between a flush and a reload of the registers; phase0 = 1 resumes inside Space.step of
+   substep sub_b.  Returns -1. */
+template <bool SLOW>
+__device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_env, int sub_b, int sub_e, bool first, int phase0 = 0) {
   if (first) clear_step_scratch(E);
   const uint32_t pairs4 = broadphase_pairs(E);
+  if (SLOW && phase0) {
+    unsigned own, g0, g1, g2, g3;
+    __syncwarp();
+    const int prevStepped = E.i[RC_S_STEPPED];
+    record_broadphase(E, pairs4, own, g0, g1, g2, g3);
+    contact_half(E, own, g0, g1, g2, g3, pairs4, prevStepped);
+    if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
+    __syncwarp();
+    sub_b++;
+  }
   const int lane = E.lane;
   const int P = E.c->P, nPl = E.c->n_players;
   const bool isFoot = lane < 2 * P;       /* an existing robot's foot */
@@ -167,7 +183,10 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
       if (__any_sync(FULLMASK, need)) {
         RC_DBG(1, true);
         regs_store(E, B, R, U);
-        return 2 * sub;
+        if (!SLOW) return 2 * sub;
+        robots_phase(E, sub, actions_env);
+        regs_load(E, B, R, U);
+        forcesPending = true; biasPending = true;
       } else {
        bool restored = false;
        if (isFoot) {
@@ -453,19 +472,33 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
         g0 = gh[0]; g1 = gh[1]; g2 = gh[2]; g3 = gh[3];
       }
       RC_DBG(2, own); RC_DBG(3, g0 | g1 | g2 | g3); RC_DBG(4, nArb);
-      /* groups that came close: exact test of their shape pairs on the cached geometry */
-      int kept = 0;
-      if (own | g0 | g1 | g2 | g3) {
-        if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
-        __syncwarp();
-        kept = filter_candidates(E, own, g0, g1, g2, g3);
-      }
-      RC_DBG(5, kept);
-      if (kept | nArb) { /* a pair touches or is cached: the contact half of the substep runs on the record */
-        RC_DBG(6, true);
-        regs_store(E, B, R, U);
-        return 2 * sub + 1;
+      if (SLOW) {
+        if (own | g0 | g1 | g2 | g3 | (unsigned)nArb) { /* a pair is close or cached: the contact half runs on the record */
+          if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
+          regs_store(E, B, R, U);
+          contact_half(E, own, g0, g1, g2, g3, pairs4, prevStepped);
+          regs_load(E, B, R, U);
+          forcesPending = true; biasPending = true;
+          U.elapsed += 1;
+          __syncwarp();
+          continue;
+        }
       } else {
+        /* groups that came close: exact test of their shape pairs on the cached geometry */
+        int kept = 0;
+        if (own | g0 | g1 | g2 | g3) {
+          if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
+          __syncwarp();
+          kept = filter_candidates(E, own, g0, g1, g2, g3);
+        }
+        RC_DBG(5, kept);
+        if (kept | nArb) { /* a pair touches or is cached: the contact half of the substep runs on the record */
+          RC_DBG(6, true);
+          regs_store(E, B, R, U);
+          return 2 * sub + 1;
+        }
+      }
+      {
         if (!prevStepped && lane == 0) E.i[RC_S_STEPPED] = 1;
         const float biasCoef = 6.1259606640e-02f; /* 1 - collisionBias^dt, collisionBias = 0.9^60 */
         /* velocity update through the friction callbacks (cutils.py:93-140) */

@@ -251,6 +251,7 @@ __device__ __noinline__ void fall(const Env E, int r, int punish) {
   if (punish) E.f[X_REW + r] -= 2.f;
   /* space.point_query(pos, 40, filter) on the geometry cached at the last collision phase; the
      inf/NaN forces the reference applies to static posts are never integrated: skipped */
+#pragma unroll 1
   for (int s = 0; s <= BALL; s++) {
     if (!shape_active(E, s)) continue;
     if (s == 2 * r || s == 2 * r + 1) continue;
@@ -286,11 +287,13 @@ __device__ __noinline__ void free_penalty_spot(const Env E, int r, V2* spot, flo
   float sy = y > H_ / 2 ? SIDE : H_ - SIDE;
   V2 sel = v2(0, 0);
   bool found = false;
+#pragma unroll 1
   for (int k = 0; k < 7 && !found; k++) {
     float sx = team > 0 ? SIDE + (k + 1) * ROB_TOTAL * 3 : W_ - SIDE - (k + 1) * ROB_TOTAL * 3;
     V2 sp = v2(sx, sy);
     if (k == 0) sel = sp;
     bool ok = true;
+#pragma unroll 1
     for (int o = 0; o < E.c->P; o++) {
       if (o == r) continue;
       if (len(sp - robot_pos(E, o)) < ROB_TOTAL * 3) { ok = false; break; }
@@ -883,17 +886,13 @@ __device__ __noinline__ void narrowphase(const Env E, int a, int b, V2 dab, Mani
   }
 }
 
-/* cpSpaceCollideShapes + cpArbiterUpdate + begin callbacks for an AABB-overlapping pair i < j */
-__device__ __noinline__ void collide_pair(const Env E, int i, int j) {
-  int a = i, b = j;
-  if (is_foot(a) && !is_foot(b)) { a = j; b = i; } /* cpCollide orders by primitive type */
-  Manifold m;
-  V2 dab = pos_diff(E, b, a);
-  narrowphase(E, a, b, dab, &m);
-  if (m.cnt == 0) return;
+/* cpArbiterUpdate + begin callbacks of a touching pair (a, b in cpCollide order, dab = position of b relative to a,
+   m = its contact manifold): one lane, pairs in ascending (i, j) order */
+__device__ __noinline__ void arbiter_update(const Env E, int a, int b, V2 dab, const Manifold& m) {
   int nArb = E.i[RC_S_NARB];
   int key16 = a | (b << 8);
   int k = 0;
+#pragma unroll 1
   for (; k < nArb; k++)
     if ((E.i[RC_S_ARBKEY + k] & 0xffff) == key16) break;
   if (k == nArb) {
@@ -908,6 +907,7 @@ __device__ __noinline__ void collide_pair(const Env E, int i, int j) {
   int con = E.i[RC_S_ARBCON + k];
   int oldN = con & 255, oh0 = (con >> 8) & 255, oh1 = (con >> 16) & 255;
   float ojn0 = E.f[RC_S_ARBJN0 + k], ojt0 = E.f[RC_S_ARBJT0 + k], ojn1 = E.f[RC_S_ARBJN1 + k], ojt1 = E.f[RC_S_ARBJT1 + k];
+#pragma unroll
   for (int c = 0; c < 2; c++) {
     int ci = 2 * nact + c;
     float jn = 0, jt = 0;
@@ -937,6 +937,17 @@ __device__ __noinline__ void collide_pair(const Env E, int i, int j) {
   E.i[X_TOUCHED] |= 1 << k;
 }
 
+/* cpSpaceCollideShapes + cpArbiterUpdate + begin callbacks for an AABB-overlapping pair i < j */
+__device__ __noinline__ void collide_pair(const Env E, int i, int j) {
+  int a = i, b = j;
+  if (is_foot(a) && !is_foot(b)) { a = j; b = i; } /* cpCollide orders by primitive type */
+  Manifold m;
+  V2 dab = pos_diff(E, b, a);
+  narrowphase(E, a, b, dab, &m);
+  if (m.cnt == 0) return;
+  arbiter_update(E, a, b, dab, m);
+}
+
 /* ================================================================= space.step */
 struct BodyVel {
   float vx, vy, w;
@@ -954,6 +965,7 @@ __device__ __forceinline__ void load_body(const Env E, int s, float* vx, float* 
 /* cpArbiterApplyImpulse for every active contact, in order (Gauss-Seidel): lane 0 */
 __device__ __noinline__ void contacts_iteration(const Env E) {
   int nact = E.i[X_NACTIVE];
+#pragma unroll 1
   for (int q = 0; q < nact; q++) {
     int key = E.i[RC_S_ARBKEY + E.i[X_ACTIVE + q]];
     int a = key & 255, b = (key >> 8) & 255;
@@ -964,6 +976,7 @@ __device__ __noinline__ void contacts_iteration(const Env E) {
     float avx, avy, aw, avbx, avby, awb, bvx, bvy, bw, bvbx, bvby, bwb;
     load_body(E, a, &avx, &avy, &aw, &avbx, &avby, &awb);
     load_body(E, b, &bvx, &bvy, &bw, &bvbx, &bvby, &bwb);
+#pragma unroll 1
     for (int c = 0; c < ncon; c++) {
       int ci = 2 * q + c;
       V2 r1 = v2(E.f[X_CR1X + ci], E.f[X_CR1Y + ci]), r2 = v2(E.f[X_CR2X + ci], E.f[X_CR2Y + ci]);
@@ -1107,6 +1120,7 @@ __device__ __noinline__ void prestep_contacts(const Env E, float biasCoef) {
 __device__ __noinline__ void warm_start_contacts(const Env E, float dt_coef) {
   if (E.lane == 0) {
     const int nact = E.i[X_NACTIVE];
+#pragma unroll 1
     for (int q = 0; q < nact; q++) {
       int k = E.i[X_ACTIVE + q];
       int key = E.i[RC_S_ARBKEY + k];
@@ -1114,6 +1128,7 @@ __device__ __noinline__ void warm_start_contacts(const Env E, float dt_coef) {
       int a = key & 255, b = (key >> 8) & 255;
       int ncon = E.i[RC_S_ARBCON + k] & 255;
       V2 n = v2(E.f[X_ANX + q], E.f[X_ANY + q]);
+#pragma unroll 1
       for (int c = 0; c < ncon; c++) {
         int ci = 2 * q + c;
         float jn = E.f[X_CJN + ci], jt = E.f[X_CJT + ci];
@@ -1145,6 +1160,7 @@ __device__ __noinline__ void post_solve(const Env E) {
   }
   __syncwarp();
   if (lane == 0) {
+#pragma unroll 1
     for (int q = 0; q < nact; q++) {
       int key = E.i[RC_S_ARBKEY + E.i[X_ACTIVE + q]];
       int a = key & 255, b = (key >> 8) & 255;
@@ -1186,6 +1202,7 @@ __device__ __noinline__ int filter_candidates(const Env E, unsigned own, unsigne
       cand[n++] = (j - 1) * 32 + j;
     }
     unsigned g[4] = {g0, g1, g2, g3};
+#pragma unroll 1
     for (int w = 0; w < 4; w++) {
       unsigned m = g[w];
       while (m) {
@@ -1194,7 +1211,9 @@ __device__ __noinline__ int filter_candidates(const Env E, unsigned own, unsigne
         int a = g_pairs[k][0], b = g_pairs[k][1];
         int a0 = a < 10 ? 2 * a : a + 10, na = a < 10 ? 2 : 1;
         int b0 = b < 10 ? 2 * b : b + 10, nb = b < 10 ? 2 : 1;
+#pragma unroll 1
         for (int x = 0; x < na; x++)
+#pragma unroll 1
           for (int y = 0; y < nb; y++) {
             int i = a0 + x, j = b0 + y;
             float dx = E.f[X_BCX + i] - E.f[X_BCX + j], dy = E.f[X_BCY + i] - E.f[X_BCY + j];
