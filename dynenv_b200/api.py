@@ -13,6 +13,9 @@
 
 Same names, argument meaning and error behaviour.  The simulation itself runs in the CUDA library; these
 classes only validate, launch and convert formats."""
+from dataclasses import dataclass
+from typing import Any, List, Tuple
+
 import numpy as np
 
 from . import layout as L
@@ -21,6 +24,56 @@ from . import spaces as S
 from .enums import DynEnvType, NoiseType, ObservationType
 
 _ACT_HI = (5, 3, 3, 7)
+
+
+# ---- reconstruction descriptors (DynEnv/environment_base.py:18-38): what `env.recoDescriptor` /
+# `vec_env.get_attr('recoDescriptor', 0)` hand to the reconstruction head of the learner (examples/main.py:42)
+@dataclass
+class StateSpaceDescriptor:
+    numItemsPerGridCell: int
+    space: Any
+
+
+@dataclass
+class PredictionDescriptor:
+    numContinuous: int = None  # position not included
+    numBinary: int = 0         # confidence not included
+    contIdx: List[int] = None
+    binaryIdx: List[int] = None
+    posIdx: List[int] = (0, 1)
+    categoricIdx: int = None
+
+
+@dataclass
+class RecoDescriptor:
+    featureGridSize: Tuple[int, int]
+    fullStateSpace: List[StateSpaceDescriptor]
+    targetDefs: List[PredictionDescriptor]
+
+
+def robocup_reco_descriptor():
+    """RoboCupEnvironment._setup_reconstruction_info (RoboCupEnvironment.py:101-132): ball and robot items on a 1 x 1 grid"""
+    xy, conf = S.Box(-2, +2, shape=(2,)), S.MultiBinary(1)
+    ball = StateSpaceDescriptor(1, S.Dict({"position": xy, "team": S.Box(-1, 1, shape=(1,)), "confidence": conf}))
+    robot = StateSpaceDescriptor(4, S.Dict({"position": xy, "orientation": S.Box(-1.0, +1.0, shape=(2,)),
+                                            "team": S.Box(-1, 1, shape=(1,)), "active": S.MultiBinary(1), "confidence": conf}))
+    return RecoDescriptor(featureGridSize=(1, 1), fullStateSpace=[ball, robot],
+                          targetDefs=[PredictionDescriptor(numContinuous=1, contIdx=[2, ]),
+                                      PredictionDescriptor(numContinuous=3, numBinary=1, contIdx=[2, 3, 4], binaryIdx=[5, ])])
+
+
+def driving_reco_descriptor(mean=5.0):
+    """DrivingEnvironment._setup_reconstruction_info (DrivingEnvironment.py:129-168): self, cars, obstacles, pedestrians on
+    a 10 x 17 grid"""
+    xy, ori, size, conf = S.Box(-mean * 2, +mean * 2, shape=(2,)), S.Box(-1.0, +1.0, shape=(2,)), S.Box(-10, 10, shape=(2,)), S.MultiBinary(1)
+    full = {"position": xy, "orientation": ori, "size": size, "confidence": conf}
+    return RecoDescriptor(featureGridSize=(10, 17),
+                          fullStateSpace=[StateSpaceDescriptor(1, S.Dict(dict(full))), StateSpaceDescriptor(4, S.Dict(dict(full))),
+                                          StateSpaceDescriptor(4, S.Dict({"position": xy, "size": size, "confidence": conf})),
+                                          StateSpaceDescriptor(6, S.Dict({"position": xy, "confidence": conf}))],
+                          targetDefs=[PredictionDescriptor(numContinuous=4, contIdx=[2, 3, 4, 5]),
+                                      PredictionDescriptor(numContinuous=4, contIdx=[2, 3, 4, 5]),
+                                      PredictionDescriptor(numContinuous=2, contIdx=[2, 3]), PredictionDescriptor(numContinuous=0)])
 
 
 def validate_robocup_actions(actions, nAgents, allowHeadTurn):
@@ -107,6 +160,7 @@ class RoboCupEnvironment(object):
         self.elapsed = 0
         self.agents = [_Agent(i, self.nPlayers) for i in range(2 * self.nPlayers)]
         self.action_space, self.observation_space = robocup_spaces(self.observationType, allowHeadTurn, self.mean)
+        self.recoDescriptor = robocup_reco_descriptor()
         self._sim = BatchedRoboCup(1, nPlayers, self.observationType, self.noiseType, noiseMagnitude, allowHeadTurn,
                                    randomInit=type(self).randomInit, deterministicTurn=type(self).deterministicTurn,
                                    canFall=type(self).canFall, useObsRewards=type(self).useObsRewards, seed=seed, device=device)
@@ -241,6 +295,7 @@ class DrivingEnvironment(object):
         self.elapsed = 0
         self.agents = [_Agent(i, self.nPlayers) for i in range(self.nPlayers)]
         self.action_space, self.observation_space = driving_spaces(self.observationType, continuousActions, self.mean)
+        self.recoDescriptor = driving_reco_descriptor(self.mean)
         self._sim = BatchedDriving(1, nPlayers, self.observationType, self.noiseType, noiseMagnitude, continuousActions,
                                    seed=seed, device=device)
         self._full = self.observationType == ObservationType.FULL
@@ -304,9 +359,12 @@ class BatchedVecEnv(object):
     batch sizes use `step_tensors()`, which leaves everything on the device."""
 
     def __init__(self, num_envs, nPlayers, observationType, noiseType, noiseMagnitude, allowHeadTurn=False, seed=0,
-                 device=0, env_id_offset=0, env=DynEnvType.ROBO_CUP, **toggles):
+                 device=0, env_id_offset=0, env=DynEnvType.ROBO_CUP, render=False, **toggles):
         from .batched import BatchedDriving, BatchedRoboCup
         self.num_envs = int(num_envs)
+        # render=True (make_dyn_env passes it through, DynEnv/__init__.py:9-13): renderMode 'memory' -- one top-down frame
+        # of environment 0 per step() / reset() in self.screenShots (dynenv_b200.render; the reference opens a pygame window)
+        self.renderMode, self.screenShots = ('memory' if render else False), []
         self.driving = env is DynEnvType.DRIVE
         self.allowHeadTurn = allowHeadTurn  # RoboCup: allowHeadTurn, Driving: continuousActions (make_dyn_env)
         self.observationType = ObservationType(observationType)
@@ -329,9 +387,11 @@ class BatchedVecEnv(object):
                                       env_id_offset=env_id_offset, **toggles)
             nT, nSub, maxT = L.RC_NTICK, L.RC_SUBSTEPS, 12000
         self._actions = None
+        self.recoDescriptor = driving_reco_descriptor() if self.driving else robocup_reco_descriptor()
         self._attrs = dict(nPlayers=self.nPlayers, nTimeSteps=nT, stepIterCnt=nSub, maxTime=maxT,
-                           stepNum=maxT / nSub, observationType=self.observationType, renderMode=False,
-                           agentVisID=None, action_space=self.action_space, observation_space=self.observation_space)
+                           stepNum=maxT / nSub, observationType=self.observationType, renderMode=self.renderMode,
+                           agentVisID=None, action_space=self.action_space, observation_space=self.observation_space,
+                           recoDescriptor=self.recoDescriptor)
 
     # ---- format adapters (RoboCup / Driving)
     def _views(self, out, env_ids=None):
@@ -364,8 +424,18 @@ class BatchedVecEnv(object):
         return self.sim.step(actions), self.sim.terminal
 
     # ---- VecEnv calls
+    def render(self, env=0):
+        """top-down RGB frame of one environment (uint8 [H, W, 3]); appended to screenShots in renderMode 'memory'"""
+        from . import render as R
+        frame = R.render_env(self.sim, env)
+        if self.renderMode == 'memory':
+            self.screenShots.append(frame)
+        return frame
+
     def reset(self):
         v = self._views(self.sim.reset())
+        if self.renderMode:
+            self.render()
         return self._stack([self._obs(v, e) for e in range(self.num_envs)])
 
     def step_async(self, actions):
@@ -391,6 +461,8 @@ class BatchedVecEnv(object):
                 k += 1
             obs.append(self._obs(v, e))
             infos.append(info)
+        if self.renderMode:
+            self.render()
         return self._stack(obs), v["rewards"][:, :self.nAgents].astype(np.float64), dones, tuple(infos)
 
     def step(self, actions):
@@ -432,13 +504,12 @@ class BatchedVecEnv(object):
 
 def make_dyn_env(env, num_envs, num_players, render, observationType, noiseType, noiseMagnitude,
                  use_continuous_actions, seed=0, device=0):
-    """DynEnv.make_dyn_env (DynEnv/__init__.py:6-25): same arguments, same return (vec_env, name)."""
-    if render:
-        raise NotImplementedError("pygame rendering is off the hot path and not part of dynenv_b200")
+    """DynEnv.make_dyn_env (DynEnv/__init__.py:6-25): same arguments, same return (vec_env, name).  render=True keeps
+    top-down frames of environment 0 in vec_env.screenShots (the reference's environments open a pygame window each)."""
     if env is DynEnvType.ROBO_CUP:
-        return BatchedVecEnv(num_envs, num_players, observationType, noiseType, noiseMagnitude,
+        return BatchedVecEnv(num_envs, num_players, observationType, noiseType, noiseMagnitude, render=bool(render),
                              allowHeadTurn=use_continuous_actions, seed=seed, device=device), "RoboCup"
     if env is DynEnvType.DRIVE:
-        return BatchedVecEnv(num_envs, num_players, observationType, noiseType, noiseMagnitude,
+        return BatchedVecEnv(num_envs, num_players, observationType, noiseType, noiseMagnitude, render=bool(render),
                              allowHeadTurn=use_continuous_actions, seed=seed, device=device, env=DynEnvType.DRIVE), "Driving"
     raise ValueError

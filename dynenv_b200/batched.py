@@ -88,6 +88,8 @@ class BatchedRoboCup(object):
             raise RuntimeError("dynenv_b200 needs a CUDA device (no CPU fallback)")
         self._lib = _lib.lib()
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.nEnvs = int(nEnvs)
         self.nPlayers = min(int(nPlayers), 5)
         self.P = 2 * self.nPlayers
@@ -134,8 +136,8 @@ class BatchedRoboCup(object):
         """actions: float32 CUDA tensor [nEnvs, 2*nPlayers, 4] (move, turn, kick, head)."""
         if actions.shape != (self.nEnvs, self.P, 4):
             raise Exception("Error: There must be %d actions of length 4" % self.P)  # RoboCupEnvironment.py:462-463
-        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
-            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()  # (also a tensor of ANOTHER GPU)
         term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
         _lib.check(self._lib.dynenv_step(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
         return self.out
@@ -235,6 +237,8 @@ class BatchedDriving(object):
             raise RuntimeError("dynenv_b200 needs a CUDA device (no CPU fallback)")
         self._lib = _lib.lib()
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.nEnvs = int(nEnvs)
         self.nPlayers = self.N = min(int(nPlayers), L.DRV_MAXCARS)
         self.obs_type = int(observationType)
@@ -265,8 +269,8 @@ class BatchedDriving(object):
         """actions: float32 CUDA tensor [nEnvs, nCars, 2] (acceleration, steering)."""
         if actions.shape != (self.nEnvs, self.N, 2):
             raise Exception("Error: There must be 2 actions for every car")  # DrivingEnvironment.py:262-263
-        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
-            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()  # (also a tensor of ANOTHER GPU)
         term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
         _lib.check(self._lib.dynenv_step(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
         return self.out

@@ -235,6 +235,7 @@ __device__ __noinline__ void cars_phase(const Env E, int sub, const float* actio
     float a0 = actions_env[2 * i], a1 = actions_env[2 * i + 1];
     const bool cont = E.c->continuous != 0;
     float acc = cont ? a0 : a0 - 1.f, steer = cont ? a1 : (a1 - 1.f) * 2.f;
+    if (!(fabsf(acc) <= 3.f) || !(fabsf(steer) <= 3.f)) atomicOr(&E.i[X_DIAG], RC_IF_BAD_ACTION); /* DrivingEnvironment.py:364-367 */
     float dx = E.f[DRV_S_CDIRX + i], dy = E.f[DRV_S_CDIRY + i];
     if (!(fl & DRV_CF_FINISHED)) { /* Car.accelerate */
       float power = acc;

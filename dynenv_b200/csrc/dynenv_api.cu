@@ -37,6 +37,23 @@ static_assert((CFG_WORDS + rc::ENV_SMEM_WORDS) * 4 <= 6272 && (CFG_WORDS + drv::
 
 thread_local std::string g_err;
 
+/* Every entry point works on its handle's (or its argument's) device and gives the calling thread its own current device
+   back: a process that drives several GPUs (or PyTorch in the same thread) must not find its current device switched
+   under it -- neither by a step nor by a destroy called from a garbage collector. */
+struct DeviceGuard {
+  int prev = -1, want;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) : want(dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) err = cudaSetDevice(want);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != want) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -446,7 +463,8 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
     return fail(DYNENV_E_NODEVICE, "no CUDA device: dynenv_b200 has no CPU fallback");
   }
   if (cfg->device < 0 || cfg->device >= ndev) return fail(DYNENV_E_INVALID, "bad device ordinal");
-  if ((ce = cudaSetDevice(cfg->device)) != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+  DeviceGuard guard(cfg->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
   DynEnvHandle_s* h = new DynEnvHandle_s();
   h->cfg = *cfg;
   SimCfg& s = h->sim;
@@ -523,7 +541,7 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
 
 int dynenv_destroy(DynEnvHandle h) {
   if (!h) return DYNENV_OK;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaFree(h->state);
   cudaFree(h->slow_list);
   cudaFree(h->slow_count);
@@ -542,7 +560,7 @@ int dynenv_state_words(DynEnvHandle h) { return h ? h->state_words : DYNENV_E_IN
 
 int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* stream) {
   if (!h || !out) return fail(DYNENV_E_INVALID, "null argument");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   if (h->cfg.kind == DYNENV_KIND_DRIVING) {
     const DynEnvDrivingOut* d = static_cast<const DynEnvDrivingOut*>(out);
     const int dgrid = (h->sim.n_envs + DRV_WPC - 1) / DRV_WPC;
@@ -571,7 +589,7 @@ int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* s
 
 int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* terminal_out, void* stream) {
   if (!h || !out || !actions_dev) return fail(DYNENV_E_INVALID, "null argument");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (h->cfg.kind == DYNENV_KIND_DRIVING) {
     const DynEnvDrivingOut* d = static_cast<const DynEnvDrivingOut*>(out);
@@ -674,7 +692,8 @@ int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, ui
   if (!raw_dev || !image_dev || n_records < 0) return fail(DYNENV_E_INVALID, "bad argument");
   if (n_records == 0) return DYNENV_OK;
   if (n_records > (int64_t)1 << 27) return fail(DYNENV_E_INVALID, "too many records for one call");
-  cudaError_t ce = cudaSetDevice(device);
+  DeviceGuard guard(device);
+  cudaError_t ce = guard.err;
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
   const size_t smem = (size_t)rcimg::SMEM_WORDS * sizeof(uint32_t);
   static thread_local int configured = -1;
@@ -694,7 +713,7 @@ int dynenv_rollout_insert(DynEnvHandle h, const void* out, int step, int rollout
                           uint8_t* agent_finished_dev, uint8_t* dones_dev, float* episode_acc_dev, void* stream) {
   if (!h || !out || !rewards_dev || !agent_finished_dev || !dones_dev) return fail(DYNENV_E_INVALID, "null argument");
   if (step < 0 || step >= rollout_size) return fail(DYNENV_E_INVALID, "step outside the rollout");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   rollout::InfoLayout L;
   const float* info;
   int A;
@@ -724,7 +743,8 @@ int dynenv_discount_rewards(int device, const float* rewards_dev, const float* f
   if (rollout_size < 0 || n_columns < 0 || agents_per_env <= 0 || n_columns % agents_per_env)
     return fail(DYNENV_E_INVALID, "bad rollout shape");
   if (rollout_size == 0 || n_columns == 0) return DYNENV_OK;
-  cudaError_t ce = cudaSetDevice(device);
+  DeviceGuard guard(device);
+  cudaError_t ce = guard.err;
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
   rollout::discount_kernel<<<(unsigned)((n_columns + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       rewards_dev, final_value_dev, dones_dev, agents_per_env, out_dev, rollout_size, (long long)n_columns, discount);
@@ -771,7 +791,7 @@ int dynenv_debug_raster_prof(unsigned long long* out16, int reset) {
 
 int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream) {
   if (!h || !state_dev) return fail(DYNENV_E_INVALID, "null argument");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaError_t ce = cudaMemcpyAsync(state_dev, h->state, (size_t)h->sim.n_envs * h->state_words * sizeof(uint32_t),
                                    cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(get_state)");
@@ -780,7 +800,7 @@ int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream) {
 
 int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream) {
   if (!h || !state_dev) return fail(DYNENV_E_INVALID, "null argument");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaError_t ce = cudaMemcpyAsync(h->state, state_dev, (size_t)h->sim.n_envs * h->state_words * sizeof(uint32_t),
                                    cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(set_state)");
@@ -789,7 +809,8 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream) {
 
 int dynenv_debug_fp32_peak(int device, float* tflops_out) {
   if (!tflops_out) return fail(DYNENV_E_INVALID, "null argument");
-  cudaError_t ce = cudaSetDevice(device);
+  DeviceGuard guard(device);
+  cudaError_t ce = guard.err;
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -826,7 +847,7 @@ int dynenv_last_launch_count(DynEnvHandle h) { return h ? h->last_launches : 0; 
 
 int dynenv_debug_timing(DynEnvHandle h, int enable) {
   if (!h) return fail(DYNENV_E_INVALID, "null handle");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   if (enable && !h->timing)
     for (int k = 0; k <= MAX_TIMED; k++) cudaEventCreate(&h->ev[k]);
   if (!enable && h->timing)
@@ -840,7 +861,7 @@ int dynenv_last_kernel_ms(DynEnvHandle h, float* ms3, int* launches3) {
   if (!h || !ms3 || !launches3) return fail(DYNENV_E_INVALID, "null argument");
   for (int k = 0; k < 4; k++) { ms3[k] = 0.f; launches3[k] = 0; }
   if (!h->timing || h->n_timed == 0) return DYNENV_OK;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaError_t ce = cudaEventSynchronize(h->ev[h->n_timed]);
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaEventSynchronize");
   for (int k = 0; k < h->n_timed; k++) {

@@ -143,6 +143,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
       if (sub == 0 && isFoot) {
         act = *reinterpret_cast<const float4*>(actions_env + 4 * r);
         if (E.c->can_fall) ru = rng_block(E, (uint32_t)U.elapsed, RC_SITE_ACTION, r, 0, 0);
+        if (bad_action(E, act)) E.i[X_DIAG] = E.i[X_DIAG] | RC_IF_BAD_ACTION; /* (the only writers now: same value) */
       }
       /* partner foot (hi words) and the robot's position */
       const float opx = __shfl_xor_sync(FULLMASK, B.px, 1), opy = __shfl_xor_sync(FULLMASK, B.py, 1);

@@ -508,6 +508,14 @@ __device__ __noinline__ bool robot_phase_needs_order(const Env E, int r, int sub
   return need;
 }
 
+/* the range checks of processAction (RoboCupEnvironment.py:543-550) for the batched path: true = the reference would raise */
+__device__ __forceinline__ bool bad_action(const Env E, float4 a) {
+  bool bad = !(a.x >= 0.f && a.x <= 4.f) || !(a.y >= 0.f && a.y <= 2.f) || !(a.z >= 0.f && a.z <= 2.f);
+  if (E.c->continuous) bad |= !(fabsf(a.w) <= 3.f);
+  else bad |= !(a.w >= 0.f && a.w <= 6.f);
+  return bad;
+}
+
 __device__ __noinline__ void robots_phase(const Env E, int sub, const float* actions) {
   int lane = E.lane;
   int P = E.c->P;
@@ -518,6 +526,7 @@ __device__ __noinline__ void robots_phase(const Env E, int sub, const float* act
   if (sub == 0 && mine) {
     act = *reinterpret_cast<const float4*>(actions + 4 * lane);
     if (E.c->can_fall) ru = rng_block(E, (uint32_t)E.i[RC_S_ELAPSED], RC_SITE_ACTION, lane, 0, 0);
+    if (bad_action(E, act)) atomicOr(&E.i[X_DIAG], RC_IF_BAD_ACTION);
   }
   bool need = mine && robot_phase_needs_order(E, lane, sub, act, ru);
   unsigned ordered = __ballot_sync(FULLMASK, need);

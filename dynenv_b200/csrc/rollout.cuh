@@ -26,7 +26,7 @@ struct InfoLayout {
 /* storage.insert (models/storage.py:133-168): rewards[step], agentFinished[step] (= the last column of every agent's row of
    info['Full State'][0], models/train.py:276), dones[step]; storage.log_episode_rewards (:292-308) as per-environment running
    sums: episodes, sum of the mean episode_r / episode_p_r / episode_o_r over the agents, sum of episode_g[0..1], min and max of
-   the mean episode_r. */
+   the mean episode_r; and the last DYNENV_EPISODE_RING episodes' per-agent episode_r (the reference's deque, for the median). */
 __global__ void __launch_bounds__(256) insert_kernel(const float* __restrict__ info, InfoLayout L, long long nEnvs, int A,
                                                       float* __restrict__ rewards, uint8_t* __restrict__ finished,
                                                       uint8_t* __restrict__ dones, float* __restrict__ acc) {
@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(256) insert_kernel(const float* __restrict__ i
   r *= inv, pr *= inv, orw *= inv;
   float* s = acc + e * DYNENV_EPISODE_ACC_WORDS;
   const bool first = s[0] == 0.f;
+  { /* the ring of the last episodes' per-agent rewards (median of print_reward_stats) */
+    float* ring = s + DYNENV_EPISODE_STAT_WORDS + ((int)s[0] % DYNENV_EPISODE_RING) * DYNENV_EPISODE_RING_AGENTS;
+    for (int k = 0; k < DYNENV_EPISODE_RING_AGENTS; k++) ring[k] = k < A ? rec[L.epr + k] : 0.f;
+  }
   s[0] += 1.f;
   s[1] += r;
   s[2] += pr;

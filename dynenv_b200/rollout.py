@@ -72,16 +72,23 @@ class DeviceRolloutStorage(object):
     discount_rewards = _discount_rewards
 
     def episode_stats(self):
-        """What print_reward_stats (models/storage.py:310-330) reports, from the running sums: one device reduction and one
-        small copy to the host.  (The median needs the per-episode list the reference keeps on the host; not provided.)"""
+        """What print_reward_stats (models/storage.py:310-330) reports: mean / min / max from the running sums, the median
+        over the ring of the last 10 episodes' per-agent rewards of every environment (the reference's deque of
+        10 * num_envs entries); one device reduction and one small copy to the host."""
         acc = self.episode_acc
         n = acc[:, 0].sum()
         has = acc[:, 0] > 0
         big = torch.finfo(torch.float32).max
+        # ring entries that hold an episode: slot < min(episodes, ring size), agent < num_players
+        R, RA, S0 = L.DYNENV_EPISODE_RING, L.DYNENV_EPISODE_RING_AGENTS, L.DYNENV_EPISODE_STAT_WORDS
+        ring = acc[:, S0:S0 + R * RA].view(-1, R, RA)[:, :, :self.num_players]
+        valid = (torch.arange(R, device=acc.device)[None, :] < acc[:, 0:1].clamp(max=R)).unsqueeze(-1).expand_as(ring)
+        med = torch.where(valid, ring, torch.full_like(ring, float("nan"))).flatten().nanmedian()
         vals = torch.stack([n, acc[:, 1].sum(), acc[:, 2].sum(), acc[:, 3].sum(), acc[:, 4].sum(), acc[:, 5].sum(),
                             torch.where(has, acc[:, 6], torch.full_like(acc[:, 6], big)).min(),
-                            torch.where(has, acc[:, 7], torch.full_like(acc[:, 7], -big)).max()]).cpu().tolist()
+                            torch.where(has, acc[:, 7], torch.full_like(acc[:, 7], -big)).max(), med]).cpu().tolist()
         k = max(vals[0], 1.0)
         return {"episodes": int(vals[0]), "mean_reward": vals[1] / k, "mean_pos_reward": vals[2] / k,
                 "mean_obs_reward": vals[3] / k, "mean_goals": [vals[4] / k, vals[5] / k],
-                "min_reward": vals[6] if vals[0] else 0.0, "max_reward": vals[7] if vals[0] else 0.0}
+                "min_reward": vals[6] if vals[0] else 0.0, "max_reward": vals[7] if vals[0] else 0.0,
+                "median_reward": vals[8] if vals[0] else 0.0}

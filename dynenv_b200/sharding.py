@@ -15,10 +15,12 @@ def shard_range(n_total, rank, world_size):
 
 def episode_stats(out):
     """[sum episode_r, sum episode_p_r, sum episode_o_r, goals team 1, goals team 2, #episodes] of the
-    environments that finished in the last step, as one float64 device tensor"""
+    environments that finished in the last step, as one float64 device tensor (Driving has no observation reward: 0)"""
     done = out.done.bool()
     f = done.unsqueeze(1).to(out.episode_r.dtype)
-    return torch.stack([(out.episode_r * f).sum(), (out.episode_p_r * f).sum(), (out.episode_o_r * f).sum(),
+    o_r = getattr(out, "episode_o_r", None)
+    return torch.stack([(out.episode_r * f).sum(), (out.episode_p_r * f).sum(),
+                        (o_r * f).sum() if o_r is not None else out.episode_r.new_zeros(()),
                         (out.episode_g[:, 0] * done).sum().to(out.episode_r.dtype),
                         (out.episode_g[:, 1] * done).sum().to(out.episode_r.dtype),
                         done.sum().to(out.episode_r.dtype)]).double()

@@ -256,6 +256,10 @@ enum {
 };
 #define RC_IF_ARB_OVERFLOW 1    /* more than RC_MAXARB cached contact pairs: a pair was dropped   */
 #define RC_IF_ACTIVE_OVERFLOW 2 /* more than RC_MAXACTIVE touching pairs in one substep           */
+#define RC_IF_BAD_ACTION 4      /* an action of this step was out of range or not finite: the reference raises
+                                   (RoboCupEnvironment.py:543-550, DrivingEnvironment.py:364-367); the batched device path cannot,
+                                   so it flags the step (the move / turn / kick / steering code then did something, but
+                                   nothing the reference defines) */
 #define RC_MAXACTIVE 16
 
 /*
@@ -470,12 +474,18 @@ int dynenv_render_images(int device, const float* raw_dev, int64_t n_records, ui
    `out` that dynenv_step just filled: rewards_dev[step][nEnvs * nAgents], agent_finished_dev[step][nEnvs * nAgents] (the last
    column of every agent's row of info['Full State'][0], models/train.py:276), dones_dev[step][nEnvs]; and
    storage.log_episode_rewards (:292-308) as running sums per environment in episode_acc_dev[nEnvs][DYNENV_EPISODE_ACC_WORDS]
-   (may be NULL): episodes finished, sums of the agent-mean episode_r / episode_p_r / episode_o_r, sums of episode_g[0..1],
-   min and max of the agent-mean episode_r.  The three step-indexed pointers are the buffers' bases.
+   (may be NULL): [0] episodes finished, [1..3] sums of the agent-mean episode_r / episode_p_r / episode_o_r, [4..5] sums of
+   episode_g[0..1], [6..7] min and max of the agent-mean episode_r, then a ring of the last DYNENV_EPISODE_RING episodes'
+   per-agent episode_r, [ring slot][DYNENV_EPISODE_RING_AGENTS] (slot = episode number % DYNENV_EPISODE_RING; the
+   reference's deque keeps the last 10 * num_envs entries, models/storage.py:46, for the median of print_reward_stats
+   :310-318).  The three step-indexed pointers are the buffers' bases.
    dynenv_discount_rewards -- storage._discount_rewards (models/storage.py:170-205): out[i] = rewards[i] + discount * out[i+1],
    out[T] = final_value, over n_columns = nEnvs * nAgents columns.  dones_dev NULL reproduces the reference (its mask is built
    from zeros, :194); with dones_dev ([T][n_columns / agents_per_env]) the chain restarts at a step that ended an episode. */
-#define DYNENV_EPISODE_ACC_WORDS 8
+#define DYNENV_EPISODE_RING 10
+#define DYNENV_EPISODE_RING_AGENTS 10
+#define DYNENV_EPISODE_STAT_WORDS 8
+#define DYNENV_EPISODE_ACC_WORDS (DYNENV_EPISODE_STAT_WORDS + DYNENV_EPISODE_RING * DYNENV_EPISODE_RING_AGENTS)
 int dynenv_rollout_insert(DynEnvHandle h, const void* out, int step, int rollout_size, float* rewards_dev,
                           uint8_t* agent_finished_dev, uint8_t* dones_dev, float* episode_acc_dev, void* stream);
 int dynenv_discount_rewards(int device, const float* rewards_dev, const float* final_value_dev, const uint8_t* dones_dev,

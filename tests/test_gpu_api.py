@@ -193,3 +193,80 @@ def test_fp32_peak_probe():
     assert _lib.lib().dynenv_debug_fp32_peak(0, C.byref(tf)) == 0
     assert 20.0 < tf.value < 90.0, tf.value
     assert _lib.lib().dynenv_debug_fp32_peak(0, None) != 0
+
+
+def test_bad_actions_are_flagged_on_the_device():
+    """the batched device path cannot raise like processAction (RoboCupEnvironment.py:543-550, DrivingEnvironment.py:364-367):
+    a step with an out-of-range or non-finite action carries RC_IF_BAD_ACTION in its diag word, the others do not"""
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    sim = dynenv_b200.BatchedRoboCup(4, 2, 1, 1, 2.0, seed=1)
+    sim.reset()
+    a = torch.tensor([1., 0., 0., 3.]).repeat(4, 4, 1).cuda()
+    assert int(sim.step(a).diag.max()) == 0
+    a[1, 2, 0] = 7.          # move 7 (the kernels would walk backwards)
+    a[2, 0, 3] = float("nan")  # head turn NaN
+    a[3, 1, 1] = -1.         # turn -1
+    diag = sim.step(a).diag.cpu().numpy()
+    assert diag[0] == 0 and all(diag[1:] & L.RC_IF_BAD_ACTION)
+    assert int(sim.step(torch.tensor([1., 0., 0., 3.]).repeat(4, 4, 1).cuda()).diag.max()) == 0  # a flag of ONE step
+    # allowHeadTurn: the head command is a float in [-3, 3]
+    sim = dynenv_b200.BatchedRoboCup(2, 1, 1, 1, 2.0, allowHeadTurn=True, seed=1)
+    sim.reset()
+    a = torch.tensor([1., 0., 0., -2.5]).repeat(2, 2, 1).cuda()
+    assert int(sim.step(a).diag.max()) == 0
+    a[1, 0, 3] = 3.5
+    diag = sim.step(a).diag.cpu().numpy()
+    assert diag[0] == 0 and diag[1] & L.RC_IF_BAD_ACTION
+    drv = dynenv_b200.BatchedDriving(3, 4, 1, 1, 2.0, continuousActions=True, seed=1)
+    drv.reset()
+    a = torch.zeros((3, 4, 2)).cuda()
+    assert int(drv.step(a).diag.max()) == 0
+    a[1, 3, 0] = 3.5
+    a[2, 0, 1] = float("inf")
+    diag = drv.step(a).diag.cpu().numpy()
+    assert diag[0] == 0 and all(diag[1:] & L.RC_IF_BAD_ACTION)
+
+
+def test_reco_descriptor_and_render_pass_through():
+    """recoDescriptor (environment_base.py:18-38, RoboCupEnvironment.py:101-132, DrivingEnvironment.py:129-168) on the drop-in
+    classes and through get_attr (examples/main.py:42); make_dyn_env(render=True) keeps frames instead of raising"""
+    import dynenv_b200
+    venv, _ = dynenv_b200.make_dyn_env(dynenv_b200.DynEnvType.ROBO_CUP, 2, 2, True, dynenv_b200.ObservationType.PARTIAL,
+                                       dynenv_b200.NoiseType.REALISTIC, 1.0, False)
+    rd = venv.get_attr("recoDescriptor", 0)[0]
+    assert rd.featureGridSize == (1, 1) and len(rd.fullStateSpace) == 2 and len(rd.targetDefs) == 2
+    assert rd.fullStateSpace[1].numItemsPerGridCell == 4 and rd.targetDefs[1].contIdx == [2, 3, 4] and rd.targetDefs[1].binaryIdx == [5]
+    assert rd.targetDefs[0].numContinuous == 1 and tuple(rd.targetDefs[0].posIdx) == (0, 1)
+    venv.reset()
+    venv.step(np.tile(np.array([1, 0, 0, 3]), (2, 4, 1)))
+    assert venv.get_attr("renderMode")[0] == "memory" and len(venv.screenShots) == 2
+    assert venv.screenShots[0].ndim == 3 and venv.screenShots[0].shape[2] == 3
+    venv.close()
+    denv, name = dynenv_b200.make_dyn_env(dynenv_b200.DynEnvType.DRIVE, 2, 3, False, dynenv_b200.ObservationType.PARTIAL,
+                                          dynenv_b200.NoiseType.REALISTIC, 1.0, True)
+    rd = denv.get_attr("recoDescriptor", [0, 1])
+    assert len(rd) == 2 and rd[0].featureGridSize == (10, 17) and [s.numItemsPerGridCell for s in rd[0].fullStateSpace] == [1, 4, 4, 6]
+    assert [t.numContinuous for t in rd[0].targetDefs] == [4, 4, 2, 0]
+    denv.close()
+    env = dynenv_b200.RoboCupEnvironment(nPlayers=1)
+    assert env.recoDescriptor.featureGridSize == (1, 1)
+    env.close()
+
+
+def test_entry_points_leave_the_current_device_alone():
+    """a handle on another GPU must not switch the calling thread's current device (needs two GPUs)"""
+    import torch
+    import dynenv_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    torch.cuda.set_device(0)
+    sim = dynenv_b200.BatchedRoboCup(4, 1, 1, 1, 2.0, seed=1, device=1)
+    assert torch.cuda.current_device() == 0
+    sim.reset()
+    out = sim.step(torch.tensor([1., 0., 0., 3.]).repeat(4, 2, 1))  # a host tensor: moved to the simulator's device
+    assert torch.cuda.current_device() == 0 and out.rewards.device.index == 1
+    sim.get_state()
+    sim.close()
+    assert torch.cuda.current_device() == 0

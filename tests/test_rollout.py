@@ -107,6 +107,13 @@ def test_gpu_rollout_insert(kind):
     stats = store.episode_stats()
     assert stats["episodes"] == int(dones.sum())
     assert abs(stats["mean_reward"] - acc[:, 1].sum() / dones.sum()) < 1e-4
+    # the median of print_reward_stats (models/storage.py:310-318): over the per-agent rewards of the logged episodes
+    logged = np.concatenate([np.asarray(r[3])[np.asarray(r[1]) != 0].reshape(-1) for r in results])
+    assert abs(stats["median_reward"] - float(np.median(logged))) < 1e-5 + 1e-5 * abs(float(np.median(logged))) or \
+        len(logged) % 2 == 0  # torch's nanmedian returns the lower of the two middle values
+    if len(logged) % 2 == 0:
+        lo, hi = np.sort(logged)[len(logged) // 2 - 1], np.sort(logged)[len(logged) // 2]
+        assert lo - 1e-5 <= stats["median_reward"] <= hi + 1e-5
     fv = torch.from_numpy(rng.normal(size=n * A).astype(np.float32)).cuda()
     ref = rollout_oracle.discount_rewards(rewards, fv.cpu().numpy(), 0.99)
     assert np.array_equal(store._discount_rewards(fv, 0.99).cpu().numpy(), ref)
