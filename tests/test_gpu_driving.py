@@ -74,11 +74,7 @@ def test_rollout_states(nPlayers, obs, noise, mag, cont):
             total_bad += [(step,) + b for b in drv_compare_step(cfg, out, gw, outs, ow, TOL)]
         else:
             sim.step(torch.from_numpy(a).cuda())
-    # 8 compared steps x n environments; float32 ties at the reference's hard thresholds may split a few
-    envs_bad = set((b[0], b[1]) for b in total_bad)
-    assert len(envs_bad) <= (8 * n) // 50, total_bad[:12]
-    hard = [b for b in total_bad if b[2] in ("diag", "done", "state.elapsed", "state.episode")]
-    assert not hard, hard[:10]
+    assert not total_bad, total_bad[:12]  # 8 compared steps x n environments, no budget
 
 
 def test_noise_statistics_match_in_distribution():
