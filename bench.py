@@ -372,7 +372,7 @@ def run_reference(args):
 FAST_FORWARD = {"robocup": 110, "driving": 290, "image": 20}  # untimed steps in front of the warm-up: mid-episode
 
 
-def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=True, full=False, sampler=None):
+def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=True, full=False, sampler=None, arranger=False):
     """One workload on this rank's GPU.  Three passes over the SAME window of the episode (reset, `ff` untimed
     fast-forward steps, `warmup` steps, `steps` timed steps on the same actions):
       1. device-resident: actions already in HBM, CUDA events around the K steps          -> value
@@ -460,6 +460,22 @@ def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=T
         sim.debug_timing(False)
         res["kernel_ms_per_step"] = {k: v[0] / n3 for k, v in kms.items() if v[1]}
         res["kernel_launches_per_step"] = {k: v[1] / n3 for k, v in kms.items() if v[1]}
+    # ---- pass 4 (RoboCup): step + the InOutArranger kernels on the step's records (flat per-type inputs, counts, offsets)
+    if arranger:
+        from dynenv_b200.arranger import KernelArranger
+        arr = KernelArranger.for_robocup(sim)
+        rewind()
+        n4 = min(steps, 20)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for s in range(n4):
+            sim.step(pool[s % n_pool])
+            arr.rearrange_inputs()
+        a1.record(stream)
+        barrier()
+        res["ms_step_arranged"] = a0.elapsed_time(a1) / n4
+        res["arranger_rows"] = int(arr.totals[:arr.nTypes].sum().item())
+        del arr
     del sim, pool
     torch.cuda.empty_cache()
     return res
@@ -527,7 +543,8 @@ def run_gpu(args):
     wl = WORKLOADS[args.workload]()
     E = args.envs or getattr(wl, "default_envs", 65536)
     ff = FAST_FORWARD[wl.name] if args.fast_forward is None else args.fast_forward
-    r = measure(wl, E, local, rank, world, args.steps, args.warmup, ff, full=args.debug_full_obs, sampler=ClockSampler(local))
+    r = measure(wl, E, local, rank, world, args.steps, args.warmup, ff, full=args.debug_full_obs, sampler=ClockSampler(local),
+                arranger=(wl.name == "robocup" and world == 1 and not args.debug_full_obs and not args.no_other))
     ms_total, ms_e2e = r["ms_total"], r["ms_e2e"]
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
@@ -583,6 +600,11 @@ def run_gpu(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                         "note": "observations stay device-resident for the learner; rewards + done return to the host"},
                 "roofline": roofline, "diag_flags": r["diag"]}
+        if "ms_step_arranged" in r:
+            line["arranger"] = {"ms_per_step_with_arranger": r["ms_step_arranged"], "value": E / (r["ms_step_arranged"] * 1e-3), "unit": UNIT,
+                                "rows_per_step": r["arranger_rows"],
+                                "note": "step + dynenv_arrange_inputs (the learner's InOutArranger as kernels: flat per-type inputs, "
+                                        "counts, offsets, maxCount; no host synchronisation), device-resident"}
         if not args.no_cpu and world == 1:
             cpu_steps = args.cpu_steps or wl.cpu_steps
             rate, threads, dt = cpu_env_steps_per_s(wl, cpu_steps)

@@ -12,7 +12,8 @@ _LIB = None
 EXPORTS = ["dynenv_abi_version", "dynenv_last_error", "dynenv_create", "dynenv_destroy", "dynenv_state_words",
            "dynenv_reset", "dynenv_step", "dynenv_set_seed", "dynenv_get_state", "dynenv_set_state",
            "dynenv_last_launch_count", "dynenv_debug_substep_range", "dynenv_debug_timing",
-           "dynenv_last_kernel_ms", "dynenv_render_images", "dynenv_rollout_insert", "dynenv_discount_rewards", "dynenv_debug_fp32_peak"]
+           "dynenv_last_kernel_ms", "dynenv_render_images", "dynenv_rollout_insert", "dynenv_discount_rewards", "dynenv_debug_fp32_peak",
+           "dynenv_arrange_inputs", "dynenv_arrange_outputs"]
 
 
 class DynEnvConfig(C.Structure):
@@ -28,6 +29,11 @@ class DynEnvRoboCupOut(C.Structure):
 
 class DynEnvDrivingOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("info", C.c_void_p)]
+
+
+class DynEnvArrangeLayout(C.Structure):
+    _fields_ = [("n_types", C.c_int32), ("rec_words", C.c_int32), ("off", C.c_int32 * 8), ("cap", C.c_int32 * 8),
+                ("feat", C.c_int32 * 8), ("stride", C.c_int32 * 8), ("count_word", C.c_int32 * 8)]
 
 
 class DynEnvError(Exception):
@@ -63,6 +69,10 @@ def lib():
         lb.dynenv_discount_rewards.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                                C.c_int64, C.c_float, C.c_void_p]
         lb.dynenv_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_float)]
+        lb.dynenv_arrange_inputs.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(DynEnvArrangeLayout),
+                                             C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lb.dynenv_arrange_outputs.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         if lb.dynenv_abi_version() != L.DYNENV_ABI_VERSION:
             raise RuntimeError("dynenv_b200: library ABI %d != header ABI %d" % (lb.dynenv_abi_version(),
                                                                                  L.DYNENV_ABI_VERSION))

@@ -15,6 +15,7 @@
 #include "rc_phys2.cuh"
 #include "rc_raster.cuh"
 #include "rollout.cuh"
+#include "arrange.cuh"
 
 using namespace dynenv;
 
@@ -750,6 +751,52 @@ int dynenv_discount_rewards(int device, const float* rewards_dev, const float* f
       rewards_dev, final_value_dev, dones_dev, agents_per_env, out_dev, rollout_size, (long long)n_columns, discount);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "rollout discount_kernel launch");
+  return DYNENV_OK;
+}
+
+int dynenv_arrange_inputs(int device, const float* rec_dev, int64_t n_envs, int n_time, int n_players, const DynEnvArrangeLayout* layout,
+                          float* const* flat_out, int32_t* counts_out, int32_t* obj_counts_out, int32_t* offsets_out,
+                          int32_t* block_sums_out, int32_t* totals_out, void* stream) {
+  if (!rec_dev || !layout || !flat_out || !counts_out || !obj_counts_out || !offsets_out || !block_sums_out || !totals_out)
+    return fail(DYNENV_E_INVALID, "null argument");
+  if (layout->n_types <= 0 || layout->n_types > DYNENV_ARRANGE_MAXTYPES || n_envs <= 0 || n_time <= 0 || n_players <= 0)
+    return fail(DYNENV_E_INVALID, "bad arranger shape");
+  const long long Q = n_envs * n_players, n = Q * n_time;
+  if (n * 64 > 0x7fffffffLL) return fail(DYNENV_E_INVALID, "too many (time, player) pairs for 32-bit row offsets");
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nb = (int)((n + arrange::SCAN_BLOCK - 1) / arrange::SCAN_BLOCK);
+  arrange::FlatPtrs fp;
+  for (int k = 0; k < DYNENV_ARRANGE_MAXTYPES; k++) fp.p[k] = k < layout->n_types ? flat_out[k] : nullptr;
+  cudaMemsetAsync(totals_out, 0, (layout->n_types + 1) * sizeof(int32_t), st);
+  arrange::arr_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec_dev, *layout, Q, n_time, n_players, counts_out, obj_counts_out,
+                                                                           totals_out);
+  arrange::arr_scan_kernel<<<dim3(nb, layout->n_types), 256, 0, st>>>(counts_out, n, offsets_out, block_sums_out, nb);
+  arrange::arr_scan_sums_kernel<<<layout->n_types, 1024, 0, st>>>(block_sums_out, nb, totals_out);
+  arrange::arr_compact_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(rec_dev, *layout, Q, n_time, n_players, counts_out, offsets_out,
+                                                                                block_sums_out, nb, fp);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "arranger kernels launch");
+  return DYNENV_OK;
+}
+
+int dynenv_arrange_outputs(int device, const float* const* emb, int n_features, int n_types, int64_t n_envs, int n_time, int n_players,
+                           const int32_t* counts, const int32_t* offsets, const int32_t* block_sums, const int32_t* obj_counts,
+                           int max_count, float* padded_out, uint8_t* mask_out, void* stream) {
+  if (!emb || !counts || !offsets || !block_sums || !obj_counts || !padded_out) return fail(DYNENV_E_INVALID, "null argument");
+  if (n_types <= 0 || n_types > DYNENV_ARRANGE_MAXTYPES || n_features <= 0 || max_count <= 0) return fail(DYNENV_E_INVALID, "bad arranger shape");
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+  const long long Q = n_envs * n_players, n = Q * n_time;
+  const int nb = (int)((n + arrange::SCAN_BLOCK - 1) / arrange::SCAN_BLOCK);
+  arrange::FlatPtrs fp;
+  for (int k = 0; k < DYNENV_ARRANGE_MAXTYPES; k++) fp.p[k] = k < n_types ? const_cast<float*>(emb[k]) : nullptr;
+  const long long threads = n * max_count;
+  arrange::arr_pad_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fp, n_features, n_types, Q, n_time, counts, offsets, block_sums, nb, obj_counts, max_count, padded_out, mask_out);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "arr_pad_kernel launch");
   return DYNENV_OK;
 }
 

@@ -492,6 +492,32 @@ int dynenv_discount_rewards(int device, const float* rewards_dev, const float* f
                             int agents_per_env, float* out_dev, int rollout_size, int64_t n_columns, float discount,
                             void* stream);
 
+/* The learner-side re-shuffle of the observation records on the device: InOutArranger (models/models.py:127-274).
+   A layout describes where each object type's rows and count sit in one observer's record (rec[E][T][P][rec_words]).
+   dynenv_arrange_inputs  -- rearrange_inputs (models.py:220-247): flat_out[k] = all rows of type k in (time step,
+     environment x player, row) order ([rows][feat[k]]; capacity: T * E * P * cap[k] rows, or NULL to skip the type),
+     counts_out[n_types][T][E*P], obj_counts_out[T][E*P], offsets_out[n_types][T][E*P] + block_sums_out[n_types][nb]
+     (nb = ceil(T*E*P / 1024); row of (k, t, q) = offsets[k][t*Q+q] + block_sums[k][(t*Q+q) / 1024]), totals_out[n_types + 1]
+     (rows per type; [n_types] = maxCount).  Nothing returns to the host.
+   dynenv_arrange_outputs -- rearrange_outputs (models.py:249-274): emb[k] = the type's embeddings [rows][F] (NULL: the type has no
+     block) -> padded_out[T][max_count][E*P][F] (per player its rows of type 0, then type 1, ..., zeros behind) and
+     mask_out[T][E*P][max_count] (1 = padding, may be NULL).  max_count: the caller's static bound (>= totals[n_types]). */
+#define DYNENV_ARRANGE_MAXTYPES 8
+typedef struct DynEnvArrangeLayout {
+  int32_t n_types, rec_words;
+  int32_t off[DYNENV_ARRANGE_MAXTYPES];        /* first word of the type's rows in the record */
+  int32_t cap[DYNENV_ARRANGE_MAXTYPES];        /* rows the record can hold */
+  int32_t feat[DYNENV_ARRANGE_MAXTYPES];       /* floats per row handed on */
+  int32_t stride[DYNENV_ARRANGE_MAXTYPES];     /* floats per row in the record (>= feat) */
+  int32_t count_word[DYNENV_ARRANGE_MAXTYPES]; /* word of the record holding the row count (int32); -1: always one row */
+} DynEnvArrangeLayout;
+int dynenv_arrange_inputs(int device, const float* rec_dev, int64_t n_envs, int n_time, int n_players, const DynEnvArrangeLayout* layout,
+                          float* const* flat_out, int32_t* counts_out, int32_t* obj_counts_out, int32_t* offsets_out,
+                          int32_t* block_sums_out, int32_t* totals_out, void* stream);
+int dynenv_arrange_outputs(int device, const float* const* emb, int n_features, int n_types, int64_t n_envs, int n_time, int n_players,
+                           const int32_t* counts, const int32_t* offsets, const int32_t* block_sums, const int32_t* obj_counts,
+                           int max_count, float* padded_out, uint8_t* mask_out, void* stream);
+
 /* copy the whole state ([nEnvs][state_words] 32-bit words) to / from a device buffer */
 int dynenv_get_state(DynEnvHandle h, uint32_t* state_dev, void* stream);
 int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);

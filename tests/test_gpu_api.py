@@ -270,3 +270,67 @@ def test_entry_points_leave_the_current_device_alone():
     sim.get_state()
     sim.close()
     assert torch.cuda.current_device() == 0
+
+
+def test_kernel_arranger_matches_the_reference_class():
+    """dynenv_arrange_inputs / dynenv_arrange_outputs (the InOutArranger kernels) on observation records packed from the golden
+    rows, against the outputs of the reference's OWN InOutArranger (tests/golden/arranger.npz, gen_golden_arranger.py)"""
+    import os
+    import torch
+    from dynenv_b200 import layout as L
+    from dynenv_b200.arranger import KernelArranger
+    from helpers import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "arranger.npz")))
+    E, T, P = g["counts"].shape[:3]
+    rec = np.zeros((E, T, P, L.RC_OBS_WORDS), np.float32)
+    offs = [L.RC_O_BALL, L.RC_O_ROBOT, L.RC_O_POST, L.RC_O_CROSS, L.RC_O_FCROSS, L.RC_O_LINE]
+    for k in range(6):
+        r = g["rows%d" % k]
+        rec[..., offs[k]:offs[k] + r.shape[3] * r.shape[4]] = r.reshape(E, T, P, -1)
+    rec.view(np.int32)[..., L.RC_O_COUNTS:L.RC_O_COUNTS + 6] = g["counts"]
+    arr = KernelArranger(torch.from_numpy(rec).cuda(), KernelArranger.robocup_layout())
+    inputs, (counts, maxCount, objCounts) = arr.rearrange_inputs()
+    assert int(maxCount) == int(g["maxCount"])
+    assert np.array_equal(counts.cpu().numpy(), g["ref_counts"]) and np.array_equal(objCounts.cpu().numpy(), g["objCounts"])
+    exact = arr.compact(inputs)
+    for k in range(6):
+        assert np.array_equal(exact[k].cpu().numpy(), g["inputs%d" % k]), k
+    padded, masks = arr.rearrange_outputs([x[:, :3].contiguous() for x in inputs], max_count=int(g["maxCount"]))
+    assert np.array_equal(padded.cpu().numpy(), g["padded"]) and np.array_equal(masks.cpu().numpy(), g["masks"])
+    # a static bound larger than maxCount only adds padding
+    padded2, masks2 = arr.rearrange_outputs([x[:, :3].contiguous() for x in inputs], max_count=int(g["maxCount"]) + 5)
+    assert np.array_equal(padded2.cpu().numpy()[:, :int(g["maxCount"])], g["padded"]) and float(padded2[:, int(g["maxCount"]):].abs().sum()) == 0
+    assert bool(masks2[..., int(g["maxCount"]):].all())
+    # a type without an embedding block takes no slots
+    padded3, masks3 = arr.rearrange_outputs([None] + [x[:, :3].contiguous() for x in inputs[1:]], max_count=20)
+    ref = g["objCounts"] - g["ref_counts"][0]
+    assert np.array_equal((~masks3.cpu().numpy()).sum(-1), np.minimum(ref, 20))
+
+
+def test_kernel_arranger_on_simulator_outputs():
+    """the kernels on a step's records == the torch formulation on the same step (RoboCup and Driving), at a size with
+    several scan blocks"""
+    import torch
+    import dynenv_b200
+    from dynenv_b200.arranger import DeviceArranger, KernelArranger, driving_rows, robocup_rows
+    sim = dynenv_b200.BatchedRoboCup(300, 5, noiseMagnitude=2.0, seed=3)
+    sim.reset()
+    out = sim.step((torch.rand((300, 10, 4)) * torch.tensor([5, 3, 3, 7])).floor().cuda())
+    karr = KernelArranger.for_robocup(sim)
+    kin, (kc, kmax, ko) = karr.rearrange_inputs()
+    tin, (tc, tmax, to) = DeviceArranger(*robocup_rows(out)).rearrange_inputs()
+    assert int(kmax) == tmax and torch.equal(kc.long(), tc) and torch.equal(ko.long(), to)
+    for a, b in zip(karr.compact(kin), tin):
+        assert torch.equal(a, b)
+    kp, km = karr.rearrange_outputs([x[:, :2].contiguous() for x in kin], max_count=tmax)
+    tp, tm = DeviceArranger(*robocup_rows(out)).rearrange_outputs([x[:, :2] for x in tin])
+    assert torch.equal(kp, tp) and torch.equal(km, torch.stack(tm))
+    drv = dynenv_b200.BatchedDriving(200, 10, noiseMagnitude=2.0, continuousActions=True, seed=3)
+    drv.reset()
+    dout = drv.step((torch.rand((200, 10, 2)) * 6 - 3).cuda())
+    karr = KernelArranger.for_driving(drv)
+    kin, (kc, kmax, ko) = karr.rearrange_inputs()
+    tin, (tc, tmax, to) = DeviceArranger(*driving_rows(dout)).rearrange_inputs()
+    assert int(kmax) == tmax and torch.equal(kc.long(), tc)
+    for a, b in zip(karr.compact(kin), tin):
+        assert torch.equal(a, b)
