@@ -640,7 +640,16 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
     /* fork: the handed-over environments finish their substeps (and are observed) on the side stream ... */
     cudaEventRecord(h->ev_fork[bi], st);
     cudaStreamWaitEvent(h->side, h->ev_fork[bi], 0);
+#ifdef RC_SLOW_BPS /* dev experiment: fewer resident blocks of the handed-over environments' kernel per SM */
+    {
+      const size_t smem_slow = (size_t)(227 * 1024) / RC_SLOW_BPS - 1024;
+      static bool once = false;
+      if (!once) { cudaFuncSetAttribute(rc_phys_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slow); once = true; }
+      rc_phys_slow_kernel<<<h->sms * RC_SLOW_BPS, 32, smem_slow, h->side>>>(h->sim, h->state, actions_dev, e, h->slow_list, cnt);
+    }
+#else
     rc_phys_slow_kernel<<<h->sms * 32, 32, smem, h->side>>>(h->sim, h->state, actions_dev, e, h->slow_list, cnt);
+#endif
     launches++;
     if (e % 10 == 0) {
       /* ... while the caller's stream observes all the others */

@@ -30,7 +30,7 @@ namespace rc {
 
 #ifdef RC_DBG_COUNTERS
 __device__ unsigned long long g_dbg[16];
-#define RC_DBG(k, c) do { if (E.lane == 0 && (c)) atomicAdd(&g_dbg[k], 1ull); } while (0)
+#define RC_DBG(k, c) do { if (E.lane == 0 && (c)) atomicAdd(&g_dbg[(SLOW ? 8 : 0) + (k)], 1ull); } while (0)
 #define RC_DBGN(k, n) do { if (E.lane == 0) atomicAdd(&g_dbg[k], (unsigned long long)(n)); } while (0)
 #else
 #define RC_DBG(k, c)
@@ -475,6 +475,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
       RC_DBG(2, own); RC_DBG(3, g0 | g1 | g2 | g3); RC_DBG(4, nArb);
       if (SLOW) {
         if (own | g0 | g1 | g2 | g3 | (unsigned)nArb) { /* a pair is close or cached: the contact half runs on the record */
+          RC_DBG(6, true);
           if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
           regs_store(E, B, R, U);
           contact_half(E, own, g0, g1, g2, g3, pairs4, prevStepped);

@@ -42,7 +42,7 @@ constexpr int PRIM_WORDS = sizeof(raster::Prim) / 4;
 constexpr int S_CONIC = S_PRIMS + PLANE_PRIMS * PRIM_WORDS;   /* Conic */
 constexpr int CONIC_WORDS = (sizeof(raster::Conic) + 3) / 4;
 constexpr int S_PARAMS = (S_CONIC + CONIC_WORDS + 1) / 2 * 2; /* double[8]: conic parameters, centre */
-constexpr int S_MISC = S_PARAMS + 16;                         /* [0] number of primitives, [1] conic present */
+constexpr int S_MISC = S_PARAMS + 16;                         /* [0] number of primitives, [1] conic present, [2] next work unit */
 constexpr int SMEM_WORDS = S_MISC + 4;
 static_assert(5 * (SMEM_WORDS * 4 + 1024) <= 228 * 1024, "five blocks per SM");
 static_assert(3 * raster::CONIC_ROWS <= raster::PLANE_WORDS, "conic scratch inside the plane");
@@ -85,7 +85,7 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   int* misc = reinterpret_cast<int*>(g_smem + S_MISC);
   RPROF(__shared__ unsigned long long pmax[2]; const long long t0 = clock64(); if (tid == 0) { pmax[0] = pmax[1] = 0; })
   for (int w = tid; w < RC_RAW_WORDS; w += THREADS) sraw[w] = raw[rec * RC_RAW_WORDS + w];
-  if (tid == 0) { misc[0] = 0; misc[1] = 0; conic->n = 0; }
+  if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[2] = 0; conic->n = 0; }
   __syncthreads();
   /* primitives of this plane's channel, compacted (the order does not matter: drawing is a bitwise OR); float64
      projections, one slot per thread; the conic fit on the last warp */
@@ -145,6 +145,35 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   const int nprims = misc[0];
   const int nseg = conic->n > 1 ? 2 * (conic->n - 1) : 0;
   const raster::Lanes L = {lane, 32};
+  const raster::Lanes one = {0, 1};
+#ifndef RASTER_STATIC_SPLIT
+  /* Large primitives (a field line next to the robot is hundreds of pixels thick): rows over the whole block.  Everything
+     else is a queue of work units -- a small primitive (one warp, its rows / pixels on the lanes) or 32 of the conic's
+     ~2 x 479 one-pixel-high poly-line segments (one lane each) -- that the warps draw from until it is empty: with a
+     fixed primitive -> warp assignment the block waited at its barrier for the warp that had drawn the longest ones
+     (27 k cycles against a mean of 17 k, profiles/r01_ncu_rc_raster.txt: stalled_barrier 11.5 per issue). */
+  {
+    const raster::Lanes B = {tid, THREADS};
+    for (int w = 0; w < nprims; w++) {
+      const raster::Prim p = prims[w];
+      if (raster::prim_is_big(p)) raster::draw_prim(plane, p, B);
+    }
+    const int nunits = nprims + (nseg + 31) / 32;
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = atomicAdd(&misc[2], 1);
+      u = __shfl_sync(FULLMASK, u, 0);
+      if (u >= nunits) break;
+      if (u < nprims) {
+        const raster::Prim p = prims[u];
+        if (!raster::prim_is_big(p)) raster::draw_prim(plane, p, L);
+      } else {
+        const int sgm = (u - nprims) * 32 + lane;
+        if (sgm < nseg) raster::draw_conic_segment(plane, *conic, sgm, one);
+      }
+    }
+  }
+#else
   {
     /* large primitives (a field line next to the robot is hundreds of pixels thick): rows over the whole block;
        the others: one warp per primitive, rows / pixels on its lanes */
@@ -152,23 +181,13 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     int k = 0; /* small primitives seen so far (block-uniform) */
     for (int w = 0; w < nprims; w++) {
       const raster::Prim p = prims[w];
-#ifdef RASTER_SKIP_PRIMS
-      continue;
-#endif
-      if (raster::prim_is_big(p)) {
-#ifndef RASTER_SKIP_BIG
-        raster::draw_prim(plane, p, B);
-#endif
-      } else if ((k++ % WARPS) == warp) raster::draw_prim(plane, p, L);
+      if (raster::prim_is_big(p)) raster::draw_prim(plane, p, B);
+      else if ((k++ % WARPS) == warp) raster::draw_prim(plane, p, L);
     }
   }
-  RPROF(const long long t3 = clock64(); if (lane == 0) { atomicAdd(&g_raster_prof[3], (unsigned long long)(t3 - t2)); atomicMax(&pmax[0], (unsigned long long)(t3 - t2)); })
   /* the conic's ~2 x 479 poly-line segments are one pixel high and `thickness` wide: one thread per segment */
-  const raster::Lanes one = {0, 1};
-#ifndef RASTER_SKIP_CONIC
   for (int sgm = tid; sgm < nseg; sgm += THREADS) raster::draw_conic_segment(plane, *conic, sgm, one);
 #endif
-  RPROF(const long long t4 = clock64(); if (lane == 0) { atomicAdd(&g_raster_prof[5], (unsigned long long)(t4 - t3)); atomicMax(&pmax[1], (unsigned long long)(t4 - t3)); })
   __syncthreads();
   RPROF(const long long t5 = clock64();)
 #ifdef RASTER_BULK_STORE
