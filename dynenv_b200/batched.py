@@ -18,10 +18,10 @@ _TYPES = [("ball", L.RC_O_BALL, L.RC_CAP_BALL, L.RC_F_BALL), ("robot", L.RC_O_RO
           ("fcross", L.RC_O_FCROSS, L.RC_CAP_FCROSS, L.RC_F_FCROSS), ("line", L.RC_O_LINE, L.RC_CAP_LINE, L.RC_F_LINE)]
 
 
-def _flags(randomInit, deterministicTurn, canFall, useObsRewards, auto_reset):
+def _flags(randomInit, deterministicTurn, canFall, useObsRewards, auto_reset, sparse_obs=False):
     return ((L.DYNENV_FLAG_RANDOM_INIT if randomInit else 0) | (L.DYNENV_FLAG_DETERMINISTIC_TURN if deterministicTurn else 0)
             | (L.DYNENV_FLAG_CAN_FALL if canFall else 0) | (L.DYNENV_FLAG_USE_OBS_REWARDS if useObsRewards else 0)
-            | (L.DYNENV_FLAG_AUTO_RESET if auto_reset else 0))
+            | (L.DYNENV_FLAG_AUTO_RESET if auto_reset else 0) | (L.DYNENV_FLAG_SPARSE_OBS if sparse_obs else 0))
 
 
 class RoboCupOutputs(object):
@@ -83,7 +83,10 @@ class BatchedRoboCup(object):
 
     def __init__(self, nEnvs, nPlayers, observationType=ObservationType.PARTIAL, noiseType=NoiseType.REALISTIC,
                  noiseMagnitude=2.0, allowHeadTurn=False, randomInit=False, deterministicTurn=False, canFall=True,
-                 useObsRewards=True, auto_reset=False, seed=0, device=0, env_id_offset=0, terminal_outputs=False):
+                 useObsRewards=True, auto_reset=False, seed=0, device=0, env_id_offset=0, terminal_outputs=False,
+                 sparse_obs=False):
+        """sparse_obs (DYNENV_FLAG_SPARSE_OBS): PARTIAL records are a counts-prefixed stream -- rows behind `counts` keep
+        whatever the output buffer held (zeros after construction, stale rows later); read them through `counts`."""
         if not torch.cuda.is_available():
             raise RuntimeError("dynenv_b200 needs a CUDA device (no CPU fallback)")
         self._lib = _lib.lib()
@@ -91,12 +94,13 @@ class BatchedRoboCup(object):
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.nEnvs = int(nEnvs)
+        self.sparse_obs = bool(sparse_obs)
         self.nPlayers = min(int(nPlayers), 5)
         self.P = 2 * self.nPlayers
         self.obs_type = int(observationType)
         cfg = _lib.DynEnvConfig(L.DYNENV_ABI_VERSION, L.DYNENV_KIND_ROBOCUP, self.nEnvs, int(nPlayers), self.obs_type,
                                 int(noiseType), float(noiseMagnitude), int(bool(allowHeadTurn)),
-                                _flags(randomInit, deterministicTurn, canFall, useObsRewards, auto_reset),
+                                _flags(randomInit, deterministicTurn, canFall, useObsRewards, auto_reset, sparse_obs),
                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset), self.device.index or 0)
         self._h = C.c_void_p()
         _lib.check(self._lib.dynenv_create(C.byref(cfg), C.byref(self._h)))

@@ -9,8 +9,8 @@ import sys
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libdynenv_b200.so")
-SOURCES = ["csrc/dynenv_api.cu"]
-HEADERS = ["csrc/dynenv_common.cuh", "csrc/rc_sim.cuh", "csrc/drv_sim.cuh", "csrc/rc_raster.cuh", "csrc/rollout.cuh", "csrc/raster_compose.cuh", "csrc/raster_prims.cuh", "../include/dynenv_b200.h", "../include/dynenv_rng.h"]
+SOURCES = ["csrc/dynenv_api.cu", "csrc/rc_slow.cu"]
+HEADERS = ["csrc/dynenv_common.cuh", "csrc/rc_sim.cuh", "csrc/drv_sim.cuh", "csrc/rc_raster.cuh", "csrc/rc_obs.cuh", "csrc/rc_phys2.cuh", "csrc/rc_contact.cuh", "csrc/rc_slow.h", "csrc/arrange.cuh", "csrc/rollout.cuh", "csrc/raster_compose.cuh", "csrc/raster_prims.cuh", "../include/dynenv_b200.h", "../include/dynenv_rng.h"]
 # --use_fast_math: float32 division / square root / exp as the 2-ulp hardware approximations (MUFU.RCP, MUFU.RSQ,
 # MUFU.EX2 + a multiply) with denormals flushed, instead of the IEEE sequences and their slow-path calls.  The step
 # kernels are bound by instruction fetch: the flag shrinks them by ~20 % (rc_phys_kernel 105 -> 82 KB of SASS) and buys

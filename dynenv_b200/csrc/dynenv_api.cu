@@ -13,6 +13,7 @@
 #include "rc_sim.cuh"
 #include "rc_obs.cuh"
 #include "rc_phys2.cuh"
+#include "rc_slow.h"
 #include "rc_raster.cuh"
 #include "rollout.cuh"
 #include "arrange.cuh"
@@ -105,7 +106,7 @@ __device__ __forceinline__ rc::Env make_env(int base, const SimCfg& cfg, int e, 
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
                int sub_b, int sub_e, int first, uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count,
-               uint8_t* __restrict__ slow_mark) {
+               uint8_t* __restrict__ slow_mark, uint32_t* __restrict__ slow_bins) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RC_WPC + warp;
   stage_cfg(cfg);
@@ -122,14 +123,22 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
   if (lane == 0) {
     slow_mark[e] = handover >= 0;
-    if (handover >= 0) slow_list[atomicAdd(slow_count, 1u)] = ((uint32_t)handover << 24) | (uint32_t)e;
+    if (handover >= 0) {
+      /* the flat list (walked by the handed-over environments' observation launches) and the same environments binned
+         by hand-over point, 2 (sub - sub_b) + phase: rc_slow.cu gives a block environments of one bin */
+      slow_list[atomicAdd(slow_count, 1u)] = ((uint32_t)handover << 24) | (uint32_t)e;
+      const int bin = handover - 2 * sub_b;
+      slow_bins[(size_t)bin * cfg.n_envs + atomicAdd(slow_count + DYNENV_SLOW_BIN0 + bin, 1u)] = (uint32_t)e;
+    }
   }
 #endif
 }
 
 /* the environments rc_phys_kernel handed over (falls, penalties, touching or cached pairs: a few percent of them): the
    rest of their substeps, still register-resident between the ordered robot phases (rc_sim.cuh) and the contact halves
-   (rc_contact.cuh) they need.  A fixed grid walks the list. */
+   (rc_contact.cuh) they need.  A fixed grid walks the list.  This is the first, one-warp-per-block version, kept for
+   comparison (-DRC_SLOW_ONE_WARP): the product launches rc_slow.cu's phase-synchronised multi-warp kernel. */
+#ifdef RC_SLOW_ONE_WARP
 __global__ void __launch_bounds__(32, 32)
 rc_phys_slow_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions, int sub_e,
                     const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ slow_count) {
@@ -151,6 +160,7 @@ rc_phys_slow_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ s
     __syncwarp();
   }
 }
+#endif
 
 /* The observation kernels run twice per tick: on the caller's stream for every environment that rc_phys_kernel finished
    itself (slow_mark[e] == 0; slow_list == nullptr), and on the side stream, behind rc_phys_slow_kernel, for the
@@ -426,7 +436,8 @@ struct DynEnvHandle_s {
   SimCfg sim;
   uint32_t* state;
   uint32_t* slow_list;   /* RoboCup: environments handed over to rc_phys_slow_kernel, (2 sub + phase) << 24 | env */
-  uint32_t* slow_count;  /* [8] one counter per substep block of the step */
+  uint32_t* slow_count;  /* [8][DYNENV_SLOW_CNT_WORDS] per substep block of the step: [0] length of the list, [DYNENV_SLOW_BIN0 + k] of bin k */
+  uint32_t* slow_bins;   /* [DYNENV_SLOW_BINS][n_envs] the same environments by hand-over point */
   uint8_t* slow_mark;    /* [n_envs] 1 = handed over in the substep block in flight */
   cudaStream_t side;     /* the handed-over environments' substeps and observations run here, beside the others' observations */
   cudaEvent_t ev_fork[8], ev_join[8];
@@ -483,6 +494,7 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   s.deterministic_turn = !!(cfg->flags & DYNENV_FLAG_DETERMINISTIC_TURN);
   s.can_fall = !!(cfg->flags & DYNENV_FLAG_CAN_FALL);
   s.use_obs_rewards = !!(cfg->flags & DYNENV_FLAG_USE_OBS_REWARDS);
+  s.sparse_obs = !!(cfg->flags & DYNENV_FLAG_SPARSE_OBS);
   s.auto_reset = !!(cfg->flags & DYNENV_FLAG_AUTO_RESET);
   s.seed_lo = (uint32_t)cfg->seed;
   s.seed_hi = (uint32_t)(cfg->seed >> 32);
@@ -505,6 +517,7 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   }
   h->slow_list = nullptr;
   h->slow_count = nullptr;
+  h->slow_bins = nullptr;
   h->slow_mark = nullptr;
   h->side = nullptr;
   h->sms = 148;
@@ -520,16 +533,28 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
       return fail(DYNENV_E_INVALID, "at most 2^24 - 1 RoboCup environments per handle");
     }
     if ((ce = cudaMalloc(&h->slow_list, (size_t)cfg->n_envs * sizeof(uint32_t))) != cudaSuccess ||
-        (ce = cudaMalloc(&h->slow_count, 8 * sizeof(uint32_t))) != cudaSuccess ||
+        (ce = cudaMalloc(&h->slow_count, 8 * DYNENV_SLOW_CNT_WORDS * sizeof(uint32_t))) != cudaSuccess ||
+        (ce = cudaMalloc(&h->slow_bins, (size_t)DYNENV_SLOW_BINS * cfg->n_envs * sizeof(uint32_t))) != cudaSuccess ||
         (ce = cudaMalloc(&h->slow_mark, (size_t)cfg->n_envs)) != cudaSuccess ||
         (ce = cudaMemset(h->slow_mark, 0, (size_t)cfg->n_envs)) != cudaSuccess ||
         (ce = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
       cudaFree(h->slow_list);
       cudaFree(h->slow_count);
+      cudaFree(h->slow_bins);
       cudaFree(h->slow_mark);
       cudaFree(h->state);
       delete h;
       return cuda_fail(ce, "cudaMalloc(slow list)");
+    }
+    if ((ce = dynenv_slow_configure()) != cudaSuccess) {
+      cudaFree(h->slow_list);
+      cudaFree(h->slow_count);
+      cudaFree(h->slow_bins);
+      cudaFree(h->slow_mark);
+      cudaFree(h->state);
+      cudaStreamDestroy(h->side);
+      delete h;
+      return cuda_fail(ce, "cudaFuncSetAttribute(rc_phys_slow_kernel)");
     }
     for (int k = 0; k < 8; k++) {
       cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming);
@@ -546,6 +571,7 @@ int dynenv_destroy(DynEnvHandle h) {
   cudaFree(h->state);
   cudaFree(h->slow_list);
   cudaFree(h->slow_count);
+  cudaFree(h->slow_bins);
   cudaFree(h->slow_mark);
   if (h->side) {
     cudaStreamDestroy(h->side);
@@ -624,7 +650,7 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
     cudaEventRecord(h->ev[nmark++], st);
   };
   int blk = 0;
-  cudaMemsetAsync(h->slow_count, 0, 8 * sizeof(uint32_t), st);
+  cudaMemsetAsync(h->slow_count, 0, 8 * DYNENV_SLOW_CNT_WORDS * sizeof(uint32_t), st);
   mark(-1);
   /* blocks of substeps up to the next observation tick (every 10th substep); each is followed by the few environments
      it handed over to the record-based code */
@@ -632,23 +658,18 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
     int e = (b / 10 + 1) * 10;
     if (e > h->sim.sub_end) e = h->sim.sub_end;
     const int bi = blk++ & 7;
-    uint32_t* cnt = h->slow_count + bi;
+    uint32_t* cnt = h->slow_count + bi * DYNENV_SLOW_CNT_WORDS;
     rc_phys_kernel<<<grid, RC_WPC * 32, smem, st>>>(h->sim, h->state, actions_dev, b, e, b == h->sim.sub_begin, h->slow_list, cnt,
-                                                     h->slow_mark);
+                                                     h->slow_mark, h->slow_bins);
     launches++;
     mark(0);
     /* fork: the handed-over environments finish their substeps (and are observed) on the side stream ... */
     cudaEventRecord(h->ev_fork[bi], st);
     cudaStreamWaitEvent(h->side, h->ev_fork[bi], 0);
-#ifdef RC_SLOW_BPS /* dev experiment: fewer resident blocks of the handed-over environments' kernel per SM */
-    {
-      const size_t smem_slow = (size_t)(227 * 1024) / RC_SLOW_BPS - 1024;
-      static bool once = false;
-      if (!once) { cudaFuncSetAttribute(rc_phys_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slow); once = true; }
-      rc_phys_slow_kernel<<<h->sms * RC_SLOW_BPS, 32, smem_slow, h->side>>>(h->sim, h->state, actions_dev, e, h->slow_list, cnt);
-    }
-#else
+#ifdef RC_SLOW_ONE_WARP
     rc_phys_slow_kernel<<<h->sms * 32, 32, smem, h->side>>>(h->sim, h->state, actions_dev, e, h->slow_list, cnt);
+#else
+    dynenv_slow_launch(&h->sim, h->state, actions_dev, b, e, h->slow_bins, cnt, h->sms, h->side);
 #endif
     launches++;
     if (e % 10 == 0) {

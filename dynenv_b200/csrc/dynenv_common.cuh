@@ -29,6 +29,7 @@ struct SimCfg {
   uint32_t seed_lo, seed_hi;
   uint32_t env_id_offset;
   int sub_begin, sub_end; /* substeps run by one step call: 0..RC_SUBSTEPS (a debugging aid narrows it) */
+  int sparse_obs;         /* DYNENV_FLAG_SPARSE_OBS */
 };
 
 struct V2 {
@@ -137,17 +138,33 @@ __device__ __forceinline__ void bounds_check(int word) {
 #else
 #define DYNENV_BC(word)
 #endif
-/* One warp per thread block everywhere: the slice starts right behind the SimCfg copy, so
-   every shared-memory address is an immediate or lane * stride + immediate. */
+/* One warp per thread block in every kernel of dynenv_api.cu: the slice starts right behind the
+   SimCfg copy, so every shared-memory address is an immediate or lane * stride + immediate.  The translation unit of the
+   handed-over environments (rc_slow.cu, DYNENV_MW_SLICE_WORDS defined) runs several warps per block, each on its own
+   slice: there the base is a per-warp register. */
+#ifdef DYNENV_MW_SLICE_WORDS
+struct SharedF {
+  static __device__ __forceinline__ int base_() { return CFG_WORDS + (int)(threadIdx.x >> 5) * DYNENV_MW_SLICE_WORDS; }
+  __device__ __forceinline__ float& operator[](int k) const { DYNENV_BC(base_() + k); return reinterpret_cast<float*>(g_smem)[base_() + k]; }
+  __device__ __forceinline__ float* operator+(int k) const { return reinterpret_cast<float*>(g_smem) + base_() + k; }
+};
+struct SharedI {
+  static __device__ __forceinline__ int base_() { return SharedF::base_(); }
+  __device__ __forceinline__ int& operator[](int k) const { DYNENV_BC(base_() + k); return reinterpret_cast<int*>(g_smem)[base_() + k]; }
+};
+#else
 struct SharedF { /* this warp's slice viewed as float */
   static constexpr int base = CFG_WORDS;
+  static __device__ __forceinline__ constexpr int base_() { return base; }
   __device__ __forceinline__ float& operator[](int k) const { DYNENV_BC(base + k); return reinterpret_cast<float*>(g_smem)[base + k]; }
   __device__ __forceinline__ float* operator+(int k) const { return reinterpret_cast<float*>(g_smem) + base + k; }
 };
 struct SharedI { /* ... and as int */
   static constexpr int base = CFG_WORDS;
+  static __device__ __forceinline__ constexpr int base_() { return base; }
   __device__ __forceinline__ int& operator[](int k) const { DYNENV_BC(base + k); return reinterpret_cast<int*>(g_smem)[base + k]; }
 };
+#endif
 struct SharedCfg {
   __device__ __forceinline__ const SimCfg* operator->() const { return reinterpret_cast<const SimCfg*>(g_smem); }
   __device__ __forceinline__ const SimCfg& operator*() const { return *reinterpret_cast<const SimCfg*>(g_smem); }

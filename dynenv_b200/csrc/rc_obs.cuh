@@ -250,7 +250,7 @@ __device__ __noinline__ void o_process(const Env E, uint32_t tick, int head, int
 /* The lines of every observer -- isLineInArea (cutils.py:751-821), addNoiseLine (:352-378), normalizeLine (:333-347) --
    flat over item = 11 * observer + line.  A launch of its own (rc_obsl_kernel) in front of the point objects': together
    the two would not fit the instruction cache.  Also zero-fills the tick's records (rows behind the counts
-   stay zero) and leaves each observer's line count in the record (RC_O_COUNTS + 5) and in O_CNT (the caller adds it to the
+   stay zero; not with DYNENV_FLAG_SPARSE_OBS) and leaves each observer's line count in the record (RC_O_COUNTS + 5) and in O_CNT (the caller adds it to the
    processSeens sum). */
 __device__ __noinline__ void observe_lines(const Env E, uint32_t tick, float* __restrict__ obs_tick) {
   const int lane = E.lane;
@@ -259,7 +259,7 @@ __device__ __noinline__ void observe_lines(const Env E, uint32_t tick, float* __
   const bool realistic = E.c->noise_type == DYNENV_NOISE_REALISTIC;
   const float maxVis1 = (W_ * 0.8f) * (W_ * 0.8f);
   const unsigned lt = (1u << lane) - 1;
-  if (obs_tick) {
+  if (obs_tick && !E.c->sparse_obs) { /* (DYNENV_FLAG_SPARSE_OBS: rows behind the counts keep what the buffer held) */
     float4* dst = reinterpret_cast<float4*>(obs_tick);
 #pragma unroll 2
     for (int w = lane; w < P * (RC_OBS_WORDS / 4); w += 32) dst[w] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -102,10 +102,22 @@ __device__ __forceinline__ void regs_store(const Env E, const Body& B, const Rob
    the handed-over environments, which run the rare code in place: the ordered robot phase of rc_sim.cuh and the contact
    half of rc_contact.cuh, each between a flush and a reload of the registers; phase0 = 1 resumes inside Space.step of
    substep sub_b.  Returns -1. */
+/* RC_MW (rc_slow.cu: several handed-over environments per block, one per warp): every warp of the block walks the
+   substeps [sub_lo, sub_e) of the launch and meets the others at two block barriers per substep -- in front of the robot
+   phase and in front of the velocity / contact half -- so that the warps of a block execute the same code at the same
+   time and share its instruction fetches (the one-warp-per-block kernel issued at 28 % with 15 stalled-for-instruction
+   warps per issue, whatever its occupancy).  A warp idles through the substeps in front of its environment's hand-over
+   point (sub_b; phase0 = 1: it enters at the contact half of substep sub_b) and, without an environment (valid =
+   false), through all of them. */
 template <bool SLOW>
-__device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_env, int sub_b, int sub_e, bool first, int phase0 = 0) {
+__device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_env, int sub_b, int sub_e, bool first, int phase0 = 0,
+                                              int sub_lo = 0, bool valid = true) {
   if (first) clear_step_scratch(E);
   const uint32_t pairs4 = broadphase_pairs(E);
+#ifdef RC_MW
+  static_assert(SLOW, "the multi-warp build holds only the handed-over environments' kernel");
+#else
+  (void)sub_lo; (void)valid;
   if (SLOW && phase0) {
     unsigned own, g0, g1, g2, g3;
     __syncwarp();
@@ -116,6 +128,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
     __syncwarp();
     sub_b++;
   }
+#endif
   const int lane = E.lane;
   const int P = E.c->P, nPl = E.c->n_players;
   const bool isFoot = lane < 2 * P;       /* an existing robot's foot */
@@ -134,9 +147,19 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
   const float penX = SIDE + PEN_LENGTH + LINEW / 2;
 
 #pragma unroll 1
+#ifdef RC_MW
+  for (int sub = sub_lo; sub < sub_e; sub++) {
+    __syncthreads();
+    const bool act = valid && sub >= sub_b;            /* warp-uniform */
+    const bool resume = act && phase0 && sub == sub_b; /* handed over in mid-substep: positions are integrated */
+    const bool front = act && !resume;
+#else
   for (int sub = sub_b; sub < sub_e; sub++) {
+    const bool act = true, resume = false, front = true;
+    (void)act;
+#endif
     /* ------------------------------------------------------------------ robots: processAction (sub 0) + tick */
-    {
+    if (front) {
       float4 act = make_float4(0, 0, 0, 0);
       Rand6 ru;
       ru.w[0] = ru.w[1] = ru.w[2] = ru.w[3] = 0;
@@ -290,7 +313,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
       __syncwarp();
     }
     /* ------------------------------------------------------------------ ball rules (isBallOutOfField) */
-    {
+    if (front) {
       float cr0 = 0, cr1 = 0, oldx = 0, oldy = 0;
       if (lane == BALL) {
         int finished = 0;
@@ -397,8 +420,11 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
     {
       const int prevStepped = E.i[RC_S_STEPPED];
       const int nArb = E.i[RC_S_NARB];
+      float bcx = 0, bcy = 0, dRLx = 0, dRLy = 0, dRLa = 0;
+      unsigned own = 0, g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+      if (front) {
       /* integrate positions (cpBodyUpdatePosition), refresh the cached shape geometry */
-      float bcx = 0, bcy = 0, tax = 0, tay = 0, tbx = 0, tby = 0;
+      float tax = 0, tay = 0, tbx = 0, tby = 0;
       if (isBody) {
         float vbx = 0.f, vby = 0.f, wb = 0.f;
         if (biasPending) {
@@ -426,9 +452,9 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
       const float Rx = side ? B.px : opx, Rxl = side ? B.pxl : opxl, Lx = side ? opx : B.px, Lxl = side ? opxl : B.pxl;
       const float Ry = side ? B.py : opy, Ryl = side ? B.pyl : opyl, Ly = side ? opy : B.py, Lyl = side ? opyl : B.pyl;
       const float Ra = side ? B.an : oan, Ral = side ? B.anl : oanl, La = side ? oan : B.an, Lal = side ? oanl : B.anl;
-      const float dRLx = __fadd_rn(__fsub_rn(Rx, Lx), __fsub_rn(Rxl, Lxl));
-      const float dRLy = __fadd_rn(__fsub_rn(Ry, Ly), __fsub_rn(Ryl, Lyl));
-      const float dRLa = __fadd_rn(__fsub_rn(Ra, La), __fsub_rn(Ral, Lal));
+      dRLx = __fadd_rn(__fsub_rn(Rx, Lx), __fsub_rn(Rxl, Lxl));
+      dRLy = __fadd_rn(__fsub_rn(Ry, Ly), __fsub_rn(Ryl, Lyl));
+      dRLa = __fadd_rn(__fsub_rn(Ra, La), __fsub_rn(Ral, Lal));
       /* broad phase on groups, lane = pair, four rounds.  A robot's group circle: every point of a foot (a capsule
          (-10, +-10)-(10, +-10) of radius 7.5 around its body position) lies within sqrt(200) + 7.5 of the foot's body
          position, whatever its angle, and the body positions within half their distance of their midpoint.  (Penalised
@@ -459,8 +485,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
         }
       }
       __syncwarp();
-      const unsigned own = __ballot_sync(FULLMASK, ownFeetApart);
-      unsigned g0, g1, g2, g3;
+      own = __ballot_sync(FULLMASK, ownFeetApart);
       {
         unsigned gh[4];
 #pragma unroll
@@ -472,12 +497,22 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
         }
         g0 = gh[0]; g1 = gh[1]; g2 = gh[2]; g3 = gh[3];
       }
+      } else if (resume) {
+        __syncwarp();
+        record_broadphase(E, pairs4, own, g0, g1, g2, g3);
+      }
+#ifdef RC_MW
+      __syncthreads();
+      if (!act) continue;
+#endif
       RC_DBG(2, own); RC_DBG(3, g0 | g1 | g2 | g3); RC_DBG(4, nArb);
       if (SLOW) {
-        if (own | g0 | g1 | g2 | g3 | (unsigned)nArb) { /* a pair is close or cached: the contact half runs on the record */
+        if (resume | own | g0 | g1 | g2 | g3 | (unsigned)nArb) { /* a pair is close or cached: the contact half runs on the record */
           RC_DBG(6, true);
-          if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
-          regs_store(E, B, R, U);
+          if (!resume) {
+            if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
+            regs_store(E, B, R, U);
+          }
           contact_half(E, own, g0, g1, g2, g3, pairs4, prevStepped);
           regs_load(E, B, R, U);
           forcesPending = true; biasPending = true;

@@ -1202,7 +1202,7 @@ __device__ bool shapes_touch(const Env E, int i, int j) {
    of the record: the register-resident substep calls it without flushing. */
 __device__ __noinline__ int filter_candidates(const Env E, unsigned own, unsigned g0, unsigned g1, unsigned g2, unsigned g3) {
   const int lane = E.lane;
-  unsigned short* cand = reinterpret_cast<unsigned short*>(g_smem + E.i.base + X_CAND);
+  unsigned short* cand = reinterpret_cast<unsigned short*>(g_smem + E.i.base_() + X_CAND);
   if (lane == 0) {
     int n = 0;
     while (own) {
@@ -1254,7 +1254,7 @@ __device__ __noinline__ int filter_candidates(const Env E, unsigned own, unsigne
 
 /* the touching candidates (filter_candidates left them in X_CAND) collided in ascending (i, j) order: lane 0 */
 __device__ __noinline__ void collide_kept(const Env E, int kept) {
-  unsigned short* cand = reinterpret_cast<unsigned short*>(g_smem + E.i.base + X_CAND);
+  unsigned short* cand = reinterpret_cast<unsigned short*>(g_smem + E.i.base_() + X_CAND);
   if (E.lane == 0) {
     for (int x = 1; x < kept; x++) { /* insertion sort: tiny */
       int key = cand[x], y = x - 1;

@@ -53,6 +53,11 @@ extern "C" {
 #define DYNENV_FLAG_CAN_FALL 4u
 #define DYNENV_FLAG_USE_OBS_REWARDS 8u
 #define DYNENV_FLAG_AUTO_RESET 16u /* vec-env semantics: done envs are re-initialised in step */
+/* RoboCup PARTIAL observations as a counts-prefixed stream: a record's rows BEHIND its counts (RC_O_COUNTS) are left as
+   the caller's buffer had them instead of being zero-filled -- a consumer that honours the counts (dynenv_arrange_inputs,
+   the reference's own list format) reads the same rows, and the step writes ~25 KB of observations per env-step instead
+   of 83 KB (70 % of a padded record is padding).  Off: every record is fully written, rows behind the counts are zero. */
+#define DYNENV_FLAG_SPARSE_OBS 32u
 
 typedef struct DynEnvConfig {
   int32_t abi_version;      /* DYNENV_ABI_VERSION */

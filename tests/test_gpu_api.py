@@ -334,3 +334,51 @@ def test_kernel_arranger_on_simulator_outputs():
     assert int(kmax) == tmax and torch.equal(kc.long(), tc)
     for a, b in zip(karr.compact(kin), tin):
         assert torch.equal(a, b)
+
+
+def test_sparse_observation_stream_matches_the_padded_records():
+    """DYNENV_FLAG_SPARSE_OBS: the same simulation with rows behind the counts left unwritten.  The output buffer is
+    poisoned with NaN first: counts / flags / rewards / states are identical, every row in front of its count is
+    bit-identical to the zero-filled run, nothing behind the counts was written (still NaN), and the arranger kernels
+    -- a consumer that honours the counts -- produce identical inputs from both."""
+    import torch
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    from dynenv_b200.arranger import KernelArranger
+    n, P = 96, 10
+    kw = dict(noiseMagnitude=2.0, canFall=True, auto_reset=True, seed=11)
+    dense = dynenv_b200.BatchedRoboCup(n, 5, **kw)
+    sparse = dynenv_b200.BatchedRoboCup(n, 5, sparse_obs=True, **kw)
+    g = torch.Generator().manual_seed(5)
+    lists = [("ball", L.RC_CAP_BALL), ("robot", L.RC_CAP_ROBOT), ("post", L.RC_CAP_POST), ("cross", L.RC_CAP_CROSS),
+             ("fcross", L.RC_CAP_FCROSS), ("line", L.RC_CAP_LINE)]
+    written_bytes, steps = 0, 0
+    for s in range(8):
+        sparse.out.obs.fill_(float("nan"))
+        if s == 0:
+            do, so = dense.reset(), sparse.reset()
+        else:
+            a = (torch.rand((n, P, 4), generator=g) * torch.tensor([5, 3, 3, 7])).floor().cuda()
+            do, so = dense.step(a), sparse.step(a)
+        torch.cuda.synchronize()
+        assert torch.equal(do.counts, so.counts) and torch.equal(do.num_landmarks, so.num_landmarks)
+        assert torch.equal(do.balls_seen, so.balls_seen) and torch.equal(do.robots_seen, so.robots_seen)
+        assert torch.equal(do.rewards, so.rewards) and torch.equal(dense.get_state(), sparse.get_state())
+        for k, (name, cap) in enumerate(lists):
+            dr, sr = getattr(do, name), getattr(so, name)                      # [n, T, P, cap, F]
+            live = torch.arange(cap, device="cuda")[None, None, None, :] < do.counts[..., k:k + 1]
+            assert torch.equal(dr[live], sr[live]), name
+            assert torch.isnan(sr[~live]).all(), name                         # nothing behind the counts was touched
+            assert (dr[~live] == 0).all(), name
+        written_bytes += int((~torch.isnan(so.obs)).sum().item()) * 4
+        steps += 1
+        ka, kb = KernelArranger.for_robocup(dense), KernelArranger.for_robocup(sparse)
+        ia, (ca, ma, oa) = ka.rearrange_inputs()
+        ib, (cb, mb, ob) = kb.rearrange_inputs()
+        assert int(ma) == int(mb) and torch.equal(ca, cb) and torch.equal(oa, ob)
+        for x, y in zip(ka.compact(ia), kb.compact(ib)):
+            assert torch.equal(x, y)
+    per_env_step = written_bytes / steps / n
+    print("sparse stream: %.1f KB of observations written per env-step (padded records: %.1f KB)" % (
+        per_env_step / 1e3, 5 * P * L.RC_OBS_WORDS * 4 / 1e3))
+    assert per_env_step < 30e3

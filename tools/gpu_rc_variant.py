@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, ".")
 import dynenv_b200
 E = 65536
-sim = dynenv_b200.BatchedRoboCup(E, 5, 1, 1, 2.0, canFall=True, auto_reset=True, seed=42)
+sim = dynenv_b200.BatchedRoboCup(E, 5, 1, 1, 2.0, canFall=True, auto_reset=True, seed=42, sparse_obs=bool(int(os.environ.get("SPARSE", "0"))))
 sim.reset()
 g = torch.Generator(device="cuda"); g.manual_seed(1234)
 hi = torch.tensor([5, 3, 3, 7], device="cuda")

@@ -9,7 +9,7 @@ rows = list(csv.reader(open('/tmp/src.csv')))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
 col = {h: i for i, h in enumerate(rows[hi])}
 data = rows[hi + 1:]
-out = subprocess.run("cd /tmp/cub && nvdisasm -c *.cubin", shell=True, capture_output=True, text=True).stdout.splitlines()
+out = subprocess.run("cd /tmp/cub && for f in *.cubin; do nvdisasm -c $f; done", shell=True, capture_output=True, text=True).stdout.splitlines()
 funcs, n, insec = [], 0, False
 for ln in out:
     if ln.startswith('//---') and '.text.' in ln:

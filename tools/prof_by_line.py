@@ -10,7 +10,7 @@ rows = list(csv.reader(open('/tmp/src.csv')))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
 col = {h: i for i, h in enumerate(rows[hi])}
 data = rows[hi + 1:]
-out = subprocess.run("cd /tmp/cub && nvdisasm -g -c *.cubin", shell=True, capture_output=True, text=True).stdout.splitlines()
+out = subprocess.run("cd /tmp/cub && for f in *.cubin; do nvdisasm -g -c $f; done", shell=True, capture_output=True, text=True).stdout.splitlines()
 lines, insec, cur = [], False, ("?", 0)
 for ln in out:
     if ln.startswith('//---') and '.text.' in ln:

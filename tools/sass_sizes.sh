@@ -4,7 +4,7 @@
 K=${1:-rc_phys_kernel}
 LIB=${2:-/root/repo/dynenv_b200/libdynenv_b200.so}
 rm -rf /tmp/cub_sizes && mkdir -p /tmp/cub_sizes && cd /tmp/cub_sizes && cuobjdump -xelf all "$LIB" > /dev/null 2>&1
-nvdisasm -c *.cubin 2>/dev/null | awk -v K="$K" '
+(for f in *.cubin; do nvdisasm -c $f; done) 2>/dev/null | awk -v K="$K" '
 /^\/\/-+ \.text\./ {insec = (index($0, K) > 0); fn="(kernel body)"; next}
 /^\/\/-+/ {insec=0}
 insec && /^\$[_A-Za-z0-9$]+:/ {fn=$1}
