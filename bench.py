@@ -49,12 +49,30 @@ class RoboCupWorkload(object):
     prefix = "rc"
     cpu_steps, ref_steps, cpu_warm = 20000, 1000, 50  # env-steps per host thread: cpu_baseline sample, reference-arm step, warm-up
     default_steps = 240  # one whole episode (12000 / 50): contacts, falls and penalties build up over an episode
+    # DYNENV_FLAG_SPARSE_OBS: counts-prefixed observation stream, rows behind the counts are not written (--dense-obs: zero-filled
+    # padded records).  obs_bytes = observation bytes written per env-step, measured on the last timed step (dense: the records).
+    sparse_obs = True
+    obs_bytes = None
 
     def make_sim(self, E, local, rank, full=False):
         import dynenv_b200
         obs_type = dynenv_b200.ObservationType.FULL if full else dynenv_b200.ObservationType.PARTIAL
         return dynenv_b200.BatchedRoboCup(E, 5, obs_type, dynenv_b200.NoiseType.REALISTIC, 2.0, canFall=True,
-                                          useObsRewards=True, auto_reset=True, seed=42, device=local, env_id_offset=rank * E)
+                                          useObsRewards=True, auto_reset=True, seed=42, device=local, env_id_offset=rank * E,
+                                          sparse_obs=self.sparse_obs and not full)
+
+    def measure_obs_bytes(self, sim):
+        """bytes of observation records one env-step writes: the rows in front of the counts + the 17 count / flag words per
+        observer and tick (sparse stream), from the counts of the step just taken; the padded records otherwise"""
+        from dynenv_b200 import layout as L
+        import torch
+        out = getattr(sim, "out", None)
+        if not self.sparse_obs or out is None or getattr(out, "counts", None) is None:
+            self.obs_bytes = 4 * L.RC_NTICK * self.P * L.RC_OBS_WORDS
+            return
+        feat = torch.tensor([L.RC_F_BALL, L.RC_F_ROBOT, L.RC_F_POST, L.RC_F_CROSS, L.RC_F_FCROSS, L.RC_F_LINE], device=out.counts.device)
+        rows = (out.counts.long() * feat).sum().item() / out.counts.shape[0]
+        self.obs_bytes = 4 * (rows + L.RC_NTICK * self.P * (L.RC_NTYPES + 2 + L.RC_MAXP - 1))
 
     def make_actions(self, E, g, dev):
         """int uniform move [0,5) turn [0,3) kick [0,3) head [0,7)"""
@@ -63,13 +81,22 @@ class RoboCupWorkload(object):
         return (torch.rand((E, self.P, 4), generator=g, device=dev) * hi).floor().contiguous()
 
     def config(self, L):
-        return {"substeps": L.RC_SUBSTEPS, "obs_ticks": L.RC_NTICK, "observers": self.P}
+        c = {"substeps": L.RC_SUBSTEPS, "obs_ticks": L.RC_NTICK, "observers": self.P}
+        if self.name == "robocup":
+            c["obs_stream"] = ("counts-prefixed rows (DYNENV_FLAG_SPARSE_OBS): %.1f KB of observations written per env-step, padded "
+                               "records would be %.1f KB" % ((self.obs_bytes or 0) / 1e3, 4 * L.RC_NTICK * self.P * L.RC_OBS_WORDS / 1e3)
+                               if self.sparse_obs else "padded records, zero-filled behind the counts (--dense-obs)")
+        return c
+
+    def _obs_bytes(self):
+        from dynenv_b200 import layout as L
+        return self.obs_bytes if self.obs_bytes is not None else 4 * L.RC_NTICK * self.P * L.RC_OBS_WORDS
 
     def algorithmic_bytes_per_env_step(self):
         """step-boundary HBM traffic of one env-step: state record in + out, actions in,
-        5 x 10 observation records, result record."""
+        5 x 10 observation records (sparse stream: the rows and counts actually written), result record."""
         from dynenv_b200 import layout as L
-        return 4 * (2 * L.RC_STATE_WORDS + self.P * 4 + L.RC_NTICK * self.P * L.RC_OBS_WORDS + L.RC_INFO_WORDS)
+        return 4 * (2 * L.RC_STATE_WORDS + self.P * 4 + L.RC_INFO_WORDS) + self._obs_bytes()
 
     def kernel_bytes_per_env(self):
         """algorithmic HBM bytes per environment of ONE launch of each kernel class"""
@@ -78,7 +105,7 @@ class RoboCupWorkload(object):
         return {"phys": 2 * rec + 4 * self.P * 4,                                   # record in + out, actions
                 # one tick: the robot table of the record (21 positions, 20 angles, 10 heads, 10 flags, 7 scalars) twice,
                 # 10 records out, the processSeens sums in + out
-                "obs": 2 * 4 * 89 + 4 * self.P * L.RC_OBS_WORDS + 2 * 4 * (L.RC_S_STEP_END - L.RC_S_STEP_LSUM),
+                "obs": 2 * 4 * 89 + self._obs_bytes() / L.RC_NTICK + 2 * 4 * (L.RC_S_STEP_END - L.RC_S_STEP_LSUM),
                 "finish": 2 * rec + 4 * L.RC_INFO_WORDS}
 
     def cpu_env(self, i):
@@ -193,6 +220,7 @@ class ImageWorkload(RoboCupWorkload):
     workload = "RoboCup 5v5 IMAGE (top / bottom camera raster, 8 x 480 x 640 bit-planes per robot and tick) allowHeadTurn REALISTIC noise 2, auto-reset"
     launches_per_step = {"phys": 5, "phys_slow": 5, "obs": 5, "finish": 1, "raster": 1}
     chunk = 1024
+    sparse_obs = False  # IMAGE mode writes whole records (staged in shared memory)
     default_envs = 16384
     cpu_steps, ref_steps, cpu_warm = 16, 4, 1  # an env-step draws 100 images with cv2 (~0.3 s)
     default_steps = 10
@@ -424,6 +452,8 @@ def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=T
         res["clocks"] = sampler.stop()
     res["ms_total"] = t0.elapsed_time(t1)
     res["diag"] = int(sim.out.diag.max().item())
+    if hasattr(wl, "measure_obs_bytes"):
+        wl.measure_obs_bytes(sim)
     # ---- pass 2: end to end through the host-facing call
     n_res = (L.DRV_I_DONE if wl.name == "driving" else L.RC_I_DONE) + 1
     res["h2d"], res["d2h"] = E * P * wl.act * 4, E * n_res * 4
@@ -541,6 +571,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]()
+    if args.dense_obs and hasattr(wl, "sparse_obs"):
+        wl.sparse_obs = False
     E = args.envs or getattr(wl, "default_envs", 65536)
     ff = FAST_FORWARD[wl.name] if args.fast_forward is None else args.fast_forward
     r = measure(wl, E, local, rank, world, args.steps, args.warmup, ff, full=args.debug_full_obs, sampler=ClockSampler(local),
@@ -648,6 +680,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="robocup", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dense-obs", action="store_true", help="RoboCup: zero-filled padded observation records instead of the sparse stream")
     ap.add_argument("--no-other", action="store_true", help="skip the short legs of the other workloads / the drop-in API")
     ap.add_argument("--fast-forward", type=int, default=None, help="untimed steps in front of the warm-up (default: to mid-episode)")
     ap.add_argument("--debug-full-obs", action="store_true", help="(profiling aid) FULL observations: physics and rules only")

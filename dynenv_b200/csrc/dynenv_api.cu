@@ -861,7 +861,8 @@ int dynenv_debug_counters(unsigned long long* out16, int reset) {
 int dynenv_debug_raster_prof(unsigned long long* out16, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out16, rcimg::g_raster_prof, 16 * sizeof(unsigned long long));
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rcimg::g_raster_prof, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out16 + 16, rcimg::g_raster_prof2, 8 * sizeof(unsigned long long)); /* out16: 24 words */
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rcimg::g_raster_prof, z, sizeof(z)); cudaMemcpyToSymbol(rcimg::g_raster_prof2, z, 8 * sizeof(unsigned long long)); }
   return 0;
 }
 #endif

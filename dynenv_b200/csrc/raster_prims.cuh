@@ -39,7 +39,11 @@ RP_FN void or_word(uint32_t* p, uint32_t m) {
     dynenv::bounds_check(w < 0 || w >= PLANE_WORDS ? -1 : (int)w);
   }
 #endif
+#ifdef RASTER_NONATOMIC /* dev ablation (racy: wrong pixels) */
+  *p |= m;
+#else
   atomicOr(p, m);
+#endif
 #else
   *p |= m;
 #endif

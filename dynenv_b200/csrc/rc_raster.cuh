@@ -60,9 +60,10 @@ __device__ __forceinline__ void bulk_store_plane(uint32_t* gdst, const uint32_t*
 
 #ifdef RASTER_PROFILE
 /* dev experiment: cycles per phase, summed over the non-empty planes of a launch.  [0] blocks, [1] setup, [2] conic rows,
-   [3] sum over warps of the primitive loop, [4] its max over warps x 8, [5] sum of the conic segments, [6] max x 8,
+   [3] drawing (big primitives + work queue), [4] / [5] planes without / with a conic,
    [7] store, [8] total */
 __device__ unsigned long long g_raster_prof[16];
+__device__ unsigned long long g_raster_prof2[8]; /* lines channel with / without the conic: planes, total, big-primitive loop, queue */
 #define RPROF(x) x
 #else
 #define RPROF(x)
@@ -141,12 +142,13 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) p4[w] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  RPROF(const long long t2 = clock64();)
+  RPROF(const long long t2 = clock64(); long long t3s = t2;)
   const int nprims = misc[0];
   const int nseg = conic->n > 1 ? 2 * (conic->n - 1) : 0;
   const raster::Lanes L = {lane, 32};
   const raster::Lanes one = {0, 1};
-#ifndef RASTER_STATIC_SPLIT
+#ifdef RASTER_SKIP_DRAW /* dev ablation: set-up and store only */
+#elif !defined(RASTER_STATIC_SPLIT)
   /* Large primitives (a field line next to the robot is hundreds of pixels thick): rows over the whole block.  Everything
      else is a queue of work units -- a small primitive (one warp, its rows / pixels on the lanes) or 32 of the conic's
      ~2 x 479 one-pixel-high poly-line segments (one lane each) -- that the warps draw from until it is empty: with a
@@ -158,6 +160,9 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
       const raster::Prim p = prims[w];
       if (raster::prim_is_big(p)) raster::draw_prim(plane, p, B);
     }
+    RPROF(const long long t3 = clock64(); t3s = t3; if (tid == 0) { int nb = 0; for (int w = 0; w < nprims; w++) nb += raster::prim_is_big(prims[w]) ? 1 : 0;
+      atomicAdd(&g_raster_prof[6], (unsigned long long)(t3 - t2)); atomicAdd(&g_raster_prof[13], (unsigned long long)nprims);
+      atomicAdd(&g_raster_prof[14], (unsigned long long)nb); atomicAdd(&g_raster_prof[15], (unsigned long long)nseg); })
     const int nunits = nprims + (nseg + 31) / 32;
     for (;;) {
       int u = 0;
@@ -169,7 +174,9 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
         if (!raster::prim_is_big(p)) raster::draw_prim(plane, p, L);
       } else {
         const int sgm = (u - nprims) * 32 + lane;
+#ifndef RASTER_SKIP_CONIC
         if (sgm < nseg) raster::draw_conic_segment(plane, *conic, sgm, one);
+#endif
       }
     }
   }
@@ -190,7 +197,9 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
 #endif
   __syncthreads();
   RPROF(const long long t5 = clock64();)
-#ifdef RASTER_BULK_STORE
+#ifdef RASTER_SKIP_STORE /* dev ablation: one word per thread keeps the drawing alive */
+  images[(size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS + tid] = plane[tid * 37];
+#elif defined(RASTER_BULK_STORE)
   if (tid == 0) bulk_store_plane(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS, plane);
 #else
   {
@@ -201,9 +210,11 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   }
 #endif
   RPROF(if (tid == 0) { const long long t6 = clock64(); atomicAdd(&g_raster_prof[0], 1ull); atomicAdd(&g_raster_prof[1], (unsigned long long)(t1 - t0));
-    atomicAdd(&g_raster_prof[2], (unsigned long long)(t2 - t1)); atomicAdd(&g_raster_prof[4], 8 * pmax[0]); atomicAdd(&g_raster_prof[6], 8 * pmax[1]);
+    atomicAdd(&g_raster_prof[2], (unsigned long long)(t2 - t1)); atomicAdd(&g_raster_prof[3], (unsigned long long)(t5 - t2)); atomicAdd(&g_raster_prof[4 + (misc[1] ? 1 : 0)], 1ull);
     atomicAdd(&g_raster_prof[7], (unsigned long long)(t6 - t5)); atomicAdd(&g_raster_prof[8], (unsigned long long)(t6 - t0));
-    atomicAdd(&g_raster_prof[9 + (plane_id & 3)], (unsigned long long)(t6 - t0)); })
+    atomicAdd(&g_raster_prof[9 + (plane_id & 3)], (unsigned long long)(t6 - t0));
+    if (ch == 3) { atomicAdd(&g_raster_prof2[misc[1] ? 0 : 4], 1ull); atomicAdd(&g_raster_prof2[misc[1] ? 1 : 5], (unsigned long long)(t6 - t0));
+      atomicAdd(&g_raster_prof2[misc[1] ? 2 : 6], (unsigned long long)(t3s - t2)); atomicAdd(&g_raster_prof2[misc[1] ? 3 : 7], (unsigned long long)(t5 - t3s)); } })
 }
 
 }  // namespace rcimg

@@ -8,12 +8,14 @@ import torch
 import dynenv_b200
 
 n, P = 1024, 10
-sim = dynenv_b200.BatchedRoboCup(n, 5, dynenv_b200.ObservationType.IMAGE, 1, 2.0, allowHeadTurn=True, auto_reset=True, seed=42)
+sim = dynenv_b200.BatchedRoboCup(n, 5, dynenv_b200.ObservationType.IMAGE, 1, 2.0, allowHeadTurn=True, canFall=True, auto_reset=True, seed=42)
 sim.reset()
 g = torch.Generator(device="cuda").manual_seed(1234)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 25):
-    a = (torch.rand((n, P, 4), generator=g, device="cuda") * torch.tensor([5, 3, 3, 7], device="cuda")).floor()
-    sim.step(a)
+    a = torch.rand((n, P, 4), generator=g, device="cuda")  # the bench's image workload: head turn uniform in [-3, 3)
+    a[..., :3] = (a[..., :3] * torch.tensor([5, 3, 3], device="cuda")).floor()
+    a[..., 3] = a[..., 3] * 6.0 - 3.0
+    sim.step(a.contiguous())
 out = torch.empty((256, 5, P, 8, 480, 20), dtype=torch.int32, device="cuda")
 sim.render_images(0, 256, out)
 best = 1e9
