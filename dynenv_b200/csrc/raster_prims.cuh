@@ -27,9 +27,17 @@ constexpr int IMG_W = 640, IMG_H = 480, WORDS_PER_ROW = IMG_W / 32, PLANE_WORDS 
 constexpr int XY_SHIFT = 16;
 constexpr int64_t XY_ONE = (int64_t)1 << XY_SHIFT;
 
-struct P2 { /* cv::Point2l */
-  int64_t x, y;
+/* cv::Point2l.  OpenCV computes in 64-bit integers so that end points anywhere in int range work; the routines below are
+   templates over the integer type and run in 32 bits whenever every coordinate they can produce fits (a primitive whose 16.16
+   fixed-point coordinates stay below 2^29, i.e. within +-8191 px: all but the far-off-image ones) -- the same operations
+   on the same values, half the integer instructions on a GPU without 64-bit integer ALUs. */
+template <class I>
+struct P2T {
+  I x, y;
 };
+typedef P2T<int64_t> P2;
+typedef P2T<int32_t> P2s;
+constexpr int SMALL_PX = 8191; /* |coordinate| <= SMALL_PX px: 16.16 fixed point fits 32 bits with headroom for sums of two */
 
 RP_FN void or_word(uint32_t* p, uint32_t m) {
 #ifdef __CUDA_ARCH__
@@ -59,7 +67,8 @@ RP_FN void hline(uint32_t* plane, int y, int x1, int x2) {
   for (int w = w1 + 1; w < w2; w++) or_word(row + w, 0xffffffffu);
   or_word(row + w2, m2);
 }
-RP_FN void put_point(uint32_t* plane, int64_t x, int64_t y) {
+template <class I>
+RP_FN void put_point(uint32_t* plane, I x, I y) {
   if (x >= 0 && x < IMG_W && y >= 0 && y < IMG_H) or_word(plane + (int)y * WORDS_PER_ROW + ((int)x >> 5), 1u << ((int)x & 31));
 }
 
@@ -79,36 +88,37 @@ RP_FN int64_t div_trunc(int64_t a, int64_t b) {
 }
 
 /* cv::clipLine(Size2l, Point2l&, Point2l&) */
-RP_FN bool clip_line(int64_t width, int64_t height, P2& pt1, P2& pt2) {
-  const int64_t right = width - 1, bottom = height - 1;
+template <class I>
+RP_FN bool clip_line(I width, I height, P2T<I>& pt1, P2T<I>& pt2) {
+  const I right = width - 1, bottom = height - 1;
   if (width <= 0 || height <= 0) return false;
-  int64_t &x1 = pt1.x, &y1 = pt1.y, &x2 = pt2.x, &y2 = pt2.y;
+  I &x1 = pt1.x, &y1 = pt1.y, &x2 = pt2.x, &y2 = pt2.y;
   int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
   int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
   if ((c1 & c2) == 0 && (c1 | c2) != 0) {
-    int64_t a;
+    I a;
     if (c1 & 12) {
       a = c1 < 8 ? 0 : bottom;
-      x1 += (int64_t)((double)(a - y1) * (x2 - x1) / (y2 - y1));
+      x1 += (I)((double)(a - y1) * (x2 - x1) / (y2 - y1));
       y1 = a;
       c1 = (x1 < 0) + (x1 > right) * 2;
     }
     if (c2 & 12) {
       a = c2 < 8 ? 0 : bottom;
-      x2 += (int64_t)((double)(a - y2) * (x2 - x1) / (y2 - y1));
+      x2 += (I)((double)(a - y2) * (x2 - x1) / (y2 - y1));
       y2 = a;
       c2 = (x2 < 0) + (x2 > right) * 2;
     }
     if ((c1 & c2) == 0 && (c1 | c2) != 0) {
       if (c1) {
         a = c1 == 1 ? 0 : right;
-        y1 += (int64_t)((double)(a - x1) * (y2 - y1) / (x2 - x1));
+        y1 += (I)((double)(a - x1) * (y2 - y1) / (x2 - x1));
         x1 = a;
         c1 = 0;
       }
       if (c2) {
         a = c2 == 1 ? 0 : right;
-        y2 += (int64_t)((double)(a - x2) * (y2 - y1) / (x2 - x1));
+        y2 += (I)((double)(a - x2) * (y2 - y1) / (x2 - x1));
         x2 = a;
         c2 = 0;
       }
@@ -130,7 +140,7 @@ struct Lanes {
 RP_BIG void line_thin(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
   if ((uint64_t)pt1.x >= (uint64_t)IMG_W || (uint64_t)pt2.x >= (uint64_t)IMG_W || (uint64_t)pt1.y >= (uint64_t)IMG_H ||
       (uint64_t)pt2.y >= (uint64_t)IMG_H) {
-    if (!clip_line(IMG_W, IMG_H, pt1, pt2)) return;
+    if (!clip_line<int64_t>(IMG_W, IMG_H, pt1, pt2)) return;
   }
   int delta_x = 1, delta_y = 1;
   int dx = (int)(pt2.x - pt1.x), dy = (int)(pt2.y - pt1.y);
@@ -151,61 +161,69 @@ RP_BIG void line_thin(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
 }
 
 /* Line2(): line between fixed-point (XY_SHIFT) end points */
-RP_BIG void line2(uint32_t* plane, P2 pt1, P2 pt2, Lanes L) {
-  if (!clip_line((int64_t)IMG_W << XY_SHIFT, (int64_t)IMG_H << XY_SHIFT, pt1, pt2)) return;
-  int64_t dx = pt2.x - pt1.x, dy = pt2.y - pt1.y;
-  int64_t j = dx < 0 ? -1 : 0;
-  const int64_t ax = (dx ^ j) - j;
-  int64_t i = dy < 0 ? -1 : 0;
-  const int64_t ay = (dy ^ i) - i;
-  int64_t x_step, y_step;
+template <class I>
+RP_BIG void line2(uint32_t* plane, P2T<I> pt1, P2T<I> pt2, Lanes L) {
+  const I ONE = (I)XY_ONE;
+  if (!clip_line<I>((I)IMG_W << XY_SHIFT, (I)IMG_H << XY_SHIFT, pt1, pt2)) return;
+  I dx = pt2.x - pt1.x, dy = pt2.y - pt1.y;
+  I j = dx < 0 ? -1 : 0;
+  const I ax = (dx ^ j) - j;
+  I i = dy < 0 ? -1 : 0;
+  const I ay = (dy ^ i) - i;
+  I x_step, y_step;
   int ecount;
   if (ax > ay) {
     dy = (dy ^ j) - j;
     pt1.x ^= pt2.x & j; pt2.x ^= pt1.x & j; pt1.x ^= pt2.x & j;
     pt1.y ^= pt2.y & j; pt2.y ^= pt1.y & j; pt1.y ^= pt2.y & j;
-    x_step = XY_ONE;
-    y_step = div_trunc(dy << XY_SHIFT, ax | 1);
+    x_step = ONE;
+    y_step = (I)div_trunc((int64_t)dy << XY_SHIFT, (int64_t)(ax | 1)); /* |dy| <= ax: the quotient fits 17 bits */
     ecount = (int)((pt2.x - pt1.x) >> XY_SHIFT);
   } else {
     dx = (dx ^ i) - i;
     pt1.x ^= pt2.x & i; pt2.x ^= pt1.x & i; pt1.x ^= pt2.x & i;
     pt1.y ^= pt2.y & i; pt2.y ^= pt1.y & i; pt1.y ^= pt2.y & i;
-    x_step = div_trunc(dx << XY_SHIFT, ay | 1);
-    y_step = XY_ONE;
+    x_step = (I)div_trunc((int64_t)dx << XY_SHIFT, (int64_t)(ay | 1));
+    y_step = ONE;
     ecount = (int)((pt2.y - pt1.y) >> XY_SHIFT);
   }
-  pt1.x += (XY_ONE >> 1);
-  pt1.y += (XY_ONE >> 1);
-  if (L.lane == 0) put_point(plane, (pt2.x + (XY_ONE >> 1)) >> XY_SHIFT, (pt2.y + (XY_ONE >> 1)) >> XY_SHIFT);
+  pt1.x += (ONE >> 1);
+  pt1.y += (ONE >> 1);
+  if (L.lane == 0) put_point<I>(plane, (pt2.x + (ONE >> 1)) >> XY_SHIFT, (pt2.y + (ONE >> 1)) >> XY_SHIFT);
   if (ax > ay) {
-    const int64_t xs = pt1.x >> XY_SHIFT;
-    for (int k = L.lane; k <= ecount; k += L.n) put_point(plane, xs + k, (pt1.y + k * y_step) >> XY_SHIFT);
+    const I xs = pt1.x >> XY_SHIFT;
+    for (int k = L.lane; k <= ecount; k += L.n) put_point<I>(plane, xs + k, (pt1.y + k * y_step) >> XY_SHIFT);
   } else {
-    const int64_t ys = pt1.y >> XY_SHIFT;
-    for (int k = L.lane; k <= ecount; k += L.n) put_point(plane, (pt1.x + k * x_step) >> XY_SHIFT, ys + k);
+    const I ys = pt1.y >> XY_SHIFT;
+    for (int k = L.lane; k <= ecount; k += L.n) put_point<I>(plane, (pt1.x + k * x_step) >> XY_SHIFT, ys + k);
   }
 }
 
 /* vertex k (k in 0..3) of a quadrilateral held in registers (no indexed array: local memory is what the raster kernel
    cannot afford, its blocks leave the SM almost no L1) */
-struct Quad {
-  P2 a, b, c, d;
+template <class I>
+struct QuadT {
+  P2T<I> a, b, c, d;
 };
-RP_FN P2 qget(const Quad& q, int k) { return k == 0 ? q.a : (k == 1 ? q.b : (k == 2 ? q.c : q.d)); }
+typedef QuadT<int64_t> Quad;
+template <class I>
+RP_FN P2T<I> qget(const QuadT<I>& q, int k) { return k == 0 ? q.a : (k == 1 ? q.b : (k == 2 ? q.c : q.d)); }
 
 /* one edge cursor of FillConvexPoly: up to three re-seeding events (row, x, dx) */
+template <class I>
 struct EdgeEvents {
   int n, y0, y1, y2;
-  int64_t x0, x1, x2, dx0, dx1, dx2;
+  I x0, x1, x2, dx0, dx1, dx2;
 };
-RP_FN void ev_push(EdgeEvents& e, int y, int64_t x, int64_t dx) {
+template <class I>
+RP_FN void ev_push(EdgeEvents<I>& e, int y, I x, I dx) {
   if (e.n == 0) { e.y0 = y; e.x0 = x; e.dx0 = dx; }
   else if (e.n == 1) { e.y1 = y; e.x1 = x; e.dx1 = dx; }
   else { e.y2 = y; e.x2 = x; e.dx2 = dx; }
   e.n++;
 }
-RP_FN int64_t ev_x_at(const EdgeEvents& e, int yy) { /* the cursor's x in row yy: last event at or above yy */
+template <class I>
+RP_FN I ev_x_at(const EdgeEvents<I>& e, int yy) { /* the cursor's x in row yy: last event at or above yy */
   if (e.n > 2 && e.y2 <= yy) return e.x2 + e.dx2 * (yy - e.y2);
   if (e.n > 1 && e.y1 <= yy) return e.x1 + e.dx1 * (yy - e.y1);
   return e.x0 + e.dx0 * (yy - e.y0);
@@ -215,10 +233,11 @@ RP_FN int64_t ev_x_at(const EdgeEvents& e, int yy) { /* the cursor's x in row yy
    rows with two edge cursors (x += dx per row) that it re-seeds at vertex rows; here the re-seeding events are found
    first (row, x, dx per cursor: the same control flow, jumping from vertex row to vertex row), then every row's span
    follows in closed form and the rows are spread over the lanes. */
-RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
+template <class I>
+RP_BIG void fill_convex4(uint32_t* plane, const QuadT<I> v, int shift, Lanes L) {
   const int npts = 4;
   int e_idx0, e_idx1, e_ye0, e_ye1; /* the two cursors: current vertex, end row */
-  EdgeEvents ev0, ev1;
+  EdgeEvents<I> ev0, ev1;
   ev0.n = ev1.n = 0;
   ev0.y0 = ev0.y1 = ev0.y2 = ev1.y0 = ev1.y1 = ev1.y2 = 0;
   ev0.x0 = ev0.x1 = ev0.x2 = ev0.dx0 = ev0.dx1 = ev0.dx2 = 0;
@@ -226,9 +245,9 @@ RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
   const int delta = 1 << shift >> 1;
   int i, y, imin = 0;
   int edges = npts;
-  int64_t xmin, xmax, ymin, ymax;
+  I xmin, xmax, ymin, ymax;
   const int delta1 = (int)(XY_ONE >> 1);
-  P2 p0 = v.d;
+  P2T<I> p0 = v.d;
   p0.x <<= XY_SHIFT - shift;
   p0.y <<= XY_SHIFT - shift;
   xmin = xmax = v.a.x;
@@ -237,7 +256,7 @@ RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
 #pragma unroll
 #endif
   for (i = 0; i < npts; i++) {
-    P2 p = qget(v, i);
+    P2T<I> p = qget(v, i);
     if (p.y < ymin) { ymin = p.y; imin = i; }
     ymax = ymax > p.y ? ymax : p.y;
     xmax = xmax > p.x ? xmax : p.x;
@@ -248,7 +267,7 @@ RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
       P2 a, b;
       a.x = p0.x >> XY_SHIFT; a.y = p0.y >> XY_SHIFT; b.x = p.x >> XY_SHIFT; b.y = p.y >> XY_SHIFT;
       line_thin(plane, a, b, L);
-    } else line2(plane, p0, p, L);
+    } else line2<I>(plane, p0, p, L);
     p0 = p;
   }
   xmin = (xmin + delta) >> shift;
@@ -270,14 +289,14 @@ RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
         if (idx >= npts) idx -= npts;
         int ty = 0;
         for (; edges-- > 0;) {
-          const P2 pv = qget(v, idx);
+          const P2T<I> pv = qget(v, idx);
           ty = (int)((pv.y + delta) >> shift);
           if (ty > y) {
-            int64_t xs = qget(v, idx0).x, xe = pv.x;
+            I xs = qget(v, idx0).x, xe = pv.x;
             if (shift != XY_SHIFT) { xs <<= XY_SHIFT - shift; xe <<= XY_SHIFT - shift; }
-            const int64_t dxe = div_trunc((xe - xs) * 2 + (ty - y), 2 * (int64_t)(ty - y));
-            if (i) { e_ye1 = ty; e_idx1 = idx; ev_push(ev1, y, xs, dxe); }
-            else { e_ye0 = ty; e_idx0 = idx; ev_push(ev0, y, xs, dxe); }
+            const I dxe = (I)div_trunc((int64_t)(xe - xs) * 2 + (ty - y), 2 * (int64_t)(ty - y));
+            if (i) { e_ye1 = ty; e_idx1 = idx; ev_push<I>(ev1, y, xs, dxe); }
+            else { e_ye0 = ty; e_idx0 = idx; ev_push<I>(ev0, y, xs, dxe); }
             break;
           }
           idx0 = idx;
@@ -294,8 +313,8 @@ RP_BIG void fill_convex4(uint32_t* plane, const Quad v, int shift, Lanes L) {
   if (ev0.n == 0 || ev1.n == 0) return;
   const int ystart = (int)ymin > 0 ? (int)ymin : 0;
   for (int yy = ystart + L.lane; yy <= yend; yy += L.n) {
-    const int64_t xa = ev_x_at(ev0, yy), xb = ev_x_at(ev1, yy);
-    const int64_t xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
+    const I xa = ev_x_at<I>(ev0, yy), xb = ev_x_at<I>(ev1, yy);
+    const I xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
     int xx1 = (int)((xl + delta1) >> XY_SHIFT);
     int xx2 = (int)((xr + delta1) >> XY_SHIFT);
     if (xx2 >= 0 && xx1 < IMG_W) {
@@ -357,7 +376,7 @@ RP_BIG void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, 
   { /* OpenCV 4.13 first clips the centre line to the image grown by `thickness` on every side */
     const int64_t m = thickness;
     p0.x += m; p0.y += m; p1.x += m; p1.y += m;
-    if (!clip_line(IMG_W + 2 * m, IMG_H + 2 * m, p0, p1)) return;
+    if (!clip_line<int64_t>(IMG_W + 2 * m, IMG_H + 2 * m, p0, p1)) return;
     p0.x -= m; p0.y -= m; p1.x -= m; p1.y -= m;
   }
   p0.x <<= XY_SHIFT; p0.y <<= XY_SHIFT; p1.x <<= XY_SHIFT; p1.y <<= XY_SHIFT;
@@ -367,6 +386,7 @@ RP_BIG void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, 
   double dx = (p0.x - p1.x) * INV_XY_ONE, dy = (p1.y - p0.y) * INV_XY_ONE;
   double r = dx * dx + dy * dy;
   const int oddThickness = thickness & 1;
+  const bool small = thickness <= 2048; /* the clipped end points lie within the image grown by the thickness: every corner within +-3712 px */
   thickness <<= XY_SHIFT - 1;
   if ((r < 0 ? -r : r) > 2.220446049250313e-16) {
 #ifdef __CUDA_ARCH__
@@ -380,7 +400,12 @@ RP_BIG void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, 
     pt.b.x = p0.x - dp.x; pt.b.y = p0.y - dp.y;
     pt.c.x = p1.x - dp.x; pt.c.y = p1.y - dp.y;
     pt.d.x = p1.x + dp.x; pt.d.y = p1.y + dp.y;
-    fill_convex4(plane, pt, XY_SHIFT, L);
+    if (small) {
+      QuadT<int32_t> q;
+      q.a.x = (int32_t)pt.a.x; q.a.y = (int32_t)pt.a.y; q.b.x = (int32_t)pt.b.x; q.b.y = (int32_t)pt.b.y;
+      q.c.x = (int32_t)pt.c.x; q.c.y = (int32_t)pt.c.y; q.d.x = (int32_t)pt.d.x; q.d.y = (int32_t)pt.d.y;
+      fill_convex4<int32_t>(plane, q, XY_SHIFT, L);
+    } else fill_convex4<int64_t>(plane, pt, XY_SHIFT, L);
   }
   for (int i = 0; i < 2; i++) {
     if (flags & (i + 1)) {
@@ -399,9 +424,17 @@ RP_FN void cv_line(uint32_t* plane, int x0, int y0, int x1, int y1, int thicknes
 }
 /* cv2.rectangle(img, p0, p1, 1, -1) */
 RP_FN void cv_rectangle_filled(uint32_t* plane, int x0, int y0, int x1, int y1, Lanes L) {
+  const bool small = x0 >= -SMALL_PX && x0 <= SMALL_PX && x1 >= -SMALL_PX && x1 <= SMALL_PX && y0 >= -SMALL_PX && y0 <= SMALL_PX &&
+                     y1 >= -SMALL_PX && y1 <= SMALL_PX;
+  if (small) {
+    QuadT<int32_t> q;
+    q.a.x = x0; q.a.y = y0; q.b.x = x1; q.b.y = y0; q.c.x = x1; q.c.y = y1; q.d.x = x0; q.d.y = y1;
+    fill_convex4<int32_t>(plane, q, 0, L);
+    return;
+  }
   Quad pt;
   pt.a.x = x0; pt.a.y = y0; pt.b.x = x1; pt.b.y = y0; pt.c.x = x1; pt.c.y = y1; pt.d.x = x0; pt.d.y = y1;
-  fill_convex4(plane, pt, 0, L);
+  fill_convex4<int64_t>(plane, pt, 0, L);
 }
 /* segment i (1 <= i < count) of cv2.polylines(img, [pts], False, 1, thickness): PolyLine() caps the first segment at
    both ends and every later one at its far end */

@@ -163,17 +163,18 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
     RPROF(const long long t3 = clock64(); t3s = t3; if (tid == 0) { int nb = 0; for (int w = 0; w < nprims; w++) nb += raster::prim_is_big(prims[w]) ? 1 : 0;
       atomicAdd(&g_raster_prof[6], (unsigned long long)(t3 - t2)); atomicAdd(&g_raster_prof[13], (unsigned long long)nprims);
       atomicAdd(&g_raster_prof[14], (unsigned long long)nb); atomicAdd(&g_raster_prof[15], (unsigned long long)nseg); })
-    const int nunits = nprims + (nseg + 31) / 32;
+    /* the conic's units first: they are the long ones (32 thick poly-line segments, one per lane), the small primitives fill the tail */
+    const int ncu = (nseg + 31) / 32, nunits = ncu + nprims;
     for (;;) {
       int u = 0;
       if (lane == 0) u = atomicAdd(&misc[2], 1);
       u = __shfl_sync(FULLMASK, u, 0);
       if (u >= nunits) break;
-      if (u < nprims) {
-        const raster::Prim p = prims[u];
+      if (u >= ncu) {
+        const raster::Prim p = prims[u - ncu];
         if (!raster::prim_is_big(p)) raster::draw_prim(plane, p, L);
       } else {
-        const int sgm = (u - nprims) * 32 + lane;
+        const int sgm = u * 32 + lane;
 #ifndef RASTER_SKIP_CONIC
         if (sgm < nseg) raster::draw_conic_segment(plane, *conic, sgm, one);
 #endif

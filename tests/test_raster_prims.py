@@ -131,3 +131,29 @@ def test_compose_matches_raster_oracle(lib):
                 assert np.array_equal(planes, ref), (os.path.basename(path), t, a)
                 n += 1
     assert n >= 40
+
+
+def test_both_integer_widths_match_cv2(lib):
+    """the fixed-point routines run in 32-bit integers when every coordinate fits (thickness <= 2048, rectangle corners
+    within +-8191 px) and in OpenCV's own 64 bits otherwise: primitives on both sides of the switch, and exactly at it"""
+    rng = np.random.default_rng(17)
+    for it in range(160):
+        x0, y0 = _coord(rng, True)
+        x1, y1 = _coord(rng, True)
+        t = int(rng.choice([2047, 2048, 2049, 2050, 3000, 700, 1500, 5000, 32767])) if it % 2 else int(rng.integers(100, 2600))
+        ref = np.zeros((480, 640))
+        cv2.line(ref, (x0, y0), (x1, y1), 1, t)
+        p = np.zeros((480, 20), np.uint32)
+        lib.rp_line(p.ctypes.data, x0, y0, x1, y1, t)
+        assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("line", x0, y0, x1, y1, t)
+    edge = [8190, 8191, 8192, 8193, -8190, -8191, -8192, -8193, 20000, -20000, 1000000, -1000000]
+    for it in range(300):
+        x0, y0 = (int(rng.choice(edge)) if rng.random() < 0.5 else int(rng.integers(-700, 1300))), int(rng.integers(-600, 1100))
+        x1, y1 = int(rng.integers(-700, 1300)), (int(rng.choice(edge)) if rng.random() < 0.5 else int(rng.integers(-600, 1100)))
+        if rng.random() < 0.5:
+            x0, y0, x1, y1 = x1, y1, x0, y0
+        ref = np.zeros((480, 640))
+        cv2.rectangle(ref, (x0, y0), (x1, y1), 1, -1)
+        p = np.zeros((480, 20), np.uint32)
+        lib.rp_rect(p.ctypes.data, x0, y0, x1, y1)
+        assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("rectangle", x0, y0, x1, y1)
