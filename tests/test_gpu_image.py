@@ -104,7 +104,7 @@ def test_image_pipeline_against_oracle(nPlayers, noise, mag, rinit):
     from dynenv_b200 import layout as L
     from helpers import rel_err
     from oracle import raster_oracle
-    from oracle.oracle import RcOracle, f32_record_to_words, raw_to_record
+    from oracle.oracle import RcOracle, f32_record_to_words, raw_to_record, record_to_raw
     n, seed, P = 6, 321, 2 * nPlayers
     flags = L.DYNENV_FLAG_CAN_FALL | L.DYNENV_FLAG_USE_OBS_REWARDS | (L.DYNENV_FLAG_RANDOM_INIT if rinit else 0)
     sim = dynenv_b200.BatchedRoboCup(n, nPlayers, dynenv_b200.ObservationType.IMAGE, noise, mag, randomInit=rinit, canFall=True, seed=seed)
@@ -140,6 +140,12 @@ def test_image_pipeline_against_oracle(nPlayers, noise, mag, rinit):
                     assert d.max() < 1e-4, (step, e, t, ag, int(d.argmax()) + 7, float(got_rec[7 + d.argmax()]), float(ref_rec[7 + d.argmax()]))
                     assert rel_err(got_rec[L.RC_R_LINE:], ref_rec[L.RC_R_LINE:]) < 5e-3, (step, e, t, ag)  # clipped lines: see helpers.LINE_TOL
                     if t == 0 or step:
+                        # the pipeline = detections (float32: the tolerances above) followed by the reference's drawing calls:
+                        # the image must be EXACTLY what cv2 draws from the record the kernel itself emitted ...
+                        own = raster_oracle.pack(raster_oracle.render(record_to_raw(got_rec)))
+                        assert np.array_equal(imgs[e, t, ag], own), (step, e, t, ag)
+                        # ... and what cv2 draws from the oracle's float64 detections, up to a primitive whose projected
+                        # coordinate crosses an int() boundary between the two (counted, bounded)
                         ref = raster_oracle.pack(raster_oracle.render(rv))
                         diff = int(np.unpackbits((imgs[e, t, ag] ^ ref).view(np.uint8)).sum())
                         total += 1

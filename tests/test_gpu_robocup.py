@@ -145,3 +145,68 @@ def test_noise_statistics_match_in_distribution():
         pg, pc = g.mean(), c.mean()
         sigma = np.sqrt(pc * (1 - pc) / n_cpu + pg * (1 - pg) / n_gpu) + 1e-9
         assert abs(pg - pc) < 4 * sigma + 1e-3, (pg, pc, sigma)
+
+
+def test_noise_statistics_every_list_and_false_positives():
+    """The same comparison for everything else the noise model touches (cutils.py:417-468, RoboCupEnvironment.py:1254-1316):
+    how many rows every list has per observer -- false negatives, misclassified balls / crosses changing lists, random
+    false positives per class, false balls next to robots -- as a chi-square test of homogeneity of the count histograms;
+    position / size noise of robots, posts, crosses and line crosses and the angle noise of line crosses as two-sample KS
+    tests.  GPU: Philox streams over 8192 environments; oracle: an independent sequential stream for each of 1500.  The
+    family of tests is held to 0.01 overall (Bonferroni: every p-value above 0.01 / number of tests)."""
+    import torch
+    from scipy import stats
+    import dynenv_b200
+    from dynenv_b200 import layout as L
+    from oracle.oracle import RcOracle
+    n_gpu, n_cpu, P = 8192, 1500, 4
+    sim = dynenv_b200.BatchedRoboCup(n_gpu, 2, 1, 1, 3.0, canFall=True, seed=6)
+    out = sim.reset()
+    torch.cuda.synchronize()
+    names = ["ball", "robot", "post", "cross", "fcross", "line"]
+    G = {k: getattr(out, k).cpu().numpy() for k in names}          # [n, T, P, cap, F]
+    G["counts"] = out.counts.cpu().numpy()                          # [n, T, P, 6]
+    rng = np.random.default_rng(78)
+    flags = L.DYNENV_FLAG_CAN_FALL | L.DYNENV_FLAG_USE_OBS_REWARDS
+    C = {k: [] for k in names + ["counts"]}
+    for i in range(n_cpu):
+        orc = RcOracle(2, 1, 1, 3.0, False, flags)
+        orc.set_tape(rng.random(6000))
+        orc.reset()
+        o = orc.reset_obs()
+        assert not orc.tape_underflow()
+        for k in names:
+            C[k].append(np.array(o[k][:, :P]))
+        C["counts"].append(np.array(o["counts"][:, :P]))
+    C = {k: np.array(v) for k, v in C.items()}
+    pvals = {}
+    # One sample per environment and test: the scene itself is drawn per environment (jittered kick-off spots, a
+    # permutation of who takes which), so the five ticks and the four observers of ONE environment are dependent samples
+    # and must not be pooled.  List lengths per (observer, type) at tick 0:
+    for a in range(P):
+        for k in range(6):
+            gc, cc = G["counts"][:, 0, a, k], C["counts"][:, 0, a, k]
+            hi = int(max(gc.max(), cc.max())) + 1
+            hg, hc = np.bincount(gc, minlength=hi).astype(float), np.bincount(cc, minlength=hi).astype(float)
+            # merge sparse bins from the top so that every expected cell count is >= 5
+            while len(hg) > 1 and (hg[-1] + hc[-1]) * min(hg.sum(), hc.sum()) / (hg.sum() + hc.sum()) < 5:
+                hg[-2] += hg[-1]; hc[-2] += hc[-1]; hg, hc = hg[:-1], hc[:-1]
+            keep = (hg + hc) > 0
+            hg, hc = hg[keep], hc[keep]
+            if len(hg) > 1:
+                pvals[("count", a, names[k])] = stats.chi2_contingency(np.stack([hg, hc]))[1]
+            else:
+                assert np.array_equal(np.unique(gc), np.unique(cc)), (a, k)
+    # noisy values of the first row of a list: one observer of either team, tick 0
+    for a in (0, 2):
+        for name, cols in (("robot", (0, 1, 2)), ("post", (0, 3)), ("cross", (0, 3)), ("fcross", (0, 3, 6, 7))):
+            k = names.index(name)
+            gm, cm = G["counts"][:, 0, a, k] > 0, C["counts"][:, 0, a, k] > 0
+            for col in cols:
+                gv, cv = G[name][:, 0, a, 0, col][gm], C[name][:, 0, a, 0, col][cm]
+                assert len(gv) > 1000 and len(cv) > 300, (name, col, len(gv), len(cv))
+                pvals[("value", a, name, col)] = stats.ks_2samp(gv, cv).pvalue
+    alpha = 0.01 / len(pvals)
+    worst = sorted(pvals.items(), key=lambda kv: kv[1])[:5]
+    print("noise statistics: %d tests, Bonferroni threshold %.1e, smallest p-values %s" % (len(pvals), alpha, worst))
+    assert all(p > alpha for p in pvals.values()), worst
