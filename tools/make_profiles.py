@@ -23,6 +23,7 @@ METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", 
            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
            "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
@@ -30,11 +31,14 @@ METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", 
            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
            "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
-KERNELS = {"rc_phys": ("rc_phys_kernel", "65536 RoboCup 5v5 environments, 10 substeps each; step 100 of the episode", 65536 * 10),
+KERNELS = {"rc_phys": ("rc_phys_kernel", "65536 RoboCup 5v5 environments, 10 substeps each; step 120 of the episode", 65536 * 10),
+           "rc_phys_slow": ("rc_phys_slow", "the environments rc_phys_kernel handed over in one block of 10 substeps (6-9 % of 65536), 16 per thread block; step 120", 65536 * 10 * 0.08),
+           "rc_obsl": ("rc_obsp_kernelILb1", "65536 RoboCup 5v5 environments, the field lines of one observation tick (10 observers each); step 120, sparse stream", 65536 * 10),
+           "rc_obsp": ("rc_obsp_kernelILb0", "65536 RoboCup 5v5 environments, the point objects of one observation tick (10 observers each); step 120, sparse stream", 65536 * 10),
            "rc_obs": ("rc_obs_kernel", "65536 RoboCup 5v5 environments, one observation tick (10 observers each); step 100", 65536 * 10),
            "drv_phys": ("drv_phys_kernel", "65536 Driving environments (10 cars), 10 substeps each; step 100 of the episode", 65536 * 10),
            "drv_obs": ("drv_obs_kernel", "65536 Driving environments, observation of 10 cars + rewards / info; step 100", 65536 * 10),
-           "rc_raster": ("rc_raster_kernel", "1024 RoboCup environments x 5 ticks x 10 robots x 8 planes = 409600 blocks (one plane each)", 409600)}
+           "rc_raster": ("rc_raster_kernel", "256 RoboCup environments x 5 ticks x 10 robots x 8 planes = 102400 blocks (one plane each), the bench's IMAGE workload at step 23", 102400)}
 traffic = {}
 BYTE_UNITS = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 for short, (kern, what, units) in KERNELS.items():
@@ -51,7 +55,7 @@ for short, (kern, what, units) in KERNELS.items():
             lines.append("  %-92s %-16s %s" % (m, u[i], v[i]))
             if m.startswith("dram__bytes"):
                 dram += float(v[i]) * BYTE_UNITS.get(u[i], 1)
-    traffic[kern] = {"dram_bytes_per_launch": dram, "envs": 1024 if short == "rc_raster" else 65536,
+    traffic[kern] = {"dram_bytes_per_launch": dram, "envs": 256 if short == "rc_raster" else 65536,
                      "source": "profiles/%s_ncu_%s.txt" % (tag, short)}
     env = dict(os.environ, KERNEL=kern, NENV=str(units))
     tab = subprocess.run([sys.executable, "tools/prof_by_func.py", rep], capture_output=True, text=True, env=env).stdout

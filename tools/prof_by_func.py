@@ -34,7 +34,7 @@ for r in data:
     k = (int(r[col['Address']], 16) - base) // 16
     while fi + 1 < len(funcs) and funcs[fi + 1][0] <= k:
         fi += 1
-    nm = re.sub(r'^\$_ZN46[^$]*\$', '', funcs[fi][1])
+    nm = re.sub(r'^\$_ZN\d+_GLOBAL[^$]*\$', '', funcs[fi][1])
     a = agg[nm]
     a[0] += int(r[col['# Samples']] or 0)
     a[1] += int(r[col['Instructions Executed']] or 0)
