@@ -1,23 +1,26 @@
 /*
  * IMAGE observation raster kernel: one thread block draws ONE bit-plane (480 x 640 bits, 38 400 bytes) of one raw
- * detection record (include/dynenv_b200.h RC_R_*, raster_compose.cuh) in shared memory and hands it to the TMA engine
- * (cp.async.bulk shared -> global), so that the next block on the SM draws while the previous plane drains to HBM.
+ * detection record (include/dynenv_b200.h RC_R_*, raster_compose.cuh) in shared memory and streams it to HBM with
+ * 128-bit stores while the other resident blocks of the SM draw.
  *
  * Replaces the drawing half of getAgentVision (RoboCupEnvironment.py:1318-1467) -- cv2.line / polylines / rectangle /
  * circle on 2 x 4 planes of 480 x 640 float64 per robot and tick, 19.7 MB in the reference -- by 307 KB of bit-planes.
- * HBM-write bound by construction: every plane is written exactly once.  Drawing: one warp per primitive (or
- * poly-line segment of the centre-circle conic), its rows / pixels in closed form on the 32 lanes (raster_prims.cuh),
- * atomicOr on shared-memory words.  Three blocks of 256 threads per SM.
+ * HBM-write bound by construction: every plane is written exactly once (zero + store alone: 6.0 TB/s, 92 % of the HBM
+ * peak); what keeps the kernel at 15 % of that roof is the drawing.  Drawing: the primitives' rows / pixels in closed
+ * form on the lanes (raster_prims.cuh), atomicOr on shared-memory words; large primitives over the whole block, small
+ * ones and the centre circle's poly-line segments (32 per unit, one per lane) from a work queue that the block's
+ * warps drain.  Three blocks of 256 threads per SM.
  *
- * Measured (1024 environments = 409 600 planes per launch): zero + store alone 2.6 ms (6.0 TB/s, 92 % of the HBM peak);
- * with the primitives 12 ms, with the centre-circle conic 13 ms, everything 24-27 ms (RASTER_SKIP_* ablations below):
- * the drawing, not the store, is what keeps this kernel off its roofline.  Per non-empty plane (clock64 per phase,
- * -DRASTER_PROFILE, tools/gpu_raster_prof.py): 48 k cycles = set-up 5 k + primitives 27 k (slowest warp; mean 17 k) +
- * conic segments 13 k (mean 4 k) + store 8 k; the lines channel costs 33 k of them.  The launch shape does not matter
- * (256 x 3 blocks per SM 41.0 k env-steps/s, 320 x 3 41.0, 384 x 2 40.5, 512 x 2 39.4, 256 x 4 38.3, 192 x 4 37.9,
- * 128 x 5 35.9): the warps are bound by the latency of their own 64-bit integer chains, i.e. by the work per plane.
- * The drawing routines are compiled once (noinline): inlined into their three call sites the kernel is 207 KB of SASS
- * and 50 % slower (instruction fetch).
+ * Measured on the bench's IMAGE workload (1024 environments = 409 600 planes, 66 % of them non-empty; clock64 per
+ * phase with -DRASTER_PROFILE, tools/gpu_raster_prof.py; ablations -DRASTER_SKIP_DRAW / _SKIP_STORE / _SKIP_CONIC /
+ * _NONATOMIC): 16.0 ms, of which set-up + store 3.1 ms, primitives 6 ms, the conic's segments 7 ms; a lines-channel
+ * plane with the centre circle takes 170 k cycles, without it 38 k, the other channels 3-7 k.  The store is not the
+ * problem: a TMA bulk store (cp.async.bulk shared -> global, -DRASTER_BULK_STORE) gives the same time, a block that
+ * draws nothing lives 6 k cycles.  The launch shape does not matter either (256 x 3 blocks per SM 41.0 k env-steps/s,
+ * 320 x 3 41.0, 384 x 2 40.5, 512 x 2 39.4, 256 x 4 38.3, 192 x 4 37.9, 128 x 5 35.9 in round 1): the warps are bound
+ * by the latency of their own integer chains -- the exact OpenCV fixed-point set-up of every primitive -- i.e. by the
+ * work per plane.  The drawing routines are compiled once (noinline): inlined into their call sites the kernel is
+ * 207 KB of SASS and 50 % slower (instruction fetch).
  */
 #pragma once
 #include "dynenv_common.cuh"
@@ -84,7 +87,7 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   int* tmp = reinterpret_cast<int*>(plane);
   double* params = reinterpret_cast<double*>(g_smem + S_PARAMS);
   int* misc = reinterpret_cast<int*>(g_smem + S_MISC);
-  RPROF(__shared__ unsigned long long pmax[2]; const long long t0 = clock64(); if (tid == 0) { pmax[0] = pmax[1] = 0; })
+  RPROF(const long long t0 = clock64();)
   for (int w = tid; w < RC_RAW_WORDS; w += THREADS) sraw[w] = raw[rec * RC_RAW_WORDS + w];
   if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[2] = 0; conic->n = 0; }
   __syncthreads();
