@@ -8,7 +8,7 @@
  *       arr_counts_kernel    counts per (type, time, player), objects per (time, player), their maximum
  *       arr_scan_kernel      exclusive prefix sums of the counts in (time, player) order: 1024 per block ...
  *       arr_scan_sums_kernel ... and over the block sums (one block per type); totals[type] = rows of the flat array
- *       arr_compact_kernel   the rows, each to its place
+ *       arr_compact_kernel   the rows, each to its place (eight lanes per (time, player))
  *   rearrange_outputs (models.py:249-274)  per-type embeddings [n_i][F] -> padded [T][maxCount][players][F] (per player:
  *                     its rows of type 0, then type 1, ...; zeros behind) + padding masks [T][players][maxCount]
  *       arr_pad_kernel
@@ -104,28 +104,43 @@ struct FlatPtrs {
   float* p[DYNENV_ARRANGE_MAXTYPES];
 };
 
-/* one warp per (time, player): its rows of every type to their places in the flat arrays */
+/* eight lanes per (time, player): its rows of every type to their places in the flat arrays.  An observer has ~1.7 rows per
+   type (~10 words): a whole warp per (time, player), as in the first version, kept 30 % of its lanes busy behind 18
+   dependent loads of counts / offsets; here lane k of a group loads type k's count and row offset, the group shares them
+   by shuffle and copies with stride 8. */
+static_assert(DYNENV_ARRANGE_MAXTYPES <= 8, "one lane of a group of eight per type");
 __global__ void __launch_bounds__(256) arr_compact_kernel(const float* __restrict__ rec, DynEnvArrangeLayout L, long long Q, int T, int P,
                                                           const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
                                                           const int32_t* __restrict__ block_sums, int n_blocks, FlatPtrs flat) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; /* i = t * Q + q */
-  const int lane = threadIdx.x & 31;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; /* i = t * Q + q */
+  const int gl = threadIdx.x & 7;
   const long long n = (long long)T * Q;
-  if (i >= n) return;
-  const int t = (int)(i / Q);
-  const long long q = i - (long long)t * Q;
+  const bool valid = i < n;
+  const long long ii = valid ? i : n - 1;
+  const int t = (int)(ii / Q);
+  const long long q = ii - (long long)t * Q;
   const long long e = q / P;
   const int a = (int)(q - e * P);
   const float* r = rec + ((e * T + t) * P + a) * (long long)L.rec_words;
+  int c_l = 0, row_l = 0;
+  if (valid && gl < L.n_types) {
+    c_l = counts[(long long)gl * n + ii];
+    row_l = offsets[(long long)gl * n + ii] + block_sums[(long long)gl * n_blocks + (int)(ii / SCAN_BLOCK)];
+  }
   for (int k = 0; k < L.n_types; k++) {
-    const int c = counts[(long long)k * n + i];
+    const int c = __shfl_sync(0xffffffffu, c_l, k, 8);
+    const int row0 = __shfl_sync(0xffffffffu, row_l, k, 8);
     if (c == 0 || !flat.p[k]) continue;
-    const long long row0 = (long long)offsets[(long long)k * n + i] + block_sums[(long long)k * n_blocks + (int)(i / SCAN_BLOCK)];
     const int f = L.feat[k], words = c * f;
-    float* dst = flat.p[k] + row0 * f;
-    for (int w = lane; w < words; w += 32) {
-      const int row = w / f;
-      dst[w] = r[L.off[k] + row * L.stride[k] + (w - row * f)];
+    float* dst = flat.p[k] + (long long)row0 * f;
+    const float* src = r + L.off[k];
+    if (L.stride[k] == f) { /* rows are contiguous in the record */
+      for (int w = gl; w < words; w += 8) dst[w] = src[w];
+    } else {
+      for (int w = gl; w < words; w += 8) {
+        const int row = w / f;
+        dst[w] = src[row * L.stride[k] + (w - row * f)];
+      }
     }
   }
 }

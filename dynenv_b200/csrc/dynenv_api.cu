@@ -804,7 +804,7 @@ int dynenv_arrange_inputs(int device, const float* rec_dev, int64_t n_envs, int 
                                                                            totals_out);
   arrange::arr_scan_kernel<<<dim3(nb, layout->n_types), 256, 0, st>>>(counts_out, n, offsets_out, block_sums_out, nb);
   arrange::arr_scan_sums_kernel<<<layout->n_types, 1024, 0, st>>>(block_sums_out, nb, totals_out);
-  arrange::arr_compact_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(rec_dev, *layout, Q, n_time, n_players, counts_out, offsets_out,
+  arrange::arr_compact_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(rec_dev, *layout, Q, n_time, n_players, counts_out, offsets_out,
                                                                                 block_sums_out, nb, fp);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "arranger kernels launch");
