@@ -93,5 +93,5 @@ void dynenv_slow_launch(const void* sim_cfg, uint32_t* state, const float* actio
                         const uint32_t* slow_count, int sms, cudaStream_t stream) {
   SimCfg cfg;
   memcpy(&cfg, sim_cfg, sizeof(cfg));
-  rc_phys_slow_kernel<<<sms * (32 / W), 32 * W, dynenv_slow_smem_bytes(), stream>>>(cfg, state, actions, sub_lo, sub_e, slow_bins, slow_count);
+  rc_phys_slow_kernel<<<sms * DYNENV_SLOW_BLOCKS_PER_SM, 32 * W, dynenv_slow_smem_bytes(), stream>>>(cfg, state, actions, sub_lo, sub_e, slow_bins, slow_count);
 }

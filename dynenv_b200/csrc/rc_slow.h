@@ -8,6 +8,9 @@
 #ifndef DYNENV_SLOW_WARPS
 #define DYNENV_SLOW_WARPS 16 /* environments (warps) per block of rc_phys_slow_kernel */
 #endif
+#ifndef DYNENV_SLOW_BLOCKS_PER_SM
+#define DYNENV_SLOW_BLOCKS_PER_SM (32 / DYNENV_SLOW_WARPS) /* resident blocks of the persistent grid per SM */
+#endif
 #define DYNENV_SLOW_CFG_BYTES 76 /* sizeof(SimCfg), asserted on both sides */
 /* hand-over points of one block of ten substeps: bin = 2 (substep - first substep of the block) + phase */
 #define DYNENV_SLOW_BINS 20
