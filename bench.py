@@ -198,9 +198,9 @@ class _ImageSim(object):
             self.ev[1].record()
         return out
 
-    def debug_timing(self, enable=True):
+    def debug_timing(self, enable=True, serialise=False):
         self.timing = bool(enable)
-        self.sim.debug_timing(enable)
+        self.sim.debug_timing(enable, serialise)
 
     def last_kernel_ms(self):
         k = self.sim.last_kernel_ms()
@@ -478,7 +478,12 @@ def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=T
     # ---- pass 3: per kernel class (the events serialise nothing, but the blocking read does: its own pass)
     if per_kernel:
         rewind()
-        sim.debug_timing(True)
+        # RoboCup: the handed-over environments' kernels on the caller's stream for this pass, so that every kernel class has a
+        # duration of its own (comparable with an ncu launch list); the timed passes above run them beside the observations
+        try:
+            sim.debug_timing(True, serialise=True)
+        except TypeError:
+            sim.debug_timing(True)
         kms = {}
         n3 = min(steps, 40)
         for s in range(n3):
@@ -617,8 +622,9 @@ def run_gpu(args):
         roofline["kernel_launches_per_step"] = k_n
         roofline["share_of_step"] = {k: v / max(sum(k_ms.values()), 1e-9) for k, v in k_ms.items()}
         roofline["note"] = ("traffic: not measurable inside the run (ncu captures of the same command: profiles/); kernel_ms_per_step from "
-                            "a separate, untimed pass over the same episode window; phys_slow = what the handed-over environments' "
-                            "side stream adds beyond the observations it runs beside")
+                            "a separate, untimed pass over the same episode window in which the handed-over environments' kernels "
+                            "(phys_slow, and their share of obs) run on the caller's stream one after the other -- in the timed step "
+                            "they run on a side stream beside the others' observations, so the classes add up to more than ms_per_step")
         line = {"metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -164,8 +164,10 @@ class BatchedRoboCup(object):
                                                   self._stream()))
         return out.view(shape)
 
-    def debug_timing(self, enable=True):
-        _lib.check(self._lib.dynenv_debug_timing(self._h, int(bool(enable))))
+    def debug_timing(self, enable=True, serialise=False):
+        """serialise: the handed-over environments' kernels on the caller's stream instead of beside the observations, so that
+        every kernel class has a duration of its own (slower than the production step)"""
+        _lib.check(self._lib.dynenv_debug_timing(self._h, (2 if serialise else 1) if enable else 0))
 
     def last_kernel_ms(self):
         """{'phys': (ms, launches), 'obs': ..., 'finish': ..., 'phys_slow': ...} of the last step (needs debug_timing(True));

@@ -663,20 +663,26 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
                                                      h->slow_mark, h->slow_bins);
     launches++;
     mark(0);
-    /* fork: the handed-over environments finish their substeps (and are observed) on the side stream ... */
-    cudaEventRecord(h->ev_fork[bi], st);
-    cudaStreamWaitEvent(h->side, h->ev_fork[bi], 0);
+    /* fork: the handed-over environments finish their substeps (and are observed) on the side stream ...
+       (dynenv_debug_timing(h, 2): on the caller's stream, one after the other, so that every kernel class can be timed) */
+    const bool serial = h->timing == 2;
+    cudaStream_t side = serial ? st : h->side;
+    if (!serial) {
+      cudaEventRecord(h->ev_fork[bi], st);
+      cudaStreamWaitEvent(h->side, h->ev_fork[bi], 0);
+    }
 #ifdef RC_SLOW_ONE_WARP
-    rc_phys_slow_kernel<<<h->sms * 32, 32, smem, h->side>>>(h->sim, h->state, actions_dev, e, h->slow_list, cnt);
+    rc_phys_slow_kernel<<<h->sms * 32, 32, smem, side>>>(h->sim, h->state, actions_dev, e, h->slow_list, cnt);
 #else
-    dynenv_slow_launch(&h->sim, h->state, actions_dev, b, e, h->slow_bins, cnt, h->sms, h->side);
+    dynenv_slow_launch(&h->sim, h->state, actions_dev, b, e, h->slow_bins, cnt, h->sms, side);
 #endif
+    if (serial) mark(3);
     launches++;
     if (e % 10 == 0) {
       /* ... while the caller's stream observes all the others */
       const int tick = e / 10 - 1, left = h->sim.sub_end - e;
       for (int pass = 0; pass < 2; pass++) {
-        cudaStream_t s2 = pass ? h->side : st;
+        cudaStream_t s2 = pass ? side : st;
         const uint8_t* mk = pass ? nullptr : h->slow_mark;
         const uint32_t* ls = pass ? h->slow_list : nullptr;
         const int g2 = pass ? h->sms * 32 : grid;
@@ -696,9 +702,11 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
       mark(1);
     }
     /* join */
-    cudaEventRecord(h->ev_join[bi], h->side);
-    cudaStreamWaitEvent(st, h->ev_join[bi], 0);
-    mark(3); /* what the side stream's work took beyond the observations it ran beside */
+    if (!serial) {
+      cudaEventRecord(h->ev_join[bi], h->side);
+      cudaStreamWaitEvent(st, h->ev_join[bi], 0);
+      mark(3); /* what the side stream's work took beyond the observations it ran beside */
+    }
     b = e;
   }
   if (image) rc_finish_kernel<true><<<grid, RC_WPC * 32, smem_raw, st>>>(h->sim, h->state, o->obs, o->full, o->info, o->raw);
@@ -930,7 +938,7 @@ int dynenv_debug_timing(DynEnvHandle h, int enable) {
     for (int k = 0; k <= MAX_TIMED; k++) cudaEventCreate(&h->ev[k]);
   if (!enable && h->timing)
     for (int k = 0; k <= MAX_TIMED; k++) cudaEventDestroy(h->ev[k]);
-  h->timing = enable ? 1 : 0;
+  h->timing = enable ? (enable == 2 ? 2 : 1) : 0;
   h->n_timed = 0;
   return DYNENV_OK;
 }

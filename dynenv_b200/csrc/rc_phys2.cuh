@@ -149,7 +149,9 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
 #pragma unroll 1
 #ifdef RC_MW
   for (int sub = sub_lo; sub < sub_e; sub++) {
+#ifndef RC_MW_NO_BAR1
     __syncthreads();
+#endif
     const bool act = valid && sub >= sub_b;            /* warp-uniform */
     const bool resume = act && phase0 && sub == sub_b; /* handed over in mid-substep: positions are integrated */
     const bool front = act && !resume;
@@ -502,7 +504,9 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
         record_broadphase(E, pairs4, own, g0, g1, g2, g3);
       }
 #ifdef RC_MW
+#ifndef RC_MW_NO_BAR2
       __syncthreads();
+#endif
       if (!act) continue;
 #endif
       RC_DBG(2, own); RC_DBG(3, g0 | g1 | g2 | g3); RC_DBG(4, nArb);

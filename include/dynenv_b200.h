@@ -532,7 +532,10 @@ int dynenv_set_state(DynEnvHandle h, const uint32_t* state_dev, void* stream);
    the summed duration (ms) and the launch count per kernel class (arrays of FOUR entries): [0] substep blocks
    (rc_phys_kernel / drv_phys_kernel), [1] observation ticks (rc_obsp_kernel / rc_obs_kernel / drv_obs_kernel),
    [2] finish (rc_finish_kernel), [3] substep blocks of the environments handed over to the record-based code
-   (rc_phys_slow_kernel). */
+   (rc_phys_slow_kernel).  enable = 1: the step runs as always -- the handed-over environments on the side stream beside
+   the others' observations -- and [3] is what the side stream adds beyond them; enable = 2: the side stream's work is
+   issued on the caller's stream instead, one kernel after the other, and [3] is the hand-over kernel's own duration (the
+   per-class times then add up like an ncu launch list; the step is slower than in production). */
 int dynenv_debug_timing(DynEnvHandle h, int enable);
 int dynenv_last_kernel_ms(DynEnvHandle h, float* ms4, int* launches4);
 
