@@ -99,12 +99,21 @@ __device__ __forceinline__ void o_prologue(const Env E, RD rd, uint32_t env_id, 
   __syncwarp();
 }
 
+/* first word, floats per row and capacity of list t (0 ball .. 5 line) of an observation record: packed constants and a
+   shift instead of chains of selects (these sit in the dense passes' inner code) */
+static_assert(RC_O_LINE < 512 && RC_F_FCROSS < 16 && RC_CAP_FCROSS < 32, "packed list tables");
 __device__ __forceinline__ int list_off(int t) {
-  return t == 0 ? RC_O_BALL : t == 1 ? RC_O_ROBOT : t == 2 ? RC_O_POST : t == 3 ? RC_O_CROSS : t == 4 ? RC_O_FCROSS : RC_O_LINE;
+  constexpr unsigned long long tab = (unsigned long long)RC_O_BALL | ((unsigned long long)RC_O_ROBOT << 9) | ((unsigned long long)RC_O_POST << 18) |
+                                     ((unsigned long long)RC_O_CROSS << 27) | ((unsigned long long)RC_O_FCROSS << 36) | ((unsigned long long)RC_O_LINE << 45);
+  return (int)((tab >> (9 * t)) & 511u);
 }
-__device__ __forceinline__ int list_feat(int t) { return t == 0 ? RC_F_BALL : t == 1 ? RC_F_ROBOT : t == 4 ? RC_F_FCROSS : t == 5 ? RC_F_LINE : 6; }
+__device__ __forceinline__ int list_feat(int t) {
+  constexpr unsigned tab = RC_F_BALL | (RC_F_ROBOT << 4) | (RC_F_POST << 8) | (RC_F_CROSS << 12) | (RC_F_FCROSS << 16) | (RC_F_LINE << 20);
+  return (int)((tab >> (4 * t)) & 15u);
+}
 __device__ __forceinline__ int list_cap(int t) {
-  return t == 0 ? RC_CAP_BALL : t == 1 ? RC_CAP_ROBOT : t == 2 ? RC_CAP_POST : t == 3 ? RC_CAP_CROSS : t == 4 ? RC_CAP_FCROSS : RC_CAP_LINE;
+  constexpr unsigned tab = RC_CAP_BALL | (RC_CAP_ROBOT << 5) | (RC_CAP_POST << 10) | (RC_CAP_CROSS << 15) | (RC_CAP_FCROSS << 20) | (RC_CAP_LINE << 25);
+  return (int)((tab >> (5 * t)) & 31u);
 }
 
 /* one dense pass over up to 32 queued sightings: occlusion / proximity by the robots in view (RoboCupEnvironment.py:
@@ -601,15 +610,35 @@ __device__ __noinline__ void observe_partial(const Env E, uint32_t tick, float* 
       __syncwarp();
     }
   }
-  /* counts, numLandMarks, seen flags; running sums for processSeens */
-#pragma unroll 1
-  for (int item = lane; item < 17 * P; item += 32) {
-    const int ob = item / 17, k = item - 17 * ob;
-    const int v = k < 6 ? E.i[O_CNT + 8 * ob + k] : (k == 6 ? E.i[O_CNT + 8 * ob + 6] : E.i[O_SEEN + RC_MAXP * ob + k - 7]);
-    if (obs_tick) reinterpret_cast<int*>(obs_tick)[(size_t)ob * RC_OBS_WORDS + RC_O_COUNTS + k] = v;
-    if (k == 6) E.i[O_ACC + (RC_S_STEP_LSUM - RC_S_STEP_LSUM) + ob] += v - E.i[O_CNT + 8 * ob + 5]; /* observe_lines added the lines */
-    else if (k == 7) E.i[O_ACC + (RC_S_STEP_BSUM - RC_S_STEP_LSUM) + ob] += v;
-    else if (k > 7) E.i[O_ACC + (RC_S_STEP_RSEEN - RC_S_STEP_LSUM) + 9 * ob + k - 8] += v;
+  /* counts, numLandMarks, seen flags; running sums for processSeens.  Two lanes per observer: lane ob writes words 0 .. 8 of
+     the record's count block (6 counts, numLandMarks, ballsSeen, robotsSeen[0]), lane 16 + ob words 9 .. 16 (robotsSeen[1 .. 8]) */
+  {
+    const int ob = lane & 15, hi = lane >> 4;
+    if (ob < P) {
+      int* rc = obs_tick ? reinterpret_cast<int*>(obs_tick) + (size_t)ob * RC_OBS_WORDS + RC_O_COUNTS : nullptr;
+      const int cb = O_CNT + 8 * ob, sb = O_SEEN + RC_MAXP * ob;
+      if (!hi) {
+        int c[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) c[k] = E.i[cb + k];
+        const int bs = E.i[sb], r0 = E.i[sb + 1];
+        if (rc) {
+#pragma unroll
+          for (int k = 0; k < 7; k++) rc[k] = c[k];
+          rc[7] = bs; rc[8] = r0;
+        }
+        E.i[O_ACC + (RC_S_STEP_LSUM - RC_S_STEP_LSUM) + ob] += c[6] - c[5]; /* observe_lines added the lines */
+        E.i[O_ACC + (RC_S_STEP_BSUM - RC_S_STEP_LSUM) + ob] += bs;
+        E.i[O_ACC + (RC_S_STEP_RSEEN - RC_S_STEP_LSUM) + 9 * ob] += r0;
+      } else {
+#pragma unroll
+        for (int j = 1; j < 9; j++) {
+          const int v = E.i[sb + 1 + j];
+          if (rc) rc[8 + j] = v;
+          E.i[O_ACC + (RC_S_STEP_RSEEN - RC_S_STEP_LSUM) + 9 * ob + j] += v;
+        }
+      }
+    }
   }
   __syncwarp();
 }
