@@ -15,6 +15,10 @@
 namespace dynenv {
 namespace rc {
 
+#ifdef RC_DBG_COUNTERS
+__device__ unsigned long long g_dbg2[16];
+#endif
+
 /* minimum-penetration axis of two CROSSING core segments (deep inter-penetration: rare, out of line) */
 __device__ __noinline__ void seg_seg_cross_axis(V2 a0, V2 a1, V2 b0, V2 b1, V2* nOut, float* dOut) {
   V2 da = a1 - a0, db = b1 - b0;
@@ -245,6 +249,25 @@ __device__ __noinline__ void contact_half(const Env E, unsigned own, unsigned g0
   }
   __syncwarp();
   if (own | g0 | g1 | g2 | g3) collide_lean(E, own, g0, g1, g2, g3, pairs4);
+#ifdef RC_DBG_COUNTERS /* what the contact halves look like: active pairs, kinds of pairs, cached pairs */
+  __syncwarp();
+  if (lane == 0) {
+    const int na = E.i[X_NACTIVE];
+    atomicAdd(&g_dbg2[na < 3 ? na : 3], 1ull);
+    for (int q = 0; q < na; q++) {
+      const int key = E.i[RC_S_ARBKEY + E.i[X_ACTIVE + q]];
+      const int a = key & 255, b = (key >> 8) & 255;
+      int kind;
+      if (a == BALL || b == BALL) kind = (a >= POST0 || b >= POST0) ? 8 : 5;       /* ball-post, ball-foot */
+      else if (a >= POST0 || b >= POST0) kind = 7;                                   /* post-foot */
+      else kind = (a >> 1) == (b >> 1) ? 4 : 6;                                      /* own feet, feet of two robots */
+      atomicAdd(&g_dbg2[kind], 1ull);
+    }
+    atomicAdd(&g_dbg2[9], (unsigned long long)E.i[RC_S_NARB]);
+    atomicAdd(&g_dbg2[10], 1ull);
+  }
+  __syncwarp();
+#endif
   space_step_rest(E, 0, prevStepped);
 }
 

@@ -83,6 +83,16 @@ rc_phys_slow_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ s
 
 }  // namespace
 
+#ifdef RC_DBG_COUNTERS
+extern "C" int dynenv_slow_debug_counters(unsigned long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, rc::g_dbg, 16 * sizeof(unsigned long long));
+  cudaMemcpyFromSymbol(out32 + 16, rc::g_dbg2, 16 * sizeof(unsigned long long));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rc::g_dbg, z, sizeof(z)); cudaMemcpyToSymbol(rc::g_dbg2, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 size_t dynenv_slow_smem_bytes(void) { return ((size_t)CFG_WORDS + (size_t)W * DYNENV_MW_SLICE_WORDS) * sizeof(uint32_t); }
 
 cudaError_t dynenv_slow_configure(void) {
