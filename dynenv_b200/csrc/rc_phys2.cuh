@@ -212,7 +212,8 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
         /* The register-resident kernel hands over -- except at substep 0, where the fall draws of processAction make 8 % of
            the environments need the ordered phase: those run it here, once, and stay (handed over they would walk their
            other nine substeps through the hand-over kernel's barriers: a third of its first launch of a step). */
-#ifndef RC_HANDOVER_SUB0
+#ifdef RC_INPLACE_ALL /* experiment: every ordered phase in place */
+#elif !defined(RC_HANDOVER_SUB0)
         if (!SLOW && sub != 0) return 2 * sub;
 #else
         if (!SLOW) return 2 * sub;
