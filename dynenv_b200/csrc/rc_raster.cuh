@@ -88,6 +88,17 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   double* params = reinterpret_cast<double*>(g_smem + S_PARAMS);
   int* misc = reinterpret_cast<int*>(g_smem + S_MISC);
   RPROF(const long long t0 = clock64();)
+  { /* a third of the planes have nothing to draw (no ball in sight, no goal post ...): their list counts say so before
+       anything is staged or projected -- zeros straight from registers */
+    const int* cnt = reinterpret_cast<const int*>(raw + rec * RC_RAW_WORDS) + RC_R_COUNTS;
+    const bool nothing = ch == 0 ? cnt[0] <= 0 : ch == 1 ? cnt[1] <= 0 : ch == 2 ? cnt[2] <= 0
+                         : (cnt[3] <= 0 && cnt[4] <= 0 && cnt[5] <= 0 && reinterpret_cast<const int*>(raw + rec * RC_RAW_WORDS)[RC_R_CIRCLE_SEEN] == 0);
+    if (nothing) { /* block-uniform */
+      uint4* dst = reinterpret_cast<uint4*>(images + (size_t)rec * RC_IMG_WORDS + (size_t)plane_id * raster::PLANE_WORDS);
+      for (int w = tid; w < raster::PLANE_WORDS / 4; w += THREADS) dst[w] = make_uint4(0, 0, 0, 0);
+      return;
+    }
+  }
   for (int w = tid; w < RC_RAW_WORDS; w += THREADS) sraw[w] = raw[rec * RC_RAW_WORDS + w];
   if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[2] = 0; conic->n = 0; }
   __syncthreads();
