@@ -66,7 +66,7 @@ struct Conic {
   short y[CONIC_ROWS];
 };
 
-/* a primitive that can cover a large part of the image: drawn by the whole block instead of one warp */
+/* a primitive that can cover a large part of the image: the raster kernel queues these in front of the small ones */
 RP_FN bool prim_is_big(const Prim& p) {
   if (p.type == PRIM_LINE) return p.t >= 24;
   if (p.type == PRIM_CIRCLE) return p.t >= 40;

@@ -163,21 +163,17 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   const raster::Lanes one = {0, 1};
 #ifdef RASTER_SKIP_DRAW /* dev ablation: set-up and store only */
 #elif !defined(RASTER_STATIC_SPLIT)
-  /* Large primitives (a field line next to the robot is hundreds of pixels thick): rows over the whole block.  Everything
-     else is a queue of work units -- a small primitive (one warp, its rows / pixels on the lanes) or 32 of the conic's
-     ~2 x 479 one-pixel-high poly-line segments (one lane each) -- that the warps draw from until it is empty: with a
-     fixed primitive -> warp assignment the block waited at its barrier for the warp that had drawn the longest ones
-     (27 k cycles against a mean of 17 k, profiles/r01_ncu_rc_raster.txt: stalled_barrier 11.5 per issue). */
+  /* Everything is a queue of work units that the warps draw from until it is empty: 32 of the conic's ~2 x 479
+     one-pixel-high poly-line segments (one lane each; first: they are the long units), then the primitives, one warp each
+     with their rows / pixels on its lanes (in list order: the large ones first cost 6 % more).  With a fixed primitive -> warp assignment the block waited
+     at its barrier for the warp that had drawn the longest ones (27 k cycles against a mean of 17 k,
+     profiles/r01_ncu_rc_raster.txt: stalled_barrier 11.5 per issue); drawing the large primitives with the whole block
+     (rows over 256 threads) cost more than it gave: every warp repeats the primitive's set-up -- clipping, slopes, edge
+     events: most of its instructions -- for an eighth of the rows (15.7 -> 13.3 ms per 1024 environments without it). */
   {
-    const raster::Lanes B = {tid, THREADS};
-    for (int w = 0; w < nprims; w++) {
-      const raster::Prim p = prims[w];
-      if (raster::prim_is_big(p)) raster::draw_prim(plane, p, B);
-    }
     RPROF(const long long t3 = clock64(); t3s = t3; if (tid == 0) { int nb = 0; for (int w = 0; w < nprims; w++) nb += raster::prim_is_big(prims[w]) ? 1 : 0;
       atomicAdd(&g_raster_prof[6], (unsigned long long)(t3 - t2)); atomicAdd(&g_raster_prof[13], (unsigned long long)nprims);
       atomicAdd(&g_raster_prof[14], (unsigned long long)nb); atomicAdd(&g_raster_prof[15], (unsigned long long)nseg); })
-    /* the conic's units first: they are the long ones (32 thick poly-line segments, one per lane), the small primitives fill the tail */
     const int ncu = (nseg + 31) / 32, nunits = ncu + nprims;
     for (;;) {
       int u = 0;
@@ -185,8 +181,7 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
       u = __shfl_sync(FULLMASK, u, 0);
       if (u >= nunits) break;
       if (u >= ncu) {
-        const raster::Prim p = prims[u - ncu];
-        if (!raster::prim_is_big(p)) raster::draw_prim(plane, p, L);
+        raster::draw_prim(plane, prims[u - ncu], L);
       } else {
         const int sgm = u * 32 + lane;
 #ifndef RASTER_SKIP_CONIC
