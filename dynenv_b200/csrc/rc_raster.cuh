@@ -9,7 +9,7 @@
  * peak); what keeps the kernel at 15 % of that roof is the drawing.  Drawing: the primitives' rows / pixels in closed
  * form on the lanes (raster_prims.cuh), atomicOr on shared-memory words; large primitives over the whole block, small
  * ones and the centre circle's poly-line segments (32 per unit, one per lane) from a work queue that the block's
- * warps drain.  Three blocks of 256 threads per SM.
+ * warps drain.  Four blocks of 256 threads per SM (64 registers).
  *
  * Measured on the bench's IMAGE workload (1024 environments = 409 600 planes, 66 % of them non-empty; clock64 per
  * phase with -DRASTER_PROFILE, tools/gpu_raster_prof.py; ablations -DRASTER_SKIP_DRAW / _SKIP_STORE / _SKIP_CONIC /
@@ -72,7 +72,7 @@ __device__ unsigned long long g_raster_prof2[8]; /* lines channel with / without
 #define RPROF(x)
 #endif
 #ifndef RASTER_MINB
-#define RASTER_MINB 3
+#define RASTER_MINB 4
 #endif
 __global__ void __launch_bounds__(THREADS, RASTER_MINB)
 rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* __restrict__ images) {
@@ -180,10 +180,17 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
       if (lane == 0) u = atomicAdd(&misc[2], 1);
       u = __shfl_sync(FULLMASK, u, 0);
       if (u >= nunits) break;
+#ifdef RASTER_PRIMS_FIRST
+      if (u < nprims) {
+        raster::draw_prim(plane, prims[u], L);
+      } else {
+        const int sgm = (u - nprims) * 32 + lane;
+#else
       if (u >= ncu) {
         raster::draw_prim(plane, prims[u - ncu], L);
       } else {
         const int sgm = u * 32 + lane;
+#endif
 #ifndef RASTER_SKIP_CONIC
         if (sgm < nseg) raster::draw_conic_segment(plane, *conic, sgm, one);
 #endif
