@@ -157,3 +157,22 @@ def test_both_integer_widths_match_cv2(lib):
         p = np.zeros((480, 20), np.uint32)
         lib.rp_rect(p.ctypes.data, x0, y0, x1, y1)
         assert np.array_equal(_unpack(p), ref.astype(np.uint8)), ("rectangle", x0, y0, x1, y1)
+
+
+def test_segment_pattern_does_not_depend_on_its_position(lib):
+    """an integer translation of a thick one-row poly-line segment translates its pixels (nothing clipped): OpenCV's integer /
+    fixed-point routines have no position-dependent rounding.  (A stamp-based drawing of the centre circle rests on this; it was
+    built, bit-exact, and measured slower than the exact routines per segment -- DESIGN.md section 8.)"""
+    rng = np.random.default_rng(31)
+    for t in range(2, 31):
+        for dx in range(-7, 8):
+            ref = np.zeros((480, 20), np.uint32)
+            lib.rp_segment(ref.ctypes.data, 320, 100, 320 + dx, 101, t, 2)
+            ref = _unpack(ref)
+            ys, xs = np.nonzero(ref)
+            assert xs.min() >= 288 and xs.max() <= 351 and ys.min() >= 81 and ys.max() <= 120, (t, dx)  # the stamp window
+            for _ in range(3):
+                xa, ya = int(rng.integers(40, 601)), int(rng.integers(20, 459))
+                got = np.zeros((480, 20), np.uint32)
+                lib.rp_segment(got.ctypes.data, xa, ya, xa + dx, ya + 1, t, 2)
+                assert np.array_equal(_unpack(got), np.roll(np.roll(ref, ya - 100, 0), xa - 320, 1)), (t, dx, xa, ya)
