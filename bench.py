@@ -53,6 +53,7 @@ class RoboCupWorkload(object):
     # padded records).  obs_bytes = observation bytes written per env-step, measured on the last timed step (dense: the records).
     sparse_obs = True
     obs_bytes = None
+    byte_actions = True  # e2e: the MultiDiscrete action indices travel as uint8 (dynenv_step_u8)
 
     def make_sim(self, E, local, rank, full=False):
         import dynenv_b200
@@ -221,6 +222,7 @@ class ImageWorkload(RoboCupWorkload):
     launches_per_step = {"phys": 5, "phys_slow": 5, "obs": 5, "finish": 1, "raster": 1}
     chunk = 1024
     sparse_obs = False  # IMAGE mode writes whole records (staged in shared memory)
+    byte_actions = False  # allowHeadTurn: the head action is continuous
     default_envs = 16384
     cpu_steps, ref_steps, cpu_warm = 16, 4, 1  # an env-step draws 100 images with cv2 (~0.3 s)
     default_steps = 10
@@ -456,11 +458,15 @@ def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=T
         wl.measure_obs_bytes(sim)
     # ---- pass 2: end to end through the host-facing call
     n_res = (L.DRV_I_DONE if wl.name == "driving" else L.RC_I_DONE) + 1
-    res["h2d"], res["d2h"] = E * P * wl.act * 4, E * n_res * 4
+    # MultiDiscrete action spaces (RoboCup here) reach the device as bytes (dynenv_step_u8): what a host-side policy emits
+    # are action indices; continuous actions (Driving here, IMAGE's head turn) stay float32
+    byte_actions = bool(getattr(wl, "byte_actions", False))
+    act_bytes = 1 if byte_actions else 4
+    res["h2d"], res["d2h"] = E * P * wl.act * act_bytes, E * n_res * 4
     if e2e:
         n_host = min(n_pool, max(8, int(3.5e9 // (E * P * wl.act * 4))))  # at most ~3.5 GB of pinned actions per rank
-        h_act = [p.cpu().pin_memory() for p in pool[:n_host]]
-        d_act = torch.empty((E, P, wl.act), device=dev)
+        h_act = [(p.to(torch.uint8) if byte_actions else p).cpu().pin_memory() for p in pool[:n_host]]
+        d_act = torch.empty((E, P, wl.act), device=dev, dtype=torch.uint8 if byte_actions else torch.float32)
         # rewards [maxAgents] and done are the first words of every environment's result record: one strided copy
         h_res = torch.empty((E, n_res), dtype=torch.float32).pin_memory()
         rewind()
@@ -636,7 +642,8 @@ def run_gpu(args):
                                **wl.config(L)),
                 "clocks": r["clocks"], "gpu_launches": r["launches"],
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                        "note": "observations stay device-resident for the learner; rewards + done return to the host"},
+                        "note": "observations stay device-resident for the learner; rewards + done return to the host"
+                                + ("; actions: MultiDiscrete indices as uint8 (dynenv_step_u8)" if getattr(wl, "byte_actions", False) else "")},
                 "roofline": roofline, "diag_flags": r["diag"]}
         if "ms_step_arranged" in r:
             line["arranger"] = {"ms_per_step_with_arranger": r["ms_step_arranged"], "value": E / (r["ms_step_arranged"] * 1e-3), "unit": UNIT,

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("DYNENV_B200_LIB") or os.path.join(_DIR, "libdynenv_b2
 _LIB = None
 
 EXPORTS = ["dynenv_abi_version", "dynenv_last_error", "dynenv_create", "dynenv_destroy", "dynenv_state_words",
-           "dynenv_reset", "dynenv_step", "dynenv_set_seed", "dynenv_get_state", "dynenv_set_state",
+           "dynenv_reset", "dynenv_step", "dynenv_step_u8", "dynenv_set_seed", "dynenv_get_state", "dynenv_set_state",
            "dynenv_last_launch_count", "dynenv_debug_substep_range", "dynenv_debug_timing",
            "dynenv_last_kernel_ms", "dynenv_render_images", "dynenv_rollout_insert", "dynenv_discount_rewards", "dynenv_debug_fp32_peak",
            "dynenv_arrange_inputs", "dynenv_arrange_outputs"]
@@ -56,6 +56,7 @@ def lib():
         lb.dynenv_state_words.argtypes = [C.c_void_p]
         lb.dynenv_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lb.dynenv_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lb.dynenv_step_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lb.dynenv_set_seed.argtypes = [C.c_void_p, C.c_uint64]
         lb.dynenv_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lb.dynenv_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

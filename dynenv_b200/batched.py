@@ -137,9 +137,16 @@ class BatchedRoboCup(object):
         return self.out
 
     def step(self, actions):
-        """actions: float32 CUDA tensor [nEnvs, 2*nPlayers, 4] (move, turn, kick, head)."""
+        """actions: float32 CUDA tensor [nEnvs, 2*nPlayers, 4] (move, turn, kick, head); a uint8 tensor of the same shape takes
+        the byte entry point (dynenv_step_u8: MultiDiscrete action indices, a quarter of the bytes to bring to the device)."""
         if actions.shape != (self.nEnvs, self.P, 4):
             raise Exception("Error: There must be %d actions of length 4" % self.P)  # RoboCupEnvironment.py:462-463
+        if actions.dtype == torch.uint8:
+            if actions.device != self.device or not actions.is_contiguous():
+                actions = actions.to(device=self.device).contiguous()
+            term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
+            _lib.check(self._lib.dynenv_step_u8(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
+            return self.out
         if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()  # (also a tensor of ANOTHER GPU)
         term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
@@ -272,9 +279,15 @@ class BatchedDriving(object):
     set_state = BatchedRoboCup.set_state
 
     def step(self, actions):
-        """actions: float32 CUDA tensor [nEnvs, nCars, 2] (acceleration, steering)."""
+        """actions: float32 CUDA tensor [nEnvs, nCars, 2] (acceleration, steering); uint8 (discrete action indices): dynenv_step_u8."""
         if actions.shape != (self.nEnvs, self.N, 2):
             raise Exception("Error: There must be 2 actions for every car")  # DrivingEnvironment.py:262-263
+        if actions.dtype == torch.uint8:
+            if actions.device != self.device or not actions.is_contiguous():
+                actions = actions.to(device=self.device).contiguous()
+            term = C.byref(self.terminal.c_struct) if self.terminal is not None else None
+            _lib.check(self._lib.dynenv_step_u8(self._h, actions.data_ptr(), C.byref(self.out.c_struct), term, self._stream()))
+            return self.out
         if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()  # (also a tensor of ANOTHER GPU)
         term = C.byref(self.terminal.c_struct) if self.terminal is not None else None

@@ -439,6 +439,7 @@ struct DynEnvHandle_s {
   uint32_t* slow_count;  /* [8][DYNENV_SLOW_CNT_WORDS] per substep block of the step: [0] length of the list, [DYNENV_SLOW_BIN0 + k] of bin k */
   uint32_t* slow_bins;   /* [DYNENV_SLOW_BINS][n_envs] the same environments by hand-over point */
   uint8_t* slow_mark;    /* [n_envs] 1 = handed over in the substep block in flight */
+  float* act_f32;        /* [n_envs][agents][action words] dynenv_step_u8's widened actions (allocated on first use) */
   cudaStream_t side;     /* the handed-over environments' substeps and observations run here, beside the others' observations */
   cudaEvent_t ev_fork[8], ev_join[8];
   int sms;
@@ -519,6 +520,7 @@ int dynenv_create(const DynEnvConfig* cfg, DynEnvHandle* out) {
   h->slow_count = nullptr;
   h->slow_bins = nullptr;
   h->slow_mark = nullptr;
+  h->act_f32 = nullptr;
   h->side = nullptr;
   h->sms = 148;
   cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -573,6 +575,7 @@ int dynenv_destroy(DynEnvHandle h) {
   cudaFree(h->slow_count);
   cudaFree(h->slow_bins);
   cudaFree(h->slow_mark);
+  cudaFree(h->act_f32);
   if (h->side) {
     cudaStreamDestroy(h->side);
     for (int k = 0; k < 8; k++) { cudaEventDestroy(h->ev_fork[k]); cudaEventDestroy(h->ev_join[k]); }
@@ -717,6 +720,36 @@ int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* termi
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "rc step kernels launch");
   return DYNENV_OK;
+}
+
+__global__ void __launch_bounds__(256) act_widen_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; /* four actions per thread */
+  if (4 * i + 3 < n) {
+    const uchar4 v = reinterpret_cast<const uchar4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  } else {
+    for (long long k = 4 * i; k < n; k++) dst[k] = (float)src[k];
+  }
+}
+
+int dynenv_step_u8(DynEnvHandle h, const uint8_t* actions_u8_dev, void* out, void* terminal_out, void* stream) {
+  if (!h || !out || !actions_u8_dev) return fail(DYNENV_E_INVALID, "null argument");
+  if (h->cfg.continuous) return fail(DYNENV_E_INVALID, "byte actions are for MultiDiscrete action spaces (allowHeadTurn / continuousActions off)");
+  const long long n = (long long)h->sim.n_envs * h->sim.P * (h->cfg.kind == DYNENV_KIND_DRIVING ? 2 : 4);
+  {
+    DeviceGuard guard(h->cfg.device);
+    if (!h->act_f32) {
+      cudaError_t ce = cudaMalloc(&h->act_f32, (size_t)((n + 3) / 4 * 4) * sizeof(float));
+      if (ce != cudaSuccess) return cuda_fail(ce, "cudaMalloc(actions)");
+    }
+    const long long n4 = (n + 3) / 4;
+    act_widen_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(actions_u8_dev, h->act_f32, n);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return cuda_fail(ce, "act_widen_kernel launch");
+  }
+  const int rc = dynenv_step(h, h->act_f32, out, terminal_out, stream);
+  if (rc == DYNENV_OK) h->last_launches += 1;
+  return rc;
 }
 
 int dynenv_set_seed(DynEnvHandle h, uint64_t seed) {

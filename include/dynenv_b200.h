@@ -462,6 +462,12 @@ int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* s
    (move, turn, kick, head), Driving float32 [E][N][2].  With DYNENV_FLAG_AUTO_RESET,
    `terminal_out` (same struct type, may be NULL) receives the observations of environments
    that finished this step while `out` receives their post-reset observations. */
+/* (dynenv_step_u8: the same step for MultiDiscrete action spaces -- RoboCup without allowHeadTurn, Driving without
+   continuousActions (RoboCupEnvironment.py:400-408, DrivingEnvironment.py:200-207) -- with the action indices as bytes,
+   uint8 [E][P][4] / [E][N][2]: a quarter of the host -> device traffic of a step.  The bytes are widened to the handle's own
+   float32 buffer by a kernel on `stream`, then the step runs as below; a value a float action could not have is flagged like
+   one (RC_IF_BAD_ACTION).) */
+int dynenv_step_u8(DynEnvHandle h, const uint8_t* actions_u8_dev, void* out, void* terminal_out, void* stream);
 int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* terminal_out,
                 void* stream);
 

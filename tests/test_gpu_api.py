@@ -382,3 +382,35 @@ def test_sparse_observation_stream_matches_the_padded_records():
     print("sparse stream: %.1f KB of observations written per env-step (padded records: %.1f KB)" % (
         per_env_step / 1e3, 5 * P * L.RC_OBS_WORDS * 4 / 1e3))
     assert per_env_step < 30e3
+
+
+def test_byte_actions_step_like_float_actions():
+    """dynenv_step_u8: MultiDiscrete action indices as bytes give the step the float actions give, bit for bit (RoboCup and
+    Driving, an odd number of Driving action words included); continuous action spaces refuse them"""
+    import torch
+    import dynenv_b200
+    kw = dict(noiseMagnitude=2.0, canFall=True, auto_reset=True, seed=21)
+    a, b = dynenv_b200.BatchedRoboCup(77, 5, **kw), dynenv_b200.BatchedRoboCup(77, 5, **kw)
+    a.reset(); b.reset()
+    g = torch.Generator().manual_seed(4)
+    for s in range(6):
+        act = (torch.rand((77, 10, 4), generator=g) * torch.tensor([5, 3, 3, 7])).floor()
+        oa, ob = a.step(act.cuda()), b.step(act.to(torch.uint8).cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(a.get_state(), b.get_state()) and torch.equal(oa.obs.view(torch.int32), ob.obs.view(torch.int32))
+        assert torch.equal(oa.info.view(torch.int32), ob.info.view(torch.int32))
+    assert b.last_launch_count() == a.last_launch_count() + 1
+    bad = torch.zeros((77, 10, 4), dtype=torch.uint8)
+    bad[3, 2, 0] = 9
+    assert int(b.step(bad.cuda()).diag[3].item()) & dynenv_b200.layout.RC_IF_BAD_ACTION
+    d0, d1 = [dynenv_b200.BatchedDriving(33, 3, noiseMagnitude=2.0, continuousActions=False, auto_reset=True, seed=2) for _ in range(2)]
+    d0.reset(); d1.reset()
+    for s in range(6):
+        act = (torch.rand((33, 3, 2), generator=g) * 3).floor()  # 198 action words: not a multiple of four
+        o0, o1 = d0.step(act.cuda()), d1.step(act.to(torch.uint8).cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(d0.get_state(), d1.get_state()) and torch.equal(o0.record.view(torch.int32), o1.record.view(torch.int32))
+    cont = dynenv_b200.BatchedRoboCup(4, 2, allowHeadTurn=True, seed=1)
+    cont.reset()
+    with pytest.raises(Exception, match="MultiDiscrete"):
+        cont.step(torch.zeros((4, 4, 4), dtype=torch.uint8).cuda())
