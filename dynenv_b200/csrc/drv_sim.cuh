@@ -974,6 +974,10 @@ __device__ __noinline__ void contacts_substep(const Env E, int prevStepped, bool
   __syncwarp();
 }
 
+#ifdef DRV_DBG_COUNTERS
+__device__ unsigned long long g_drv_dbg[8]; /* substeps, with a contact half, with cached pairs, environment-launches with a contact half */
+#define X_DBGFLAG (ENV_SMEM_WORDS - 1)
+#endif
 __device__ __noinline__ void space_step(const Env E) {
   /* cpSpaceStep (Chipmunk2D 7.0.x), dt = 0.01; lanes 0..9 = cars, lanes 10..29 = pedestrians */
   const int lane = E.lane;
@@ -1103,6 +1107,10 @@ __device__ __noinline__ void space_step(const Env E) {
     const bool haveCand = __any_sync(FULLMASK, (mask[0] | mask[1]) != 0);
     const unsigned keepMask = __ballot_sync(FULLMASK, lane < nArb && !(pairBodies & dirty)); /* cached pairs left alone */
     const bool dirtyCached = __any_sync(FULLMASK, lane < nArb && (pairBodies & dirty) != 0);
+#ifdef DRV_DBG_COUNTERS
+    if (lane == 0) { atomicAdd(&g_drv_dbg[0], 1ull); if (haveCand || dirtyCached) atomicAdd(&g_drv_dbg[1], 1ull); if (nArb) atomicAdd(&g_drv_dbg[2], 1ull);
+      if ((haveCand || dirtyCached) && !E.i[X_DBGFLAG]) { E.i[X_DBGFLAG] = 1; atomicAdd(&g_drv_dbg[3], 1ull); } }
+#endif
     if (haveCand || dirtyCached) {
       if (haveCand) {
         E.i[X_BPMASK + lane] = mask[0];
@@ -1128,6 +1136,10 @@ __device__ __forceinline__ void phys_substeps(const Env E, const float* actions_
     refresh_trig(E, lane, load_ang(E, lane));
   }
   __syncwarp();
+#ifdef DRV_DBG_COUNTERS
+  if (lane == 0) E.i[X_DBGFLAG] = 0;
+  __syncwarp();
+#endif
   const int N = E.c->P;
 #pragma unroll 1
   for (int sub = sub_b; sub < sub_e; sub++) {

@@ -898,6 +898,14 @@ int dynenv_debug_counters(unsigned long long* out16, int reset) {
   return 0;
 }
 #endif
+#ifdef DRV_DBG_COUNTERS
+int dynenv_debug_drv_counters(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, drv::g_drv_dbg, 8 * sizeof(unsigned long long));
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(drv::g_drv_dbg, z, sizeof(z)); }
+  return 0;
+}
+#endif
 #ifdef RASTER_PROFILE
 int dynenv_debug_raster_prof(unsigned long long* out16, int reset) {
   cudaDeviceSynchronize();
