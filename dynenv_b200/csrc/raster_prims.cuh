@@ -50,7 +50,7 @@ RP_FN void or_word(uint32_t* p, uint32_t m) {
 #ifdef RASTER_NONATOMIC /* dev ablation (racy: wrong pixels) */
   *p |= m;
 #else
-  atomicOr(p, m);
+  atomicOr(p, m); /* (testing the word first -- bits only ever get set -- is slower: the load queues behind the atomics) */
 #endif
 #else
   *p |= m;
@@ -190,7 +190,29 @@ RP_BIG void line2(uint32_t* plane, P2T<I> pt1, P2T<I> pt2, Lanes L) {
   pt1.x += (ONE >> 1);
   pt1.y += (ONE >> 1);
   if (L.lane == 0) put_point<I>(plane, (pt2.x + (ONE >> 1)) >> XY_SHIFT, (pt2.y + (ONE >> 1)) >> XY_SHIFT);
-  if (ax > ay) {
+  if (L.n == 1) {
+    /* one lane walks the whole line (the conic's poly-line segments, one per lane): its pixels are neighbours, and those of
+       one 32-pixel word go out as ONE OR.  The raster kernel is bound by its shared-memory atomics -- behind the drawing
+       barrier a block waits ~30 k cycles for them to drain, ~4 cycles per lane-level atomic and SM -- and half of them were
+       the single pixels of these edges. */
+    int cw = -1;
+    uint32_t cm = 0;
+    const bool horiz = ax > ay;
+    const I xs = pt1.x >> XY_SHIFT, ys = pt1.y >> XY_SHIFT;
+    for (int k = 0; k <= ecount; k++) {
+      const I x = horiz ? xs + k : (pt1.x + k * x_step) >> XY_SHIFT, y = horiz ? (pt1.y + k * y_step) >> XY_SHIFT : ys + k;
+      if (x >= 0 && x < IMG_W && y >= 0 && y < IMG_H) {
+        const int w = (int)y * WORDS_PER_ROW + ((int)x >> 5);
+        if (w != cw) {
+          if (cm) or_word(plane + cw, cm);
+          cw = w;
+          cm = 0;
+        }
+        cm |= 1u << ((int)x & 31);
+      }
+    }
+    if (cm) or_word(plane + cw, cm);
+  } else if (ax > ay) {
     const I xs = pt1.x >> XY_SHIFT;
     for (int k = L.lane; k <= ecount; k += L.n) put_point<I>(plane, xs + k, (pt1.y + k * y_step) >> XY_SHIFT);
   } else {
