@@ -353,6 +353,15 @@ RP_BIG void circle_filled(uint32_t* plane, int cx, int cy, int radius, Lanes L) 
   int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
   int it = 0;
   while (dx >= dy) {
+    /* the walk's next state first: OpenCV draws the rows cy -+ dx in EVERY iteration, each time a little wider (dy grows
+       while dx stands); the spans of one row nest, so only the widest -- the last before dx changes or the walk ends --
+       is drawn here: the same pixels with half the shared-memory writes (what the raster kernel is bound by) */
+    const int dy1 = dy + 1;
+    int err1 = err + plus;
+    const int mask = (err1 <= 0) - 1;
+    err1 -= minus & mask;
+    const int dx1 = dx + mask;
+    const bool widest = mask != 0 || dx1 < dy1;
     if (it % L.n == L.lane) {
       const int y11 = cy - dy, y12 = cy + dy, y21 = cy - dx, y22 = cy + dx;
       int x11 = cx - dx, x12 = cx + dx, x21 = cx - dy, x22 = cx + dy;
@@ -360,22 +369,20 @@ RP_BIG void circle_filled(uint32_t* plane, int cx, int cy, int radius, Lanes L) 
         x11 = x11 > 0 ? x11 : 0;
         x12 = x12 < IMG_W - 1 ? x12 : IMG_W - 1;
         if ((unsigned)y11 < (unsigned)IMG_H) hline(plane, y11, x11, x12);
-        if ((unsigned)y12 < (unsigned)IMG_H) hline(plane, y12, x11, x12);
-        if (x21 < IMG_W && x22 >= 0) {
+        if (dy && (unsigned)y12 < (unsigned)IMG_H) hline(plane, y12, x11, x12);
+        if (widest && x21 < IMG_W && x22 >= 0) {
           x21 = x21 > 0 ? x21 : 0;
           x22 = x22 < IMG_W - 1 ? x22 : IMG_W - 1;
           if ((unsigned)y21 < (unsigned)IMG_H) hline(plane, y21, x21, x22);
-          if ((unsigned)y22 < (unsigned)IMG_H) hline(plane, y22, x21, x22);
+          if (dx && (unsigned)y22 < (unsigned)IMG_H) hline(plane, y22, x21, x22);
         }
       }
     }
     it++;
-    dy++;
-    err += plus;
+    dy = dy1;
+    err = err1;
     plus += 2;
-    const int mask = (err <= 0) - 1;
-    err -= minus & mask;
-    dx += mask;
+    dx = dx1;
     minus -= mask & 2;
   }
 }
