@@ -212,12 +212,11 @@ RP_BIG void line2(uint32_t* plane, P2T<I> pt1, P2T<I> pt2, Lanes L) {
       }
     }
     if (cm) or_word(plane + cw, cm);
-  } else if (ax > ay) {
-    const I xs = pt1.x >> XY_SHIFT;
-    for (int k = L.lane; k <= ecount; k += L.n) put_point<I>(plane, xs + k, (pt1.y + k * y_step) >> XY_SHIFT);
-  } else {
-    const I ys = pt1.y >> XY_SHIFT;
-    for (int k = L.lane; k <= ecount; k += L.n) put_point<I>(plane, (pt1.x + k * x_step) >> XY_SHIFT, ys + k);
+  } else { /* several lanes share the line: pixel k on lane k % n (one loop for both major axes: the kernel is short of instruction cache) */
+    const bool horiz = ax > ay;
+    const I xs = pt1.x >> XY_SHIFT, ys = pt1.y >> XY_SHIFT;
+    for (int k = L.lane; k <= ecount; k += L.n)
+      put_point<I>(plane, horiz ? xs + k : (pt1.x + k * x_step) >> XY_SHIFT, horiz ? (pt1.y + k * y_step) >> XY_SHIFT : ys + k);
   }
 }
 
@@ -275,7 +274,7 @@ RP_BIG void fill_convex4(uint32_t* plane, const QuadT<I> v, int shift, Lanes L) 
   xmin = xmax = v.a.x;
   ymin = ymax = v.a.y;
 #ifdef __CUDA_ARCH__
-#pragma unroll
+#pragma unroll 1
 #endif
   for (i = 0; i < npts; i++) {
     P2T<I> p = qget(v, i);
