@@ -301,6 +301,9 @@ RP_BIG void fill_convex4(uint32_t* plane, const QuadT<I> v, int shift, Lanes L) 
   e_ye0 = e_ye1 = y = (int)ymin;
   int yend;
   for (;;) { /* row y: a cursor whose edge ends here takes the next edge that reaches below y */
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
     for (i = 0; i < 2; i++) {
       const int ye = i ? e_ye1 : e_ye0;
       if (y >= ye) {
@@ -435,6 +438,9 @@ RP_BIG void thick_line(uint32_t* plane, P2 p0, P2 p1, int thickness, int flags, 
       fill_convex4<int32_t>(plane, q, XY_SHIFT, L);
     } else fill_convex4<int64_t>(plane, pt, XY_SHIFT, L);
   }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
   for (int i = 0; i < 2; i++) {
     if (flags & (i + 1)) {
       const int cx = (int)((p0.x + (XY_ONE >> 1)) >> XY_SHIFT), cy = (int)((p0.y + (XY_ONE >> 1)) >> XY_SHIFT);
