@@ -470,16 +470,43 @@ def measure(wl, E, local, rank, world, steps, warmup, ff, e2e=True, per_kernel=T
         # rewards [maxAgents] and done are the first words of every environment's result record: one strided copy
         h_res = torch.empty((E, n_res), dtype=torch.float32).pin_memory()
         rewind()
+        # The step's ~31 launches (two streams, fork / join events) as ONE CUDA graph over the static action buffer: with a
+        # synchronisation per step the host's launch latency is on the critical path, and a busy host core showed up as
+        # +-15 % on this number.  The same kernels run; without graph support the calls are made directly.
+        graph = None
+        d_act.copy_(h_act[0], non_blocking=True)
+        sim.step(d_act)  # (first use of the byte-action path allocates inside the library: not during a capture)
+        torch.cuda.synchronize()
+        try:
+            cap = torch.cuda.Stream(device=dev)
+            cap.wait_stream(stream)
+            with torch.cuda.stream(cap):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=cap):
+                    out = sim.step(d_act)
+            stream.wait_stream(cap)
+            rewind()  # (the capture ran nothing, the rewind restores the window in any case)
+        except Exception as ex:  # noqa: BLE001 -- fall back to direct launches
+            graph = None
+            res["e2e_graph_error"] = repr(ex)
+            torch.cuda.synchronize()
+            rewind()
+        res["e2e_graph"] = graph is not None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for s in range(steps):
             d_act.copy_(h_act[s % n_host], non_blocking=True)
-            out = sim.step(d_act)
+            if graph is not None:
+                graph.replay()
+                out = sim.out
+            else:
+                out = sim.step(d_act)
             h_res.copy_(out.info[:, :n_res], non_blocking=True)
             stream.synchronize()
         e1.record(stream)
         barrier()
         res["ms_e2e"] = e0.elapsed_time(e1)
+        del graph
         del h_act, h_res
     # ---- pass 3: per kernel class (the events serialise nothing, but the blocking read does: its own pass)
     if per_kernel:
@@ -642,6 +669,7 @@ def run_gpu(args):
                                **wl.config(L)),
                 "clocks": r["clocks"], "gpu_launches": r["launches"],
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                        "cuda_graph": bool(r.get("e2e_graph", False)),
                         "note": "observations stay device-resident for the learner; rewards + done return to the host"
                                 + ("; actions: MultiDiscrete indices as uint8 (dynenv_step_u8)" if getattr(wl, "byte_actions", False) else "")},
                 "roofline": roofline, "diag_flags": r["diag"]}

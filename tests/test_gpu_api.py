@@ -414,3 +414,33 @@ def test_byte_actions_step_like_float_actions():
     cont.reset()
     with pytest.raises(Exception, match="MultiDiscrete"):
         cont.step(torch.zeros((4, 4, 4), dtype=torch.uint8).cuda())
+
+
+def test_step_replayed_as_a_cuda_graph():
+    """the ~31 launches of a RoboCup step (two streams, fork / join events, a device-side work queue) captured once over a
+    static action buffer and replayed give what the direct calls give, bit for bit, auto-resets included"""
+    import torch
+    import dynenv_b200
+    kw = dict(noiseMagnitude=2.0, canFall=True, auto_reset=True, seed=8, sparse_obs=True)
+    a, b = dynenv_b200.BatchedRoboCup(512, 5, **kw), dynenv_b200.BatchedRoboCup(512, 5, **kw)
+    a.reset(); b.reset()
+    buf = torch.zeros((512, 10, 4), dtype=torch.uint8, device="cuda")
+    b.step(buf)  # (the byte path allocates on first use: outside the capture)
+    a.step(buf)
+    torch.cuda.synchronize()
+    cap = torch.cuda.Stream()
+    cap.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(cap):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            b.step(buf)
+    torch.cuda.current_stream().wait_stream(cap)
+    g = torch.Generator().manual_seed(12)
+    for s in range(8):
+        act = (torch.rand((512, 10, 4), generator=g) * torch.tensor([5, 3, 3, 7])).floor().to(torch.uint8).cuda()
+        oa = a.step(act)
+        buf.copy_(act)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(a.get_state(), b.get_state())
+        assert torch.equal(oa.info.view(torch.int32), b.out.info.view(torch.int32)) and torch.equal(oa.counts, b.out.counts)
