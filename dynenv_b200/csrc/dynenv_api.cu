@@ -98,10 +98,13 @@ __device__ __forceinline__ rc::Env make_env(int base, const SimCfg& cfg, int e, 
 }
 
 /*
- * One env step = RC_NTICK x { rc_phys_kernel (10 substeps), rc_obs_kernel (one observation tick) } +
- * rc_finish_kernel, all on the caller's stream.  Every kernel: grid = ceil(nEnvs / RC_WPC) CTAs of RC_WPC
- * warps, warp w of CTA b owns environment b*RC_WPC + w, whose record it loads into its shared-memory slice
- * and stores back (coalesced).  See rc_sim.cuh (phys_substeps) for why the phases are separate launches.
+ * One env step = RC_NTICK x { rc_phys_kernel (10 substeps; the few environments it hands over finish them in
+ * rc_phys_slow_kernel on the side stream), the tick's observation kernels (rc_obsp_kernel<true> field lines,
+ * rc_obsp_kernel<false> points; rc_obs_kernel for FULL and IMAGE) } + rc_finish_kernel (dynenv_step below).  rc_phys / rc_finish / rc_reset: grid = ceil(nEnvs / RC_WPC) CTAs
+ * of RC_WPC warps, warp w of CTA b owns environment b*RC_WPC + w, whose record it loads into its shared-memory slice
+ * and stores back (coalesced).  The phases are separate launches because each one's hot code then fits the SM's
+ * instruction cache; fused into one kernel the warps of an SM sit in different phases and the step is bound by
+ * instruction fetch.
  */
 __global__ void __launch_bounds__(RC_WPC * 32, RC_MINB_)
 rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state, const float* __restrict__ actions,
@@ -115,10 +118,6 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
   uint32_t* S = g_smem + base;
   load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
   rc::Env E = make_env(base, cfg, e, lane);
-#ifdef RC_PHYS_RECORD /* the first version: every phase on the record in shared memory */
-  rc::phys_substeps(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
-  store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
-#else
   const int handover = rc::phys_substeps2<false>(E, actions + (size_t)e * cfg.P * 4, sub_b, sub_e, first != 0);
   store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
   if (lane == 0) {
@@ -131,7 +130,6 @@ rc_phys_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ state,
       slow_bins[(size_t)bin * cfg.n_envs + atomicAdd(slow_count + DYNENV_SLOW_BIN0 + bin, 1u)] = (uint32_t)e;
     }
   }
-#endif
 }
 
 /* the environments rc_phys_kernel handed over (falls, penalties, touching or cached pairs: a few percent of them): the
@@ -151,11 +149,7 @@ rc_phys_slow_kernel(const __grid_constant__ SimCfg cfg, uint32_t* __restrict__ s
     const int e = (int)(item & 0xFFFFFFu), code = (int)(item >> 24);
     load_record(S, state + (size_t)e * RC_STATE_WORDS, lane);
     rc::Env E = make_env(CFG_WORDS, cfg, e, lane);
-#ifdef RC_SLOW_RECORD /* the first version: the handed-over environments entirely on the record-based code */
-    rc::phys_resume(E, actions + (size_t)e * cfg.P * 4, code >> 1, code & 1, sub_e);
-#else
     rc::phys_substeps2<true>(E, actions + (size_t)e * cfg.P * 4, code >> 1, sub_e, false, code & 1);
-#endif
     store_record(state + (size_t)e * RC_STATE_WORDS, S, lane);
     __syncwarp();
   }

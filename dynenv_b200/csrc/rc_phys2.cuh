@@ -1,7 +1,7 @@
 /*
  * RoboCup physics substeps with the body state in registers.
  *
- * Same functions as rc_sim.cuh's phys_substeps (reference paths under DynEnv/):
+ * The substep loop of RoboCupEnvironment.step (reference paths under DynEnv/):
  *   processAction / Robot.step,turn,kick,turnHead   RoboCupEnvironment.py:527-581, Robot.py:103-138
  *   tick                                            :862-1007
  *   isBallOutOfField / ballFreeKickProcess          :622-732, :600-619
@@ -96,7 +96,7 @@ __device__ __forceinline__ void regs_store(const Env E, const Body& B, const Rob
 /* 10 substeps [sub_b, sub_e) of one environment; the record is in shared memory on entry and on exit.  Returns -1, or
    2 * sub + phase when substep `sub` needs the record-based code: phase 0 = from its start (ordered robot phase),
    phase 1 = from the narrow phase of its Space.step (a pair touches or is cached; positions are integrated).  The caller
-   queues the environment for rc_phys_slow_kernel, which runs the rest of the launch's substeps (phys_resume): keeping
+   queues the environment for rc_phys_slow_kernel, which runs the rest of the launch's substeps (SLOW = true): keeping
    the rare code out of this kernel keeps its instruction footprint at the size of the common substep. */
 /* SLOW = false: rc_phys_kernel, as above.  SLOW = true: rc_phys_slow_kernel -- the same register-resident substeps for
    the handed-over environments, which run the rare code in place: the ordered robot phase of rc_sim.cuh and the contact
@@ -149,9 +149,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
 #pragma unroll 1
 #ifdef RC_MW
   for (int sub = sub_lo; sub < sub_e; sub++) {
-#ifndef RC_MW_NO_BAR1
     __syncthreads();
-#endif
     const bool act = valid && sub >= sub_b;            /* warp-uniform */
     const bool resume = act && phase0 && sub == sub_b; /* handed over in mid-substep: positions are integrated */
     const bool front = act && !resume;
@@ -212,12 +210,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
         /* The register-resident kernel hands over -- except at substep 0, where the fall draws of processAction make 8 % of
            the environments need the ordered phase: those run it here, once, and stay (handed over they would walk their
            other nine substeps through the hand-over kernel's barriers: a third of its first launch of a step). */
-#ifdef RC_INPLACE_ALL /* experiment: every ordered phase in place */
-#elif !defined(RC_HANDOVER_SUB0)
         if (!SLOW && sub != 0) return 2 * sub;
-#else
-        if (!SLOW) return 2 * sub;
-#endif
         robots_phase(E, sub, actions_env);
         regs_load(E, B, R, U);
         forcesPending = true; biasPending = true;
@@ -512,9 +505,7 @@ __device__ __forceinline__ int phys_substeps2(const Env E, const float* actions_
         record_broadphase(E, pairs4, own, g0, g1, g2, g3);
       }
 #ifdef RC_MW
-#ifndef RC_MW_NO_BAR2
       __syncthreads();
-#endif
       if (!act) continue;
 #endif
       RC_DBG(2, own); RC_DBG(3, g0 | g1 | g2 | g3); RC_DBG(4, nArb);

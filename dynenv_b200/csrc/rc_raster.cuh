@@ -161,11 +161,11 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
   const int nseg = conic->n > 1 ? 2 * (conic->n - 1) : 0;
   const raster::Lanes L = {lane, 32};
   const raster::Lanes one = {0, 1};
-#ifdef RASTER_SKIP_DRAW /* dev ablation: set-up and store only */
-#elif !defined(RASTER_STATIC_SPLIT)
+#ifndef RASTER_SKIP_DRAW /* (dev ablation: set-up and store only) */
   /* Everything is a queue of work units that the warps draw from until it is empty: 32 of the conic's ~2 x 479
      one-pixel-high poly-line segments (one lane each; first: they are the long units), then the primitives, one warp each
-     with their rows / pixels on its lanes (in list order: the large ones first cost 6 % more).  With a fixed primitive -> warp assignment the block waited
+     with their rows / pixels on its lanes (in list order: the large ones first cost 6 % more, the primitives in front of
+     the conic units were slower too).  With a fixed primitive -> warp assignment the block waited
      at its barrier for the warp that had drawn the longest ones (27 k cycles against a mean of 17 k,
      profiles/r01_ncu_rc_raster.txt: stalled_barrier 11.5 per issue); drawing the large primitives with the whole block
      (rows over 256 threads) cost more than it gave: every warp repeats the primitive's set-up -- clipping, slopes, edge
@@ -180,37 +180,16 @@ rc_raster_kernel(const float* __restrict__ raw, long long n_records, uint32_t* _
       if (lane == 0) u = atomicAdd(&misc[2], 1);
       u = __shfl_sync(FULLMASK, u, 0);
       if (u >= nunits) break;
-#ifdef RASTER_PRIMS_FIRST
-      if (u < nprims) {
-        raster::draw_prim(plane, prims[u], L);
-      } else {
-        const int sgm = (u - nprims) * 32 + lane;
-#else
       if (u >= ncu) {
         raster::draw_prim(plane, prims[u - ncu], L);
       } else {
         const int sgm = u * 32 + lane;
-#endif
 #ifndef RASTER_SKIP_CONIC
         if (sgm < nseg) raster::draw_conic_segment(plane, *conic, sgm, one);
 #endif
       }
     }
   }
-#else
-  {
-    /* large primitives (a field line next to the robot is hundreds of pixels thick): rows over the whole block;
-       the others: one warp per primitive, rows / pixels on its lanes */
-    const raster::Lanes B = {tid, THREADS};
-    int k = 0; /* small primitives seen so far (block-uniform) */
-    for (int w = 0; w < nprims; w++) {
-      const raster::Prim p = prims[w];
-      if (raster::prim_is_big(p)) raster::draw_prim(plane, p, B);
-      else if ((k++ % WARPS) == warp) raster::draw_prim(plane, p, L);
-    }
-  }
-  /* the conic's ~2 x 479 poly-line segments are one pixel high and `thickness` wide: one thread per segment */
-  for (int sgm = tid; sgm < nseg; sgm += THREADS) raster::draw_conic_segment(plane, *conic, sgm, one);
 #endif
   __syncthreads();
   RPROF(const long long t5 = clock64();)

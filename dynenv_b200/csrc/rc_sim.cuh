@@ -1285,92 +1285,6 @@ __device__ __forceinline__ uint32_t broadphase_pairs(const Env E) {
   return packed;
 }
 
-__device__ __noinline__ void space_step_rest(const Env E, int kept, int prevStepped);
-
-__device__ __noinline__ void space_step(const Env E, const uint32_t pairs4, const bool integrate = true) {
-  /* cpSpaceStep (Chipmunk2D 7.0.x), dt = 0.01.  integrate = false: the positions were integrated and the shape geometry
-     cached already (an environment handed over by the register-resident substep of rc_phys2.cuh in mid-substep) */
-  const int lane = E.lane;
-  const int P = E.c->P;
-  const float dt = DT;
-  const int prevStepped = E.i[RC_S_STEPPED];
-  int nArb = E.i[RC_S_NARB];
-  __syncwarp();
-  if (lane == 0) {
-    E.i[RC_S_STEPPED] = 1;
-    E.i[X_NACTIVE] = 0;
-    E.i[X_TOUCHED] = 0;
-  }
-  if (lane < nArb) { /* first-touch pairs of the previous substep become normal */
-    int key = E.i[RC_S_ARBKEY + lane];
-    if (((key >> 16) & 255) == RC_ARB_FIRST) E.i[RC_S_ARBKEY + lane] = (key & ~0xff0000) | (RC_ARB_NORMAL << 16);
-  }
-  /* integrate positions (cpBodyUpdatePosition), refresh shape geometry, bounding circles in registers */
-  float bcx = 0, bcy = 0; /* bounding-circle centre of this lane's shape (radius: 17.5 for a foot, 10 otherwise) */
-  const bool active = lane < NSHAPE && shape_active(E, lane);
-  if (lane <= BALL && active && !integrate) {
-    bcx = (E.f[RC_S_CAX + lane] + E.f[RC_S_CBX + lane]) * 0.5f; bcy = (E.f[RC_S_CAY + lane] + E.f[RC_S_CBY + lane]) * 0.5f;
-  } else if (lane <= BALL && active) {
-    float px = E.f[RC_S_PX + lane], pxl = E.f[RC_S_PXL + lane];
-    float py = E.f[RC_S_PY + lane], pyl = E.f[RC_S_PYL + lane];
-    float an = E.f[RC_S_ANG + lane], anl = E.f[RC_S_ANGL + lane];
-    two_add(px, pxl, __fmul_rn(E.f[RC_S_VX + lane] + E.f[RC_S_VBX + lane], dt));
-    two_add(py, pyl, __fmul_rn(E.f[RC_S_VY + lane] + E.f[RC_S_VBY + lane], dt));
-    two_add(an, anl, __fmul_rn(E.f[RC_S_W + lane] + E.f[RC_S_WB + lane], dt));
-    E.f[RC_S_PX + lane] = px; E.f[RC_S_PY + lane] = py; E.f[RC_S_ANG + lane] = an;
-    E.f[RC_S_PXL + lane] = pxl; E.f[RC_S_PYL + lane] = pyl; E.f[RC_S_ANGL + lane] = anl;
-    E.f[RC_S_VBX + lane] = 0.f; E.f[RC_S_VBY + lane] = 0.f; E.f[RC_S_WB + lane] = 0.f;
-    V2 ta, tb;
-    shape_world(lane, px, py, an, &ta, &tb);
-    E.f[RC_S_CAX + lane] = ta.x; E.f[RC_S_CAY + lane] = ta.y;
-    E.f[RC_S_CBX + lane] = tb.x; E.f[RC_S_CBY + lane] = tb.y;
-    bcx = (ta.x + tb.x) * 0.5f; bcy = (ta.y + tb.y) * 0.5f;
-  } else if (lane >= POST0 && lane < NSHAPE) {
-    V2 p = post_pos(lane - POST0);
-    bcx = p.x; bcy = p.y;
-  }
-  __syncwarp();
-  /* collide.  Broad phase on groups first (robot = bounding circle of its two feet, ball, posts): 99 group
-     pairs, lane = pair, four rounds; only groups that come close are expanded into shape pairs, which are
-     then collided in ascending (i, j) insertion order like Chipmunk's.  (Its bounding-box test is implied:
-     shapes that touch have overlapping boxes; the margins cover the float32 rounding of the centres.) */
-  {
-    if (lane < NSHAPE) { E.f[X_BCX + lane] = bcx; E.f[X_BCY + lane] = bcy; }
-    float ocx = __shfl_xor_sync(FULLMASK, bcx, 1), ocy = __shfl_xor_sync(FULLMASK, bcy, 1);
-    bool ownFeetApart = false; /* own-feet pairs only matter once a kick or a turn has pulled the feet apart */
-    if (lane < 20) {
-      if (!(lane & 1)) {
-        float ddx = bcx - ocx, ddy = bcy - ocy;
-        E.f[X_GX + (lane >> 1)] = (bcx + ocx) * 0.5f;
-        E.f[X_GY + (lane >> 1)] = (bcy + ocy) * 0.5f;
-        E.f[X_GR + (lane >> 1)] = ROB_LEN + ROB_RAD + 0.5f * sqrtf(ddx * ddx + ddy * ddy);
-      } else if (lane < 2 * P) {
-        V2 d = pos_diff(E, lane, lane - 1);
-        float da = __fadd_rn(__fsub_rn(E.f[RC_S_ANG + lane], E.f[RC_S_ANG + lane - 1]), __fsub_rn(E.f[RC_S_ANGL + lane], E.f[RC_S_ANGL + lane - 1]));
-        ownFeetApart = !(fabsf(d.x) + fabsf(d.y) < 2.f && fabsf(da) < 0.1f);
-      }
-    } else if (lane < NSHAPE) {
-      E.f[X_GX + lane - 10] = bcx; E.f[X_GY + lane - 10] = bcy; E.f[X_GR + lane - 10] = 10.f;
-    }
-    __syncwarp();
-    unsigned own = __ballot_sync(FULLMASK, ownFeetApart);
-    unsigned g0, g1, g2, g3;
-    {
-      unsigned gh[4];
-#pragma unroll
-      for (int rnd = 0; rnd < 4; rnd++) {
-        const int a = (pairs4 >> (8 * rnd + 4)) & 15, b = (pairs4 >> (8 * rnd)) & 15;
-        float dx = E.f[X_GX + a] - E.f[X_GX + b], dy = E.f[X_GY + a] - E.f[X_GY + b];
-        float rr = E.f[X_GR + a] + E.f[X_GR + b] + 0.05f;
-        gh[rnd] = __ballot_sync(FULLMASK, dx * dx + dy * dy < rr * rr);
-      }
-      g0 = gh[0]; g1 = gh[1]; g2 = gh[2]; g3 = gh[3];
-    }
-    const int kept = (own | g0 | g1 | g2 | g3) ? filter_candidates(E, own, g0, g1, g2, g3) : 0;
-    space_step_rest(E, kept, prevStepped);
-  }
-}
-
 /* cpSpaceStep after the positions are integrated and the broad phase has run: narrow phase of the candidate pairs,
    cached-pair ageing, friction callbacks, warm start, solver sweeps, post-solve.  Reads and writes the record in shared
    memory (the register-resident substep of rc_phys2.cuh enters here whenever a pair comes close or is cached). */
@@ -2197,50 +2111,6 @@ __device__ __noinline__ void fill_info(const Env E, float* info_env) {
 __device__ __forceinline__ void clear_step_scratch(const Env E) {
   for (int w = RC_S_STEP_REW + E.lane; w < RC_S_STEP_END; w += 32) E.i[w] = 0;
   __syncwarp();
-}
-
-/* RoboCupEnvironment.step (RoboCupEnvironment.py:446-524) is a sequence of launches: blocks of substeps
-   [b, e) that end at an observation tick, the tick's observations, and the finish.  The phases are
-   separate kernels because each one's hot code then fits the SM's instruction cache; fused into one
-   kernel the warps of an SM sit in different phases and the step is instruction-fetch bound. */
-__device__ __forceinline__ void phys_substeps(const Env E, const float* actions_env, int sub_b, int sub_e, bool first) {
-  if (first) clear_step_scratch(E);
-  const uint32_t pairs4 = broadphase_pairs(E);
-#ifndef RC_PHASE_SYNC
-#define RC_PHASE_SYNC 0
-#endif
-  for (int sub = sub_b; sub < sub_e; sub++) {
-    /* (RC_PHASE_SYNC: the warps of a block enter every phase together, so that they share its instructions in the
-       instruction cache -- the kernel is bound by instruction fetch) */
-    if (RC_PHASE_SYNC >= 1) __syncthreads();
-    robots_phase(E, sub, actions_env);
-    if (RC_PHASE_SYNC >= 2) __syncthreads();
-    ball_out_of_field(E);
-    if (RC_PHASE_SYNC >= 2) __syncthreads();
-    space_step(E, pairs4);
-    if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
-    __syncwarp();
-  }
-}
-
-/* an environment the register-resident substeps (rc_phys2.cuh) handed over: at the start of substep `sub` (phase 0) or
-   inside its Space.step, positions integrated (phase 1); the rest of the launch's substeps runs on the record */
-__device__ __forceinline__ void phys_resume(const Env E, const float* actions_env, int sub, int phase, int sub_e) {
-  const uint32_t pairs4 = broadphase_pairs(E);
-  __syncwarp();
-  if (phase == 1) {
-    space_step(E, pairs4, false);
-    if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
-    __syncwarp();
-    sub++;
-  }
-  for (; sub < sub_e; sub++) {
-    robots_phase(E, sub, actions_env);
-    ball_out_of_field(E);
-    space_step(E, pairs4);
-    if (E.lane == 0) E.i[RC_S_ELAPSED] += 1;
-    __syncwarp();
-  }
 }
 
 __device__ __forceinline__ void finish_step(const Env E, float* info_env) {
