@@ -132,7 +132,6 @@ struct Env {
 __device__ __forceinline__ Rand6 rng_block(const Env E, uint32_t tick, int site, int a, int b, int blk);
 
 __device__ __forceinline__ bool is_foot(int s) { return s < 20; }
-__device__ __forceinline__ float shape_radius(int s) { return s < 20 ? ROB_RAD : 10.f; } /* Ball.py:13, Goalpost.py:11 */
 __device__ __forceinline__ float shape_e(int s) { return s < 20 ? 0.3f : (s == BALL ? 0.98f : 0.95f); }
 __device__ __forceinline__ float shape_u(int s) { return s < 20 ? 2.5f : (s == BALL ? 3.0f : 0.f); }
 __device__ __forceinline__ float body_minv(int s) { return s < 20 ? FOOT_MINV : (s == BALL ? BALL_MINV : 0.f); }
@@ -142,10 +141,6 @@ __device__ __forceinline__ V2 post_pos(int k) { return v2(k < 2 ? SIDE : W_ - SI
 __device__ __forceinline__ int team_of(const Env E, int r) { return r < E.c->n_players ? 1 : -1; }
 __device__ __forceinline__ bool shape_active(const Env E, int s) { return s >= 20 || s < 2 * E.c->P; }
 
-__device__ __forceinline__ V2 body_pos(const Env E, int s) { /* hi words: float32 view */
-  if (s < RC_NBODY) return v2(E.f[RC_S_PX + s], E.f[RC_S_PY + s]);
-  return post_pos(s - POST0);
-}
 /* position of body b relative to body a, from both words: exact where it matters (close bodies) */
 __device__ __forceinline__ V2 pos_diff(const Env E, int b, int a) {
   float bx, by, bxl = 0.f, byl = 0.f, ax, ay, axl = 0.f, ayl = 0.f;
@@ -543,116 +538,6 @@ __device__ __noinline__ void robots_phase(const Env E, int sub, const float* act
     }
     __syncwarp();
   }
-}
-
-/* ---- ball rules */
-__device__ void ball_free_kick(const Env E, int team) {
-  /* RoboCupEnvironment.py:600-619 */
-  if (team == 0) {
-    const float time = 10.f;
-    float g = E.f[RC_S_GRACE];
-    if (g > 0) {
-      g -= time;
-      if (g < 0) { g = 0; E.f[RC_S_BALLFREE] = 9999.f; }
-      E.f[RC_S_GRACE] = g;
-    } else if (E.f[RC_S_BALLFREE] > 0) {
-      float b = E.f[RC_S_BALLFREE] - time;
-      if (b < 0) { b = 0; E.i[RC_S_BALLOWNED] = 0; }
-      E.f[RC_S_BALLFREE] = b;
-    }
-  } else {
-    E.i[RC_S_BALLOWNED] = team;
-    E.f[RC_S_GRACE] = 14999.f;
-    E.f[RC_S_BALLFREE] = 0.f;
-  }
-}
-
-__device__ __noinline__ void ball_out_of_field(const Env E) {
-  /* RoboCupEnvironment.py:622-732 */
-  int lane = E.lane;
-  int P = E.c->P, nPl = E.c->n_players;
-  if (lane == 0) {
-    int finished = 0;
-    V2 pos = ball_pos(E);
-    float cr0 = 0, cr1 = 0;
-    const float outMin = SIDE - BALL_RADIUS, outMaxX = W_ - SIDE + BALL_RADIUS, outMaxY = H_ - SIDE + BALL_RADIUS;
-    int team = 0;
-    if (pos.y < outMin || pos.x < outMin || pos.y > outMaxY || pos.x > outMaxX) {
-      float x = W_ / 2, y = H_ / 2;
-      team = E.i[RC_S_NLASTK] ? team_of(E, E.i[RC_S_LASTK]) : 1;
-      if (pos.y < outMin || pos.y > outMaxY) {
-        x = team < 0 ? pos.x + 50 : pos.x - 50;
-        y = pos.y < outMin ? outMin + BALL_RADIUS : outMaxY - BALL_RADIUS;
-      } else {
-        if (pos.y < H_ / 2 + GOAL_W && pos.y > H_ / 2 - GOAL_W) {
-          finished = 1;
-          if (pos.x < outMin) { cr0 += -25; cr1 += 25; E.i[RC_S_GOALS + 1] += 1; }
-          else { cr0 += 25; cr1 += -25; E.i[RC_S_GOALS] += 1; }
-        } else {
-          if (pos.x < outMin) {
-            if (team < 0) x = SIDE + PEN_LENGTH;
-            else { x = SIDE; y = pos.y < H_ / 2 ? SIDE : H_ - SIDE; }
-          } else {
-            if (team > 0) x = W_ - (SIDE + PEN_LENGTH);
-            else { x = W_ - SIDE; y = pos.y < H_ / 2 ? SIDE : H_ - SIDE; }
-          }
-        }
-      }
-      E.f[RC_S_PX + BALL] = x; E.f[RC_S_PY + BALL] = y;
-      E.f[RC_S_PXL + BALL] = 0.f; E.f[RC_S_PYL + BALL] = 0.f;
-      E.f[RC_S_VX + BALL] = 0; E.f[RC_S_VY + BALL] = 0; E.f[RC_S_W + BALL] = 0;
-    }
-    ball_free_kick(E, -team);
-    float bx = E.f[RC_S_PX + BALL];
-    if (!finished) {
-      float d = (bx - E.f[RC_S_BPREVX]) / 20.f;
-      cr0 += d;
-      cr1 -= d;
-    }
-    E.f[RC_S_BPREVX] = bx;
-    E.f[RC_S_BPREVY] = E.f[RC_S_PY + BALL];
-    float disc = 1.f;
-    for (int k = 0; k < E.i[RC_S_NLASTK]; k++) {
-      int id = E.i[RC_S_LASTK + k];
-      float rew = (id < nPl ? cr0 : cr1) * disc;
-      E.f[X_REW + id] += rew;
-      E.f[X_POSREW + id] += fmaxf(0.f, rew);
-      disc *= 0.5f;
-    }
-    E.f[X_TEAMREW] += cr0 * 0.1f;
-    E.f[X_TEAMREW + 1] += cr1 * 0.1f;
-    E.f[X_CURREW] = cr0;
-    E.f[X_CURREW + 1] = cr1;
-    E.f[X_OLDBX] = pos.x;
-    E.f[X_OLDBY] = pos.y;
-  }
-  __syncwarp();
-  /* robots near the (old) ball position or closest to it share negative rewards; closest robots */
-  float d2 = INFINITY;
-  if (lane < P) {
-    V2 rp = robot_pos(E, lane);
-    bool cond1 = (lane == E.i[RC_S_CLOSEST] || lane == E.i[RC_S_CLOSEST + 1]);
-    bool cond2 = len(rp - v2(E.f[X_OLDBX], E.f[X_OLDBY])) < 150.f;
-    if ((cond1 || cond2) && !in_last_kicked(E, lane))
-      E.f[X_REW + lane] += fminf(0.f, E.f[X_CURREW + (lane < nPl ? 0 : 1)] * 0.5f);
-    d2 = lensq(ball_pos(E) - rp);
-  }
-  __syncwarp();
-  /* argmin per team, first minimum wins (strict <) */
-  {
-    /* non-negative floats order like their bit patterns: one warp-wide integer min per team, the
-       lowest lane holding the minimum is the first minimal index */
-    unsigned bits = __float_as_uint(d2);
-    unsigned m0 = __reduce_min_sync(FULLMASK, lane < nPl ? bits : 0xffffffffu);
-    unsigned m1 = __reduce_min_sync(FULLMASK, (lane >= nPl && lane < P) ? bits : 0xffffffffu);
-    unsigned w0 = __ballot_sync(FULLMASK, lane < nPl && bits == m0);
-    unsigned w1 = __ballot_sync(FULLMASK, lane >= nPl && lane < P && bits == m1);
-    if (lane == 0) {
-      E.i[RC_S_CLOSEST] = w0 ? __ffs(w0) - 1 : 0;
-      E.i[RC_S_CLOSEST + 1] = w1 ? __ffs(w1) - 1 : nPl;
-    }
-  }
-  __syncwarp();
 }
 
 /* ================================================================= collision callbacks (serial) */
@@ -1400,21 +1285,6 @@ __device__ __noinline__ void space_step_rest(const Env E, int kept, int prevStep
 }
 
 /* ================================================================= observations */
-__device__ __forceinline__ int does_interact(float ax, float ay, bool ahas, float bx, float by, bool bhas, float radius,
-                                             bool canOcclude) {
-  /* cutils.py:546-565 */
-  if (!ahas || !bhas) return I_NO;
-  int type = I_NO;
-  float dx = ax - bx, dy = ay - by;
-  if (dx * dx + dy * dy < radius * radius) type = I_NEARBY;
-  if (canOcclude) {
-    float cr = ax * by - ay * bx;
-    float la = ax * ax + ay * ay;
-    if (cr * cr < radius * radius * la && la < bx * bx + by * by) type = I_OCCLUDE;
-  }
-  return type;
-}
-
 /* getFullState(agent): RoboCupEnvironment.py:1162-1188 -> one RC_FULL_WORDS record, lanes cooperate */
 __device__ __noinline__ void full_state_agent(const Env E, int ag, float* dst /* global or shared */) {
   int lane = E.lane;
