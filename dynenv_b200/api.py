@@ -157,6 +157,9 @@ class RoboCupEnvironment(object):
         # render=True: renderMode 'memory' -- one top-down frame per step() / reset() in self.screenShots (the reference
         # draws every substep into a pygame window, environment_base.py:152-159; here frames come from dynenv_b200.render)
         self.renderMode, self.agentVisID, self.screenShots = ('memory' if render else False), None, []
+        # agentVisID = an agent's id: its agent-view debug images (RoboCupEnvironment.py:1469-1516) of the last step's
+        # ticks in self.obsVis -- IMAGE mode only, see agent_view()
+        self.obsVis = []
         self.elapsed = 0
         self.agents = [_Agent(i, self.nPlayers) for i in range(2 * self.nPlayers)]
         self.action_space, self.observation_space = robocup_spaces(self.observationType, allowHeadTurn, self.mean)
@@ -225,7 +228,20 @@ class RoboCupEnvironment(object):
         frame = R.render_env(self._sim, 0)
         if self.renderMode == 'memory':
             self.screenShots.append(frame)
+            if self.agentVisID is not None and self._image:
+                self.obsVis = [self.agent_view(self.agentVisID, t) for t in range(self.nTimeSteps)]
         return frame
+
+    def agent_view(self, agent, tick=-1):
+        """the reference's agent-view debug image (RoboCupEnvironment.py:1469-1516) of one agent at one observation tick of
+        the last step() / reset(): uint8 [940, 1040, 3].  Drawn on the host from the raw detection record of that (tick,
+        agent), which the observation kernel emits in IMAGE mode only -- in PARTIAL mode the lists leave the device encoded
+        (line rows keep distance and direction, not the end points), so there is nothing to draw from."""
+        from . import render as R
+        if not self._image:
+            raise RuntimeError("agent_view needs observationType=ObservationType.IMAGE (raw detection records)")
+        a = agent.id if hasattr(agent, "id") else int(agent)
+        return R.render_agent_view(self._sim.out.raw[0, tick, a].cpu().numpy())
 
     def close(self):
         self._sim.close()

@@ -7,7 +7,9 @@ reference uses for its own agent-view debug image): same canvas size, same colou
 (255, 0, 0), feet by team (255, 127(1-t), 127(1+t)), posts (0, 0, 255); Driving: (50, 50, 50) ground, lane lines white /
 red edges / yellow walkways, cars (0, 255, 0) or (255, 10, 10) once crashed, pedestrians (0, 255, 255) or (255, 0, 0) dead,
 obstacles and buildings (200, 200, 200)), RGB order like renderMode 'memory'.  pygame is not available in this image, so
-there is no pixel golden for these frames; tests check the geometry (tests/test_render.py).
+there is no pixel golden for these frames; tests check the geometry (tests/test_render.py).  The agent-view debug image
+(render_agent_view) is drawn with cv2 by the reference too, and is held pixel for pixel against images its own code drew
+(tests/golden/agent_view.npz).
 
 This module is a debugging aid, not a product hot path: it needs cv2 and numpy only.
 """
@@ -132,6 +134,52 @@ def render_driving(record, nPlayers):
         crashed = bool(cfl[k] & L.DRV_CF_CRASHED)
         # Car.py:9-13,49: box of half length 10 + 5 t along the heading and half width 5 + t
         _box(cv2, img, cpx[k], cpy[k], 10.0 + 5.0 * t, 5.0 + t, float(cang[k]), (255, 10, 10) if crashed else (0, 255, 0))
+    return img
+
+
+# RoboCupEnvironment.py:1472-1475: canvas of the agent view (H = W // 2 - 50 rows above and below the observer, who sits at
+# column xOffs looking along +x); Robot.py:16 fieldOfView
+AV_H, AV_W, AV_XOFFS, AV_FOV = RC_W // 2 - 50, RC_W // 2, 150, math.pi / 4
+_AV_LISTS = (("RC_R_CROSS", "RC_CAP_CROSS", 3, (255, 255, 255)), ("RC_R_FCROSS", "RC_CAP_FCROSS", 4, (255, 255, 255)),
+             ("RC_R_POST", "RC_CAP_POST", 2, (255, 0, 0)), ("RC_R_ROBOT", "RC_CAP_ROBOT", 1, (0, 255, 0)),
+             ("RC_R_BALL", "RC_CAP_BALL", 0, (0, 0, 255)))
+
+
+def render_agent_view(raw_record, dim=None):
+    """The reference's agent-view debug image (getAgentVision, RoboCupEnvironment.py:1469-1516: what ONE observer detects
+    at one tick, in its head frame, drawn from the observer outwards) from a raw detection record -- one
+    [RC_RAW_WORDS] slice of DynEnvRoboCupOut.raw (BatchedRoboCup(..., observationType=IMAGE).out.raw[e, t, p]): the lists
+    the reference draws, after noise, false negatives and false positives.  Returns uint8 [940, 1040, 3] in the reference's
+    channel order.
+
+    The reference dims Partial / Distant sightings (colour 127 instead of 255); the record does not carry the sighting
+    type, so everything is drawn bright unless `dim` (bool [RC_RAW_WORDS], True at the first word of a row) says otherwise.
+    A float64 record holds its counts as numbers (tests/golden/agent_view.npz); float32 / uint32 words hold them as int32."""
+    cv2 = _cv2()
+    rec = np.ascontiguousarray(np.asarray(raw_record))
+    if rec.dtype == np.float64:
+        val, cnt = rec, rec.astype(np.int64)
+    else:
+        val, cnt = rec.view(np.float32).astype(np.float64), rec.view(np.int32)
+    H, xo = AV_H, AV_XOFFS
+    img = np.zeros((2 * H, 2 * AV_W, 3), np.uint8)
+
+    def shade(col, off):
+        return tuple(c // 2 for c in col) if dim is not None and dim[off] else col
+
+    for a in (AV_FOV, -AV_FOV):  # the two edges of the field of view
+        cv2.line(img, (xo, H), (int(xo + math.cos(a) * 1000), int(H - math.sin(a) * 1000)), (255, 255, 0))
+    for i in range(int(cnt[L.RC_R_COUNTS + 5])):
+        o = L.RC_R_LINE + 4 * i
+        cv2.line(img, (int(xo + val[o]), int(-val[o + 1] + H)), (int(xo + val[o + 2]), int(-val[o + 3] + H)), shade((255, 255, 255), o), RC_LINEW)
+    if cnt[L.RC_R_CIRCLE_SEEN]:
+        o = L.RC_R_CIRCLE
+        cv2.circle(img, (int(xo + val[o]), int(-val[o + 1] + H)), int(val[o + 2]), shade((255, 0, 255), o), RC_LINEW)
+    for off_name, cap_name, k, col in _AV_LISTS:
+        off = getattr(L, off_name)
+        for i in range(min(int(cnt[L.RC_R_COUNTS + k]), getattr(L, cap_name))):
+            o = off + 3 * i
+            cv2.circle(img, (int(xo + val[o]), int(-val[o + 1] + H)), int(val[o + 2]), shade(col, o), -1)
     return img
 
 
