@@ -733,6 +733,9 @@ int dynenv_step_u8(DynEnvHandle h, const uint8_t* actions_u8_dev, void* out, voi
   {
     DeviceGuard guard(h->cfg.device);
     if (!h->act_f32) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone; /* (an allocation would invalidate a capture in progress) */
+      if (cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+        return fail(DYNENV_E_INVALID, "dynenv_step_u8: call it once outside stream capture first (its first call allocates the widened action buffer)");
       cudaError_t ce = cudaMalloc(&h->act_f32, (size_t)((n + 3) / 4 * 4) * sizeof(float));
       if (ce != cudaSuccess) return cuda_fail(ce, "cudaMalloc(actions)");
     }

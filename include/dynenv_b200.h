@@ -466,7 +466,8 @@ int dynenv_reset(DynEnvHandle h, const uint8_t* env_mask_dev, void* out, void* s
    continuousActions (RoboCupEnvironment.py:400-408, DrivingEnvironment.py:200-207) -- with the action indices as bytes,
    uint8 [E][P][4] / [E][N][2]: a quarter of the host -> device traffic of a step.  The bytes are widened to the handle's own
    float32 buffer by a kernel on `stream`, then the step runs as below; a value a float action could not have is flagged like
-   one (RC_IF_BAD_ACTION).) */
+   one (RC_IF_BAD_ACTION).  The first call allocates that buffer: make it before capturing the step into a CUDA graph --
+   under capture it returns DYNENV_E_INVALID instead.) */
 int dynenv_step_u8(DynEnvHandle h, const uint8_t* actions_u8_dev, void* out, void* terminal_out, void* stream);
 int dynenv_step(DynEnvHandle h, const float* actions_dev, void* out, void* terminal_out,
                 void* stream);

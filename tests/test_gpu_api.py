@@ -444,3 +444,16 @@ def test_step_replayed_as_a_cuda_graph():
         torch.cuda.synchronize()
         assert torch.equal(a.get_state(), b.get_state())
         assert torch.equal(oa.info.view(torch.int32), b.out.info.view(torch.int32)) and torch.equal(oa.counts, b.out.counts)
+    # the byte path's first call allocates: under capture it must refuse (and leave the capture intact), not break it
+    c = dynenv_b200.BatchedRoboCup(64, 5, **kw)
+    c.reset()
+    small = torch.zeros((64, 10, 4), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with pytest.raises(Exception, match="outside stream capture"):
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(g2, stream=cap):
+                c.step(small)
+    torch.cuda.synchronize()
+    c.step(small)  # fine outside
+    torch.cuda.synchronize()
