@@ -1,4 +1,4 @@
-"""Dev tool (here): turns what gpu_prof.sh brought back in gpurun_out/ into the tracked summaries under profiles/:
+"""Dev tool (here): turns what tools/gpu/gpu_prof*.sh brought back in gpurun_out/ into the tracked summaries under profiles/:
   profiles/rNN_ncu_<kernel>.txt       selected metrics of the ncu --set full capture + per-function instruction / stall table
   profiles/rNN_launches_<workload>.txt per-kernel launch counts, mean duration, share of the step kernels
   profiles/rNN_bench_<workload>.json   the bench lines (GPU arm and reference arm)
