@@ -222,8 +222,9 @@ def make_ref_env(ns, cfg, tape):
     return env
 
 
-def run_scenario(ns, name):
-    cfg, craft, actions_fn, steps, seed = SCENARIOS[name]
+def build_record(ns, cfg, craft, actions_fn, steps, seed):
+    """-> (the fixture's arrays, statistics of the run); also what tests/test_oracle_live.py checks the oracle against on
+    scenarios that are not among the committed ones"""
     tape = UniformTape(seed)
     env = make_ref_env(ns, cfg, tape)
     P = 2 * min(cfg["nPlayers"], 5)
@@ -283,6 +284,12 @@ def run_scenario(ns, name):
                cfg=np.array([cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"],
                              int(cfg["canFall"]), int(cfg["allowHeadTurn"]), int(cfg["randomInit"])],
                             dtype=np.float64))
+    return rec, stats
+
+
+def run_scenario(ns, name):
+    cfg, craft, actions_fn, steps, seed = SCENARIOS[name]
+    rec, stats = build_record(ns, cfg, craft, actions_fn, steps, seed)
     np.savez_compressed(os.path.join(OUT, "robocup_%s.npz" % name), **rec)
     print("%-24s steps=%3d max cached pairs=%2d fallen-robot-steps=%3d penalized-robot-steps=%3d goals=%d"
           % (name, steps, stats["maxarb"], stats["fallen"], stats["penal"], stats["goals"]))

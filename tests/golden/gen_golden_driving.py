@@ -143,8 +143,9 @@ def make_ref_env(ns, cfg, tape):
     return env
 
 
-def run_scenario(ns, name):
-    cfg, craft, actions_fn, steps, seed = SCENARIOS[name]
+def build_record(ns, cfg, craft, actions_fn, steps, seed):
+    """-> (the fixture's arrays, statistics of the run, uniforms drawn); also what tests/test_oracle_live.py checks the
+    oracle against on scenarios that are not among the committed ones"""
     tape = UniformTape(seed)
     env = make_ref_env(ns, cfg, tape)
     N = min(cfg["nPlayers"], NC)
@@ -196,9 +197,15 @@ def run_scenario(ns, name):
     rec.update(actions=np.array(acts), tape_off=np.array(tape_off), states=np.array(states), rewards=np.array(rewards),
                dones=np.array(dones), fs_cars=np.array(fs),
                cfg=np.array([cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"], int(cfg["continuous"])], dtype=np.float64))
+    return rec, stats, tape.count
+
+
+def run_scenario(ns, name):
+    cfg, craft, actions_fn, steps, seed = SCENARIOS[name]
+    rec, stats, n_uniforms = build_record(ns, cfg, craft, actions_fn, steps, seed)
     np.savez_compressed(os.path.join(OUT, "driving_%s.npz" % name), **rec)
     print("%-22s steps=%3d max cached pairs=%2d crashed=%2d finished=%2d dead peds=%2d uniforms=%d"
-          % (name, steps, stats["maxarb"], stats["crashed"], stats["finished"], stats["dead"], tape.count))
+          % (name, steps, stats["maxarb"], stats["crashed"], stats["finished"], stats["dead"], n_uniforms))
 
 
 if __name__ == "__main__":

@@ -21,8 +21,8 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 SCENARIOS = {"5v5_realistic": (5, 1, 2.0, False, 51), "3v3_random_init": (3, 0, 3.0, True, 52), "2v2_clean": (2, 1, 0.0, True, 53)}
 
 
-def run(ns, name):
-    nPlayers, noiseType, mag, rinit, seed = SCENARIOS[name]
+def build_record(ns, nPlayers, noiseType, mag, rinit, seed):
+    """-> the fixture's arrays (also built on the spot for other seeds by tests/test_oracle_live.py)"""
     tape = UniformTape(seed)
     ns.RoboCupEnvironment.randomInit = rinit
     try:
@@ -38,10 +38,16 @@ def run(ns, name):
     P = 2 * nPlayers
     imgs = np.stack([np.stack([raster_oracle.pack(obs[t][a]) for a in range(P)]) for t in range(len(obs))])
     assert all(set(np.unique(obs[t][a])) <= {0.0, 1.0} for t in range(len(obs)) for a in range(P))
-    np.savez_compressed(os.path.join(OUT, "image_%s.npz" % name), images=imgs, tape_seed=np.array(seed),
-                        tape_reset_off=np.array([tape.count - len(reset_tape), tape.count]), tape_reset_sum=np.array(reset_tape.sum()),
-                        state_reset=ref_state.robocup_get_state(env),
-                        cfg=np.array([nPlayers, 2, noiseType, mag, 1, 0, int(rinit)], dtype=np.float64))
+    return dict(images=imgs, tape_seed=np.array(seed),
+                tape_reset_off=np.array([tape.count - len(reset_tape), tape.count]), tape_reset_sum=np.array(reset_tape.sum()),
+                state_reset=ref_state.robocup_get_state(env),
+                cfg=np.array([nPlayers, 2, noiseType, mag, 1, 0, int(rinit)], dtype=np.float64))
+
+
+def run(ns, name):
+    rec = build_record(ns, *SCENARIOS[name])
+    imgs, P = rec["images"], rec["images"].shape[1]
+    np.savez_compressed(os.path.join(OUT, "image_%s.npz" % name), **rec)
     print("%-18s agents=%d set pixels per image: %s" % (name, P, [int(raster_oracle.unpack(imgs[0, a]).sum()) for a in range(P)]))
 
 

@@ -33,7 +33,11 @@ def test_goldens_exist():
 
 @pytest.mark.parametrize("name", NAMES)
 def test_oracle_matches_reference(name):
-    g = load_golden(name)
+    check_oracle_against(load_golden(name))
+
+
+def check_oracle_against(g):
+    """g: a fixture of tests/golden/gen_golden.py (committed, or built on the spot: tests/test_oracle_live.py)"""
     cfg = golden_cfg(g)
     seed = int(g["tape_seed"])
     P = 2 * cfg["nPlayers"]

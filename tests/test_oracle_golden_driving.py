@@ -45,7 +45,11 @@ def test_driving_goldens_exist():
 
 @pytest.mark.parametrize("name", NAMES)
 def test_driving_oracle_matches_reference(name):
-    g = dict(np.load(os.path.join(GOLDEN, "driving_%s.npz" % name)))
+    check_driving_oracle_against(dict(np.load(os.path.join(GOLDEN, "driving_%s.npz" % name))))
+
+
+def check_driving_oracle_against(g):
+    """g: a fixture of tests/golden/gen_golden_driving.py (committed, or built on the spot: tests/test_oracle_live.py)"""
     cfg = drv_cfg(g)
     seed = int(g["tape_seed"])
     orc = DrvOracle(cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"], cfg["continuous"])

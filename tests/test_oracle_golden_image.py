@@ -21,7 +21,11 @@ def test_image_goldens_exist():
 
 @pytest.mark.parametrize("name", NAMES)
 def test_raster_oracle_matches_reference(name):
-    g = dict(np.load(os.path.join(GOLDEN, "image_%s.npz" % name)))
+    check_raster_oracle_against(dict(np.load(os.path.join(GOLDEN, "image_%s.npz" % name))))
+
+
+def check_raster_oracle_against(g):
+    """g: a fixture of tests/golden/gen_golden_image.py (committed, or built on the spot: tests/test_oracle_live.py)"""
     cfg = golden_cfg(g)
     P = 2 * cfg["nPlayers"]
     orc = RcOracle(cfg["nPlayers"], cfg["obsType"], cfg["noiseType"], cfg["noiseMag"], cfg["allowHeadTurn"], cfg["flags"])
