@@ -21,11 +21,15 @@ RC_LIVE = [(5, 1, 1, 2.0, True, False, False, 24, 1001, None), (4, 1, 1, 4.0, Tr
            # contact-rich starts of the fixture generator under other seeds / noise: robots walking into each other (falls,
            # pushing penalties, cached pairs), two robots face to face, a robot at a goal post
            (5, 1, 1, 3.0, True, False, False, 30, 1006, "scrum"), (5, 1, 0, 1.0, True, False, False, 30, 1007, "scrum"),
-           (2, 1, 1, 4.0, True, False, False, 16, 1008, "face_to_face"), (1, 1, 1, 2.0, True, False, False, 16, 1009, "robot_at_post")]
+           (2, 1, 1, 4.0, True, False, False, 16, 1008, "face_to_face"), (1, 1, 1, 2.0, True, False, False, 16, 1009, "robot_at_post"),
+           # a whole 240-step episode of random play: 74 fallen-robot-steps, 40 penalised-robot-steps, the episode end
+           (5, 1, 1, 2.0, True, False, True, 240, 1010, None)]
 # (nPlayers, obs, noise type, magnitude, continuous, steps, seed, hand-made start state or None)
 DRV_LIVE = [(10, 1, 1, 2.0, False, 24, 2001, None), (7, 1, 0, 4.0, False, 24, 2002, None), (10, 1, 1, 3.0, True, 24, 2003, None),
             (3, 0, 1, 0.0, False, 30, 2004, None),
-            (6, 1, 1, 4.0, False, 10, 2005, "car_car"), (5, 1, 0, 2.0, False, 12, 2006, "car_ped"), (4, 1, 1, 1.0, False, 10, 2007, "car_static")]
+            (6, 1, 1, 4.0, False, 10, 2005, "car_car"), (5, 1, 0, 2.0, False, 12, 2006, "car_ped"), (4, 1, 1, 1.0, False, 10, 2007, "car_static"),
+            # 300 steps of ten cars at full throttle: 8 crash, 9 reach their goal, a pedestrian is run over
+            (10, 1, 1, 2.0, False, 300, 2011, "accelerate_10")]
 
 
 @pytest.fixture(scope="module")
@@ -53,6 +57,8 @@ def test_robocup_oracle_on_a_fresh_scenario(ns, case):
         ns.RoboCupEnvironment.canFall, ns.RoboCupEnvironment.randomInit = True, False  # the class defaults
     if start:
         assert stats["maxarb"] > 0  # the bodies did touch
+    if steps >= 240:
+        assert stats["fallen"] > 20 and stats["penal"] > 10 and rec["dones"][-1]
     for k in ("state0", "states", "state_reset"):
         rec[k] = pad_words(rec[k])
     check_oracle_against(rec)
